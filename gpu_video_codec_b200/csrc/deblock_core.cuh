@@ -1,0 +1,476 @@
+/*
+ * deblock_core.cuh -- the filter arithmetic of the B200 deblocking path.
+ *
+ * One CUDA thread owns one padded 8x8 block (the reference's unit of work,
+ * hevc_deblocking_filter_cpu.h ("cpu.h") :146-156) entirely in registers:
+ * sixteen 32-bit words, row r = { lo[r] : columns 0..3, hi[r] : columns 4..7 }.
+ * The four edge segments of the block are filtered in the reference's order
+ * (cpu.h:158-446): upper vertical, lower vertical, left horizontal, right
+ * horizontal.
+ *
+ * Arithmetic is SIMD-within-a-register: the four lines of a segment are held
+ * as two "pair" registers per tap, each carrying two lines as 16-bit halves
+ *     pair X = lines (0,3)   -- the two lines the decisions look at (cpu.h:1074-1114)
+ *     pair Y = lines (1,2)
+ * and evaluated with the sm_100a packed-halfword instructions VIADD.16x2,
+ * VIMNMX.S16x2, VIADDMNMX.S16x2(.RELU), IDP.2A and PRMT.  Signed intermediate
+ * values are carried with a positive bias so that plain 32-bit adds and shifts
+ * act on both halves at once.  No tensor cores: this is an integer stencil.
+ *
+ * The same header compiles for the host when HDB_HOST_EMU is defined: the five
+ * packed primitives are then plain C.  tests/emu/ uses that build to prove the
+ * arithmetic bit-exact against the oracle on a machine without a GPU.  The
+ * product library never compiles the host flavour.
+ */
+#pragma once
+
+#include <stdint.h>
+
+#if defined(HDB_HOST_EMU)
+#define HDB_FN static inline
+#else
+#define HDB_FN __device__ __forceinline__
+#endif
+
+namespace hdb {
+
+typedef uint32_t u32;
+
+/* ------------------------------------------------------------------ */
+/* packed-halfword primitives                                          */
+/* ------------------------------------------------------------------ */
+#if defined(HDB_HOST_EMU)
+static inline int16_t Lo(u32 a) { return (int16_t)(a & 0xffffu); }
+static inline int16_t Hi(u32 a) { return (int16_t)(a >> 16); }
+static inline u32 Pk(int lo, int hi) { return ((u32)lo & 0xffffu) | ((u32)hi << 16); }
+static inline int Mn(int a, int b) { return a < b ? a : b; }
+static inline int Mx(int a, int b) { return a > b ? a : b; }
+HDB_FN u32 Add2(u32 a, u32 b) { return Pk(Lo(a) + Lo(b), Hi(a) + Hi(b)); }
+HDB_FN u32 Max2(u32 a, u32 b) { return Pk(Mx(Lo(a), Lo(b)), Mx(Hi(a), Hi(b))); }
+HDB_FN u32 Min2(u32 a, u32 b) { return Pk(Mn(Lo(a), Lo(b)), Mn(Hi(a), Hi(b))); }
+HDB_FN u32 AddMax2(u32 a, u32 b, u32 c) {
+	return Pk(Mx((int16_t)(Lo(a) + Lo(b)), Lo(c)), Mx((int16_t)(Hi(a) + Hi(b)), Hi(c)));
+}
+HDB_FN u32 AddMin2(u32 a, u32 b, u32 c) {
+	return Pk(Mn((int16_t)(Lo(a) + Lo(b)), Lo(c)), Mn((int16_t)(Hi(a) + Hi(b)), Hi(c)));
+}
+HDB_FN u32 AddMinRelu2(u32 a, u32 b, u32 c) {
+	return Pk(Mx(Mn((int16_t)(Lo(a) + Lo(b)), Lo(c)), 0), Mx(Mn((int16_t)(Hi(a) + Hi(b)), Hi(c)), 0));
+}
+HDB_FN u32 Prmt(u32 x, u32 y, u32 s) {
+	uint64_t v = ((uint64_t)y << 32) | x;
+	u32 r = 0;
+	for (int i = 0; i < 4; i++) r |= (u32)((v >> (8 * ((s >> (4 * i)) & 7))) & 0xff) << (8 * i);
+	return r;
+}
+HDB_FN u32 SumHalves(u32 a) { return (a & 0xffffu) + (a >> 16); }
+#else
+HDB_FN u32 Add2(u32 a, u32 b) { return __vadd2(a, b); }                          /* VIADD.16x2 */
+HDB_FN u32 Max2(u32 a, u32 b) { return __vmaxs2(a, b); }                         /* VIMNMX.S16x2 */
+HDB_FN u32 Min2(u32 a, u32 b) { return __vmins2(a, b); }
+HDB_FN u32 AddMax2(u32 a, u32 b, u32 c) { return __viaddmax_s16x2(a, b, c); }    /* VIADDMNMX.S16x2 */
+HDB_FN u32 AddMin2(u32 a, u32 b, u32 c) { return __viaddmin_s16x2(a, b, c); }
+HDB_FN u32 AddMinRelu2(u32 a, u32 b, u32 c) { return __viaddmin_s16x2_relu(a, b, c); }
+HDB_FN u32 Prmt(u32 x, u32 y, u32 s) { return __byte_perm(x, y, s); }            /* PRMT */
+HDB_FN u32 SumHalves(u32 a) { return __dp2a_lo(a, 0x0101u, 0u); }                /* IDP.2A: lo*1 + hi*1 */
+#endif
+
+/* both halves = v (v may be negative: two's complement per half) */
+HDB_FN u32 Rep2(int v) { return ((u32)v & 0xffffu) * 0x10001u; }
+
+/* ------------------------------------------------------------------ */
+/* per-frame filter parameters (cpu.h:1021-1033, 1064-1072)            */
+/* ------------------------------------------------------------------ */
+struct FilterParams {
+	int beta, tc;
+	/* derived once per frame, all as packed or biased constants */
+	int dE_lim;      /* 2048 + beta            : dE test on the biased sum      cpu.h:1086-1087 */
+	int dEpq_lim;    /* 1024 + 3*beta/16       : dEp / dEq                      cpu.h:1245, 1249 */
+	u32 k_b8;        /* (0x8000 + beta/8 - 1) x2 : "< beta/8" on both halves    cpu.h:1099-1105 */
+	u32 k_tc52;      /* (0x8000 + 5*tc/2 - 1) x2 : "< 5*tc/2" on both halves    cpu.h:1109-1110 */
+	u32 c2_neg, c2_pos;       /* -2tc, +2tc replicated                          cpu.h:1191, 1235 */
+	u32 k_e_lo;      /* (2tc - 256) x2 */
+	u32 k_tc10;      /* (256 + 10tc + 1) x2                                     cpu.h:1254 */
+	u32 k_half;      /* (512 - 2tc) x2 */
+	u32 h_neg, h_lo, h_2; /* -(tc/2), (tc/2 - 256), 2*(tc/2) replicated         cpu.h:1236 */
+	u32 h_rep, c2_rep4; /* (tc/2) x2 ; (4tc) x2 */
+	u32 ct_neg, ct_lo, ct_2; /* chroma, c = tc: -tc, (tc - 256), 2tc replicated cpu.h:1442 */
+};
+
+HDB_FN void MakeFilterParams(FilterParams &fp, int beta, int tc)
+{
+	fp.beta = beta; fp.tc = tc;
+	fp.dE_lim = 2048 + beta;
+	fp.dEpq_lim = 1024 + 3 * beta / 16;
+	fp.k_b8 = Rep2(0x8000 + beta / 8 - 1);
+	fp.k_tc52 = Rep2(0x8000 + 5 * tc / 2 - 1);
+	fp.c2_neg = Rep2(-2 * tc); fp.c2_pos = Rep2(2 * tc);
+	fp.k_e_lo = Rep2(2 * tc - 256);
+	fp.k_tc10 = Rep2(256 + 10 * tc + 1);
+	fp.k_half = Rep2(512 - 2 * tc);
+	fp.h_neg = Rep2(-(tc / 2)); fp.h_lo = Rep2(tc / 2 - 256); fp.h_2 = Rep2(2 * (tc / 2));
+	fp.h_rep = Rep2(tc / 2); fp.c2_rep4 = Rep2(4 * tc);
+	fp.ct_neg = Rep2(-tc); fp.ct_lo = Rep2(tc - 256); fp.ct_2 = Rep2(2 * tc);
+}
+
+/* Taps of one line pair, unsigned 0..255 in each half. */
+struct LumaPair { u32 p3, p2, p1, p0, q0, q1, q2, q3; };
+struct ChromaPair { u32 p1, p0, q0, q1; };
+
+/* 512 + |a2 - 2*a1 + a0| per half (cpu.h:1086: the second-derivative terms) */
+HDB_FN u32 SecondDiffBiased(u32 a2, u32 a1, u32 a0)
+{
+	u32 t = a2 + a0 + 0x02000200u - 2u * a1; /* 512 + (a2 - 2a1 + a0) in [2, 1022] */
+	u32 n = 0x04000400u - t;                 /* 512 - (...) */
+	return Max2(t, n);
+}
+
+/* |a - b| per half for unsigned halves */
+HDB_FN u32 AbsDiff2(u32 a, u32 b) { return Max2(a, b) - Min2(a, b); }
+
+/*
+ * Strong filter on one line pair (cpu.h:1128-1213).  With x + delta_x equal to
+ * the all-positive sums below (adding a multiple of 8 commutes with >> 3),
+ *   x' = Clip255(x + Clip(-2tc, 2tc, delta_x)) = min(max(F_x, x - 2tc), x + 2tc)
+ * and the 0..255 clip is the identity because 0 <= F_x <= 255.
+ */
+HDB_FN void StrongPair(LumaPair &t, const FilterParams &fp)
+{
+	const u32 m8 = 0x00ff00ffu;
+	u32 s2 = t.p0 + t.q0 + 0x00020002u;       /* p0 + q0 + 2 */
+	u32 t1p = t.p2 + t.p1 + s2;               /* p2 + p1 + p0 + q0 + 2          -> >>2  cpu.h:1160 */
+	u32 t1q = t.q2 + t.q1 + s2;               /*                                         cpu.h:1179 */
+	u32 m = t.p1 + t.q1 + s2;
+	u32 t0p = t1p + m;                        /* p2 + 2p1 + 2p0 + 2q0 + q1 + 4  -> >>3  cpu.h:1154 */
+	u32 t0q = t1q + m;                        /*                                         cpu.h:1173 */
+	u32 t2p = 2u * (t.p3 + t.p2 + 0x00010001u) + t1p; /* 2p3 + 3p2 + p1 + p0 + q0 + 4 -> >>3  cpu.h:1166 */
+	u32 t2q = 2u * (t.q3 + t.q2 + 0x00010001u) + t1q; /*                                       cpu.h:1185 */
+	u32 f0p = (t0p >> 3) & m8, f1p = (t1p >> 2) & m8, f2p = (t2p >> 3) & m8;
+	u32 f0q = (t0q >> 3) & m8, f1q = (t1q >> 2) & m8, f2q = (t2q >> 3) & m8;
+	t.p0 = AddMin2(t.p0, fp.c2_pos, AddMax2(t.p0, fp.c2_neg, f0p)); /* cpu.h:1192-1211 */
+	t.p1 = AddMin2(t.p1, fp.c2_pos, AddMax2(t.p1, fp.c2_neg, f1p));
+	t.p2 = AddMin2(t.p2, fp.c2_pos, AddMax2(t.p2, fp.c2_neg, f2p));
+	t.q0 = AddMin2(t.q0, fp.c2_pos, AddMax2(t.q0, fp.c2_neg, f0q));
+	t.q1 = AddMin2(t.q1, fp.c2_pos, AddMax2(t.q1, fp.c2_neg, f1q));
+	t.q2 = AddMin2(t.q2, fp.c2_pos, AddMax2(t.q2, fp.c2_neg, f2q));
+}
+
+/*
+ * Normal filter on one line pair (cpu.h:1215-1357).  dEp/dEq are the
+ * segment-wide side decisions (cpu.h:1243-1249); the |delta| < 10*tc test is
+ * per line (cpu.h:1254), hence a per-half mask.
+ */
+HDB_FN void NormalPair(LumaPair &t, const FilterParams &fp, bool dEp, bool dEq)
+{
+	/* 4096 + 9(q0-p0) - 3(q1-p1) + 8, each half in [1044, 7164] */
+	u32 num = 3u * (3u * (t.q0 - t.p0) + t.p1 - t.q1) + 0x10081008u;
+	u32 e = (num >> 4) & 0x01ff01ffu;                  /* 256 + delta              cpu.h:1253 */
+	u32 a = Max2(e, 0x02000200u - e);                  /* 256 + |delta| */
+	u32 on = AddMinRelu2(~a, fp.k_tc10, 0x00010001u);  /* 1 where |delta| < 10tc   cpu.h:1254 */
+	u32 mask = on * 0xffffu;
+	u32 d = AddMinRelu2(e, fp.k_e_lo, fp.c2_rep4);     /* Clip(delta) + 2tc in [0, 4tc]  cpu.h:1256 */
+	d = (d & mask) | (fp.c2_pos & ~mask);              /* lines that are off: delta = 0 */
+	u32 dn = fp.c2_rep4 - d;                           /* 2tc - Clip(delta) */
+	u32 p0 = AddMinRelu2(Add2(t.p0, fp.c2_neg), d, 0x00ff00ffu);   /* cpu.h:1268 */
+	u32 q0 = AddMinRelu2(Add2(t.q0, fp.c2_neg), dn, 0x00ff00ffu);  /* cpu.h:1269 */
+	if (dEp) {
+		u32 avg = ((t.p2 + t.p0 + 0x00010001u) >> 1) & 0x01ff01ffu; /* (p2 + p0 + 1) >> 1  cpu.h:1259 */
+		u32 h = ((avg + d + fp.k_half - t.p1) >> 1) & 0x7fff7fffu;  /* 256 + ((avg - p1 + D) >> 1) */
+		u32 dp = AddMinRelu2(h, fp.h_lo, fp.h_2);                   /* Clip(., tc/2) + tc/2  cpu.h:1260 */
+		dp = (dp & mask) | (fp.h_rep & ~mask);
+		t.p1 = AddMinRelu2(Add2(t.p1, fp.h_neg), dp, 0x00ff00ffu);  /* cpu.h:1272 */
+	}
+	if (dEq) {
+		u32 avg = ((t.q2 + t.q0 + 0x00010001u) >> 1) & 0x01ff01ffu; /* cpu.h:1264 */
+		u32 h = ((avg + dn + fp.k_half - t.q1) >> 1) & 0x7fff7fffu; /* 256 + ((avg - q1 - D) >> 1) */
+		u32 dq = AddMinRelu2(h, fp.h_lo, fp.h_2);                   /* cpu.h:1265 */
+		dq = (dq & mask) | (fp.h_rep & ~mask);
+		t.q1 = AddMinRelu2(Add2(t.q1, fp.h_neg), dq, 0x00ff00ffu);  /* cpu.h:1275 */
+	}
+	t.p0 = p0; t.q0 = q0;
+}
+
+enum { kSegOff = 0, kSegNormal = 1, kSegStrong = 2 };
+
+/*
+ * One luma edge segment (cpu.h:1359-1429).  x = lines (0,3), y = lines (1,2).
+ * Returns which taps may have changed: kSegOff none, kSegNormal p1,p0,q0,q1,
+ * kSegStrong p2..q2.
+ */
+HDB_FN int LumaSegment(LumaPair &x, LumaPair &y, const FilterParams &fp)
+{
+	u32 dP = SecondDiffBiased(x.p2, x.p1, x.p0);       /* 512 + dp0 | 512 + dp3 */
+	u32 dQ = SecondDiffBiased(x.q2, x.q1, x.q0);
+	u32 s = dP + dQ;                                   /* 1024 + dp+dq per line */
+	if (!((int)SumHalves(s) < fp.dE_lim)) return kSegOff;           /* cpu.h:1086-1087 */
+	/* strong decision, lines 0 and 3 at once (cpu.h:1099-1110) */
+	u32 c3 = AbsDiff2(x.p3, x.p0) + AbsDiff2(x.q0, x.q3);
+	u32 c4 = AbsDiff2(x.p0, x.q0);
+	u32 m1 = Max2(s - 0x04000400u, c3);
+	u32 ok = (fp.k_b8 - m1) & (fp.k_tc52 - c4) & 0x80008000u;
+	if (ok == 0x80008000u) {
+		StrongPair(x, fp);
+		StrongPair(y, fp);
+		return kSegStrong;
+	}
+	bool dEp = (int)SumHalves(dP) < fp.dEpq_lim;                    /* cpu.h:1245 */
+	bool dEq = (int)SumHalves(dQ) < fp.dEpq_lim;                    /* cpu.h:1249 */
+	NormalPair(x, fp, dEp, dEq);
+	NormalPair(y, fp, dEp, dEq);
+	return kSegNormal;
+}
+
+/* One chroma line pair (cpu.h:1431-1488); only p0 and q0 change. */
+HDB_FN void ChromaPairFilter(ChromaPair &t, const FilterParams &fp)
+{
+	/* 2048 + 4(p0-q0) + p1 - q1 + 4 in [777, 3327]; the q numerator is 8 - (p numerator - 4) + ... */
+	u32 np = 4u * (t.p0 - t.q0) + t.p1 - t.q1 + 0x08040804u;        /* cpu.h:1453 */
+	u32 nq = 0x10081008u - np;                                      /* cpu.h:1458 */
+	u32 ep = (np >> 3) & 0x01ff01ffu;                               /* 256 + delta_p */
+	u32 eq = (nq >> 3) & 0x01ff01ffu;                               /* 256 + delta_q */
+	u32 dp = AddMinRelu2(ep, fp.ct_lo, fp.ct_2);                    /* Clip(delta_p) + tc   cpu.h:1464 */
+	u32 dq = fp.ct_2 - AddMinRelu2(eq, fp.ct_lo, fp.ct_2);          /* tc - Clip(delta_q)   cpu.h:1469 */
+	t.p0 = AddMinRelu2(Add2(t.p0, fp.ct_neg), dp, 0x00ff00ffu);     /* cpu.h:1475 */
+	t.q0 = AddMinRelu2(Add2(t.q0, fp.ct_neg), dq, 0x00ff00ffu);     /* cpu.h:1476 */
+}
+
+/* ------------------------------------------------------------------ */
+/* register block <-> line pairs                                       */
+/* ------------------------------------------------------------------ */
+
+/*
+ * Vertical edge (cpu.h:159-284): lines are rows r0..r0+3, taps run along the
+ * row: p_k = column 3-k (word lo, byte 3-k), q_k = column 4+k (word hi, byte k).
+ * Pair (ra, rb): half lo = row ra, half hi = row rb.
+ */
+HDB_FN void LoadVertPair(LumaPair &t, u32 la, u32 lb, u32 ha, u32 hb)
+{
+	const u32 m8 = 0x00ff00ffu;
+	u32 g1 = Prmt(la, lb, 0x5410);  /* a.b0 a.b1 b.b0 b.b1 = p3a p2a p3b p2b */
+	u32 g2 = Prmt(la, lb, 0x7632);  /* p1a p0a p1b p0b */
+	u32 h1 = Prmt(ha, hb, 0x5410);  /* q0a q1a q0b q1b */
+	u32 h2 = Prmt(ha, hb, 0x7632);  /* q2a q3a q2b q3b */
+	t.p3 = g1 & m8; t.p2 = (g1 >> 8) & m8;
+	t.p1 = g2 & m8; t.p0 = (g2 >> 8) & m8;
+	t.q0 = h1 & m8; t.q1 = (h1 >> 8) & m8;
+	t.q2 = h2 & m8; t.q3 = (h2 >> 8) & m8;
+}
+
+HDB_FN void StoreVertPair(const LumaPair &t, int kind, u32 &la, u32 &lb, u32 &ha, u32 &hb)
+{
+	u32 g2 = Prmt(t.p1, t.p0, 0x6240);  /* p1a p0a p1b p0b */
+	u32 h1 = Prmt(t.q0, t.q1, 0x6240);  /* q0a q1a q0b q1b */
+	if (kind == kSegStrong) {
+		u32 wa = Prmt(la, t.p2, 0x0040);    /* a.b0 p2a . . */
+		u32 wb = Prmt(lb, t.p2, 0x0060);    /* b.b0 p2b . . */
+		la = Prmt(wa, g2, 0x5410);
+		lb = Prmt(wb, g2, 0x7610);
+		u32 va = Prmt(ha, t.q2, 0x3400);    /* . . q2a a.b3 */
+		u32 vb = Prmt(hb, t.q2, 0x3600);    /* . . q2b b.b3 */
+		ha = Prmt(h1, va, 0x7610);
+		hb = Prmt(h1, vb, 0x7632);
+	} else {
+		la = Prmt(la, g2, 0x5410);
+		lb = Prmt(lb, g2, 0x7610);
+		ha = Prmt(h1, ha, 0x7610);
+		hb = Prmt(h1, hb, 0x7632);
+	}
+}
+
+/*
+ * Horizontal edge (cpu.h:287-446): lines are columns, the four bytes of a row
+ * word are the four lines of one tap.  x = bytes (0,3), y = bytes (1,2).
+ */
+HDB_FN void SplitRow(u32 w, u32 &x, u32 &y) { x = Prmt(w, 0u, 0x4340); y = Prmt(w, 0u, 0x4241); }
+HDB_FN u32 JoinRow(u32 x, u32 y) { return Prmt(x, y, 0x2640); }
+
+/* chroma, vertical edge: p1 p0 = columns 2,3 ; q0 q1 = columns 4,5 */
+HDB_FN void LoadVertPairChroma(ChromaPair &t, u32 la, u32 lb, u32 ha, u32 hb)
+{
+	const u32 m8 = 0x00ff00ffu;
+	u32 g = Prmt(la, lb, 0x7632);  /* p1a p0a p1b p0b */
+	u32 h = Prmt(ha, hb, 0x5410);  /* q0a q1a q0b q1b */
+	t.p1 = g & m8; t.p0 = (g >> 8) & m8;
+	t.q0 = h & m8; t.q1 = (h >> 8) & m8;
+}
+
+HDB_FN void StoreVertPairChroma(const ChromaPair &t, u32 &la, u32 &lb, u32 &ha, u32 &hb)
+{
+	la = Prmt(la, t.p0, 0x4210);
+	lb = Prmt(lb, t.p0, 0x6210);
+	ha = Prmt(ha, t.q0, 0x3214);
+	hb = Prmt(hb, t.q0, 0x3216);
+}
+
+/* ------------------------------------------------------------------ */
+/* tables and boundary-strength resolution                             */
+/* ------------------------------------------------------------------ */
+
+/*
+ * beta / tc lookup, QP clamped to 51 (cpu.h:1021-1033, 1064-1072).  The tables
+ * depend on QP only -- in the reference the boundary strength gates the edge
+ * (cpu.h:164, 463) but does not offset tc.  ptxas places them in the constant bank.
+ */
+HDB_FN int BetaOf(unsigned qp)
+{
+	static const unsigned char beta_of_qp[52] = {
+		0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15,
+		16, 17, 18, 20, 22, 24, 26, 28, 30, 32, 34, 36, 38, 40, 42, 44, 46, 48, 50, 52,
+		54, 56, 58, 60, 62, 64 };
+	return beta_of_qp[qp > 51 ? 51 : qp];
+}
+
+HDB_FN int TcOf(unsigned qp)
+{
+	static const unsigned char tc_of_qp[52] = {
+		0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1,
+		1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 5, 5, 6, 6, 7, 8, 9, 10, 11, 13, 14, 16,
+		18, 20 };
+	return tc_of_qp[qp > 51 ? 51 : qp];
+}
+
+/* Sizes of the boundary-strength arrays (cpu.h:86-87, 104-105), unsigned left-to-right. */
+HDB_FN unsigned NumVertBs(unsigned w, unsigned h) { return (w / 8 + 1) * h / 8; }
+HDB_FN unsigned NumHorBs(unsigned w, unsigned h) { return (h / 8 + 1) * w / 8; }
+
+/*
+ * The four boundary strengths of luma block (bx, by), packed
+ * BS_ver1 | BS_ver2 << 8 | BS_hor1 << 16 | BS_hor2 << 24  (cpu.h:159-163, 223-227, 287-291, 368-372).
+ * w8 = W/8; nbx = W/8 + 1, nby = H/8 + 1 are the padded block counts.
+ */
+HDB_FN u32 LumaBsOfBlock(int bx, int by, int w8, int nbx, int nby,
+	const unsigned char *vert_bs, const unsigned char *hor_bs)
+{
+	u32 r = 0;
+	if (by > 0) r |= (u32)vert_bs[(by - 1) * (w8 + 1) + bx];
+	if (by < nby - 1) r |= (u32)vert_bs[by * (w8 + 1) + bx] << 8;
+	if (bx > 0) r |= (u32)hor_bs[by * w8 + bx - 1] << 16;
+	if (bx < nbx - 1) r |= (u32)hor_bs[by * w8 + bx] << 24;
+	return r;
+}
+
+/*
+ * Same for a chroma block.  Chroma strengths are never caller-set: they are the
+ * constructor defaults (cpu.h:110-117: 2, except index % (cw/8+1) == 0 for the
+ * vertical and index % (ch/8+1) == 0 for the horizontal array), read with the
+ * LUMA block counts as limits (cpu.h:515, 645) and therefore past the end of
+ * the arrays on the last chroma block row / column; reads past the end are 0
+ * (zero-extension).
+ */
+HDB_FN u32 ChromaBsOfBlock(int bx, int by, unsigned cw, unsigned ch, int luma_nbx, int luma_nby)
+{
+	const unsigned cw8 = cw / 8, ch8 = ch / 8;
+	const unsigned ncv = NumVertBs(cw, ch), nch = NumHorBs(cw, ch);
+	u32 r = 0;
+	if (by > 0) {
+		unsigned i = (unsigned)(by - 1) * (cw8 + 1) + bx;
+		if (i < ncv && i % (cw8 + 1) != 0) r |= 2u;
+	}
+	if (by < luma_nby - 1) {
+		unsigned i = (unsigned)by * (cw8 + 1) + bx;
+		if (i < ncv && i % (cw8 + 1) != 0) r |= 2u << 8;
+	}
+	if (bx > 0) {
+		unsigned i = (unsigned)by * cw8 + bx - 1;
+		if (i < nch && i % (ch8 + 1) != 0) r |= 2u << 16;
+	}
+	if (bx < luma_nbx - 1) {
+		unsigned i = (unsigned)by * cw8 + bx;
+		if (i < nch && i % (ch8 + 1) != 0) r |= 2u << 24;
+	}
+	return r;
+}
+
+/* ------------------------------------------------------------------ */
+/* one padded 8x8 block                                                 */
+/* ------------------------------------------------------------------ */
+
+/*
+ * Luma block, cpu.h:158-446.  bs[0..3] = BS_ver1, BS_ver2, BS_hor1, BS_hor2 as
+ * resolved by the caller (zero where the reference's guards skip the lookup).
+ */
+HDB_FN void LumaBlock(u32 (&lo)[8], u32 (&hi)[8], u32 bs_ver1, u32 bs_ver2, u32 bs_hor1, u32 bs_hor2,
+	const FilterParams &fp)
+{
+	/* upper (rows 0-3) and lower (rows 4-7) vertical edge segments */
+#pragma unroll
+	for (int s = 0; s < 2; s++) {
+		const int r = 4 * s;
+		if ((s == 0 ? bs_ver1 : bs_ver2) > 0) {                     /* cpu.h:164, 228 */
+			LumaPair x, y;
+			LoadVertPair(x, lo[r], lo[r + 3], hi[r], hi[r + 3]);
+			LoadVertPair(y, lo[r + 1], lo[r + 2], hi[r + 1], hi[r + 2]);
+			int kind = LumaSegment(x, y, fp);
+			if (kind != kSegOff) {
+				StoreVertPair(x, kind, lo[r], lo[r + 3], hi[r], hi[r + 3]);
+				StoreVertPair(y, kind, lo[r + 1], lo[r + 2], hi[r + 1], hi[r + 2]);
+			}
+		}
+	}
+	/* left horizontal edge segment: columns 0-3, p rows 3..0, q rows 4..7 (cpu.h:287-365) */
+	if (bs_hor1 > 0) {
+		LumaPair x, y;
+		SplitRow(lo[0], x.p3, y.p3); SplitRow(lo[1], x.p2, y.p2);
+		SplitRow(lo[2], x.p1, y.p1); SplitRow(lo[3], x.p0, y.p0);
+		SplitRow(lo[4], x.q0, y.q0); SplitRow(lo[5], x.q1, y.q1);
+		SplitRow(lo[6], x.q2, y.q2); SplitRow(lo[7], x.q3, y.q3);
+		int kind = LumaSegment(x, y, fp);
+		if (kind != kSegOff) {
+			lo[2] = JoinRow(x.p1, y.p1); lo[3] = JoinRow(x.p0, y.p0);
+			lo[4] = JoinRow(x.q0, y.q0); lo[5] = JoinRow(x.q1, y.q1);
+			if (kind == kSegStrong) { lo[1] = JoinRow(x.p2, y.p2); lo[6] = JoinRow(x.q2, y.q2); }
+		}
+	}
+	/* right horizontal edge segment: p = columns 4-7 of rows 3..0, q = columns 0-3 of
+	 * rows 4..7 -- the reference's pairing (cpu.h:383-445), reproduced as is */
+	if (bs_hor2 > 0) {
+		LumaPair x, y;
+		SplitRow(hi[0], x.p3, y.p3); SplitRow(hi[1], x.p2, y.p2);
+		SplitRow(hi[2], x.p1, y.p1); SplitRow(hi[3], x.p0, y.p0);
+		SplitRow(lo[4], x.q0, y.q0); SplitRow(lo[5], x.q1, y.q1);
+		SplitRow(lo[6], x.q2, y.q2); SplitRow(lo[7], x.q3, y.q3);
+		int kind = LumaSegment(x, y, fp);
+		if (kind != kSegOff) {
+			hi[2] = JoinRow(x.p1, y.p1); hi[3] = JoinRow(x.p0, y.p0);
+			lo[4] = JoinRow(x.q0, y.q0); lo[5] = JoinRow(x.q1, y.q1);
+			if (kind == kSegStrong) { hi[1] = JoinRow(x.p2, y.p2); lo[6] = JoinRow(x.q2, y.q2); }
+		}
+	}
+}
+
+/* Chroma block, cpu.h:453-721 (and 724-992): same geometry, taps k = 0,1, BS == 2 only. */
+HDB_FN void ChromaBlock(u32 (&lo)[8], u32 (&hi)[8], u32 bs_ver1, u32 bs_ver2, u32 bs_hor1, u32 bs_hor2,
+	const FilterParams &fp)
+{
+#pragma unroll
+	for (int s = 0; s < 2; s++) {
+		const int r = 4 * s;
+		if ((s == 0 ? bs_ver1 : bs_ver2) == 2) {                    /* cpu.h:463, 519 */
+			ChromaPair x, y;
+			LoadVertPairChroma(x, lo[r], lo[r + 3], hi[r], hi[r + 3]);
+			LoadVertPairChroma(y, lo[r + 1], lo[r + 2], hi[r + 1], hi[r + 2]);
+			ChromaPairFilter(x, fp);
+			ChromaPairFilter(y, fp);
+			StoreVertPairChroma(x, lo[r], lo[r + 3], hi[r], hi[r + 3]);
+			StoreVertPairChroma(y, lo[r + 1], lo[r + 2], hi[r + 1], hi[r + 2]);
+		}
+	}
+	if (bs_hor1 == 2) {                                             /* cpu.h:572 */
+		ChromaPair x, y;
+		SplitRow(lo[2], x.p1, y.p1); SplitRow(lo[3], x.p0, y.p0);
+		SplitRow(lo[4], x.q0, y.q0); SplitRow(lo[5], x.q1, y.q1);
+		ChromaPairFilter(x, fp);
+		ChromaPairFilter(y, fp);
+		lo[3] = JoinRow(x.p0, y.p0); lo[4] = JoinRow(x.q0, y.q0);
+	}
+	if (bs_hor2 == 2) {                                             /* cpu.h:649 */
+		ChromaPair x, y;
+		SplitRow(hi[2], x.p1, y.p1); SplitRow(hi[3], x.p0, y.p0);
+		SplitRow(lo[4], x.q0, y.q0); SplitRow(lo[5], x.q1, y.q1);
+		ChromaPairFilter(x, fp);
+		ChromaPairFilter(y, fp);
+		hi[3] = JoinRow(x.p0, y.p0); lo[4] = JoinRow(x.q0, y.q0);
+	}
+}
+
+} // namespace hdb

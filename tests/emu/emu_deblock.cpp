@@ -1,0 +1,75 @@
+/*
+ * emu_deblock.cpp -- TEST INFRASTRUCTURE ONLY.
+ *
+ * Compiles the product's arithmetic header (gpu_video_codec_b200/csrc/deblock_core.cuh)
+ * for the HOST with the packed-halfword primitives emulated in C, and drives it
+ * over whole frames exactly like the generic CUDA kernel does (padded planes,
+ * one 8x8 block at a time).  tests/test_core_emu.py compares it with the oracle,
+ * which proves the register-level formulation bit-exact without a GPU.  It is
+ * not part of, nor reachable from, the product library.
+ */
+#define HDB_HOST_EMU 1
+#include "../../gpu_video_codec_b200/csrc/deblock_core.cuh"
+
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+using namespace hdb;
+
+static void FilterPlane(uint8_t *pl, int nbx, int nby, size_t pitch, bool chroma,
+	unsigned w, unsigned h, int luma_nbx, int luma_nby,
+	const uint8_t *vbs, const uint8_t *hbs, const FilterParams &fp)
+{
+	for (int by = 0; by < nby; by++)
+		for (int bx = 0; bx < nbx; bx++) {
+			uint8_t *b = pl + (size_t)by * 8 * pitch + (size_t)bx * 8;
+			u32 lo[8], hi[8];
+			for (int r = 0; r < 8; r++) {
+				memcpy(&lo[r], b + r * pitch, 4);
+				memcpy(&hi[r], b + r * pitch + 4, 4);
+			}
+			u32 bs = chroma ? ChromaBsOfBlock(bx, by, w, h, luma_nbx, luma_nby)
+				: LumaBsOfBlock(bx, by, (int)(w / 8), nbx, nby, vbs, hbs);
+			if (chroma) ChromaBlock(lo, hi, bs & 0xff, (bs >> 8) & 0xff, (bs >> 16) & 0xff, bs >> 24, fp);
+			else LumaBlock(lo, hi, bs & 0xff, (bs >> 8) & 0xff, (bs >> 16) & 0xff, bs >> 24, fp);
+			for (int r = 0; r < 8; r++) {
+				memcpy(b + r * pitch, &lo[r], 4);
+				memcpy(b + r * pitch + 4, &hi[r], 4);
+			}
+		}
+}
+
+extern "C" int emu_beta(unsigned qp) { return BetaOf(qp); }
+extern "C" int emu_tc(unsigned qp) { return TcOf(qp); }
+
+extern "C" int emu_deblock_frame(const uint8_t *in, uint8_t *out, unsigned w, unsigned h, unsigned qp,
+	const uint8_t *vbs, const uint8_t *hbs)
+{
+	if (w % 8 || h % 8) return 1;
+	unsigned cw = w / 2, ch = h / 2;
+	unsigned nw = w + 8, nh = h + 8, ncw = cw + 8, nch = ch + 8;
+	int nbx = nw / 8, nby = nh / 8, cnbx = ncw / 8, cnby = nch / 8;
+	FilterParams fp;
+	MakeFilterParams(fp, BetaOf(qp), TcOf(qp));
+	std::vector<uint8_t> dv, dh;
+	if (!vbs) {
+		dv.resize(NumVertBs(w, h)); dh.resize(NumHorBs(w, h));
+		for (size_t i = 0; i < dv.size(); i++) dv[i] = (i % (w / 8 + 1) == 0) ? 0 : 2;
+		for (size_t i = 0; i < dh.size(); i++) dh[i] = (i % (h / 8 + 1) == 0) ? 0 : 2;
+		vbs = dv.data(); hbs = dh.data();
+	}
+	std::vector<uint8_t> Y((size_t)nw * nh, 0), C((size_t)ncw * nch);
+	for (unsigned r = 0; r < h; r++) memcpy(&Y[(size_t)(r + 4) * nw + 4], in + (size_t)r * w, w);
+	FilterPlane(Y.data(), nbx, nby, (size_t)nbx * 8, false, w, h, nbx, nby, vbs, hbs, fp);
+	for (unsigned r = 0; r < h; r++) memcpy(out + (size_t)r * w, &Y[(size_t)(r + 4) * nw + 4], w);
+	for (int p = 0; p < 2; p++) {
+		const uint8_t *src = in + (size_t)w * h + (size_t)p * cw * ch;
+		uint8_t *dst = out + (size_t)w * h + (size_t)p * cw * ch;
+		std::fill(C.begin(), C.end(), 0);
+		for (unsigned r = 0; r < ch; r++) memcpy(&C[(size_t)(r + 4) * ncw + 4], src + (size_t)r * cw, cw);
+		FilterPlane(C.data(), cnbx, cnby, (size_t)cnbx * 8, true, cw, ch, nbx, nby, nullptr, nullptr, fp);
+		for (unsigned r = 0; r < ch; r++) memcpy(dst + (size_t)r * cw, &C[(size_t)(r + 4) * ncw + 4], cw);
+	}
+	return 0;
+}
