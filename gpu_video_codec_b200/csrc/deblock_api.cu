@@ -1,0 +1,551 @@
+/*
+ * deblock_api.cu -- host side of the library: context, tensor maps, the pinned
+ * multi-stream pipeline and the single-GPU C-ABI entry points of
+ * include/hevc_deblock_b200.h.  Replaces the reference's GPU host path
+ * (gpu.cu:1074-1306: Initialize / ExecuteGpu / Release), which allocates per
+ * call, copies synchronously on the default stream and keeps its state in
+ * file-scope globals (gpu.cu:35-77).
+ */
+#include "deblock_api.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+
+namespace hdb {
+
+static const char *kMsgFileSize = "Incorrect file size";                                             /* cpu.h:44 */
+static const char *kMsgDims = "Width and height of image must be multiplier of sample block size";   /* cpu.h:47 */
+static const char *kMsgBsSize = "Incorrect size of input boundary strenght array";                    /* cpu.h:123 */
+
+static std::string g_create_error;
+
+int Fail(hdb_context *ctx, int status, const std::string &msg)
+{
+	if (ctx) ctx->err = msg; else g_create_error = msg;
+	return status;
+}
+
+int FailCuda(hdb_context *ctx, cudaError_t e, const char *what)
+{
+	return Fail(ctx, HDB_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define HDB_CUDA(ctx, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return FailCuda(ctx, e__, #call); } while (0)
+
+/* ------------------------------------------------------------------ */
+/* context                                                             */
+/* ------------------------------------------------------------------ */
+static int CreateContext(hdb_context **out, int device)
+{
+	if (!out) return Fail(nullptr, HDB_ERR_INVALID_ARG, "ctx is NULL");
+	*out = nullptr;
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess || count == 0)
+		return Fail(nullptr, HDB_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
+	if (device < 0 || device >= count) return Fail(nullptr, HDB_ERR_INVALID_ARG, "device ordinal out of range");
+	hdb_context *ctx = new (std::nothrow) hdb_context();
+	if (!ctx) return Fail(nullptr, HDB_ERR_NO_MEMORY, "out of host memory");
+	ctx->device = device;
+	DeviceGuard guard(device);
+	if ((e = cudaGetDeviceProperties(&ctx->prop, device)) != cudaSuccess) {
+		delete ctx;
+		return FailCuda(nullptr, e, "cudaGetDeviceProperties");
+	}
+	if (ctx->prop.major != 10) {
+		char buf[256];
+		snprintf(buf, sizeof buf, "device %d (%s) is compute capability %d.%d; this library is built for sm_100a only",
+			device, ctx->prop.name, ctx->prop.major, ctx->prop.minor);
+		delete ctx;
+		return Fail(nullptr, HDB_ERR_CUDA, buf);
+	}
+	void *fn = nullptr;
+	cudaDriverEntryPointQueryResult qres;
+	e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+	if (e != cudaSuccess || !fn || qres != cudaDriverEntryPointSuccess) {
+		delete ctx;
+		return Fail(nullptr, HDB_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+	}
+	ctx->encode = reinterpret_cast<EncodeTiledFn>(fn);
+	bool ok = cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking) == cudaSuccess
+		&& cudaStreamCreateWithFlags(&ctx->s_k, cudaStreamNonBlocking) == cudaSuccess
+		&& cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking) == cudaSuccess
+		&& cudaMalloc(&ctx->sched, TiledSchedBytes()) == cudaSuccess
+		&& cudaMemset(ctx->sched, 0, TiledSchedBytes()) == cudaSuccess;
+	if (!ok) {
+		e = cudaGetLastError();
+		DestroyContext(ctx);
+		return FailCuda(nullptr, e, "context resources");
+	}
+	*out = ctx;
+	return HDB_OK;
+}
+
+void DestroyContext(hdb_context *ctx)
+{
+	if (!ctx) return;
+	DeviceGuard guard(ctx->device);
+	cudaDeviceSynchronize();
+	for (auto &s : ctx->sizes) { cudaFree(s.chroma_bs); cudaFree(s.def_vbs); cudaFree(s.def_hbs); }
+	for (auto &sl : ctx->slots) { cudaFree(sl.frames); cudaFree(sl.vbs); cudaFree(sl.hbs); cudaFree(sl.qp); }
+	for (auto ev : ctx->event_pool) cudaEventDestroy(ev);
+	cudaFree(ctx->generic_scratch);
+	cudaFree(ctx->sched);
+	if (ctx->stage_in) cudaFreeHost(ctx->stage_in);
+	if (ctx->stage_out) cudaFreeHost(ctx->stage_out);
+	if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
+	if (ctx->s_k) cudaStreamDestroy(ctx->s_k);
+	if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
+	delete ctx;
+}
+
+/* per-size device tables: resolved chroma strengths, default luma strengths */
+int GetSizeState(hdb_context *ctx, int w, int h, SizeState **out)
+{
+	for (auto &s : ctx->sizes) if (s.w == w && s.h == h) { *out = &s; return HDB_OK; }
+	SizeState s{};
+	s.w = w; s.h = h;
+	const size_t ncb = (size_t)((w / 2 + 8) / 8) * ((h / 2 + 8) / 8);
+	const unsigned nv = (unsigned)(w / 8 + 1) * h / 8, nh = (unsigned)(h / 8 + 1) * w / 8;
+	HDB_CUDA(ctx, cudaMalloc(&s.chroma_bs, std::max<size_t>(ncb, 1) * sizeof(uint32_t)));
+	HDB_CUDA(ctx, cudaMalloc(&s.def_vbs, std::max(nv, 1u)));
+	HDB_CUDA(ctx, cudaMalloc(&s.def_hbs, std::max(nh, 1u)));
+	/* built on the legacy default stream, then a full sync: visible to every stream afterwards */
+	HDB_CUDA(ctx, LaunchChromaBsTable(s.chroma_bs, w, h, 0));
+	HDB_CUDA(ctx, LaunchDefaultLumaBs(s.def_vbs, s.def_hbs, w, h, 0));
+	HDB_CUDA(ctx, cudaDeviceSynchronize());
+	ctx->sizes.push_back(s);
+	*out = &ctx->sizes.back();
+	return HDB_OK;
+}
+
+static int EncodePlaneMap(hdb_context *ctx, CUtensorMap *map, const void *base, int pw, int ph, int n,
+	long long frame_stride, int box_rows)
+{
+	cuuint64_t dims[3] = { (cuuint64_t)pw, (cuuint64_t)ph, (cuuint64_t)n };
+	cuuint64_t strides[2] = { (cuuint64_t)pw, (cuuint64_t)frame_stride };
+	cuuint32_t box[3] = { 256u, (cuuint32_t)box_rows, 1u };
+	cuuint32_t estr[3] = { 1u, 1u, 1u };
+	CUresult r = ctx->encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(base), dims, strides, box, estr,
+		CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+		CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	if (r != CUDA_SUCCESS) {
+		char buf[160];
+		snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d) for a %dx%d plane, %d frames", (int)r, pw, ph, n);
+		return Fail(ctx, HDB_ERR_CUDA, buf);
+	}
+	return HDB_OK;
+}
+
+bool TiledPathUsable(int w, int h, const void *d_in, const void *d_out)
+{
+	(void)h;
+	return w % 32 == 0 && ((uintptr_t)d_in % 16 == 0) && ((uintptr_t)d_out % 16 == 0);
+}
+
+/*
+ * Enqueue the filter for frames resident in device memory.  view describes which
+ * rows the buffers hold (whole frames unless a strip).  No synchronisation.
+ */
+int EnqueueFilter(hdb_context *ctx, const FrameView &view, const unsigned char *d_in, unsigned char *d_out,
+	int n, const unsigned *d_qp, unsigned qp_value, const unsigned char *d_vbs, long long vbs_stride,
+	const unsigned char *d_hbs, long long hbs_stride, cudaStream_t stream, int *path)
+{
+	const int w = view.width, h = view.height;
+	SizeState *ss = nullptr;
+	int rc = GetSizeState(ctx, w, h, &ss);
+	if (rc) return rc;
+	if (!d_vbs || !d_hbs) { d_vbs = ss->def_vbs; d_hbs = ss->def_hbs; vbs_stride = hbs_stride = 0; }
+	const TiledConfig cfg = GetTiledConfig();
+
+	if (view.whole_frame && !TiledPathUsable(w, h, d_in, d_out)) {
+		/* generic path: explicit padded planes in scratch memory */
+		if (path) *path = 2;
+		const size_t per = GenericScratchBytes(w, h);
+		const int max_n = (int)std::max<size_t>(1, ((size_t)256 << 20) / per);
+		const int chunk = std::min(n, max_n);
+		if (ctx->generic_scratch_bytes < per * chunk) {
+			HDB_CUDA(ctx, cudaStreamSynchronize(stream));
+			cudaFree(ctx->generic_scratch);
+			ctx->generic_scratch = nullptr; ctx->generic_scratch_bytes = 0;
+			HDB_CUDA(ctx, cudaMalloc(&ctx->generic_scratch, per * chunk));
+			ctx->generic_scratch_bytes = per * chunk;
+		}
+		/* a single uniform QP is materialised on the device for this path */
+		const long long fs = (long long)w * h * 3 / 2;
+		for (int f0 = 0; f0 < n; f0 += chunk) {
+			GenericBatch g{};
+			g.n_frames = std::min(chunk, n - f0); g.width = w; g.height = h;
+			g.in = d_in + f0 * fs; g.out = d_out + f0 * fs; g.frame_stride = fs;
+			g.scratch = ctx->generic_scratch;
+			g.qp = d_qp ? d_qp + f0 : nullptr; g.qp_value = qp_value;
+			g.vert_bs = d_vbs + f0 * vbs_stride; g.hor_bs = d_hbs + f0 * hbs_stride;
+			g.vert_bs_stride = vbs_stride; g.hor_bs_stride = hbs_stride;
+			HDB_CUDA(ctx, LaunchGeneric(g, stream));
+			ctx->launches += 3;
+		}
+		return HDB_OK;
+	}
+
+	if (path) *path = 1;
+	const int cw = w / 2, ch = h / 2;
+	TiledBatch b{};
+	b.width = w; b.height = h;
+	b.luma_nbx = (w + 8) / 8; b.luma_nby = (h + 8) / 8;
+	b.chroma_nbx = (cw + 8) / 8; b.chroma_nby = (ch + 8) / 8;
+	b.luma_row0 = view.luma_row0; b.luma_rows = view.luma_rows;
+	b.chroma_row0 = view.chroma_row0; b.chroma_rows = view.chroma_rows;
+	b.luma_y_org = view.luma_row0 == 0 ? -4 : 0;
+	b.chroma_y_org = view.chroma_row0 == 0 ? -4 : 0;
+	b.vert_bs_stride = vbs_stride; b.hor_bs_stride = hbs_stride;
+	b.chroma_bs = ss->chroma_bs;
+	b.qp_value = qp_value;
+	/* frames per launch bounded by the 31-bit item counter */
+	b.n_frames = 1;
+	FinalizeTiledBatch(b);
+	const long long max_frames = std::max<long long>(1, ((1ll << 31) - (1 << 20)) / std::max(b.items_per_frame, 1));
+	const long long fs = view.frame_stride;
+	for (long long f0 = 0; f0 < n; f0 += max_frames) {
+		const int nf = (int)std::min<long long>(max_frames, n - f0);
+		b.n_frames = nf;
+		FinalizeTiledBatch(b);
+		b.qp = d_qp ? d_qp + f0 : nullptr;
+		b.vert_bs = d_vbs + f0 * vbs_stride;
+		b.hor_bs = d_hbs + f0 * hbs_stride;
+		TensorMaps6 maps;
+		const unsigned char *in0 = d_in + f0 * fs;
+		unsigned char *out0 = d_out + f0 * fs;
+		const long long off[3] = { 0, view.u_offset, view.v_offset };
+		const int pw[3] = { w, cw, cw };
+		const int ph[3] = { view.luma_buf_rows, view.chroma_buf_rows, view.chroma_buf_rows };
+		for (int p = 0; p < 3; p++) {
+			if ((rc = EncodePlaneMap(ctx, &maps.in[p], in0 + off[p], pw[p], ph[p], nf, fs, 8 * cfg.block_rows_per_item))) return rc;
+			if ((rc = EncodePlaneMap(ctx, &maps.out[p], out0 + off[p], pw[p], ph[p], nf, fs, 8 * cfg.block_rows_per_item))) return rc;
+		}
+		HDB_CUDA(ctx, LaunchTiled(maps, b, ctx->sched, ctx->prop.multiProcessorCount, stream));
+		ctx->launches += 1;
+	}
+	return HDB_OK;
+}
+
+FrameView WholeFrameView(int w, int h)
+{
+	FrameView v{};
+	v.width = w; v.height = h; v.whole_frame = true;
+	v.luma_row0 = 0; v.luma_rows = (h + 8) / 8;
+	v.chroma_row0 = 0; v.chroma_rows = (h / 2 + 8) / 8;
+	v.luma_buf_rows = h; v.chroma_buf_rows = h / 2;
+	v.u_offset = (long long)w * h; v.v_offset = (long long)w * h + (long long)(w / 2) * (h / 2);
+	v.frame_stride = (long long)w * h * 3 / 2;
+	return v;
+}
+
+int ValidateFrameArgs(hdb_context *ctx, unsigned w, unsigned h, const unsigned char *vbs, unsigned nv,
+	const unsigned char *hbs, unsigned nh, bool sizes_given)
+{
+	if (w == 0 || h == 0 || w % 8 != 0 || h % 8 != 0) return Fail(ctx, HDB_ERR_DIMENSIONS, kMsgDims);
+	if (w > (1u << 20) || h > (1u << 20)) return Fail(ctx, HDB_ERR_INVALID_ARG, "frame too large");
+	if ((vbs != nullptr) != (hbs != nullptr))
+		return Fail(ctx, HDB_ERR_INVALID_ARG, "vert_bs and hor_bs must both be given or both be NULL");
+	if (vbs && sizes_given && (nv != (w / 8 + 1) * h / 8 || nh != (h / 8 + 1) * w / 8))
+		return Fail(ctx, HDB_ERR_BS_SIZE, kMsgBsSize);
+	return HDB_OK;
+}
+
+/* ------------------------------------------------------------------ */
+/* pinned multi-stream pipeline                                        */
+/* ------------------------------------------------------------------ */
+static int EnsureSlots(hdb_context *ctx, size_t frame_bytes, int chunk, unsigned nv, unsigned nh, bool with_bs)
+{
+	for (auto &sl : ctx->slots) {
+		if (sl.frames_cap < frame_bytes * chunk) {
+			cudaFree(sl.frames); sl.frames = nullptr; sl.frames_cap = 0;
+			HDB_CUDA(ctx, cudaMalloc(&sl.frames, frame_bytes * chunk));
+			sl.frames_cap = frame_bytes * chunk;
+		}
+		if (with_bs && sl.vbs_cap < (size_t)nv * chunk) {
+			cudaFree(sl.vbs); sl.vbs = nullptr; sl.vbs_cap = 0;
+			HDB_CUDA(ctx, cudaMalloc(&sl.vbs, std::max<size_t>((size_t)nv * chunk, 1)));
+			sl.vbs_cap = (size_t)nv * chunk;
+		}
+		if (with_bs && sl.hbs_cap < (size_t)nh * chunk) {
+			cudaFree(sl.hbs); sl.hbs = nullptr; sl.hbs_cap = 0;
+			HDB_CUDA(ctx, cudaMalloc(&sl.hbs, std::max<size_t>((size_t)nh * chunk, 1)));
+			sl.hbs_cap = (size_t)nh * chunk;
+		}
+		if (sl.qp_cap < (size_t)chunk) {
+			cudaFree(sl.qp); sl.qp = nullptr; sl.qp_cap = 0;
+			HDB_CUDA(ctx, cudaMalloc(&sl.qp, sizeof(unsigned) * chunk));
+			sl.qp_cap = chunk;
+		}
+	}
+	return HDB_OK;
+}
+
+static int GetEvents(hdb_context *ctx, size_t n)
+{
+	while (ctx->event_pool.size() < n) {
+		cudaEvent_t ev;
+		HDB_CUDA(ctx, cudaEventCreate(&ev));
+		ctx->event_pool.push_back(ev);
+	}
+	return HDB_OK;
+}
+
+/*
+ * Host buffers in, host buffers out.  The batch is cut into slices of `chunk`
+ * frames that cycle through kSlots device slots: slice i's H2D copy, slice i-1's
+ * kernel and slice i-2's D2H copy run concurrently on three streams, chained by
+ * events.  A single slice runs on one stream.
+ */
+int BatchHost(hdb_context *ctx, const unsigned char *in, unsigned char *out, unsigned n, unsigned w, unsigned h,
+	const unsigned *qp, const unsigned char *vbs, const unsigned char *hbs, hdb_timing *timing)
+{
+	if (!ctx) return HDB_ERR_INVALID_ARG;
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	if (!in || !out || !qp || n == 0) return Fail(ctx, HDB_ERR_INVALID_ARG, "NULL buffer or empty batch");
+	int rc = ValidateFrameArgs(ctx, w, h, vbs, 0, hbs, 0, false);
+	if (rc) return rc;
+	DeviceGuard guard(ctx->device);
+	const auto t_begin = std::chrono::steady_clock::now();
+	const size_t fb = (size_t)w * h * 3 / 2;
+	const unsigned nv = (w / 8 + 1) * h / 8, nh = (h / 8 + 1) * w / 8;
+	const int chunk = (int)std::min<size_t>(n, std::max<size_t>(1, ((size_t)ctx->chunk_bytes) / fb));
+	const int nchunks = (int)((n + chunk - 1) / chunk);
+	if ((rc = EnsureSlots(ctx, fb, chunk, nv, nh, vbs != nullptr))) return rc;
+	const FrameView view = WholeFrameView((int)w, (int)h);
+
+	PinHostRange pin_in(in, fb * n), pin_out(out != in ? out : nullptr, fb * n);
+	PinHostRange pin_v(vbs, (size_t)nv * n), pin_h(hbs, (size_t)nh * n);
+
+	const bool timed = timing != nullptr;
+	if (timed && (rc = GetEvents(ctx, (size_t)nchunks * 6))) return rc;
+	const bool single = nchunks == 1;
+	cudaStream_t s_h2d = single ? ctx->s_k : ctx->s_h2d, s_k = ctx->s_k, s_d2h = single ? ctx->s_k : ctx->s_d2h;
+	int path = 0;
+	unsigned long long launches0 = ctx->launches;
+
+	for (int c = 0; c < nchunks; c++) {
+		Slot &sl = ctx->slots[c % kSlots];
+		const unsigned f0 = (unsigned)c * chunk;
+		const int nf = (int)std::min<unsigned>(chunk, n - f0);
+		cudaEvent_t *ev = timed ? &ctx->event_pool[(size_t)c * 6] : nullptr;
+		if (!sl.ev_ready) {
+			HDB_CUDA(ctx, cudaEventCreateWithFlags(&sl.h2d_done, cudaEventDisableTiming));
+			HDB_CUDA(ctx, cudaEventCreateWithFlags(&sl.k_done, cudaEventDisableTiming));
+			HDB_CUDA(ctx, cudaEventCreateWithFlags(&sl.d2h_done, cudaEventDisableTiming));
+			sl.ev_ready = true;
+		}
+		/* the slot is free once the D2H copy of the slice that used it last has finished */
+		if (!single && c >= kSlots) HDB_CUDA(ctx, cudaStreamWaitEvent(s_h2d, sl.d2h_done, 0));
+		if (timed) HDB_CUDA(ctx, cudaEventRecord(ev[0], s_h2d));
+		HDB_CUDA(ctx, cudaMemcpyAsync(sl.frames, in + (size_t)f0 * fb, fb * nf, cudaMemcpyHostToDevice, s_h2d));
+		const bool uniform_qp = (n == 1);
+		if (!uniform_qp)
+			HDB_CUDA(ctx, cudaMemcpyAsync(sl.qp, qp + f0, sizeof(unsigned) * nf, cudaMemcpyHostToDevice, s_h2d));
+		if (vbs) {
+			HDB_CUDA(ctx, cudaMemcpyAsync(sl.vbs, vbs + (size_t)f0 * nv, (size_t)nv * nf, cudaMemcpyHostToDevice, s_h2d));
+			HDB_CUDA(ctx, cudaMemcpyAsync(sl.hbs, hbs + (size_t)f0 * nh, (size_t)nh * nf, cudaMemcpyHostToDevice, s_h2d));
+		}
+		if (timed) HDB_CUDA(ctx, cudaEventRecord(ev[1], s_h2d));
+		if (!single) {
+			HDB_CUDA(ctx, cudaEventRecord(sl.h2d_done, s_h2d));
+			HDB_CUDA(ctx, cudaStreamWaitEvent(s_k, sl.h2d_done, 0));
+		}
+		if (timed) HDB_CUDA(ctx, cudaEventRecord(ev[2], s_k));
+		rc = EnqueueFilter(ctx, view, sl.frames, sl.frames, nf, uniform_qp ? nullptr : sl.qp, qp[0],
+			vbs ? sl.vbs : nullptr, nv, vbs ? sl.hbs : nullptr, nh, s_k, &path);
+		if (rc) { cudaDeviceSynchronize(); return rc; }
+		if (timed) HDB_CUDA(ctx, cudaEventRecord(ev[3], s_k));
+		if (!single) {
+			HDB_CUDA(ctx, cudaEventRecord(sl.k_done, s_k));
+			HDB_CUDA(ctx, cudaStreamWaitEvent(s_d2h, sl.k_done, 0));
+		}
+		if (timed) HDB_CUDA(ctx, cudaEventRecord(ev[4], s_d2h));
+		HDB_CUDA(ctx, cudaMemcpyAsync(out + (size_t)f0 * fb, sl.frames, fb * nf, cudaMemcpyDeviceToHost, s_d2h));
+		if (timed) HDB_CUDA(ctx, cudaEventRecord(ev[5], s_d2h));
+		if (!single) HDB_CUDA(ctx, cudaEventRecord(sl.d2h_done, s_d2h));
+	}
+	HDB_CUDA(ctx, cudaStreamSynchronize(s_d2h));
+	HDB_CUDA(ctx, cudaStreamSynchronize(s_k));
+	const auto t_end = std::chrono::steady_clock::now();
+	if (timed) {
+		memset(timing, 0, sizeof *timing);
+		for (int c = 0; c < nchunks; c++) {
+			cudaEvent_t *ev = &ctx->event_pool[(size_t)c * 6];
+			float a = 0, k = 0, d = 0;
+			cudaEventElapsedTime(&a, ev[0], ev[1]);
+			cudaEventElapsedTime(&k, ev[2], ev[3]);
+			cudaEventElapsedTime(&d, ev[4], ev[5]);
+			timing->copy_ms += a + d;
+			timing->kernel_ms += k;
+		}
+		timing->total_ms = std::chrono::duration<double, std::milli>(t_end - t_begin).count();
+		timing->h2d_bytes = (unsigned long long)fb * n + (n == 1 ? 0 : sizeof(unsigned) * (unsigned long long)n)
+			+ (vbs ? (unsigned long long)(nv + nh) * n : 0);
+		timing->d2h_bytes = (unsigned long long)fb * n;
+		timing->kernel_launches = (int)(ctx->launches - launches0);
+		timing->path = path;
+	}
+	return HDB_OK;
+}
+
+} // namespace hdb
+
+/* ------------------------------------------------------------------ */
+/* C ABI                                                               */
+/* ------------------------------------------------------------------ */
+using namespace hdb;
+
+extern "C" {
+
+int hdb_create(hdb_context **ctx, int device) { return CreateContext(ctx, device); }
+void hdb_destroy(hdb_context *ctx) { DestroyContext(ctx); }
+const char *hdb_last_error(const hdb_context *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+const char *hdb_status_string(int status)
+{
+	switch (status) {
+	case HDB_OK: return "ok";
+	case HDB_ERR_INVALID_ARG: return "invalid argument";
+	case HDB_ERR_FILE_SIZE: return kMsgFileSize;
+	case HDB_ERR_DIMENSIONS: return kMsgDims;
+	case HDB_ERR_BS_SIZE: return kMsgBsSize;
+	case HDB_ERR_CUDA: return "CUDA error";
+	case HDB_ERR_IO: return "file I/O error";
+	case HDB_ERR_NO_MEMORY: return "out of memory";
+	}
+	return "unknown status";
+}
+
+int hdb_get_device_info(const hdb_context *ctx, hdb_device_info *info)
+{
+	if (!ctx || !info) return HDB_ERR_INVALID_ARG;
+	memset(info, 0, sizeof *info);
+	strncpy(info->name, ctx->prop.name, sizeof info->name - 1);
+	info->cc_major = ctx->prop.major; info->cc_minor = ctx->prop.minor;
+	info->sm_count = ctx->prop.multiProcessorCount; info->warp_size = ctx->prop.warpSize;
+	info->max_threads_per_block = ctx->prop.maxThreadsPerBlock;
+	info->total_global_mem = ctx->prop.totalGlobalMem; info->total_const_mem = ctx->prop.totalConstMem;
+	info->shared_mem_per_block = ctx->prop.sharedMemPerBlock;
+	return HDB_OK;
+}
+
+unsigned hdb_num_vert_bs(unsigned width, unsigned height) { return (width / 8 + 1) * height / 8; }
+unsigned hdb_num_hor_bs(unsigned width, unsigned height) { return (height / 8 + 1) * width / 8; }
+
+int hdb_default_boundary_strength(unsigned width, unsigned height, unsigned char *vert_bs, unsigned char *hor_bs)
+{
+	if (width % 8 != 0 || height % 8 != 0) return HDB_ERR_DIMENSIONS;
+	const unsigned nv = hdb_num_vert_bs(width, height), nh = hdb_num_hor_bs(width, height);
+	if (vert_bs) for (unsigned i = 0; i < nv; i++) vert_bs[i] = (i % (width / 8 + 1) == 0) ? 0 : 2;   /* cpu.h:92-95 */
+	if (hor_bs) for (unsigned i = 0; i < nh; i++) hor_bs[i] = (i % (height / 8 + 1) == 0) ? 0 : 2;    /* cpu.h:96-99 */
+	return HDB_OK;
+}
+
+int hdb_beta(unsigned qp) { return HostBeta(qp); }
+int hdb_tc(unsigned qp) { return HostTc(qp); }
+
+void *hdb_host_alloc(size_t bytes)
+{
+	void *p = nullptr;
+	if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+	return p;
+}
+
+void hdb_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+int hdb_deblock_frame(hdb_context *ctx, const unsigned char *yuv_in, unsigned char *yuv_out,
+	unsigned width, unsigned height, unsigned qp, const unsigned char *vert_bs, unsigned num_vert_bs,
+	const unsigned char *hor_bs, unsigned num_hor_bs, hdb_timing *timing)
+{
+	if (!ctx) return HDB_ERR_INVALID_ARG;
+	int rc = ValidateFrameArgs(ctx, width, height, vert_bs, num_vert_bs, hor_bs, num_hor_bs, true);
+	if (rc) return rc;
+	return BatchHost(ctx, yuv_in, yuv_out, 1, width, height, &qp, vert_bs, hor_bs, timing);
+}
+
+int hdb_deblock_planes(hdb_context *ctx, const unsigned char *y_in, const unsigned char *u_in, const unsigned char *v_in,
+	unsigned char *y_out, unsigned char *u_out, unsigned char *v_out, unsigned width, unsigned height, unsigned qp,
+	const unsigned char *vert_bs, unsigned num_vert_bs, const unsigned char *hor_bs, unsigned num_hor_bs,
+	hdb_timing *timing)
+{
+	if (!ctx) return HDB_ERR_INVALID_ARG;
+	if (!y_in || !u_in || !v_in || !y_out || !u_out || !v_out) return Fail(ctx, HDB_ERR_INVALID_ARG, "NULL plane");
+	int rc = ValidateFrameArgs(ctx, width, height, vert_bs, num_vert_bs, hor_bs, num_hor_bs, true);
+	if (rc) return rc;
+	/* gather into one pinned YV12 frame, run, scatter */
+	const size_t ysz = (size_t)width * height, csz = (size_t)(width / 2) * (height / 2), fb = ysz + 2 * csz;
+	{
+		std::lock_guard<std::mutex> lock(ctx->mu);
+		if (ctx->stage_cap < fb) {
+			if (ctx->stage_in) cudaFreeHost(ctx->stage_in);
+			ctx->stage_in = nullptr; ctx->stage_cap = 0;
+			if (cudaMallocHost(&ctx->stage_in, fb) != cudaSuccess) return FailCuda(ctx, cudaGetLastError(), "cudaMallocHost");
+			ctx->stage_cap = fb;
+		}
+	}
+	unsigned char *st = static_cast<unsigned char *>(ctx->stage_in);
+	memcpy(st, y_in, ysz); memcpy(st + ysz, u_in, csz); memcpy(st + ysz + csz, v_in, csz);
+	rc = BatchHost(ctx, st, st, 1, width, height, &qp, vert_bs, hor_bs, timing);
+	if (rc) return rc;
+	memcpy(y_out, st, ysz); memcpy(u_out, st + ysz, csz); memcpy(v_out, st + ysz + csz, csz);
+	return HDB_OK;
+}
+
+int hdb_execute_gpu(hdb_context *ctx, const char *input_file_name, const char *output_file_name,
+	unsigned width, unsigned height, unsigned qp, hdb_timing *timing)
+{
+	if (!ctx || !input_file_name || !output_file_name) return HDB_ERR_INVALID_ARG;
+	FILE *f = fopen(input_file_name, "rb");
+	if (!f) return Fail(ctx, HDB_ERR_IO, std::string("cannot open ") + input_file_name);
+	fseek(f, 0, SEEK_END);
+	const long length = ftell(f);
+	fseek(f, 0, SEEK_SET);
+	const size_t fb = (size_t)3 * width * height / 2;
+	if (length < 0 || (unsigned)length != 3 * width * height / 2) { fclose(f); return Fail(ctx, HDB_ERR_FILE_SIZE, kMsgFileSize); } /* cpu.h:43 */
+	if (width % 8 != 0 || height % 8 != 0) { fclose(f); return Fail(ctx, HDB_ERR_DIMENSIONS, kMsgDims); }                            /* cpu.h:46 */
+	unsigned char *buf = static_cast<unsigned char *>(hdb_host_alloc(fb));                                                              /* gpu.cu:1103 */
+	if (!buf) { fclose(f); return Fail(ctx, HDB_ERR_NO_MEMORY, "cudaMallocHost failed"); }
+	const bool read_ok = fread(buf, 1, fb, f) == fb;
+	fclose(f);
+	int rc = read_ok ? HDB_OK : Fail(ctx, HDB_ERR_IO, "short read");
+	if (!rc) rc = BatchHost(ctx, buf, buf, 1, width, height, &qp, nullptr, nullptr, timing);
+	if (!rc) {
+		FILE *o = fopen(output_file_name, "wb");
+		if (!o || fwrite(buf, 1, fb, o) != fb) rc = Fail(ctx, HDB_ERR_IO, std::string("cannot write ") + output_file_name);
+		if (o) fclose(o);
+	}
+	hdb_host_free(buf);
+	return rc;
+}
+
+int hdb_deblock_batch(hdb_context *ctx, const unsigned char *frames_in, unsigned char *frames_out,
+	unsigned n_frames, unsigned width, unsigned height, const unsigned *qp,
+	const unsigned char *vert_bs, const unsigned char *hor_bs, hdb_timing *timing)
+{
+	return BatchHost(ctx, frames_in, frames_out, n_frames, width, height, qp, vert_bs, hor_bs, timing);
+}
+
+int hdb_deblock_batch_device(hdb_context *ctx, const void *d_frames_in, void *d_frames_out,
+	unsigned n_frames, unsigned width, unsigned height, const unsigned *d_qp,
+	const unsigned char *d_vert_bs, const unsigned char *d_hor_bs, void *stream)
+{
+	if (!ctx) return HDB_ERR_INVALID_ARG;
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	if (!d_frames_in || !d_frames_out || !d_qp || n_frames == 0) return Fail(ctx, HDB_ERR_INVALID_ARG, "NULL buffer or empty batch");
+	int rc = ValidateFrameArgs(ctx, width, height, d_vert_bs, 0, d_hor_bs, 0, false);
+	if (rc) return rc;
+	DeviceGuard guard(ctx->device);
+	const FrameView view = WholeFrameView((int)width, (int)height);
+	return EnqueueFilter(ctx, view, static_cast<const unsigned char *>(d_frames_in),
+		static_cast<unsigned char *>(d_frames_out), (int)n_frames, d_qp, 0,
+		d_vert_bs, hdb_num_vert_bs(width, height), d_hor_bs, hdb_num_hor_bs(width, height),
+		static_cast<cudaStream_t>(stream), nullptr);
+}
+
+unsigned long long hdb_kernel_launch_count(const hdb_context *ctx) { return ctx ? ctx->launches : 0; }
+
+} // extern "C"

@@ -1,0 +1,112 @@
+/*
+ * deblock_api.h -- internal declarations shared by deblock_api.cu and
+ * deblock_multi.cu.  The public boundary is include/hevc_deblock_b200.h.
+ */
+#pragma once
+
+#include "../../include/hevc_deblock_b200.h"
+#include "deblock_kernels.cuh"
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace hdb {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+	const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+	CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct DeviceGuard {   /* make `device` current for the scope */
+	int prev = -1;
+	explicit DeviceGuard(int device) { cudaGetDevice(&prev); if (prev != device) cudaSetDevice(device); }
+	~DeviceGuard() { int cur = -1; cudaGetDevice(&cur); if (prev >= 0 && cur != prev) cudaSetDevice(prev); }
+};
+
+struct SizeState {     /* device tables that depend on the frame size only */
+	int w, h;
+	uint32_t *chroma_bs;          /* resolved chroma strengths per chroma block */
+	unsigned char *def_vbs, *def_hbs; /* reference-default luma strengths (cpu.h:92-99) */
+};
+
+constexpr int kSlots = 4;
+
+struct Slot {          /* one slice of a batch in flight */
+	unsigned char *frames = nullptr, *vbs = nullptr, *hbs = nullptr;
+	unsigned *qp = nullptr;
+	size_t frames_cap = 0, vbs_cap = 0, hbs_cap = 0, qp_cap = 0;
+	cudaEvent_t h2d_done = nullptr, k_done = nullptr, d2h_done = nullptr;
+	bool ev_ready = false;
+};
+
+/* Page-lock a caller's host buffer for the duration of a call when it is large and not
+ * already page-locked (small or already pinned buffers are left alone). */
+struct PinHostRange {
+	void *p = nullptr;
+	PinHostRange(const void *ptr, size_t bytes)
+	{
+		if (!ptr || bytes < ((size_t)8 << 20)) return;
+		cudaPointerAttributes a;
+		if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) { cudaGetLastError(); return; }
+		if (a.type != cudaMemoryTypeUnregistered) return;
+		if (cudaHostRegister(const_cast<void *>(ptr), bytes, cudaHostRegisterDefault) == cudaSuccess) p = const_cast<void *>(ptr);
+		else cudaGetLastError();
+	}
+	~PinHostRange() { if (p) cudaHostUnregister(p); }
+	PinHostRange(const PinHostRange &) = delete;
+	PinHostRange &operator=(const PinHostRange &) = delete;
+};
+
+/* Which rows of a frame a set of plane buffers holds (whole frame, or a CTU-row strip). */
+struct FrameView {
+	int width, height;             /* of the whole frame */
+	bool whole_frame;
+	int luma_row0, luma_rows;      /* padded-block rows to filter, frame-global numbering */
+	int chroma_row0, chroma_rows;
+	int luma_buf_rows, chroma_buf_rows;   /* sample rows present in the buffers */
+	long long u_offset, v_offset;  /* byte offsets of the chroma planes inside one frame's buffer */
+	long long frame_stride;        /* bytes between frames */
+};
+
+} // namespace hdb
+
+struct hdb_context {
+	int device = 0;
+	cudaDeviceProp prop{};
+	hdb::EncodeTiledFn encode = nullptr;
+	cudaStream_t s_h2d = nullptr, s_k = nullptr, s_d2h = nullptr;
+	void *sched = nullptr;
+	std::vector<hdb::SizeState> sizes;
+	hdb::Slot slots[hdb::kSlots];
+	std::vector<cudaEvent_t> event_pool;
+	unsigned char *generic_scratch = nullptr;
+	size_t generic_scratch_bytes = 0;
+	void *stage_in = nullptr, *stage_out = nullptr;
+	size_t stage_cap = 0;
+	size_t chunk_bytes = (size_t)32 << 20;   /* slice size of the host pipeline */
+	unsigned long long launches = 0;
+	std::string err;
+	std::mutex mu;
+};
+
+namespace hdb {
+
+int Fail(hdb_context *ctx, int status, const std::string &msg);
+int FailCuda(hdb_context *ctx, cudaError_t e, const char *what);
+void DestroyContext(hdb_context *ctx);
+int GetSizeState(hdb_context *ctx, int w, int h, SizeState **out);
+FrameView WholeFrameView(int w, int h);
+bool TiledPathUsable(int w, int h, const void *d_in, const void *d_out);
+int ValidateFrameArgs(hdb_context *ctx, unsigned w, unsigned h, const unsigned char *vbs, unsigned nv,
+	const unsigned char *hbs, unsigned nh, bool sizes_given);
+int EnqueueFilter(hdb_context *ctx, const FrameView &view, const unsigned char *d_in, unsigned char *d_out,
+	int n, const unsigned *d_qp, unsigned qp_value, const unsigned char *d_vbs, long long vbs_stride,
+	const unsigned char *d_hbs, long long hbs_stride, cudaStream_t stream, int *path);
+int BatchHost(hdb_context *ctx, const unsigned char *in, unsigned char *out, unsigned n, unsigned w, unsigned h,
+	const unsigned *qp, const unsigned char *vbs, const unsigned char *hbs, hdb_timing *timing);
+
+/* beta / tc on the host (cpu.h:1021-1033, 1064-1072); defined in deblock_kernels.cu next to the device tables */
+int HostBeta(unsigned qp);
+int HostTc(unsigned qp);
+
+} // namespace hdb

@@ -28,8 +28,10 @@
 
 #if defined(HDB_HOST_EMU)
 #define HDB_FN static inline
+#define HDB_HD static inline
 #else
 #define HDB_FN __device__ __forceinline__
+#define HDB_HD __host__ __device__ __forceinline__
 #endif
 
 namespace hdb {
@@ -311,7 +313,7 @@ HDB_FN void StoreVertPairChroma(const ChromaPair &t, u32 &la, u32 &lb, u32 &ha, 
  * depend on QP only -- in the reference the boundary strength gates the edge
  * (cpu.h:164, 463) but does not offset tc.  ptxas places them in the constant bank.
  */
-HDB_FN int BetaOf(unsigned qp)
+HDB_HD int BetaOf(unsigned qp)
 {
 	static const unsigned char beta_of_qp[52] = {
 		0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15,
@@ -320,7 +322,7 @@ HDB_FN int BetaOf(unsigned qp)
 	return beta_of_qp[qp > 51 ? 51 : qp];
 }
 
-HDB_FN int TcOf(unsigned qp)
+HDB_HD int TcOf(unsigned qp)
 {
 	static const unsigned char tc_of_qp[52] = {
 		0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1,
@@ -330,8 +332,8 @@ HDB_FN int TcOf(unsigned qp)
 }
 
 /* Sizes of the boundary-strength arrays (cpu.h:86-87, 104-105), unsigned left-to-right. */
-HDB_FN unsigned NumVertBs(unsigned w, unsigned h) { return (w / 8 + 1) * h / 8; }
-HDB_FN unsigned NumHorBs(unsigned w, unsigned h) { return (h / 8 + 1) * w / 8; }
+HDB_HD unsigned NumVertBs(unsigned w, unsigned h) { return (w / 8 + 1) * h / 8; }
+HDB_HD unsigned NumHorBs(unsigned w, unsigned h) { return (h / 8 + 1) * w / 8; }
 
 /*
  * The four boundary strengths of luma block (bx, by), packed

@@ -1,0 +1,496 @@
+/*
+ * deblock_kernels.cu -- sm_100a kernels of the deblocking path.
+ *
+ * DeblockTiledKernel: persistent, warp-autonomous.  Every warp runs its own
+ * TMA -> registers -> TMA pipeline over "items" = 32 horizontally adjacent
+ * padded 8x8 blocks x kRB block rows of one plane of one frame (a 256 x 8*kRB
+ * byte box).  The box origin is (8*bx0 - 4, 8*by0 - 4) in image coordinates:
+ * the reference pads every plane by 4 samples (cpu.h:55-82) so that each padded
+ * block is centred on an 8x8 grid crossing; TMA's out-of-bounds zero fill IS
+ * that padding (the oracle defines it as zero), and TMA's store clipping drops
+ * the writes the reference makes into its padding.  Blocks are independent
+ * (cpu.h:146-447 touches only the block's own 64 samples), so a box of whole
+ * blocks is filtered in place in shared memory: lane l owns block l, reads it
+ * with eight conflict-free 8-byte loads per block row, runs the vertical-edge
+ * and horizontal-edge passes fused in registers (deblock_core.cuh) and writes
+ * it back; one lane then issues the TMA store.  No CTA-wide barrier exists in
+ * the kernel; a stage is recycled when the bulk store that reads it has
+ * finished (cp.async.bulk.wait_group.read).
+ *
+ * Work is handed out dynamically in runs of consecutive items from one global
+ * counter (luma items cost ~4x chroma items, so a static split would be
+ * unbalanced); the last CTA to leave resets the counter for the next launch.
+ *
+ * The generic kernels at the end cover frame sizes TMA cannot describe.
+ */
+#include "deblock_kernels.cuh"
+#include "deblock_core.cuh"
+
+#include <algorithm>
+#include <cstdio>
+
+#ifndef HDB_RB
+#define HDB_RB 1        /* block rows per item */
+#endif
+#ifndef HDB_STAGES
+#define HDB_STAGES 3
+#endif
+#ifndef HDB_WARPS
+#define HDB_WARPS 4
+#endif
+#ifndef HDB_MIN_CTAS
+#define HDB_MIN_CTAS 4
+#endif
+
+namespace hdb {
+
+constexpr int kRB = HDB_RB;
+constexpr int kStages = HDB_STAGES;
+constexpr int kWarps = HDB_WARPS;
+constexpr int kTileW = 256;                     /* bytes: 32 blocks of 8 columns */
+constexpr int kTileH = 8 * kRB;
+constexpr int kTileBytes = kTileW * kTileH;
+constexpr int kSmemBytes = kWarps * kStages * (kTileBytes + 8 + 8);
+constexpr uint32_t kNoItem = 0xffffffffu;
+
+/* scheduler words in global memory: [0] next item, [1] CTAs done */
+struct SchedWords { unsigned int next; unsigned int done; };
+
+/* ------------------------------------------------------------------ */
+/* PTX: mbarrier, TMA, proxy fence                                     */
+/* ------------------------------------------------------------------ */
+__device__ __forceinline__ uint32_t SmemAddr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void MbarInit(uint32_t bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void FenceMbarInit()
+{
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void MbarArriveExpectTx(uint32_t bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void MbarWait(uint32_t bar, uint32_t parity)
+{
+	uint32_t done;
+	do {
+		asm volatile(
+			"{\n\t.reg .pred p;\n\t"
+			"mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+			"selp.u32 %0, 1, 0, p;\n\t}"
+			: "=r"(done) : "r"(bar), "r"(parity) : "memory");
+	} while (!done);
+}
+
+/* generic-proxy writes to shared memory -> visible to the async proxy (TMA store) */
+__device__ __forceinline__ void FenceProxyAsyncShared()
+{
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__device__ __forceinline__ void TmaLoad3D(uint32_t dst, const CUtensorMap *map, int x, int y, int z, uint32_t bar)
+{
+	asm volatile(
+		"cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+		" [%0], [%1, {%2, %3, %4}], [%5];"
+		:: "r"(dst), "l"(map), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void TmaStore3D(const CUtensorMap *map, uint32_t src, int x, int y, int z)
+{
+	asm volatile(
+		"cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+		:: "l"(map), "r"(src), "r"(x), "r"(y), "r"(z) : "memory");
+	asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+template <int kPending>
+__device__ __forceinline__ void TmaStoreWaitRead()
+{
+	asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(kPending) : "memory");
+}
+
+/* ------------------------------------------------------------------ */
+/* item bookkeeping                                                    */
+/* ------------------------------------------------------------------ */
+
+/* item id -> (frame, plane | chunk << 2 | group << 12) */
+__device__ __forceinline__ void DecodeItem(const TiledBatch &b, uint32_t id, uint32_t &frame, uint32_t &desc)
+{
+	frame = b.div_items_per_frame.Div(id);
+	uint32_t r = id - frame * (uint32_t)b.items_per_frame;
+	uint32_t plane, grp, chunk;
+	if (r < (uint32_t)b.items_luma) {
+		plane = 0;
+		grp = b.div_luma_chunks.Div(r);
+		chunk = r - grp * (uint32_t)b.luma_chunks;
+	} else {
+		r -= (uint32_t)b.items_luma;
+		plane = 1 + (r >= (uint32_t)b.items_chroma ? 1u : 0u);
+		r -= (plane - 1) * (uint32_t)b.items_chroma;
+		grp = b.div_chroma_chunks.Div(r);
+		chunk = r - grp * (uint32_t)b.chroma_chunks;
+	}
+	desc = plane | (chunk << 2) | (grp << 12);
+}
+
+__device__ __forceinline__ void ItemCoords(uint32_t desc, int &plane, int &bx0, int &lby0)
+{
+	plane = (int)(desc & 3u);
+	bx0 = (int)((desc >> 2) & 0x3ffu) * 32;
+	lby0 = (int)(desc >> 12) * kRB;
+}
+
+/* ------------------------------------------------------------------ */
+/* the kernel                                                          */
+/* ------------------------------------------------------------------ */
+__global__ void __launch_bounds__(kWarps * 32, HDB_MIN_CTAS)
+DeblockTiledKernel(const __grid_constant__ TensorMaps6 maps, const __grid_constant__ TiledBatch b,
+	SchedWords *sched, const uint32_t run_len)
+{
+	extern __shared__ __align__(1024) unsigned char smem[];
+	const int warp = threadIdx.x >> 5;
+	const int lane = threadIdx.x & 31;
+	unsigned char *tiles = smem + warp * (kStages * kTileBytes);
+	uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kWarps * kStages * kTileBytes) + warp * kStages;
+	/* what each stage holds, written by lane 0 when it issues the load: {frame, desc} */
+	uint2 *held = reinterpret_cast<uint2 *>(smem + kWarps * kStages * (kTileBytes + 8)) + warp * kStages;
+	const uint32_t tiles_s = SmemAddr(tiles);
+	const uint32_t bars_s = SmemAddr(bars);
+	const uint32_t total = (uint32_t)b.total_items;
+
+	/* lane 0 is the warp's producer: scheduler state, TMA issue */
+	uint32_t run_next = 0, run_end = 0, run_pending = 0;
+
+	auto next_item = [&]() -> uint32_t {   /* lane 0 only */
+		if (run_next == run_end) {
+			run_next = run_pending;
+			run_end = run_pending + run_len;
+			/* ask for the run after this one now; it is not needed for run_len items */
+			if (run_next < total) run_pending = atomicAdd(&sched->next, run_len);
+		}
+		uint32_t id = run_next++;
+		return id < total ? id : kNoItem;
+	};
+	auto issue_load = [&](int s) {         /* lane 0 only */
+		uint32_t id = next_item();
+		if (id == kNoItem) { held[s] = make_uint2(0u, kNoItem); return; }
+		uint32_t frame, desc;
+		DecodeItem(b, id, frame, desc);
+		held[s] = make_uint2(frame, desc);
+		int plane, bx0, lby0;
+		ItemCoords(desc, plane, bx0, lby0);
+		const uint32_t bar = bars_s + 8u * s;
+		MbarArriveExpectTx(bar, kTileBytes);
+		TmaLoad3D(tiles_s + s * kTileBytes, &maps.in[plane], 8 * bx0 - 4,
+			8 * lby0 + (plane ? b.chroma_y_org : b.luma_y_org), (int)frame, bar);
+	};
+
+	if (lane == 0) {
+		for (int s = 0; s < kStages; s++) MbarInit(bars_s + 8u * s, 1);
+		FenceMbarInit();
+		run_pending = atomicAdd(&sched->next, run_len);
+		for (int s = 0; s < kStages - 1; s++) issue_load(s);
+		held[kStages - 1] = make_uint2(0u, kNoItem);
+	}
+	__syncwarp();
+
+	int s = 0;
+	uint32_t parity = 0;
+	for (;;) {
+		const uint2 it = held[s];
+		const uint32_t frame = it.x, desc = it.y;
+		if (desc == kNoItem) break;
+		int plane, bx0, lby0;
+		ItemCoords(desc, plane, bx0, lby0);
+		const bool chroma = plane != 0;
+		const int nbx = chroma ? b.chroma_nbx : b.luma_nbx;
+		const int rows = chroma ? b.chroma_rows : b.luma_rows;
+		const int row0 = chroma ? b.chroma_row0 : b.luma_row0;
+		const int bx = bx0 + lane;
+
+		/* beta / tc of this frame (cpu.h:136-137) */
+		FilterParams fp;
+		{
+			const unsigned qp = b.qp ? __ldg(b.qp + frame) : b.qp_value;
+			MakeFilterParams(fp, BetaOf(qp), TcOf(qp));
+		}
+		/* boundary strengths of this lane's blocks; issued before the tile wait */
+		u32 bs[kRB];
+#pragma unroll
+		for (int rb = 0; rb < kRB; rb++) {
+			const int lby = lby0 + rb;
+			bs[rb] = 0;
+			if (bx < nbx && lby < rows) {
+				const int gby = row0 + lby;
+				if (chroma) bs[rb] = __ldg(b.chroma_bs + gby * b.chroma_nbx + bx);
+				else bs[rb] = LumaBsOfBlock(bx, gby, b.width >> 3, b.luma_nbx, b.luma_nby,
+					b.vert_bs + (long long)frame * b.vert_bs_stride,
+					b.hor_bs + (long long)frame * b.hor_bs_stride);
+			}
+		}
+
+		MbarWait(bars_s + 8u * s, parity);
+		unsigned char *tile = tiles + s * kTileBytes;
+#pragma unroll
+		for (int rb = 0; rb < kRB; rb++) {
+			if (bx < nbx && lby0 + rb < rows) {
+				uint2 *base = reinterpret_cast<uint2 *>(tile + rb * 8 * kTileW) + lane;
+				u32 lo[8], hi[8];
+#pragma unroll
+				for (int r = 0; r < 8; r++) {
+					uint2 v = base[r * (kTileW / 8)];
+					lo[r] = v.x; hi[r] = v.y;
+				}
+				const u32 s4 = bs[rb];
+				if (chroma) ChromaBlock(lo, hi, s4 & 0xff, (s4 >> 8) & 0xff, (s4 >> 16) & 0xff, s4 >> 24, fp);
+				else LumaBlock(lo, hi, s4 & 0xff, (s4 >> 8) & 0xff, (s4 >> 16) & 0xff, s4 >> 24, fp);
+#pragma unroll
+				for (int r = 0; r < 8; r++) base[r * (kTileW / 8)] = make_uint2(lo[r], hi[r]);
+			}
+		}
+		FenceProxyAsyncShared();
+		__syncwarp();
+		const int prev = s == 0 ? kStages - 1 : s - 1;
+		if (lane == 0) {
+			TmaStore3D(&maps.out[plane], tiles_s + s * kTileBytes, 8 * bx0 - 4,
+				8 * lby0 + (chroma ? b.chroma_y_org : b.luma_y_org), (int)frame);
+			/* the stage filtered one item ago is free once its store has read it */
+			TmaStoreWaitRead<1>();
+			issue_load(prev);
+		}
+		__syncwarp();
+		if (++s == kStages) { s = 0; parity ^= 1u; }
+	}
+	if (lane == 0) {
+		TmaStoreWaitRead<0>();
+		/* the last run request must have returned before the counter may be reset */
+		asm volatile("" :: "r"(run_pending) : "memory");
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		__threadfence();
+		if (atomicAdd(&sched->done, 1u) == gridDim.x - 1) {
+			sched->next = 0u;
+			sched->done = 0u;
+			__threadfence();
+		}
+	}
+}
+
+int HostBeta(unsigned qp) { return BetaOf(qp); }
+int HostTc(unsigned qp) { return TcOf(qp); }
+
+TiledConfig GetTiledConfig()
+{
+	TiledConfig c;
+	c.block_rows_per_item = kRB; c.stages = kStages; c.warps_per_cta = kWarps;
+	c.smem_bytes = kSmemBytes; c.max_ctas_per_sm = HDB_MIN_CTAS;
+	return c;
+}
+
+void FinalizeTiledBatch(TiledBatch &b)
+{
+	b.luma_chunks = (b.luma_nbx + 31) / 32;
+	b.chroma_chunks = (b.chroma_nbx + 31) / 32;
+	b.luma_groups = (b.luma_rows + kRB - 1) / kRB;
+	b.chroma_groups = (b.chroma_rows + kRB - 1) / kRB;
+	b.items_luma = b.luma_chunks * b.luma_groups;
+	b.items_chroma = b.chroma_chunks * b.chroma_groups;
+	b.items_per_frame = b.items_luma + 2 * b.items_chroma;
+	b.total_items = (long long)b.items_per_frame * b.n_frames;
+	b.div_items_per_frame.Init((uint32_t)b.items_per_frame);
+	b.div_luma_chunks.Init((uint32_t)b.luma_chunks);
+	b.div_chroma_chunks.Init((uint32_t)b.chroma_chunks);
+	b.div_items_chroma.Init((uint32_t)std::max(b.items_chroma, 1));
+}
+
+static int g_tiled_ctas_per_sm = 0;
+
+cudaError_t LaunchTiled(const TensorMaps6 &maps, const TiledBatch &b, void *sched, int sm_count, cudaStream_t stream)
+{
+	if (b.total_items <= 0) return cudaSuccess;
+	if (b.total_items >= (1ll << 31)) return cudaErrorInvalidValue;
+	cudaError_t err;
+	if (g_tiled_ctas_per_sm == 0) {
+		err = cudaFuncSetAttribute(DeblockTiledKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+		if (err != cudaSuccess) return err;
+		int n = 0;
+		err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, DeblockTiledKernel, kWarps * 32, kSmemBytes);
+		if (err != cudaSuccess) return err;
+		g_tiled_ctas_per_sm = std::max(n, 1);
+	}
+	const long long warps_wanted = b.total_items;
+	long long ctas = std::min<long long>((long long)sm_count * g_tiled_ctas_per_sm, (warps_wanted + kWarps - 1) / kWarps);
+	ctas = std::max<long long>(ctas, 1);
+	/* run length: consecutive items per scheduler request; short when work is scarce */
+	long long per_warp = b.total_items / (ctas * kWarps);
+	uint32_t run_len = (uint32_t)std::max<long long>(1, std::min<long long>(16, per_warp / 8));
+	DeblockTiledKernel<<<(unsigned)ctas, kWarps * 32, kSmemBytes, stream>>>(maps, b,
+		reinterpret_cast<SchedWords *>(sched), run_len);
+	return cudaGetLastError();
+}
+
+size_t TiledSchedBytes() { return sizeof(SchedWords); }
+
+/* ------------------------------------------------------------------ */
+/* small helper kernels                                                */
+/* ------------------------------------------------------------------ */
+__global__ void ChromaBsTableKernel(uint32_t *table, int width, int height)
+{
+	const int cnbx = (width / 2 + 8) / 8, cnby = (height / 2 + 8) / 8;
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= cnbx * cnby) return;
+	const int by = i / cnbx, bx = i - by * cnbx;
+	table[i] = ChromaBsOfBlock(bx, by, (unsigned)width / 2, (unsigned)height / 2, (width + 8) / 8, (height + 8) / 8);
+}
+
+cudaError_t LaunchChromaBsTable(uint32_t *table, int width, int height, cudaStream_t stream)
+{
+	const int n = ((width / 2 + 8) / 8) * ((height / 2 + 8) / 8);
+	ChromaBsTableKernel<<<(n + 255) / 256, 256, 0, stream>>>(table, width, height);
+	return cudaGetLastError();
+}
+
+/* cpu.h:92-99 */
+__global__ void DefaultLumaBsKernel(unsigned char *vert_bs, unsigned char *hor_bs, int width, int height)
+{
+	const unsigned nv = NumVertBs(width, height), nh = NumHorBs(width, height);
+	const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < nv) vert_bs[i] = (i % (width / 8 + 1) == 0) ? 0 : 2;
+	if (i < nh) hor_bs[i] = (i % (height / 8 + 1) == 0) ? 0 : 2;
+}
+
+cudaError_t LaunchDefaultLumaBs(unsigned char *vert_bs, unsigned char *hor_bs, int width, int height,
+	cudaStream_t stream)
+{
+	const unsigned n = std::max(NumVertBs(width, height), NumHorBs(width, height));
+	if (n == 0) return cudaSuccess;
+	DefaultLumaBsKernel<<<(n + 255) / 256, 256, 0, stream>>>(vert_bs, hor_bs, width, height);
+	return cudaGetLastError();
+}
+
+/* ------------------------------------------------------------------ */
+/* generic path                                                        */
+/* ------------------------------------------------------------------ */
+struct GenericPlane {
+	int w, h;            /* tight plane size */
+	int pw, ph;          /* padded size (w + 8, h + 8) */
+	int nbx, nby;        /* pw / 8, ph / 8 */
+	long long plane_off; /* offset of the plane inside a tight frame */
+	long long pad_off;   /* offset of the padded plane inside a frame's scratch */
+};
+
+__host__ __device__ inline GenericPlane MakeGenericPlane(int width, int height, int plane)
+{
+	GenericPlane g;
+	const int cw = width / 2, ch = height / 2;
+	g.w = plane ? cw : width; g.h = plane ? ch : height;
+	g.pw = g.w + 8; g.ph = g.h + 8;
+	g.nbx = g.pw / 8; g.nby = g.ph / 8;
+	g.plane_off = plane == 0 ? 0 : (long long)width * height + (long long)(plane - 1) * cw * ch;
+	const long long ysz = (((long long)(width + 8) * (height + 8)) + 15) & ~15ll;
+	const long long csz = (((long long)(cw + 8) * (ch + 8)) + 15) & ~15ll;
+	g.pad_off = plane == 0 ? 0 : ysz + (plane - 1) * csz;
+	return g;
+}
+
+size_t GenericScratchBytes(int width, int height)
+{
+	const long long ysz = (((long long)(width + 8) * (height + 8)) + 15) & ~15ll;
+	const long long csz = (((long long)(width / 2 + 8) * (height / 2 + 8)) + 15) & ~15ll;
+	return (size_t)(ysz + 2 * csz);
+}
+
+/* tight -> padded at (4,4), zero border (cpu.h:55-82 with the padding defined as zero) */
+__global__ void GenericPadKernel(GenericBatch b, long long scratch_per_frame)
+{
+	const int plane = blockIdx.y, frame = blockIdx.z;
+	const GenericPlane g = MakeGenericPlane(b.width, b.height, plane);
+	const unsigned char *src = b.in + frame * b.frame_stride + g.plane_off;
+	unsigned char *dst = b.scratch + frame * scratch_per_frame + g.pad_off;
+	const long long n = (long long)g.pw * g.ph;
+	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+		const int y = (int)(i / g.pw) - 4, x = (int)(i % g.pw) - 4;
+		dst[i] = (x >= 0 && x < g.w && y >= 0 && y < g.h) ? src[(long long)y * g.w + x] : 0;
+	}
+}
+
+/* one thread per padded block, addressing pitch nbx * 8 as in cpu.h:169-172 / 469-471 */
+__global__ void GenericFilterKernel(GenericBatch b, long long scratch_per_frame)
+{
+	const int plane = blockIdx.y, frame = blockIdx.z;
+	const GenericPlane g = MakeGenericPlane(b.width, b.height, plane);
+	const int luma_nbx = (b.width + 8) / 8, luma_nby = (b.height + 8) / 8;
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= g.nbx * g.nby) return;
+	const int by = i / g.nbx, bx = i - by * g.nbx;
+	const long long pitch = (long long)g.nbx * 8;
+	unsigned char *blk = b.scratch + frame * scratch_per_frame + g.pad_off + (long long)by * 8 * pitch + bx * 8;
+	FilterParams fp;
+	const unsigned qp = b.qp ? b.qp[frame] : b.qp_value;
+	MakeFilterParams(fp, BetaOf(qp), TcOf(qp));
+	u32 lo[8], hi[8];
+#pragma unroll
+	for (int r = 0; r < 8; r++) {
+		/* scratch planes are 16-byte aligned and pitch is a multiple of 8 */
+		const uint2 v = *reinterpret_cast<const uint2 *>(blk + r * pitch);
+		lo[r] = v.x; hi[r] = v.y;
+	}
+	if (plane == 0) {
+		const u32 s4 = LumaBsOfBlock(bx, by, b.width >> 3, g.nbx, g.nby,
+			b.vert_bs + frame * b.vert_bs_stride, b.hor_bs + frame * b.hor_bs_stride);
+		LumaBlock(lo, hi, s4 & 0xff, (s4 >> 8) & 0xff, (s4 >> 16) & 0xff, s4 >> 24, fp);
+	} else {
+		const u32 s4 = ChromaBsOfBlock(bx, by, (unsigned)g.w, (unsigned)g.h, luma_nbx, luma_nby);
+		ChromaBlock(lo, hi, s4 & 0xff, (s4 >> 8) & 0xff, (s4 >> 16) & 0xff, s4 >> 24, fp);
+	}
+#pragma unroll
+	for (int r = 0; r < 8; r++) *reinterpret_cast<uint2 *>(blk + r * pitch) = make_uint2(lo[r], hi[r]);
+}
+
+/* padded -> tight (cpu.h:995-1018) */
+__global__ void GenericCropKernel(GenericBatch b, long long scratch_per_frame)
+{
+	const int plane = blockIdx.y, frame = blockIdx.z;
+	const GenericPlane g = MakeGenericPlane(b.width, b.height, plane);
+	const unsigned char *src = b.scratch + frame * scratch_per_frame + g.pad_off;
+	unsigned char *dst = b.out + frame * b.frame_stride + g.plane_off;
+	const long long n = (long long)g.w * g.h;
+	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+		const int y = (int)(i / g.w), x = (int)(i % g.w);
+		dst[i] = src[(long long)(y + 4) * g.pw + x + 4];
+	}
+}
+
+cudaError_t LaunchGeneric(const GenericBatch &b, cudaStream_t stream)
+{
+	if (b.n_frames <= 0) return cudaSuccess;
+	const long long spf = (long long)GenericScratchBytes(b.width, b.height);
+	const long long ypix = (long long)(b.width + 8) * (b.height + 8);
+	const int nblk = ((b.width + 8) / 8) * ((b.height + 8) / 8);
+	/* blockIdx.z carries the frame: at most 65535 per launch */
+	for (int f0 = 0; f0 < b.n_frames; f0 += 65535) {
+		GenericBatch part = b;
+		part.n_frames = std::min(65535, b.n_frames - f0);
+		part.in = b.in + (long long)f0 * b.frame_stride;
+		part.out = b.out + (long long)f0 * b.frame_stride;
+		part.scratch = b.scratch + (long long)f0 * spf;
+		part.qp = b.qp ? b.qp + f0 : nullptr;
+		part.vert_bs = b.vert_bs + (long long)f0 * b.vert_bs_stride;
+		part.hor_bs = b.hor_bs + (long long)f0 * b.hor_bs_stride;
+		const dim3 gpix((unsigned)std::min<long long>((ypix + 255) / 256, 1024), 3, (unsigned)part.n_frames);
+		GenericPadKernel<<<gpix, 256, 0, stream>>>(part, spf);
+		GenericFilterKernel<<<dim3((nblk + 127) / 128, 3, (unsigned)part.n_frames), 128, 0, stream>>>(part, spf);
+		GenericCropKernel<<<gpix, 256, 0, stream>>>(part, spf);
+	}
+	return cudaGetLastError();
+}
+
+} // namespace hdb

@@ -1,0 +1,102 @@
+/*
+ * deblock_kernels.cuh -- launch-side interface of the sm_100a deblocking kernels
+ * (internal to the library; the public boundary is include/hevc_deblock_b200.h).
+ */
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hdb {
+
+/* exact n / d for 0 <= n < 2^31 with one multiply-high */
+struct FastDiv {
+	uint32_t mul, shr, d;
+	__host__ void Init(uint32_t div)
+	{
+		d = div;
+		if (div <= 1) { mul = 0; shr = 0; return; }
+		uint32_t lg = 0;
+		while ((1ull << lg) < div) lg++;
+		uint32_t p = 31 + lg;
+		mul = (uint32_t)(((1ull << p) + div - 1) / div);
+		shr = p - 32;
+	}
+	__device__ __forceinline__ uint32_t Div(uint32_t n) const { return d <= 1 ? n : __umulhi(n, mul) >> shr; }
+};
+
+/*
+ * One batch of frames of one size, as the tiled kernel sees it.  Planes are
+ * addressed through the six tensor maps (Y,U,V in, Y,U,V out); everything else
+ * is here.  "row0" describe a CTU-row strip of a larger frame (multi-GPU strip
+ * split): block rows are numbered frame-globally, the buffer holds rows starting
+ * at global block row row0 (padded-block units), and every boundary-strength
+ * index and border test uses the global numbers.  For a whole frame row0 = 0.
+ */
+struct TiledBatch {
+	int n_frames;
+	/* frame-global geometry */
+	int width, height;              /* luma */
+	int luma_nbx, luma_nby;         /* (W+8)/8, (H+8)/8 */
+	int chroma_nbx, chroma_nby;     /* (W/2+8)/8, (H/2+8)/8 */
+	/* rows held by the buffers (whole frame: 0 .. nby) */
+	int luma_row0, luma_rows;       /* first global block row, number of block rows to filter */
+	int chroma_row0, chroma_rows;
+	int luma_y_org, chroma_y_org;   /* buffer row of the first block row's first sample row:
+	                                   -4 when the buffer starts at image row 0, else 0 */
+	/* work decomposition: item = (frame, plane, row group, 32-block chunk) */
+	int luma_chunks, chroma_chunks;
+	int luma_groups, chroma_groups;
+	int items_luma, items_chroma, items_per_frame;
+	long long total_items;
+	FastDiv div_items_per_frame, div_luma_chunks, div_chroma_chunks, div_items_chroma;
+	/* per-frame inputs */
+	const unsigned *qp;             /* [n_frames], or NULL: every frame uses qp_value */
+	unsigned qp_value;
+	const unsigned char *vert_bs;   /* luma BS, reference layout */
+	const unsigned char *hor_bs;
+	long long vert_bs_stride, hor_bs_stride; /* bytes between frames; 0 = one array for all */
+	const uint32_t *chroma_bs;      /* [chroma_nby][chroma_nbx] resolved, packed 4 x u8 */
+};
+
+struct TensorMaps6 { CUtensorMap in[3]; CUtensorMap out[3]; };
+
+/* kernel configuration the library was built with */
+struct TiledConfig { int block_rows_per_item, stages, warps_per_cta, smem_bytes, max_ctas_per_sm; };
+TiledConfig GetTiledConfig();
+
+/* Fill the work-decomposition fields from the geometry fields. */
+void FinalizeTiledBatch(TiledBatch &b);
+
+/* Persistent tiled kernel: one launch filters Y, U and V of every frame of the batch. */
+cudaError_t LaunchTiled(const TensorMaps6 &maps, const TiledBatch &b, void *sched, int sm_count, cudaStream_t stream);
+/* bytes of zero-initialised device memory the scheduler needs (one per context) */
+size_t TiledSchedBytes();
+
+/* Resolved chroma boundary strengths for one frame size -> table[chroma_nby * chroma_nbx]. */
+cudaError_t LaunchChromaBsTable(uint32_t *table, int width, int height, cudaStream_t stream);
+
+/* Reference-default luma boundary strengths (cpu.h:92-99) generated on the device. */
+cudaError_t LaunchDefaultLumaBs(unsigned char *vert_bs, unsigned char *hor_bs, int width, int height,
+	cudaStream_t stream);
+
+/*
+ * Generic path for frame sizes the tensor maps cannot describe (W % 32 != 0):
+ * explicit zero-padded planes in scratch memory, the reference's own addressing
+ * pitch (blocks_x * 8), one thread per padded 8x8 block.
+ */
+struct GenericBatch {
+	int n_frames, width, height;
+	const unsigned char *in; unsigned char *out;   /* tight YV12 frames, frame_stride apart */
+	long long frame_stride;
+	unsigned char *scratch;                        /* GenericScratchBytes(width, height) * n_frames */
+	const unsigned *qp;                            /* or NULL: qp_value */
+	unsigned qp_value;
+	const unsigned char *vert_bs, *hor_bs;
+	long long vert_bs_stride, hor_bs_stride;
+};
+size_t GenericScratchBytes(int width, int height);
+cudaError_t LaunchGeneric(const GenericBatch &b, cudaStream_t stream);
+
+} // namespace hdb

@@ -1,0 +1,172 @@
+/*
+ * hevc_deblock_b200.h -- C ABI of the B200 (sm_100a) HEVC-style deblocking filter.
+ *
+ * Drop-in boundary for the deblocking path of RomanKazantsev/gpu_video_codec
+ * (directory hevc_deblocking_filter/).  Reference files cited below:
+ *   cpu.h   = hevc_deblocking_filter_cpu.h   (class ReadYuvFrame: the CPU filter and the data contract)
+ *   gpu.cu  = hevc_deblocking_filter_gpu.cu  (ExecuteGpu: the GPU entry point being replaced)
+ *   main.cu = main.cu                        (the only caller of both)
+ *
+ * Data contract (identical to the reference):
+ *   - frames are 8-bit YV12: a luma plane of width*height samples followed by two
+ *     chroma planes of (width/2)*(height/2) samples, rows tightly packed (cpu.h:66-82);
+ *   - width and height must be multiples of 8 (cpu.h:46-48);
+ *   - one quantisation parameter per frame (cpu.h:35-37), values above 51 act as 51
+ *     (cpu.h:1064-1072);
+ *   - luma boundary strengths in the reference's two arrays (cpu.h:86-99):
+ *       vert_bs[(height/8) rows][(width/8 + 1) edges]   num_vert_bs = (width/8 + 1) * height / 8
+ *       hor_bs [(height/8 + 1) edge rows][(width/8)]     num_hor_bs  = (height/8 + 1) * width / 8
+ *     an edge is filtered when its strength is > 0 (cpu.h:164).  NULL selects the
+ *     reference constructor's defaults (cpu.h:92-99).  Sizes must match exactly
+ *     (cpu.h:122-123).  Chroma strengths are not caller-settable in the reference
+ *     and are not here (always the defaults of cpu.h:110-117);
+ *   - results are bit-identical to ReadYuvFrame::DeblockingFilter(1) (cpu.h:134)
+ *     run with zero plane padding and zero-extended chroma strength arrays.
+ *
+ * Errors: the reference throws string literals (cpu.h:44, 47, 123) or prints and
+ * ignores CUDA errors (gpu.cu:1104-1169, 1271-1288).  Here every entry point
+ * returns an int status and never throws; hdb_last_error() gives the text, which
+ * for the three reference conditions is the reference's own message.
+ *
+ * There is no CPU fallback: every entry point that filters requires a CUDA
+ * device of compute capability 10.x and fails with HDB_ERR_CUDA otherwise.
+ */
+#ifndef HEVC_DEBLOCK_B200_H
+#define HEVC_DEBLOCK_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HDB_OK               0
+#define HDB_ERR_INVALID_ARG  1  /* NULL where a pointer is required, n == 0, ... */
+#define HDB_ERR_FILE_SIZE    2  /* "Incorrect file size"                                   cpu.h:43-45 */
+#define HDB_ERR_DIMENSIONS   3  /* "Width and height of image must be multiplier of ..."   cpu.h:46-48 */
+#define HDB_ERR_BS_SIZE      4  /* "Incorrect size of input boundary strenght array"       cpu.h:122-123 */
+#define HDB_ERR_CUDA         5  /* CUDA runtime / driver failure, or no sm_100 device */
+#define HDB_ERR_IO           6  /* cannot open / read / write a file */
+#define HDB_ERR_NO_MEMORY    7
+
+typedef struct hdb_context hdb_context;   /* one GPU: device memory, pinned staging, streams */
+typedef struct hdb_multi hdb_multi;       /* several GPUs of one box */
+
+/*
+ * Timing of one call, the three figures the reference prints (gpu.cu:1292, 1302-1303)
+ * plus byte counts.  Device times come from CUDA events.
+ */
+typedef struct hdb_timing {
+	double kernel_ms;          /* "Execution Time without copy on GPU"  gpu.cu:1266-1292 */
+	double copy_ms;            /* "Copy Operation Time"  (H2D + D2H busy time)  gpu.cu:1246-1258, 1294-1303 */
+	double total_ms;           /* "Execution Time with copy on GPU": wall time of the whole call */
+	unsigned long long h2d_bytes, d2h_bytes;
+	int kernel_launches;       /* filter-kernel launches made by the call */
+	int path;                  /* 1 = TMA tiled kernel, 2 = generic kernel */
+} hdb_timing;
+
+typedef struct hdb_device_info {  /* what GetGpuDeviceInfo prints, main.cu:92-107 */
+	char name[256];
+	int cc_major, cc_minor, sm_count, warp_size, max_threads_per_block;
+	unsigned long long total_global_mem, total_const_mem, shared_mem_per_block;
+} hdb_device_info;
+
+/* ---- context ---------------------------------------------------------- */
+int hdb_create(hdb_context **ctx, int device);
+void hdb_destroy(hdb_context *ctx);
+const char *hdb_last_error(const hdb_context *ctx);      /* ctx may be NULL: last creation error */
+const char *hdb_status_string(int status);
+int hdb_get_device_info(const hdb_context *ctx, hdb_device_info *info);  /* main.cu:92-107 */
+
+/* ---- the data contract, host side -------------------------------------- */
+unsigned hdb_num_vert_bs(unsigned width, unsigned height);   /* cpu.h:86 */
+unsigned hdb_num_hor_bs(unsigned width, unsigned height);    /* cpu.h:87 */
+/* constructor defaults, cpu.h:92-99; either pointer may be NULL */
+int hdb_default_boundary_strength(unsigned width, unsigned height, unsigned char *vert_bs, unsigned char *hor_bs);
+int hdb_beta(unsigned qp);   /* cpu.h:1064-1067 */
+int hdb_tc(unsigned qp);     /* cpu.h:1069-1072 */
+
+/* pinned host memory, as the reference allocates for its planes (gpu.cu:1103-1111) */
+void *hdb_host_alloc(size_t bytes);
+void hdb_host_free(void *p);
+
+/* ---- one frame, host buffers ------------------------------------------- */
+/*
+ * Replaces  ReadYuvFrame(file, w, h, Qp) [cpu.h:35] -> SetBoundaryStrenght(...) [cpu.h:120]
+ *           -> DeblockingFilter(n) [cpu.h:134] -> Save(file) [cpu.h:995]
+ * and the GPU twin ExecuteGpu(...) [gpu.cu:1230], with buffers instead of files.
+ * yuv_in / yuv_out: one tight YV12 frame, 3*width*height/2 bytes; may alias.
+ */
+int hdb_deblock_frame(hdb_context *ctx, const unsigned char *yuv_in, unsigned char *yuv_out,
+	unsigned width, unsigned height, unsigned qp,
+	const unsigned char *vert_bs, unsigned num_vert_bs,
+	const unsigned char *hor_bs, unsigned num_hor_bs, hdb_timing *timing);
+
+/* Same with the three planes given separately (the reference keeps ext_Y / ext_U / ext_V, cpu.h:1041-1048). */
+int hdb_deblock_planes(hdb_context *ctx,
+	const unsigned char *y_in, const unsigned char *u_in, const unsigned char *v_in,
+	unsigned char *y_out, unsigned char *u_out, unsigned char *v_out,
+	unsigned width, unsigned height, unsigned qp,
+	const unsigned char *vert_bs, unsigned num_vert_bs,
+	const unsigned char *hor_bs, unsigned num_hor_bs, hdb_timing *timing);
+
+/*
+ * File in, file out: ExecuteGpu(input_file_name, output_file_name, width, height, Qp, ...)
+ * of main.cu:87-90 / gpu.cu:1230-1306 (the four block-dimension arguments have no
+ * meaning for this implementation and are dropped).
+ */
+int hdb_execute_gpu(hdb_context *ctx, const char *input_file_name, const char *output_file_name,
+	unsigned width, unsigned height, unsigned qp, hdb_timing *timing);
+
+/* ---- a batch of frames, host buffers (pinned multi-stream pipeline) ----- */
+/*
+ * n_frames frames of one size back to back (frame f at frames + f*3*width*height/2).
+ * qp[n_frames]; vert_bs[n_frames][num_vert_bs], hor_bs[n_frames][num_hor_bs] or both NULL
+ * for the defaults.  H2D copy, filter kernel and D2H copy of successive slices of
+ * the batch overlap on three streams.  Host buffers that are not page-locked are
+ * page-locked for the duration of the call when large, staged otherwise.
+ */
+int hdb_deblock_batch(hdb_context *ctx, const unsigned char *frames_in, unsigned char *frames_out,
+	unsigned n_frames, unsigned width, unsigned height, const unsigned *qp,
+	const unsigned char *vert_bs, const unsigned char *hor_bs, hdb_timing *timing);
+
+/* ---- a batch of frames already in device memory ------------------------ */
+/*
+ * All pointers are device pointers on ctx's device (d_vert_bs / d_hor_bs may be NULL
+ * for the defaults; d_out may equal d_in).  The kernel is enqueued on `stream`
+ * (a cudaStream_t; NULL = the legacy default stream) and the call returns
+ * without synchronising.
+ */
+int hdb_deblock_batch_device(hdb_context *ctx, const void *d_frames_in, void *d_frames_out,
+	unsigned n_frames, unsigned width, unsigned height, const unsigned *d_qp,
+	const unsigned char *d_vert_bs, const unsigned char *d_hor_bs, void *stream);
+
+/* number of filter-kernel launches made through ctx since creation */
+unsigned long long hdb_kernel_launch_count(const hdb_context *ctx);
+
+/* ---- several GPUs of one box (no reference analogue: the reference is single-GPU, main.cu:93-95) */
+/* devices == NULL: the first n_devices visible devices; n_devices <= 0: all of them */
+int hdb_multi_create(hdb_multi **m, const int *devices, int n_devices);
+void hdb_multi_destroy(hdb_multi *m);
+int hdb_multi_device_count(const hdb_multi *m);
+const char *hdb_multi_last_error(const hdb_multi *m);
+
+/* Frame-sharded batch: contiguous frame ranges per GPU, each with its own pipeline; no collective. */
+int hdb_multi_deblock_batch(hdb_multi *m, const unsigned char *frames_in, unsigned char *frames_out,
+	unsigned n_frames, unsigned width, unsigned height, const unsigned *qp,
+	const unsigned char *vert_bs, const unsigned char *hor_bs, hdb_timing *timing);
+
+/*
+ * One large frame split into strips of CTU rows (64 luma lines), one strip per GPU.
+ * Each GPU uploads only its own rows; the 4-row input halos come from the
+ * neighbouring GPUs' memory by peer-to-peer copies (NVLink where present).
+ */
+int hdb_multi_deblock_frame_strips(hdb_multi *m, const unsigned char *yuv_in, unsigned char *yuv_out,
+	unsigned width, unsigned height, unsigned qp,
+	const unsigned char *vert_bs, unsigned num_vert_bs,
+	const unsigned char *hor_bs, unsigned num_hor_bs, hdb_timing *timing);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

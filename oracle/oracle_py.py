@@ -73,7 +73,7 @@ def ref():
         if not have_ref():
             raise RuntimeError("oracle/_ref/libref_deblock.so not built (needs /root/reference)")
         lib = C.CDLL(_REF)
-        lib.ref_deblock_frame.argtypes = [_u8p, _u8p, C.c_uint, C.c_uint, C.c_uint,
+        lib.ref_deblock_frame.argtypes = [_u8p, C.c_size_t, _u8p, C.c_uint, C.c_uint, C.c_uint,
                                           _u8p, C.c_uint, _u8p, C.c_uint, C.c_uint,
                                           C.POINTER(C.c_double), C.c_char_p, C.c_uint]
         lib.ref_deblock_batch.argtypes = [_u8p, _u8p, C.c_uint, C.c_uint, C.c_uint,
@@ -142,13 +142,13 @@ def deblock_batch(frames, w, h, qps, vert_bs=None, hor_bs=None):
 def ref_deblock_frame(frame, w, h, qp, vert_bs=None, hor_bs=None, threads=1):
     """The unmodified reference (kind "reference").  Returns (out, seconds of DeblockingFilter)."""
     frame = np.ascontiguousarray(frame, np.uint8).reshape(-1)
-    out = np.empty(max(frame.size, 1), np.uint8)
+    out = np.empty(max(frame.size, 3 * w * h // 2, 1), np.uint8)
     v = None if vert_bs is None else np.ascontiguousarray(vert_bs, np.uint8)
     hh = None if hor_bs is None else np.ascontiguousarray(hor_bs, np.uint8)
     sec = C.c_double(0.0)
     err = C.create_string_buffer(256)
     # the harness writes exactly what it is given; the reference checks the file length (cpu.h:43)
-    rc = ref().ref_deblock_frame(_ptr(frame), _ptr(out), w, h, qp,
+    rc = ref().ref_deblock_frame(_ptr(frame), frame.size, _ptr(out), w, h, qp,
                                  _ptr(v), 0 if v is None else v.size,
                                  _ptr(hh), 0 if hh is None else hh.size,
                                  threads, C.byref(sec), err, 256)

@@ -86,7 +86,7 @@ extern "C" {
  * or 2 on harness I/O failure.  *seconds (optional) receives the time of the
  * DeblockingFilter call alone.
  */
-int ref_deblock_frame(const uint8_t *in, uint8_t *out, unsigned width, unsigned height,
+int ref_deblock_frame(const uint8_t *in, size_t in_bytes, uint8_t *out, unsigned width, unsigned height,
 	unsigned qp, const uint8_t *vert_bs, unsigned num_vert_bs,
 	const uint8_t *hor_bs, unsigned num_hor_bs, unsigned threads,
 	double *seconds, char *err, unsigned err_len)
@@ -95,7 +95,8 @@ int ref_deblock_frame(const uint8_t *in, uint8_t *out, unsigned width, unsigned 
 	unsigned id = __sync_fetch_and_add(&counter, 1);
 	size_t nbytes = (size_t)3 * width * height / 2;
 	std::string fin = TempPath("in", id), fout = TempPath("out", id);
-	if (!WriteFile(fin, in, nbytes)) return 2;
+	/* the file is written with the caller's length: the reference checks it (cpu.h:43) */
+	if (!WriteFile(fin, in, in_bytes)) return 2;
 	int rc = 0;
 	try {
 		ReadYuvFrame frame(fin.c_str(), width, height, qp);

@@ -1,0 +1,65 @@
+"""The multi-GPU partitioner.  With one GPU the same code runs as N logical shards on device 0
+("1 GPU with N logical shards"); with several GPUs it uses them."""
+import numpy as np
+import pytest
+
+import gpu_video_codec_b200 as hdb
+from oracle import oracle_py as orc
+from tests import common, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _device_sets():
+    import torch
+    n = torch.cuda.device_count()
+    sets = [[0], [0, 0], [0, 0, 0, 0, 0, 0, 0, 0]]
+    if n >= 2:
+        sets.append(list(range(min(n, 8))))
+    return sets
+
+
+@pytest.mark.parametrize("devices", _device_sets(), ids=lambda d: "dev" + "".join(map(str, d)))
+def test_frame_sharded_batch(devices):
+    m = hdb.MultiDeblocker(devices)
+    assert m.device_count() == len(devices)
+    n, w, h = 21, 768, 576  # not a multiple of any device count
+    frames, qps, v, hh = synth.make_batch(31, n, w, h)
+    got = m.deblock_batch(frames, w, h, qps, v, hh)
+    want = orc.deblock_batch(frames, w, h, qps, v, hh)
+    assert np.array_equal(got, want)
+    # fewer frames than devices
+    got = m.deblock_batch(frames[:3], w, h, qps[:3])
+    assert np.array_equal(got, orc.deblock_batch(frames[:3], w, h, qps[:3]))
+    m.close()
+
+
+@pytest.mark.parametrize("devices", _device_sets()[1:], ids=lambda d: "dev" + "".join(map(str, d)))
+@pytest.mark.parametrize("size", [(7680, 4320), (1920, 1080), (3840, 2160), (256, 136), (64, 64)], ids=lambda s: "%dx%d" % s)
+def test_strip_split_equals_unsplit(devices, size):
+    """A frame cut into CTU-row strips with P2P halos == the unsplit oracle output, byte-exact."""
+    w, h = size
+    m = hdb.MultiDeblocker(devices)
+    rng = np.random.default_rng(w + h)
+    frame = synth.make_frame(rng, w, h, "blocky")
+    v, hh = synth.make_bs(rng, w, h, "uniform012")
+    t = hdb.Timing()
+    got = m.deblock_frame_strips(frame, w, h, 37, v, hh, timing=t)
+    want = orc.deblock_frame(frame, w, h, 37, v, hh)
+    assert np.array_equal(got, want), int((got != want).sum())
+    # default strengths, in place
+    buf = frame.copy()
+    m.deblock_frame_strips(buf, w, h, 33, out=buf)
+    assert np.array_equal(buf, orc.deblock_frame(frame, w, h, 33))
+    m.close()
+
+
+def test_strips_golden_8k():
+    case = [c for c in common.golden()["synthetic"] if c["w"] == 7680][0]
+    frame, v, hh = common.synth_case(case["seed"], 7680, 4320, case["kind"], case["bs_kind"])
+    import torch
+    n = torch.cuda.device_count()
+    m = hdb.MultiDeblocker(list(range(n)) if n >= 2 else [0] * 8)
+    y = m.deblock_frame_strips(frame, 7680, 4320, case["qp"], v, hh)
+    assert common.md5(y) == case["md5"]
+    m.close()

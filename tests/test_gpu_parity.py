@@ -1,0 +1,233 @@
+"""GPU parity: the sm_100a path, called through the C ABI, against the oracle and the golden
+vectors of the unmodified reference.  Bit-exact (integer byte work): every comparison is
+array_equal / md5.  Run on the B200 box with  pytest -m gpu."""
+import os
+
+import numpy as np
+import pytest
+
+import gpu_video_codec_b200 as hdb
+from oracle import oracle_py as orc
+from tests import common, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    d = hdb.Deblocker(0)
+    yield d
+    d.close()
+
+
+def test_device_is_b200(dev):
+    info = dev.device_info()
+    assert info["cc_major"] == 10 and info["sm_count"] >= 100, info
+
+
+# ---- the reference's own frames (BASELINE configs 1 and 2) -------------------------------
+@pytest.mark.parametrize("case", common.golden()["bundled"], ids=lambda c: "%s-qp%d" % (c["file"][:8], c["qp"]))
+def test_bundled_frames(dev, case):
+    x = common.fixture(case["file"])
+    t = hdb.Timing()
+    y = dev.deblock_frame(x, case["w"], case["h"], case["qp"], timing=t)
+    assert common.md5(y) == case["md5"]
+    assert common.sha256(y) == case["sha256"]
+    assert t.path == 1 and t.kernel_launches == 1 and t.kernel_ms > 0 and t.total_ms >= t.kernel_ms
+
+
+@pytest.mark.parametrize("case", common.golden()["synthetic"], ids=lambda c: "s%d-%dx%d" % (c["seed"], c["w"], c["h"]))
+def test_golden_synthetic(dev, case):
+    frame, v, hh = common.synth_case(case["seed"], case["w"], case["h"], case["kind"], case["bs_kind"])
+    assert common.md5(frame) == case["input_md5"]
+    y = dev.deblock_frame(frame, case["w"], case["h"], case["qp"], v, hh)
+    assert common.md5(y) == case["md5"], "differs in %d bytes from the reference" % -1
+
+
+# ---- sizes x content x QP x BS against the oracle -----------------------------------------
+TILED_SIZES = [(32, 8), (32, 32), (64, 48), (256, 64), (288, 72), (352, 288), (768, 576), (1024, 8), (8192, 16),
+               (1920, 1080), (2048, 1096)]
+GENERIC_SIZES = [(8, 8), (16, 16), (24, 40), (40, 24), (72, 40), (200, 120), (1912, 1080)]
+
+
+@pytest.mark.parametrize("size", TILED_SIZES + GENERIC_SIZES, ids=lambda s: "%dx%d" % s)
+def test_sizes_vs_oracle(dev, size):
+    w, h = size
+    rng = np.random.default_rng(w * 131 + h)
+    for kind, bs_kind, qp in [("blocky", "uniform012", 37), ("steps", None, 30), ("saturated", "wide", 51),
+                              ("random", "twos", 44), ("blocky", None, 22)]:
+        frame = synth.make_frame(rng, w, h, kind)
+        v, hh = (None, None) if bs_kind is None else synth.make_bs(rng, w, h, bs_kind)
+        t = hdb.Timing()
+        got = dev.deblock_frame(frame, w, h, qp, v, hh, timing=t)
+        want = orc.deblock_frame(frame, w, h, qp, v, hh)
+        assert t.path == (1 if w % 32 == 0 else 2)
+        assert np.array_equal(got, want), (size, kind, bs_kind, qp, int((got != want).sum()))
+
+
+@pytest.mark.parametrize("qp", [0, 15, 16, 17, 18, 26, 27, 35, 37, 47, 51, 52, 255, 2 ** 31])
+def test_qp_sweep(dev, qp):
+    rng = np.random.default_rng(qp % 1000)
+    w, h = 352, 288
+    frame = synth.make_frame(rng, w, h, "blocky")
+    v, hh = synth.make_bs(rng, w, h, "uniform012")
+    got = dev.deblock_frame(frame, w, h, qp, v, hh)
+    assert np.array_equal(got, orc.deblock_frame(frame, w, h, qp, v, hh))
+    if qp <= 17:
+        assert np.array_equal(got, frame)  # no-op range
+
+
+@pytest.mark.parametrize("bs_kind", ["zeros", "ones", "twos", "uniform012", "wide"])
+@pytest.mark.parametrize("kind", ["flat", "ramp", "blocky", "random", "saturated", "steps"])
+def test_bs_and_content(dev, kind, bs_kind):
+    rng = np.random.default_rng(hash((kind, bs_kind)) & 0xffff)
+    w, h = 320, 136
+    frame = synth.make_frame(rng, w, h, kind)
+    v, hh = synth.make_bs(rng, w, h, bs_kind)
+    got = dev.deblock_frame(frame, w, h, 39, v, hh)
+    assert np.array_equal(got, orc.deblock_frame(frame, w, h, 39, v, hh))
+    if bs_kind == "zeros":
+        assert np.array_equal(got[:w * h], frame[:w * h])  # luma untouched; chroma uses its own defaults
+
+
+def test_planes_entry_point(dev):
+    rng = np.random.default_rng(2)
+    w, h = 352, 288
+    frame = synth.make_frame(rng, w, h, "blocky")
+    y, u, v = frame[:w * h], frame[w * h:w * h * 5 // 4], frame[w * h * 5 // 4:]
+    yo, uo, vo = dev.deblock_planes(y, u, v, w, h, 35)
+    want = orc.deblock_frame(frame, w, h, 35)
+    assert np.array_equal(np.concatenate([yo, uo, vo]), want)
+
+
+def test_execute_gpu_files(dev, tmp_path):
+    # ExecuteGpu(input_file_name, output_file_name, width, height, Qp) -- main.cu:138
+    case = [c for c in common.golden()["bundled"] if c["file"].startswith("mother") and c["qp"] == 35][0]
+    fin, fout = tmp_path / "in.yuv", tmp_path / "out.yuv"
+    common.fixture(case["file"]).tofile(fin)
+    t = hdb.Timing()
+    dev.execute_gpu(str(fin), str(fout), 352, 288, 35, timing=t)
+    assert common.md5(np.fromfile(fout, np.uint8)) == case["md5"]
+    assert t.h2d_bytes == 152064 and t.d2h_bytes == 152064
+    with pytest.raises(hdb.DeblockError, match="Incorrect file size"):
+        dev.execute_gpu(str(fin), str(fout), 352, 280, 35)
+    with pytest.raises(hdb.DeblockError):
+        dev.execute_gpu(str(tmp_path / "missing.yuv"), str(fout), 352, 288, 35)
+
+
+def test_error_behaviour(dev):
+    frame = np.zeros(3 * 16 * 16 // 2, np.uint8)
+    with pytest.raises(hdb.DeblockError, match="multiplier of sample block size"):
+        dev.deblock_frame(np.zeros(3 * 12 * 8 // 2, np.uint8), 12, 8, 30)
+    with pytest.raises(hdb.DeblockError, match="boundary strenght"):
+        dev.deblock_frame(frame, 16, 16, 30, np.zeros(5, np.uint8), np.zeros(6, np.uint8))
+    with pytest.raises(hdb.DeblockError, match="Incorrect file size"):
+        dev.deblock_frame(frame[:-2], 16, 16, 30)
+    with pytest.raises(hdb.DeblockError):
+        dev.deblock_frame(frame, 16, 16, 30, np.zeros(hdb.num_vert_bs(16, 16), np.uint8), None)
+    # the context stays usable after errors
+    assert np.array_equal(dev.deblock_frame(frame, 16, 16, 30), orc.deblock_frame(frame, 16, 16, 30))
+
+
+# ---- batches: host pipeline and device-resident -------------------------------------------
+@pytest.mark.parametrize("n,w,h", [(1, 352, 288), (9, 352, 288), (40, 1920, 1080), (5, 24, 40), (3, 3840, 2160)])
+def test_batch_host_pipeline(dev, n, w, h):
+    frames, qps, v, hh = synth.make_batch(n * 1000 + w, n, w, h)
+    t = hdb.Timing()
+    got = dev.deblock_batch(frames, w, h, qps, v, hh, timing=t)
+    want = orc.deblock_batch(frames, w, h, qps, v, hh)
+    for f in range(n):
+        assert np.array_equal(got[f], want[f]), (f, int(qps[f]))
+    assert t.d2h_bytes == frames.nbytes and t.h2d_bytes >= frames.nbytes
+    # in place, default strengths
+    buf = frames.copy()
+    dev.deblock_batch(buf, w, h, qps, out=buf)
+    assert np.array_equal(buf, orc.deblock_batch(frames, w, h, qps))
+
+
+def test_batch_many_slices_pinned(dev):
+    """More slices than pipeline slots, pinned torch buffers (the bench's e2e path)."""
+    import torch
+    n, w, h = 64, 1920, 1080  # 32 MiB slices -> 10 frames per slice -> 7 slices over 4 slots
+    frames, qps, v, hh = synth.make_batch(77, 8, w, h)
+    reps = n // 8
+    tf = torch.from_numpy(np.tile(frames, (reps, 1))).pin_memory()
+    tq = torch.from_numpy(np.tile(qps, reps).astype(np.int32)).pin_memory()
+    tv = torch.from_numpy(np.tile(v, (reps, 1))).pin_memory()
+    th = torch.from_numpy(np.tile(hh, (reps, 1))).pin_memory()
+    out = torch.empty_like(tf).pin_memory()
+    dev.deblock_batch(tf, w, h, tq, tv, th, out=out, n_frames=n)
+    want = orc.deblock_batch(frames, w, h, qps, v, hh)
+    got = out.numpy()
+    for f in range(n):
+        assert np.array_equal(got[f], want[f % 8]), f
+
+
+@pytest.mark.parametrize("in_place", [False, True])
+def test_batch_device_resident(dev, in_place):
+    import torch
+    n, w, h = 12, 1920, 1080
+    frames, qps, v, hh = synth.make_batch(5, n, w, h)
+    d_in = torch.from_numpy(frames).cuda()
+    d_out = d_in if in_place else torch.empty_like(d_in)
+    d_qp = torch.from_numpy(qps.astype(np.int32)).cuda()
+    d_v, d_h = torch.from_numpy(v).cuda(), torch.from_numpy(hh).cuda()
+    stream = torch.cuda.current_stream().cuda_stream
+    dev.deblock_batch_device(d_in, d_out, n, w, h, d_qp, d_v, d_h, stream=stream)
+    torch.cuda.synchronize()
+    want = orc.deblock_batch(frames, w, h, qps, v, hh)
+    assert np.array_equal(d_out.cpu().numpy(), want)
+    if not in_place:
+        assert np.array_equal(d_in.cpu().numpy(), frames)  # input untouched
+    # default strengths on the device path
+    d_in2 = torch.from_numpy(frames).cuda()
+    dev.deblock_batch_device(d_in2, d_in2, n, w, h, d_qp, stream=stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_in2.cpu().numpy(), orc.deblock_batch(frames, w, h, qps))
+
+
+def test_repeated_launches_reset_scheduler(dev):
+    """The work counter is reset by the kernel itself; many back-to-back launches must all be complete."""
+    import torch
+    n, w, h = 6, 768, 576
+    frames, qps, v, hh = synth.make_batch(8, n, w, h)
+    want = orc.deblock_batch(frames, w, h, qps, v, hh)
+    d_qp = torch.from_numpy(qps.astype(np.int32)).cuda()
+    d_v, d_h = torch.from_numpy(v).cuda(), torch.from_numpy(hh).cuda()
+    src = torch.from_numpy(frames).cuda()
+    outs = [torch.empty_like(src) for _ in range(20)]
+    for o in outs:
+        dev.deblock_batch_device(src, o, n, w, h, d_qp, d_v, d_h, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    for o in outs:
+        assert np.array_equal(o.cpu().numpy(), want)
+
+
+# ---- BASELINE's full sizes through size-independent properties -----------------------------
+def test_full_size_batch_properties(dev):
+    """256 x 1080p resident in HBM (BASELINE config 3 size): every frame is a replica of one of 8
+    distinct (frame, QP, BS) inputs, so the output must be 32 identical copies of the oracle's 8."""
+    import torch
+    n, w, h, distinct = 256, 1920, 1080, 8
+    frames, qps, v, hh = synth.make_batch(123, distinct, w, h)
+    reps = n // distinct
+    d_in = torch.from_numpy(frames).cuda().repeat(reps, 1)
+    d_qp = torch.from_numpy(qps.astype(np.int32)).cuda().repeat(reps)
+    d_v, d_h = torch.from_numpy(v).cuda().repeat(reps, 1), torch.from_numpy(hh).cuda().repeat(reps, 1)
+    d_out = torch.empty_like(d_in)
+    dev.deblock_batch_device(d_in, d_out, n, w, h, d_qp, d_v, d_h, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    want = torch.from_numpy(orc.deblock_batch(frames, w, h, qps, v, hh)).cuda()
+    assert bool((d_out.view(reps, distinct, -1) == want.unsqueeze(0)).all())
+    # idempotence of the no-op QPs and determinism of a second run
+    d_out2 = torch.empty_like(d_in)
+    dev.deblock_batch_device(d_in, d_out2, n, w, h, d_qp, d_v, d_h, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert bool((d_out == d_out2).all())
+
+
+def test_8k_frame(dev):
+    case = [c for c in common.golden()["synthetic"] if c["w"] == 7680][0]
+    frame, v, hh = common.synth_case(case["seed"], 7680, 4320, case["kind"], case["bs_kind"])
+    y = dev.deblock_frame(frame, 7680, 4320, case["qp"], v, hh)
+    assert common.md5(y) == case["md5"]
