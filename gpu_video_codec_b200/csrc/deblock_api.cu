@@ -124,11 +124,12 @@ int GetSizeState(hdb_context *ctx, int w, int h, SizeState **out)
 static int EncodePlaneMap(hdb_context *ctx, CUtensorMap *map, const void *base, int pw, int ph, int n,
 	long long frame_stride, int box_rows)
 {
-	cuuint64_t dims[3] = { (cuuint64_t)pw, (cuuint64_t)ph, (cuuint64_t)n };
+	/* 32-bit elements: a box may then be 272 bytes wide (a box dimension is limited to 256 elements) */
+	cuuint64_t dims[3] = { (cuuint64_t)pw / 4, (cuuint64_t)ph, (cuuint64_t)n };
 	cuuint64_t strides[2] = { (cuuint64_t)pw, (cuuint64_t)frame_stride };
-	cuuint32_t box[3] = { 256u, (cuuint32_t)box_rows, 1u };
+	cuuint32_t box[3] = { 68u, (cuuint32_t)box_rows, 1u };
 	cuuint32_t estr[3] = { 1u, 1u, 1u };
-	CUresult r = ctx->encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(base), dims, strides, box, estr,
+	CUresult r = ctx->encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<void *>(base), dims, strides, box, estr,
 		CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
 		CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 	if (r != CUDA_SUCCESS) {
@@ -214,15 +215,17 @@ int EnqueueFilter(hdb_context *ctx, const FrameView &view, const unsigned char *
 		b.qp = d_qp ? d_qp + f0 : nullptr;
 		b.vert_bs = d_vbs + f0 * vbs_stride;
 		b.hor_bs = d_hbs + f0 * hbs_stride;
-		TensorMaps6 maps;
+		TensorMaps3 maps;
 		const unsigned char *in0 = d_in + f0 * fs;
 		unsigned char *out0 = d_out + f0 * fs;
+		b.frame_stride = fs;
+		b.luma_buf_rows = view.luma_buf_rows; b.chroma_buf_rows = view.chroma_buf_rows;
 		const long long off[3] = { 0, view.u_offset, view.v_offset };
 		const int pw[3] = { w, cw, cw };
 		const int ph[3] = { view.luma_buf_rows, view.chroma_buf_rows, view.chroma_buf_rows };
 		for (int p = 0; p < 3; p++) {
 			if ((rc = EncodePlaneMap(ctx, &maps.in[p], in0 + off[p], pw[p], ph[p], nf, fs, 8 * cfg.block_rows_per_item))) return rc;
-			if ((rc = EncodePlaneMap(ctx, &maps.out[p], out0 + off[p], pw[p], ph[p], nf, fs, 8 * cfg.block_rows_per_item))) return rc;
+			b.out_plane[p] = out0 + off[p];
 		}
 		HDB_CUDA(ctx, LaunchTiled(maps, b, ctx->sched, ctx->prop.multiProcessorCount, stream));
 		ctx->launches += 1;

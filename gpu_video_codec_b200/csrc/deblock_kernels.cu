@@ -2,20 +2,30 @@
  * deblock_kernels.cu -- sm_100a kernels of the deblocking path.
  *
  * DeblockTiledKernel: persistent, warp-autonomous.  Every warp runs its own
- * TMA -> registers -> TMA pipeline over "items" = 32 horizontally adjacent
- * padded 8x8 blocks x kRB block rows of one plane of one frame (a 256 x 8*kRB
- * byte box).  The box origin is (8*bx0 - 4, 8*by0 - 4) in image coordinates:
- * the reference pads every plane by 4 samples (cpu.h:55-82) so that each padded
- * block is centred on an 8x8 grid crossing; TMA's out-of-bounds zero fill IS
- * that padding (the oracle defines it as zero), and TMA's store clipping drops
- * the writes the reference makes into its padding.  Blocks are independent
- * (cpu.h:146-447 touches only the block's own 64 samples), so a box of whole
- * blocks is filtered in place in shared memory: lane l owns block l, reads it
- * with eight conflict-free 8-byte loads per block row, runs the vertical-edge
- * and horizontal-edge passes fused in registers (deblock_core.cuh) and writes
- * it back; one lane then issues the TMA store.  No CTA-wide barrier exists in
- * the kernel; a stage is recycled when the bulk store that reads it has
- * finished (cp.async.bulk.wait_group.read).
+ * TMA -> registers -> 128-bit-store pipeline over "items" = 32 horizontally
+ * adjacent padded 8x8 blocks x kRB block rows of one plane of one frame.
+ *
+ * Geometry.  The reference pads every plane by 4 samples (cpu.h:55-82), so padded
+ * block (bx, by) covers image columns 8bx-4 .. 8bx+3 and rows 8by-4 .. 8by+3: it
+ * is centred on an 8x8 grid crossing.  Blocks are independent (cpu.h:146-447
+ * touches only the block's own 64 samples).  A TMA box must start on a 16-byte
+ * boundary in the innermost dimension (measured: anything else faults), and the
+ * blocks of an item start 4 bytes before one, so the item's box is fetched from
+ * the 16-byte boundary 12 bytes further left: a 272 x 8*kRB byte box of 32-bit
+ * elements at x = 256*chunk - 16, y = 8*by0 - 4 -- the item's 32 blocks plus a
+ * 12-byte lead-in and a 4-byte tail that belong to the neighbouring items and
+ * are never used.  TMA's out-of-bounds zero fill IS the reference's padding
+ * (the oracle defines it as zero).  Lane l owns block l: it reads its 8x8
+ * samples from shared memory (bytes 12+8l .. 19+8l of each row), runs the
+ * vertical-edge and horizontal-edge passes fused in registers
+ * (deblock_core.cuh) and writes them back to the same place.  The warp then
+ * streams the item's own columns out of shared memory: fifteen 16-byte vectors
+ * per row (image columns 256*chunk .. +239, two rows per instruction) plus one
+ * instruction of 32-bit words for the 4 + 12 fringe bytes per row that do not
+ * fill a vector on their own; writes the reference would make into its padding
+ * are dropped by the bounds predicate.  Each output byte is written by exactly
+ * one item and only bytes an item owns are consumed, so filtering in place
+ * (out == in) is safe.  No CTA-wide barrier exists in the kernel.
  *
  * Work is handed out dynamically in runs of consecutive items from one global
  * counter (luma items cost ~4x chroma items, so a static split would be
@@ -25,6 +35,7 @@
  */
 #include "deblock_kernels.cuh"
 #include "deblock_core.cuh"
+#include "tma_ptx.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -47,74 +58,16 @@ namespace hdb {
 constexpr int kRB = HDB_RB;
 constexpr int kStages = HDB_STAGES;
 constexpr int kWarps = HDB_WARPS;
-constexpr int kTileW = 256;                     /* bytes: 32 blocks of 8 columns */
+constexpr int kLead = 12;                       /* bytes from the 16-byte-aligned box origin to block 0 */
+constexpr int kTileW = 272;                     /* bytes: lead-in + 32 blocks of 8 columns + 4 tail */
+constexpr int kTileWords = kTileW / 4;          /* 68 */
 constexpr int kTileH = 8 * kRB;
-constexpr int kTileBytes = kTileW * kTileH;
+constexpr int kTileBytes = kTileW * kTileH;     /* 2176 * kRB: a multiple of 128 */
 constexpr int kSmemBytes = kWarps * kStages * (kTileBytes + 8 + 8);
 constexpr uint32_t kNoItem = 0xffffffffu;
 
 /* scheduler words in global memory: [0] next item, [1] CTAs done */
 struct SchedWords { unsigned int next; unsigned int done; };
-
-/* ------------------------------------------------------------------ */
-/* PTX: mbarrier, TMA, proxy fence                                     */
-/* ------------------------------------------------------------------ */
-__device__ __forceinline__ uint32_t SmemAddr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void MbarInit(uint32_t bar, uint32_t count)
-{
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
-}
-
-__device__ __forceinline__ void FenceMbarInit()
-{
-	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-
-__device__ __forceinline__ void MbarArriveExpectTx(uint32_t bar, uint32_t bytes)
-{
-	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
-}
-
-__device__ __forceinline__ void MbarWait(uint32_t bar, uint32_t parity)
-{
-	uint32_t done;
-	do {
-		asm volatile(
-			"{\n\t.reg .pred p;\n\t"
-			"mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-			"selp.u32 %0, 1, 0, p;\n\t}"
-			: "=r"(done) : "r"(bar), "r"(parity) : "memory");
-	} while (!done);
-}
-
-/* generic-proxy writes to shared memory -> visible to the async proxy (TMA store) */
-__device__ __forceinline__ void FenceProxyAsyncShared()
-{
-	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-
-__device__ __forceinline__ void TmaLoad3D(uint32_t dst, const CUtensorMap *map, int x, int y, int z, uint32_t bar)
-{
-	asm volatile(
-		"cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
-		" [%0], [%1, {%2, %3, %4}], [%5];"
-		:: "r"(dst), "l"(map), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
-}
-
-__device__ __forceinline__ void TmaStore3D(const CUtensorMap *map, uint32_t src, int x, int y, int z)
-{
-	asm volatile(
-		"cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
-		:: "l"(map), "r"(src), "r"(x), "r"(y), "r"(z) : "memory");
-	asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-
-template <int kPending>
-__device__ __forceinline__ void TmaStoreWaitRead()
-{
-	asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(kPending) : "memory");
-}
 
 /* ------------------------------------------------------------------ */
 /* item bookkeeping                                                    */
@@ -151,7 +104,7 @@ __device__ __forceinline__ void ItemCoords(uint32_t desc, int &plane, int &bx0, 
 /* the kernel                                                          */
 /* ------------------------------------------------------------------ */
 __global__ void __launch_bounds__(kWarps * 32, HDB_MIN_CTAS)
-DeblockTiledKernel(const __grid_constant__ TensorMaps6 maps, const __grid_constant__ TiledBatch b,
+DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_constant__ TiledBatch b,
 	SchedWords *sched, const uint32_t run_len)
 {
 	extern __shared__ __align__(1024) unsigned char smem[];
@@ -188,7 +141,8 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps6 maps, const __grid_consta
 		ItemCoords(desc, plane, bx0, lby0);
 		const uint32_t bar = bars_s + 8u * s;
 		MbarArriveExpectTx(bar, kTileBytes);
-		TmaLoad3D(tiles_s + s * kTileBytes, &maps.in[plane], 8 * bx0 - 4,
+		/* x in 32-bit elements: (8*bx0 - 4 - kLead) / 4, a multiple of 4 elements = 16 bytes */
+		TmaLoad3D(tiles_s + s * kTileBytes, &maps.in[plane], 2 * bx0 - 4,
 			8 * lby0 + (plane ? b.chroma_y_org : b.luma_y_org), (int)frame, bar);
 	};
 
@@ -196,8 +150,7 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps6 maps, const __grid_consta
 		for (int s = 0; s < kStages; s++) MbarInit(bars_s + 8u * s, 1);
 		FenceMbarInit();
 		run_pending = atomicAdd(&sched->next, run_len);
-		for (int s = 0; s < kStages - 1; s++) issue_load(s);
-		held[kStages - 1] = make_uint2(0u, kNoItem);
+		for (int s = 0; s < kStages; s++) issue_load(s);
 	}
 	__syncwarp();
 
@@ -237,39 +190,59 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps6 maps, const __grid_consta
 		}
 
 		MbarWait(bars_s + 8u * s, parity);
-		unsigned char *tile = tiles + s * kTileBytes;
+		u32 *tile = reinterpret_cast<u32 *>(tiles + s * kTileBytes);
 #pragma unroll
 		for (int rb = 0; rb < kRB; rb++) {
 			if (bx < nbx && lby0 + rb < rows) {
-				uint2 *base = reinterpret_cast<uint2 *>(tile + rb * 8 * kTileW) + lane;
+				u32 *base = tile + rb * 8 * kTileWords + kLead / 4 + 2 * lane;
 				u32 lo[8], hi[8];
 #pragma unroll
-				for (int r = 0; r < 8; r++) {
-					uint2 v = base[r * (kTileW / 8)];
-					lo[r] = v.x; hi[r] = v.y;
-				}
+				for (int r = 0; r < 8; r++) { lo[r] = base[r * kTileWords]; hi[r] = base[r * kTileWords + 1]; }
 				const u32 s4 = bs[rb];
 				if (chroma) ChromaBlock(lo, hi, s4 & 0xff, (s4 >> 8) & 0xff, (s4 >> 16) & 0xff, s4 >> 24, fp);
 				else LumaBlock(lo, hi, s4 & 0xff, (s4 >> 8) & 0xff, (s4 >> 16) & 0xff, s4 >> 24, fp);
 #pragma unroll
-				for (int r = 0; r < 8; r++) base[r * (kTileW / 8)] = make_uint2(lo[r], hi[r]);
+				for (int r = 0; r < 8; r++) { base[r * kTileWords] = lo[r]; base[r * kTileWords + 1] = hi[r]; }
 			}
 		}
+		__syncwarp();
+
+		/* stream the item's own columns out: image columns x_img .. x_img + 251 start at tile byte kLead */
+		{
+			const int pw = chroma ? (b.width >> 1) : b.width;
+			const int buf_rows = chroma ? b.chroma_buf_rows : b.luma_buf_rows;
+			const int y0 = 8 * lby0 + (chroma ? b.chroma_y_org : b.luma_y_org);
+			const int x_img = 8 * bx0 - 4;
+			unsigned char *dst = b.out_plane[plane] + (long long)frame * b.frame_stride;
+			/* 16-byte vectors: tile bytes 16 .. 255 <-> image columns x_img + 4 .. x_img + 243; two rows per pass */
+			const int j = lane & 15, half = lane >> 4;
+			const int vcol = x_img + 4 + 16 * j;
+#pragma unroll
+			for (int rr = 0; rr < kTileH; rr += 2) {
+				const int tr = rr + half, y = y0 + tr;
+				if (j < 15 && vcol < pw && y >= 0 && y < buf_rows) {
+					const uint4 v = *reinterpret_cast<const uint4 *>(reinterpret_cast<const unsigned char *>(tile) + tr * kTileW + 16 + 16 * j);
+					*reinterpret_cast<uint4 *>(dst + (long long)y * pw + vcol) = v;
+				}
+			}
+			/* fringe words: tile word 3 (image column x_img) and words 64..66 (x_img + 244 ..): 4 per row */
+#pragma unroll
+			for (int rr = 0; rr < kTileH; rr += 8) {
+				const int tr = rr + (lane >> 2), k = lane & 3, y = y0 + tr;
+				const int word = k == 0 ? 3 : 63 + k;
+				const int col = x_img + 4 * (word - 3);
+				if (col >= 0 && col < pw && y >= 0 && y < buf_rows)
+					*reinterpret_cast<u32 *>(dst + (long long)y * pw + col) = tile[tr * kTileWords + word];
+			}
+		}
+		/* the stage is free again: refill it with the item kStages ahead */
 		FenceProxyAsyncShared();
 		__syncwarp();
-		const int prev = s == 0 ? kStages - 1 : s - 1;
-		if (lane == 0) {
-			TmaStore3D(&maps.out[plane], tiles_s + s * kTileBytes, 8 * bx0 - 4,
-				8 * lby0 + (chroma ? b.chroma_y_org : b.luma_y_org), (int)frame);
-			/* the stage filtered one item ago is free once its store has read it */
-			TmaStoreWaitRead<1>();
-			issue_load(prev);
-		}
+		if (lane == 0) issue_load(s);
 		__syncwarp();
 		if (++s == kStages) { s = 0; parity ^= 1u; }
 	}
 	if (lane == 0) {
-		TmaStoreWaitRead<0>();
 		/* the last run request must have returned before the counter may be reset */
 		asm volatile("" :: "r"(run_pending) : "memory");
 	}
@@ -313,7 +286,7 @@ void FinalizeTiledBatch(TiledBatch &b)
 
 static int g_tiled_ctas_per_sm = 0;
 
-cudaError_t LaunchTiled(const TensorMaps6 &maps, const TiledBatch &b, void *sched, int sm_count, cudaStream_t stream)
+cudaError_t LaunchTiled(const TensorMaps3 &maps, const TiledBatch &b, void *sched, int sm_count, cudaStream_t stream)
 {
 	if (b.total_items <= 0) return cudaSuccess;
 	if (b.total_items >= (1ll << 31)) return cudaErrorInvalidValue;

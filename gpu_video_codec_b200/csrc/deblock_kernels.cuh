@@ -27,9 +27,9 @@ struct FastDiv {
 };
 
 /*
- * One batch of frames of one size, as the tiled kernel sees it.  Planes are
- * addressed through the six tensor maps (Y,U,V in, Y,U,V out); everything else
- * is here.  "row0" describe a CTU-row strip of a larger frame (multi-GPU strip
+ * One batch of frames of one size, as the tiled kernel sees it.  Input planes are
+ * read through three tensor maps (Y, U, V), output planes are written with plain
+ * vector stores; everything else is here.  "row0" describe a CTU-row strip of a larger frame (multi-GPU strip
  * split): block rows are numbered frame-globally, the buffer holds rows starting
  * at global block row row0 (padded-block units), and every boundary-strength
  * index and border test uses the global numbers.  For a whole frame row0 = 0.
@@ -58,9 +58,13 @@ struct TiledBatch {
 	const unsigned char *hor_bs;
 	long long vert_bs_stride, hor_bs_stride; /* bytes between frames; 0 = one array for all */
 	const uint32_t *chroma_bs;      /* [chroma_nby][chroma_nbx] resolved, packed 4 x u8 */
+	/* output: plane base pointers of frame 0 (may equal the input's), rows present, frame pitch */
+	unsigned char *out_plane[3];
+	int luma_buf_rows, chroma_buf_rows;
+	long long frame_stride;
 };
 
-struct TensorMaps6 { CUtensorMap in[3]; CUtensorMap out[3]; };
+struct TensorMaps3 { CUtensorMap in[3]; };   /* Y, U, V input planes, 32-bit elements */
 
 /* kernel configuration the library was built with */
 struct TiledConfig { int block_rows_per_item, stages, warps_per_cta, smem_bytes, max_ctas_per_sm; };
@@ -70,7 +74,7 @@ TiledConfig GetTiledConfig();
 void FinalizeTiledBatch(TiledBatch &b);
 
 /* Persistent tiled kernel: one launch filters Y, U and V of every frame of the batch. */
-cudaError_t LaunchTiled(const TensorMaps6 &maps, const TiledBatch &b, void *sched, int sm_count, cudaStream_t stream);
+cudaError_t LaunchTiled(const TensorMaps3 &maps, const TiledBatch &b, void *sched, int sm_count, cudaStream_t stream);
 /* bytes of zero-initialised device memory the scheduler needs (one per context) */
 size_t TiledSchedBytes();
 
