@@ -1,0 +1,410 @@
+#!/usr/bin/env python
+"""bench.py -- the measurement contract.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" is one pass of the deblocking path over the whole batch of the workload.  Default
+workload = BASELINE.json configs[3], the configuration the metric is quoted on: a synthetic
+3840x2160 YV12 batch of 1024 frames with random per-frame QP and luma boundary-strength maps,
+sharded by contiguous frame ranges across the N GPUs (total work fixed => strong scaling; no
+data-path collective, NCCL only carries the barrier and the max-over-ranks of the timings).
+
+  value : Mpixel/s, whole job, frames resident in HBM when the timed region starts (one kernel
+          launch per step per GPU), CUDA events on the launching stream, max over ranks.
+  e2e   : Mpixel/s through the public C ABI (hdb_deblock_batch) with pinned HOST buffers:
+          H2D copy, kernels and D2H copy of every step inside the timed region.
+  roofline   : algorithmic bytes of one launch / its mean duration vs the measured HBM peak.
+  cpu_baseline: the reference's own CPU filter (oracle/_ref, else the oracle port) on the box's
+          host cores, rank 0 at N=1, on a bounded sample of the same frames.
+
+--impl reference times only that CPU implementation (the reference arm).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (width, height, total frames, description)  -- BASELINE.json configs[3], [2], [1]
+    "4k_batch1024": (3840, 2160, 1024, "synthetic 3840x2160 YV12 batch of 1024 frames, random QP/BS maps, sharded by frame"),
+    "1080p_batch256": (1920, 1080, 256, "synthetic 1920x1080 YV12 batch of 256 frames, random QP/BS maps"),
+    "image2_single": (768, 576, 1, "single 768x576 frame, QP 30, default BS (latency case)"),
+}
+METRIC = "deblocked Mpixel/s"
+UNIT = "Mpixel/s"
+
+
+def alg_bytes_per_frame(w, h):
+    """every sample read once and written once + every BS byte read once."""
+    cw, ch = w // 2, h // 2
+    nv, nh = (w // 8 + 1) * h // 8, (h // 8 + 1) * w // 8
+    ncv, nch = (cw // 8 + 1) * ch // 8, (ch // 8 + 1) * cw // 8
+    return 3 * w * h + nv + nh + ncv + nch
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(workload):
+    """DRAM bytes per launch from the committed ncu --set full capture, if there is one for this workload."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(workload)
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def shard(total, world, rank):
+    """Contiguous frame range of `rank`: remainder to the first ranks (same rule as hdb_multi_deblock_batch)."""
+    base, rem = divmod(total, world)
+    n = base + (1 if rank < rem else 0)
+    first = rank * base + min(rank, rem)
+    return first, n
+
+
+def device_batch(torch, n, w, h, seed):
+    """Frames ('blocky' recipe of tests/synth.py, built on the device), QPs and luma BS maps for n frames."""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    fb = 3 * w * h // 2
+    frames = torch.empty((n, fb), dtype=torch.uint8, device="cuda")
+    step = 16
+    for f0 in range(0, n, step):
+        m = min(step, n - f0)
+        off = 0
+        for (pw, ph) in ((w, h), (w // 2, h // 2), (w // 2, h // 2)):
+            xx = torch.arange(pw, device="cuda", dtype=torch.float32)[None, None, :] / pw
+            yy = torch.arange(ph, device="cuda", dtype=torch.float32)[None, :, None] / ph
+            ramp = 96.0 + 64.0 * xx + 32.0 * yy
+            bh, bw = (ph + 7) // 8, (pw + 7) // 8
+            dc = torch.randint(-12, 13, (m, bh, bw), device="cuda", generator=g, dtype=torch.int16)
+            dc = dc.repeat_interleave(8, 1).repeat_interleave(8, 2)[:, :ph, :pw]
+            noise = torch.randint(-2, 3, (m, ph, pw), device="cuda", generator=g, dtype=torch.int16)
+            frames[f0:f0 + m, off:off + pw * ph] = (ramp + dc + noise).clamp_(0, 255).to(torch.uint8).reshape(m, -1)
+            off += pw * ph
+    qp = torch.randint(18, 52, (n,), device="cuda", generator=g, dtype=torch.int32)
+    if n >= 8:  # a few frames on the no-op (QP <= 17) and clamp (QP > 51) ranges
+        qp[3::64] = 12
+        qp[5::64] = 17
+        qp[6::64] = 60
+    nv, nh = (w // 8 + 1) * h // 8, (h // 8 + 1) * w // 8
+    vbs = torch.randint(0, 3, (n, nv), device="cuda", generator=g, dtype=torch.uint8)
+    hbs = torch.randint(0, 3, (n, nh), device="cuda", generator=g, dtype=torch.uint8)
+    return frames, qp, vbs, hbs
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference arm / cpu_baseline: the reference's own CPU filter on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(frames, w, h, qps, vbs, hbs, cores):
+    """Times the CPU filter on `frames` (numpy).  Returns (Mpixel/s best, detail dict)."""
+    from oracle import oracle_py as orc
+    n = frames.shape[0]
+    mpix = n * w * h / 1e6
+    detail = {}
+    if orc.have_ref():
+        kind = "reference"
+        _, t1 = orc.ref_deblock_batch(frames[:max(1, n // 4)], w, h, qps, vbs, hbs, 1, 1)
+        detail["single_thread_mpixel_s"] = round(max(1, n // 4) * w * h / 1e6 / t1, 1)
+        _, t_omp = orc.ref_deblock_batch(frames, w, h, qps, vbs, hbs, 1, cores)          # the reference's OpenMP path
+        detail["openmp_%d_threads_mpixel_s" % cores] = round(mpix / t_omp, 1)
+        _, t_fp = orc.ref_deblock_batch(frames, w, h, qps, vbs, hbs, min(cores, n), 1)   # one frame per thread
+        detail["frame_parallel_%d_threads_mpixel_s" % min(cores, n)] = round(mpix / t_fp, 1)
+        best = mpix / min(t_omp, t_fp)
+        used = cores
+    else:
+        kind = "port"
+        t0 = time.perf_counter()
+        orc.deblock_batch(frames, w, h, qps, vbs, hbs)
+        t = time.perf_counter() - t0
+        detail["single_thread_mpixel_s"] = round(mpix / t, 1)
+        best, used = mpix / t, 1
+    return best, kind, used, detail
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    from tests import synth
+    w, h, total, desc = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    n = max(1, min(total, args.cpu_sample or min(max(cores, 16), 256)))
+    distinct = min(n, 8)   # a few distinct synthetic frames, tiled: numpy generation of 4K frames is slow
+    frames, qps, vbs, hbs = synth.make_batch(2024, distinct, w, h)
+    reps = (n + distinct - 1) // distinct
+    frames, qps = np.tile(frames, (reps, 1))[:n], np.tile(qps, reps)[:n]
+    vbs, hbs = np.tile(vbs, (reps, 1))[:n], np.tile(hbs, (reps, 1))[:n]
+    if args.workload == "image2_single":
+        from tests import common
+        frames = common.fixture("image2_768x576.yuv")[None, :]
+        qps, vbs, hbs = np.array([30], np.uint32), None, None
+    vals, kind, used, detail = [], None, None, None
+    for i in range(args.warmup + args.steps):
+        v, kind, used, detail = cpu_reference_run(frames, w, h, qps, vbs, hbs, cores)
+        if i >= args.warmup:
+            vals.append(v)
+    value = float(np.median(vals))
+    sample = "%d of %d frames per step (%s), best of OpenMP-in-frame and frame-parallel on %d threads" % (n, total, desc, used)
+    line = {"impl": "reference", "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(n * w * h / 1e3 / value, 3),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": args.workload, "description": desc, "width": w, "height": h, "frames": total},
+            "cpu_baseline": {"value": round(value, 1), "unit": UNIT, "cores": used, "kind": kind, "sample": sample, "detail": detail},
+            "e2e": {"value": round(value, 1), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import gpu_video_codec_b200 as hdb
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    w, h, total, desc = WORKLOADS[args.workload]
+    first, n = shard(total, world, rank)
+    fb = 3 * w * h // 2
+    dev = hdb.Deblocker(local_rank)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    if args.workload == "image2_single":
+        from tests import common
+        frames = torch.from_numpy(common.fixture("image2_768x576.yuv")[None, :].copy()).cuda()
+        qp = torch.tensor([30], dtype=torch.int32, device="cuda")
+        vbs = hbs = None
+        n = 1
+    else:
+        frames, qp, vbs, hbs = device_batch(torch, n, w, h, seed=1000 + first)
+    out = torch.empty_like(frames)
+
+    # ---- kernel-only: frames resident in HBM ------------------------------------------------
+    def step():
+        dev.deblock_batch_device(frames, out, n, w, h, qp, vbs, hbs, stream=stream)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = dev.kernel_launch_count()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    evs[0].record()
+    for i in range(args.steps):
+        step()
+        evs[i + 1].record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    kernel_launches = dev.kernel_launch_count() - launches0
+    total_ms = max_over_ranks(evs[0].elapsed_time(evs[-1]))
+    launch_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
+    mean_launch_ms = max_over_ranks(float(np.mean(launch_ms)))
+    ms_per_step = total_ms / args.steps
+    value = total * w * h / 1e6 / (ms_per_step / 1e3)
+
+    # ---- parity of what was just timed: a strided sample of this rank's frames vs the oracle ---
+    parity = None
+    if rank == 0:
+        from oracle import oracle_py as orc
+        idx = sorted(set([0, n // 3, (2 * n) // 3, n - 1] + ([3, 5, 6] if n > 6 else [])))
+        sel = torch.tensor(idx, device="cuda")
+        got = out[sel].cpu().numpy()
+        src = frames[sel].cpu().numpy()
+        q = qp[sel].cpu().numpy().astype(np.uint32)
+        v = None if vbs is None else vbs[sel].cpu().numpy()
+        hh = None if hbs is None else hbs[sel].cpu().numpy()
+        want = orc.deblock_batch(src, w, h, q, v, hh)
+        ok = bool(np.array_equal(got, want))
+        parity = {"bit_exact": ok, "frames_checked": len(idx), "changed_fraction": round(float((got != src).mean()), 4)}
+        if not ok:
+            raise SystemExit("PARITY FAILURE: GPU output differs from the oracle; no number is reported")
+
+    # ---- end to end: pinned host buffers through hdb_deblock_batch -----------------------------
+    h_in = torch.empty((n, fb), dtype=torch.uint8).pin_memory()
+    h_out = torch.empty((n, fb), dtype=torch.uint8).pin_memory()
+    h_in.copy_(frames)
+    h_qp = qp.cpu().pin_memory()
+    h_v = None if vbs is None else vbs.cpu().pin_memory()
+    h_h = None if hbs is None else hbs.cpu().pin_memory()
+    tm = hdb.Timing()
+
+    def e2e_step():
+        dev.deblock_batch(h_in, w, h, h_qp, h_v, h_h, out=h_out, timing=tm, n_frames=n)
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        e2e_step()
+    barrier()
+    l0 = dev.kernel_launch_count()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()     # returns after the last D2H copy has completed
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_launches = dev.kernel_launch_count() - l0
+    e2e_value = total * w * h / 1e6 / (e2e_s / args.steps)
+    h2d = int(tm.h2d_bytes)
+    d2h = int(tm.d2h_bytes)
+    if rank == 0:
+        got = h_out[:1].numpy()
+        assert np.array_equal(got, out[:1].cpu().numpy()), "e2e output differs from the device-resident output"
+    if dist is not None:
+        t = torch.tensor([h2d, d2h, kernel_launches, e2e_launches], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t)
+        h2d, d2h, kernel_launches, e2e_launches = [int(x) for x in t.tolist()]
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        alg = alg_bytes_per_frame(w, h) * n          # one launch processes this rank's n frames
+        achieved = alg / (mean_launch_ms / 1e3) / 1e9
+        line = {
+            "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": args.workload, "description": desc, "width": w, "height": h, "frames": total,
+                       "frames_per_gpu": n, "sharding": "contiguous frame ranges, no collective",
+                       "l2": "inputs larger than L2 (%.1f GB in + %.1f GB out per GPU)" % (n * fb / 1e9, n * fb / 1e9),
+                       "timing": "CUDA events on the launching stream, max over ranks"},
+            "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(achieved / peak, 4), "traffic": ncu_traffic(args.workload),
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
+                         "kernel": "DeblockTiledKernel", "mean_launch_ms": round(mean_launch_ms, 4)},
+            "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": round(e2e_s / args.steps * 1e3, 3), "launches_per_step": e2e_launches // max(args.steps, 1),
+                    "api": "hdb_deblock_batch (pinned host buffers, 3-stream pipeline)"},
+            "gpu_launches": kernel_launches,
+            "clocks": clocks,
+            "parity": parity,
+        }
+        if world == 1 and not args.no_cpu:
+            cores = os.cpu_count() or 1
+            ns = max(1, min(n, args.cpu_sample or min(max(cores, 16), 256)))
+            sel = torch.arange(ns, device="cuda")
+            src = frames[sel].cpu().numpy()
+            q = qp[sel].cpu().numpy().astype(np.uint32)
+            v = None if vbs is None else vbs[sel].cpu().numpy()
+            hh = None if hbs is None else hbs[sel].cpu().numpy()
+            best, kind, used, detail = cpu_reference_run(src, w, h, q, v, hh, cores)
+            line["cpu_baseline"] = {"value": round(best, 1), "unit": UNIT, "cores": used, "kind": kind,
+                                    "sample": "first %d of the %d frames of the workload, best of OpenMP-in-frame and "
+                                              "frame-parallel on %d threads" % (ns, total, used), "detail": detail}
+        print(json.dumps(line), flush=True)
+    dev.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="4k_batch1024", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-sample", type=int, default=0, help="frames in the CPU sample (default: max(cores, 16))")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("--gpus %d needs torchrun: python -m torch.distributed.run --nnodes=1 --nproc-per-node %d "
+                         "--master-addr 127.0.0.1 --master-port 29500 bench.py --gpus %d" % (args.gpus, args.gpus, args.gpus))
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()
