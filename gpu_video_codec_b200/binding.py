@@ -13,7 +13,8 @@ import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
-_LIB = os.path.join(_PKG, "libhevc_deblock_b200.so")
+# HDB_LIBRARY selects another build of the same library (kernel-shape tuning runs)
+_LIB = os.environ.get("HDB_LIBRARY") or os.path.join(_PKG, "libhevc_deblock_b200.so")
 _HEADER = os.path.join(_ROOT, "include", "hevc_deblock_b200.h")
 
 _u8p = C.POINTER(C.c_uint8)

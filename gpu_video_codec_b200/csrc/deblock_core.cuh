@@ -93,7 +93,7 @@ struct FilterParams {
 	u32 c2_neg, c2_pos;       /* -2tc, +2tc replicated                          cpu.h:1191, 1235 */
 	u32 k_e_lo;      /* (2tc - 256) x2 */
 	u32 k_tc10;      /* (256 + 10tc + 1) x2                                     cpu.h:1254 */
-	u32 k_half;      /* (512 - 2tc) x2 */
+	u32 k_half;      /* (513 - 4tc) x2 : bias of the merged p1/q1 numerator */
 	u32 h_neg, h_lo, h_2; /* -(tc/2), (tc/2 - 256), 2*(tc/2) replicated         cpu.h:1236 */
 	u32 h_rep, c2_rep4; /* (tc/2) x2 ; (4tc) x2 */
 	u32 ct_neg, ct_lo, ct_2; /* chroma, c = tc: -tc, (tc - 256), 2tc replicated cpu.h:1442 */
@@ -109,7 +109,7 @@ HDB_FN void MakeFilterParams(FilterParams &fp, int beta, int tc)
 	fp.c2_neg = Rep2(-2 * tc); fp.c2_pos = Rep2(2 * tc);
 	fp.k_e_lo = Rep2(2 * tc - 256);
 	fp.k_tc10 = Rep2(256 + 10 * tc + 1);
-	fp.k_half = Rep2(512 - 2 * tc);
+	fp.k_half = Rep2(513 - 4 * tc);
 	fp.h_neg = Rep2(-(tc / 2)); fp.h_lo = Rep2(tc / 2 - 256); fp.h_2 = Rep2(2 * (tc / 2));
 	fp.h_rep = Rep2(tc / 2); fp.c2_rep4 = Rep2(4 * tc);
 	fp.ct_neg = Rep2(-tc); fp.ct_lo = Rep2(tc - 256); fp.ct_2 = Rep2(2 * tc);
@@ -119,13 +119,11 @@ HDB_FN void MakeFilterParams(FilterParams &fp, int beta, int tc)
 struct LumaPair { u32 p3, p2, p1, p0, q0, q1, q2, q3; };
 struct ChromaPair { u32 p1, p0, q0, q1; };
 
-/* 512 + |a2 - 2*a1 + a0| per half (cpu.h:1086: the second-derivative terms) */
-HDB_FN u32 SecondDiffBiased(u32 a2, u32 a1, u32 a0)
-{
-	u32 t = a2 + a0 + 0x02000200u - 2u * a1; /* 512 + (a2 - 2a1 + a0) in [2, 1022] */
-	u32 n = 0x04000400u - t;                 /* 512 - (...) */
-	return Max2(t, n);
-}
+/* 512 + (a2 - 2*a1 + a0) per half, in [2, 1022] */
+HDB_FN u32 SecondDiffSigned(u32 a2, u32 a1, u32 a0) { return a2 + a0 + 0x02000200u - 2u * a1; }
+
+/* 512 + |a2 - 2*a1 + a0| per half from the signed form (cpu.h:1086: the second-derivative terms) */
+HDB_FN u32 SecondDiffAbs(u32 sd) { return Max2(sd, 0x04000400u - sd); }
 
 /* |a - b| per half for unsigned halves */
 HDB_FN u32 AbsDiff2(u32 a, u32 b) { return Max2(a, b) - Min2(a, b); }
@@ -158,11 +156,14 @@ HDB_FN void StrongPair(LumaPair &t, const FilterParams &fp)
 }
 
 /*
- * Normal filter on one line pair (cpu.h:1215-1357).  dEp/dEq are the
- * segment-wide side decisions (cpu.h:1243-1249); the |delta| < 10*tc test is
- * per line (cpu.h:1254), hence a per-half mask.
+ * Normal filter on one line pair (cpu.h:1215-1357).  m_p / m_q are the segment-wide
+ * side decisions dEp / dEq (cpu.h:1243-1249) as all-ones / all-zeros words; the
+ * |delta| < 10*tc test is per line (cpu.h:1254), hence a per-half mask.  sd_p / sd_q
+ * are 512 + (x2 - 2 x1 + x0) per half.  The p1 update uses
+ *   (((p2 + p0 + 1) >> 1) - p1 + D) >> 1  ==  (p2 + p0 - 2 p1 + 2 D + 1) >> 2
+ * (dropping the parity bit of an even numerator does not change floor(. / 4)).
  */
-HDB_FN void NormalPair(LumaPair &t, const FilterParams &fp, bool dEp, bool dEq)
+HDB_FN void NormalPair(LumaPair &t, const FilterParams &fp, u32 m_p, u32 m_q, u32 sd_p, u32 sd_q)
 {
 	/* 4096 + 9(q0-p0) - 3(q1-p1) + 8, each half in [1044, 7164] */
 	u32 num = 3u * (3u * (t.q0 - t.p0) + t.p1 - t.q1) + 0x10081008u;
@@ -173,23 +174,18 @@ HDB_FN void NormalPair(LumaPair &t, const FilterParams &fp, bool dEp, bool dEq)
 	u32 d = AddMinRelu2(e, fp.k_e_lo, fp.c2_rep4);     /* Clip(delta) + 2tc in [0, 4tc]  cpu.h:1256 */
 	d = (d & mask) | (fp.c2_pos & ~mask);              /* lines that are off: delta = 0 */
 	u32 dn = fp.c2_rep4 - d;                           /* 2tc - Clip(delta) */
-	u32 p0 = AddMinRelu2(Add2(t.p0, fp.c2_neg), d, 0x00ff00ffu);   /* cpu.h:1268 */
-	u32 q0 = AddMinRelu2(Add2(t.q0, fp.c2_neg), dn, 0x00ff00ffu);  /* cpu.h:1269 */
-	if (dEp) {
-		u32 avg = ((t.p2 + t.p0 + 0x00010001u) >> 1) & 0x01ff01ffu; /* (p2 + p0 + 1) >> 1  cpu.h:1259 */
-		u32 h = ((avg + d + fp.k_half - t.p1) >> 1) & 0x7fff7fffu;  /* 256 + ((avg - p1 + D) >> 1) */
-		u32 dp = AddMinRelu2(h, fp.h_lo, fp.h_2);                   /* Clip(., tc/2) + tc/2  cpu.h:1260 */
-		dp = (dp & mask) | (fp.h_rep & ~mask);
-		t.p1 = AddMinRelu2(Add2(t.p1, fp.h_neg), dp, 0x00ff00ffu);  /* cpu.h:1272 */
-	}
-	if (dEq) {
-		u32 avg = ((t.q2 + t.q0 + 0x00010001u) >> 1) & 0x01ff01ffu; /* cpu.h:1264 */
-		u32 h = ((avg + dn + fp.k_half - t.q1) >> 1) & 0x7fff7fffu; /* 256 + ((avg - q1 - D) >> 1) */
-		u32 dq = AddMinRelu2(h, fp.h_lo, fp.h_2);                   /* cpu.h:1265 */
-		dq = (dq & mask) | (fp.h_rep & ~mask);
-		t.q1 = AddMinRelu2(Add2(t.q1, fp.h_neg), dq, 0x00ff00ffu);  /* cpu.h:1275 */
-	}
-	t.p0 = p0; t.q0 = q0;
+	/* 256 + ((x2 + x0 - 2 x1 +- 2D + 1) >> 2), then Clip(., tc/2) + tc/2   cpu.h:1259-1265 */
+	u32 hp = ((sd_p + fp.k_half + 2u * d) >> 2) & 0x01ff01ffu;
+	u32 hq = ((sd_q + fp.k_half + 2u * dn) >> 2) & 0x01ff01ffu;
+	u32 dp = AddMinRelu2(hp, fp.h_lo, fp.h_2);
+	u32 dq = AddMinRelu2(hq, fp.h_lo, fp.h_2);
+	m_p &= mask; m_q &= mask;
+	dp = (dp & m_p) | (fp.h_rep & ~m_p);               /* side or line off: no change */
+	dq = (dq & m_q) | (fp.h_rep & ~m_q);
+	t.p1 = AddMinRelu2(Add2(t.p1, fp.h_neg), dp, 0x00ff00ffu);     /* cpu.h:1272 */
+	t.q1 = AddMinRelu2(Add2(t.q1, fp.h_neg), dq, 0x00ff00ffu);     /* cpu.h:1275 */
+	t.p0 = AddMinRelu2(Add2(t.p0, fp.c2_neg), d, 0x00ff00ffu);     /* cpu.h:1268 */
+	t.q0 = AddMinRelu2(Add2(t.q0, fp.c2_neg), dn, 0x00ff00ffu);    /* cpu.h:1269 */
 }
 
 enum { kSegOff = 0, kSegNormal = 1, kSegStrong = 2 };
@@ -201,24 +197,25 @@ enum { kSegOff = 0, kSegNormal = 1, kSegStrong = 2 };
  */
 HDB_FN int LumaSegment(LumaPair &x, LumaPair &y, const FilterParams &fp)
 {
-	u32 dP = SecondDiffBiased(x.p2, x.p1, x.p0);       /* 512 + dp0 | 512 + dp3 */
-	u32 dQ = SecondDiffBiased(x.q2, x.q1, x.q0);
-	u32 s = dP + dQ;                                   /* 1024 + dp+dq per line */
+	const u32 sdp = SecondDiffSigned(x.p2, x.p1, x.p0), sdq = SecondDiffSigned(x.q2, x.q1, x.q0);
+	const u32 dP = SecondDiffAbs(sdp);                 /* 512 + dp0 | 512 + dp3 */
+	const u32 dQ = SecondDiffAbs(sdq);
+	const u32 s = dP + dQ;                             /* 1024 + dp+dq per line */
 	if (!((int)SumHalves(s) < fp.dE_lim)) return kSegOff;           /* cpu.h:1086-1087 */
 	/* strong decision, lines 0 and 3 at once (cpu.h:1099-1110) */
-	u32 c3 = AbsDiff2(x.p3, x.p0) + AbsDiff2(x.q0, x.q3);
-	u32 c4 = AbsDiff2(x.p0, x.q0);
-	u32 m1 = Max2(s - 0x04000400u, c3);
-	u32 ok = (fp.k_b8 - m1) & (fp.k_tc52 - c4) & 0x80008000u;
+	const u32 c3 = AbsDiff2(x.p3, x.p0) + AbsDiff2(x.q0, x.q3);
+	const u32 c4 = AbsDiff2(x.p0, x.q0);
+	const u32 m1 = Max2(s - 0x04000400u, c3);
+	const u32 ok = (fp.k_b8 - m1) & (fp.k_tc52 - c4) & 0x80008000u;
 	if (ok == 0x80008000u) {
 		StrongPair(x, fp);
 		StrongPair(y, fp);
 		return kSegStrong;
 	}
-	bool dEp = (int)SumHalves(dP) < fp.dEpq_lim;                    /* cpu.h:1245 */
-	bool dEq = (int)SumHalves(dQ) < fp.dEpq_lim;                    /* cpu.h:1249 */
-	NormalPair(x, fp, dEp, dEq);
-	NormalPair(y, fp, dEp, dEq);
+	const u32 m_p = (int)SumHalves(dP) < fp.dEpq_lim ? 0xffffffffu : 0u;   /* cpu.h:1245 */
+	const u32 m_q = (int)SumHalves(dQ) < fp.dEpq_lim ? 0xffffffffu : 0u;   /* cpu.h:1249 */
+	NormalPair(x, fp, m_p, m_q, sdp, sdq);
+	NormalPair(y, fp, m_p, m_q, SecondDiffSigned(y.p2, y.p1, y.p0), SecondDiffSigned(y.q2, y.q1, y.q0));
 	return kSegNormal;
 }
 
@@ -252,10 +249,10 @@ HDB_FN void LoadVertPair(LumaPair &t, u32 la, u32 lb, u32 ha, u32 hb)
 	u32 g2 = Prmt(la, lb, 0x7632);  /* p1a p0a p1b p0b */
 	u32 h1 = Prmt(ha, hb, 0x5410);  /* q0a q1a q0b q1b */
 	u32 h2 = Prmt(ha, hb, 0x7632);  /* q2a q3a q2b q3b */
-	t.p3 = g1 & m8; t.p2 = (g1 >> 8) & m8;
-	t.p1 = g2 & m8; t.p0 = (g2 >> 8) & m8;
-	t.q0 = h1 & m8; t.q1 = (h1 >> 8) & m8;
-	t.q2 = h2 & m8; t.q3 = (h2 >> 8) & m8;
+	t.p3 = g1 & m8; t.p2 = Prmt(g1, 0u, 0x4341);
+	t.p1 = g2 & m8; t.p0 = Prmt(g2, 0u, 0x4341);
+	t.q0 = h1 & m8; t.q1 = Prmt(h1, 0u, 0x4341);
+	t.q2 = h2 & m8; t.q3 = Prmt(h2, 0u, 0x4341);
 }
 
 HDB_FN void StoreVertPair(const LumaPair &t, int kind, u32 &la, u32 &lb, u32 &ha, u32 &hb)
@@ -292,8 +289,8 @@ HDB_FN void LoadVertPairChroma(ChromaPair &t, u32 la, u32 lb, u32 ha, u32 hb)
 	const u32 m8 = 0x00ff00ffu;
 	u32 g = Prmt(la, lb, 0x7632);  /* p1a p0a p1b p0b */
 	u32 h = Prmt(ha, hb, 0x5410);  /* q0a q1a q0b q1b */
-	t.p1 = g & m8; t.p0 = (g >> 8) & m8;
-	t.q0 = h & m8; t.q1 = (h >> 8) & m8;
+	t.p1 = g & m8; t.p0 = Prmt(g, 0u, 0x4341);
+	t.q0 = h & m8; t.q1 = Prmt(h, 0u, 0x4341);
 }
 
 HDB_FN void StoreVertPairChroma(const ChromaPair &t, u32 &la, u32 &lb, u32 &ha, u32 &hb)

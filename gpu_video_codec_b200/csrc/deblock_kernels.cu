@@ -50,7 +50,7 @@
 #define HDB_WARPS 4
 #endif
 #ifndef HDB_MIN_CTAS
-#define HDB_MIN_CTAS 4
+#define HDB_MIN_CTAS 5
 #endif
 
 namespace hdb {
@@ -73,31 +73,68 @@ struct SchedWords { unsigned int next; unsigned int done; };
 /* item bookkeeping                                                    */
 /* ------------------------------------------------------------------ */
 
-/* item id -> (frame, plane | chunk << 2 | group << 12) */
-__device__ __forceinline__ void DecodeItem(const TiledBatch &b, uint32_t id, uint32_t &frame, uint32_t &desc)
-{
-	frame = b.div_items_per_frame.Div(id);
-	uint32_t r = id - frame * (uint32_t)b.items_per_frame;
-	uint32_t plane, grp, chunk;
-	if (r < (uint32_t)b.items_luma) {
-		plane = 0;
-		grp = b.div_luma_chunks.Div(r);
-		chunk = r - grp * (uint32_t)b.luma_chunks;
-	} else {
-		r -= (uint32_t)b.items_luma;
-		plane = 1 + (r >= (uint32_t)b.items_chroma ? 1u : 0u);
-		r -= (plane - 1) * (uint32_t)b.items_chroma;
-		grp = b.div_chroma_chunks.Div(r);
-		chunk = r - grp * (uint32_t)b.chroma_chunks;
-	}
-	desc = plane | (chunk << 2) | (grp << 12);
-}
-
 __device__ __forceinline__ void ItemCoords(uint32_t desc, int &plane, int &bx0, int &lby0)
 {
 	plane = (int)(desc & 3u);
 	bx0 = (int)((desc >> 2) & 0x3ffu) * 32;
 	lby0 = (int)(desc >> 12) * kRB;
+}
+
+/*
+ * Producer-side cursor over the item space.  Items are numbered frame-major, then
+ * plane (Y, U, V), then row group, then 32-block chunk.  A run of consecutive item
+ * ids is decoded once (three multiply-high divisions) and then advanced by one.
+ */
+struct ItemCursor {
+	uint32_t frame, plane, grp, chunk, chunks, groups;
+
+	__device__ __forceinline__ void Seek(const TiledBatch &b, uint32_t id)
+	{
+		frame = b.div_items_per_frame.Div(id);
+		uint32_t r = id - frame * (uint32_t)b.items_per_frame;
+		if (r < (uint32_t)b.items_luma) {
+			plane = 0; chunks = (uint32_t)b.luma_chunks; groups = (uint32_t)b.luma_groups;
+			grp = b.div_luma_chunks.Div(r);
+		} else {
+			r -= (uint32_t)b.items_luma;
+			plane = 1 + (r >= (uint32_t)b.items_chroma ? 1u : 0u);
+			r -= (plane - 1) * (uint32_t)b.items_chroma;
+			chunks = (uint32_t)b.chroma_chunks; groups = (uint32_t)b.chroma_groups;
+			grp = b.div_chroma_chunks.Div(r);
+		}
+		chunk = r - grp * chunks;
+	}
+	__device__ __forceinline__ void Next(const TiledBatch &b)
+	{
+		if (++chunk < chunks) return;
+		chunk = 0;
+		if (++grp < groups) return;
+		grp = 0;
+		if (++plane == 3) { plane = 0; frame++; }
+		chunks = (uint32_t)(plane ? b.chroma_chunks : b.luma_chunks);
+		groups = (uint32_t)(plane ? b.chroma_groups : b.luma_groups);
+	}
+	__device__ __forceinline__ uint32_t Desc() const { return plane | (chunk << 2) | (grp << 12); }
+};
+
+/* what the consumer needs to know about the plane an item belongs to */
+struct PlaneInfo {
+	int nbx, rows, row0, pw, buf_rows, y_org;
+	unsigned char *out;
+};
+
+__device__ __forceinline__ PlaneInfo MakePlaneInfo(const TiledBatch &b, int plane)
+{
+	PlaneInfo p;
+	const bool c = plane != 0;
+	p.nbx = c ? b.chroma_nbx : b.luma_nbx;
+	p.rows = c ? b.chroma_rows : b.luma_rows;
+	p.row0 = c ? b.chroma_row0 : b.luma_row0;
+	p.pw = c ? (b.width >> 1) : b.width;
+	p.buf_rows = c ? b.chroma_buf_rows : b.luma_buf_rows;
+	p.y_org = c ? b.chroma_y_org : b.luma_y_org;
+	p.out = plane == 0 ? b.out_plane[0] : (plane == 1 ? b.out_plane[1] : b.out_plane[2]);
+	return p;
 }
 
 /* ------------------------------------------------------------------ */
@@ -120,30 +157,29 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_consta
 
 	/* lane 0 is the warp's producer: scheduler state, TMA issue */
 	uint32_t run_next = 0, run_end = 0, run_pending = 0;
+	ItemCursor cur;
+	cur.frame = cur.plane = cur.grp = cur.chunk = 0; cur.chunks = cur.groups = 1;
 
-	auto next_item = [&]() -> uint32_t {   /* lane 0 only */
+	auto issue_load = [&](int s) {         /* lane 0 only */
 		if (run_next == run_end) {
 			run_next = run_pending;
 			run_end = run_pending + run_len;
-			/* ask for the run after this one now; it is not needed for run_len items */
-			if (run_next < total) run_pending = atomicAdd(&sched->next, run_len);
+			if (run_next < total) {
+				/* ask for the run after this one now; it is not needed for run_len items */
+				run_pending = atomicAdd(&sched->next, run_len);
+				cur.Seek(b, run_next);
+			}
+		} else {
+			cur.Next(b);
 		}
-		uint32_t id = run_next++;
-		return id < total ? id : kNoItem;
-	};
-	auto issue_load = [&](int s) {         /* lane 0 only */
-		uint32_t id = next_item();
-		if (id == kNoItem) { held[s] = make_uint2(0u, kNoItem); return; }
-		uint32_t frame, desc;
-		DecodeItem(b, id, frame, desc);
-		held[s] = make_uint2(frame, desc);
-		int plane, bx0, lby0;
-		ItemCoords(desc, plane, bx0, lby0);
+		if (run_next >= total) { held[s] = make_uint2(0u, kNoItem); return; }
+		run_next++;
+		held[s] = make_uint2(cur.frame, cur.Desc());
 		const uint32_t bar = bars_s + 8u * s;
 		MbarArriveExpectTx(bar, kTileBytes);
 		/* x in 32-bit elements: (8*bx0 - 4 - kLead) / 4, a multiple of 4 elements = 16 bytes */
-		TmaLoad3D(tiles_s + s * kTileBytes, &maps.in[plane], 2 * bx0 - 4,
-			8 * lby0 + (plane ? b.chroma_y_org : b.luma_y_org), (int)frame, bar);
+		TmaLoad3D(tiles_s + s * kTileBytes, &maps.in[cur.plane], 64 * (int)cur.chunk - 4,
+			8 * kRB * (int)cur.grp + (cur.plane ? b.chroma_y_org : b.luma_y_org), (int)cur.frame, bar);
 	};
 
 	if (lane == 0) {
@@ -156,6 +192,12 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_consta
 
 	int s = 0;
 	uint32_t parity = 0;
+	uint32_t cur_frame = 0xffffffffu;
+	int cur_plane = -1;
+	FilterParams fp;
+	PlaneInfo pl;
+	MakeFilterParams(fp, 0, 0);
+	pl = MakePlaneInfo(b, 0);
 	for (;;) {
 		const uint2 it = held[s];
 		const uint32_t frame = it.x, desc = it.y;
@@ -163,25 +205,24 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_consta
 		int plane, bx0, lby0;
 		ItemCoords(desc, plane, bx0, lby0);
 		const bool chroma = plane != 0;
-		const int nbx = chroma ? b.chroma_nbx : b.luma_nbx;
-		const int rows = chroma ? b.chroma_rows : b.luma_rows;
-		const int row0 = chroma ? b.chroma_row0 : b.luma_row0;
-		const int bx = bx0 + lane;
-
-		/* beta / tc of this frame (cpu.h:136-137) */
-		FilterParams fp;
-		{
+		/* beta / tc once per frame (cpu.h:136-137); plane constants once per plane.  Runs of
+		 * consecutive items share both, so these two branches are rarely taken. */
+		if (frame != cur_frame) {
+			cur_frame = frame;
 			const unsigned qp = b.qp ? __ldg(b.qp + frame) : b.qp_value;
 			MakeFilterParams(fp, BetaOf(qp), TcOf(qp));
 		}
+		if (plane != cur_plane) { cur_plane = plane; pl = MakePlaneInfo(b, plane); }
+		const int bx = bx0 + lane;
+
 		/* boundary strengths of this lane's blocks; issued before the tile wait */
 		u32 bs[kRB];
 #pragma unroll
 		for (int rb = 0; rb < kRB; rb++) {
 			const int lby = lby0 + rb;
 			bs[rb] = 0;
-			if (bx < nbx && lby < rows) {
-				const int gby = row0 + lby;
+			if (bx < pl.nbx && lby < pl.rows) {
+				const int gby = pl.row0 + lby;
 				if (chroma) bs[rb] = __ldg(b.chroma_bs + gby * b.chroma_nbx + bx);
 				else bs[rb] = LumaBsOfBlock(bx, gby, b.width >> 3, b.luma_nbx, b.luma_nby,
 					b.vert_bs + (long long)frame * b.vert_bs_stride,
@@ -193,7 +234,7 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_consta
 		u32 *tile = reinterpret_cast<u32 *>(tiles + s * kTileBytes);
 #pragma unroll
 		for (int rb = 0; rb < kRB; rb++) {
-			if (bx < nbx && lby0 + rb < rows) {
+			if (bx < pl.nbx && lby0 + rb < pl.rows) {
 				u32 *base = tile + rb * 8 * kTileWords + kLead / 4 + 2 * lane;
 				u32 lo[8], hi[8];
 #pragma unroll
@@ -209,30 +250,45 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_consta
 
 		/* stream the item's own columns out: image columns x_img .. x_img + 251 start at tile byte kLead */
 		{
-			const int pw = chroma ? (b.width >> 1) : b.width;
-			const int buf_rows = chroma ? b.chroma_buf_rows : b.luma_buf_rows;
-			const int y0 = 8 * lby0 + (chroma ? b.chroma_y_org : b.luma_y_org);
+			const int y0 = 8 * lby0 + pl.y_org;
 			const int x_img = 8 * bx0 - 4;
-			unsigned char *dst = b.out_plane[plane] + (long long)frame * b.frame_stride;
+			unsigned char *dst = pl.out + (long long)frame * b.frame_stride;
+			const unsigned char *tile8 = reinterpret_cast<const unsigned char *>(tile);
 			/* 16-byte vectors: tile bytes 16 .. 255 <-> image columns x_img + 4 .. x_img + 243; two rows per pass */
 			const int j = lane & 15, half = lane >> 4;
 			const int vcol = x_img + 4 + 16 * j;
-#pragma unroll
-			for (int rr = 0; rr < kTileH; rr += 2) {
-				const int tr = rr + half, y = y0 + tr;
-				if (j < 15 && vcol < pw && y >= 0 && y < buf_rows) {
-					const uint4 v = *reinterpret_cast<const uint4 *>(reinterpret_cast<const unsigned char *>(tile) + tr * kTileW + 16 + 16 * j);
-					*reinterpret_cast<uint4 *>(dst + (long long)y * pw + vcol) = v;
-				}
-			}
+			const bool vec_lane = j < 15 && vcol < pl.pw;
+			const unsigned char *vsrc = tile8 + half * kTileW + 16 + 16 * j;
+			unsigned char *vdst = dst + (long long)(y0 + half) * pl.pw + vcol;
+			const long long pitch2 = 2ll * pl.pw;
 			/* fringe words: tile word 3 (image column x_img) and words 64..66 (x_img + 244 ..): 4 per row */
+			const int ftr = lane >> 2, k = lane & 3;
+			const int fword = k == 0 ? 3 : 63 + k;
+			const int fcol = x_img + 4 * (fword - 3);
+			const bool f_lane = fcol >= 0 && fcol < pl.pw;
+			if (y0 >= 0 && y0 + kTileH <= pl.buf_rows) {
+				/* every row of the tile is inside the plane */
 #pragma unroll
-			for (int rr = 0; rr < kTileH; rr += 8) {
-				const int tr = rr + (lane >> 2), k = lane & 3, y = y0 + tr;
-				const int word = k == 0 ? 3 : 63 + k;
-				const int col = x_img + 4 * (word - 3);
-				if (col >= 0 && col < pw && y >= 0 && y < buf_rows)
-					*reinterpret_cast<u32 *>(dst + (long long)y * pw + col) = tile[tr * kTileWords + word];
+				for (int rr = 0; rr < kTileH; rr += 2) {
+					if (vec_lane) *reinterpret_cast<uint4 *>(vdst) = *reinterpret_cast<const uint4 *>(vsrc + rr * kTileW);
+					vdst += pitch2;
+				}
+#pragma unroll
+				for (int rr = 0; rr < kTileH; rr += 8)
+					if (f_lane) *reinterpret_cast<u32 *>(dst + (long long)(y0 + rr + ftr) * pl.pw + fcol) = tile[(rr + ftr) * kTileWords + fword];
+			} else {
+				/* first / last rows of a plane: the reference writes these into its padding; drop them */
+#pragma unroll
+				for (int rr = 0; rr < kTileH; rr += 2) {
+					const int y = y0 + rr + half;
+					if (vec_lane && y >= 0 && y < pl.buf_rows) *reinterpret_cast<uint4 *>(vdst) = *reinterpret_cast<const uint4 *>(vsrc + rr * kTileW);
+					vdst += pitch2;
+				}
+#pragma unroll
+				for (int rr = 0; rr < kTileH; rr += 8) {
+					const int y = y0 + rr + ftr;
+					if (f_lane && y >= 0 && y < pl.buf_rows) *reinterpret_cast<u32 *>(dst + (long long)y * pl.pw + fcol) = tile[(rr + ftr) * kTileWords + fword];
+				}
 			}
 		}
 		/* the stage is free again: refill it with the item kStages ahead */

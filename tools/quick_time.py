@@ -58,6 +58,8 @@ def main():
     cw, ch = w // 2, h // 2
     alg = 3 * w * h + nv + nh + hdb.num_vert_bs(cw, ch) + hdb.num_hor_bs(cw, ch)
     pix = n * w * h
+    chk = int(out.view(torch.int64).sum().item()) & 0xffffffffffff
+    print("[%s] chk=%012x " % (os.path.basename(hdb.library_path()), chk), end="")
     print("%dx%d n=%d inplace=%s: median %.3f ms  min %.3f ms | %.1f Mpixel/s | %.1f GB/s algorithmic | changed %.1f%%" % (
         w, h, n, a.inplace, np.median(ms), ms.min(), pix / np.median(ms) / 1e3, n * alg / np.median(ms) / 1e6,
         100.0 * float((out != frames).float().mean()) if not a.inplace else -1))
