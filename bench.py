@@ -73,7 +73,8 @@ def ncu_traffic(workload):
 
 
 class ClockSampler:
-    """nvidia-smi clocks and throttle reasons while the timed region runs."""
+    """SM clock and throttle reasons of one GPU while the timed region runs: NVML polled from a
+    thread every ~2 ms (nvidia-smi -lms as the fallback)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -81,8 +82,34 @@ class ClockSampler:
         self.index = index
         self.proc = None
         self.lines = []
+        self.samples = []
+        self.stop_flag = False
+        self.nvml = None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            uuid = None
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            except Exception:
+                pass
+            handle = None
+            if uuid:
+                try:
+                    handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid if not uuid.startswith("GPU-") else uuid).encode())
+                except Exception:
+                    handle = None
+            if handle is None:
+                handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.nvml = (pynvml, handle)
+            self.thr = threading.Thread(target=self._poll, daemon=True)
+            self.thr.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -92,11 +119,43 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv, h = self.nvml
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                self.samples.append((sm, reasons, pw))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _read(self):
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
     def stop(self):
+        if self.nvml:
+            self.stop_flag = True
+            self.thr.join(timeout=1)
+            nv, h = self.nvml
+            if not self.samples:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+            try:
+                mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            except Exception:
+                mx = None
+            bits = 0
+            for _, r, _ in self.samples:
+                bits |= int(r)
+            names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                     "hw_power_brake_slowdown": 0x80}
+            reasons = sorted(k for k, v in names.items() if bits & v)
+            return {"sm_mhz": float(np.median([s[0] for s in self.samples])), "sm_max_mhz": mx,
+                    "power_w_max": round(max(s[2] for s in self.samples), 1), "samples": len(self.samples),
+                    "reasons": reasons, "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -120,7 +179,7 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi"}
 
 
 def shard(total, world, rank):
@@ -226,9 +285,32 @@ def run_reference_arm(args, rank):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Send everything libraries write to fd 1 (e.g. NCCL's version banner) to stderr; the one JSON
+    line is written to the original stdout by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import gpu_video_codec_b200 as hdb
+    quiet_stdout()
 
     torch.cuda.set_device(local_rank)
     dist = None
@@ -377,7 +459,7 @@ def run_ours(args, rank, world, local_rank):
             line["cpu_baseline"] = {"value": round(best, 1), "unit": UNIT, "cores": used, "kind": kind,
                                     "sample": "first %d of the %d frames of the workload, best of OpenMP-in-frame and "
                                               "frame-parallel on %d threads" % (ns, total, used), "detail": detail}
-        print(json.dumps(line), flush=True)
+        emit(line)
     dev.close()
     if dist is not None:
         dist.barrier()

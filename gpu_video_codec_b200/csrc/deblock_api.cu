@@ -427,7 +427,7 @@ int hdb_get_device_info(const hdb_context *ctx, hdb_device_info *info)
 {
 	if (!ctx || !info) return HDB_ERR_INVALID_ARG;
 	memset(info, 0, sizeof *info);
-	strncpy(info->name, ctx->prop.name, sizeof info->name - 1);
+	snprintf(info->name, sizeof info->name, "%s", ctx->prop.name);
 	info->cc_major = ctx->prop.major; info->cc_minor = ctx->prop.minor;
 	info->sm_count = ctx->prop.multiProcessorCount; info->warp_size = ctx->prop.warpSize;
 	info->max_threads_per_block = ctx->prop.maxThreadsPerBlock;

@@ -1,0 +1,41 @@
+/*
+ * main.cpp -- the reference's benchmark driver (main.cu:109-141) against the B200 library.
+ * The reference edits its inputs in the source (main.cu:111-133); here they are arguments with the
+ * reference's committed values as defaults:
+ *     hevc_deblock_b200_demo [input.yuv width height Qp [output.yuv]]
+ * Prints the device block of GetGpuDeviceInfo and the three GPU timing lines of ExecuteGpu.
+ */
+#include <cstdlib>
+#include <iostream>
+#include <string>
+
+#include "hevc_deblocking_filter_b200.hpp"
+
+int main(int argc, char **argv)
+{
+	std::string input_file_name = "mother-daughter_352x288_yv12.yuv";            /* main.cu:128 */
+	std::string output_file_name_gpu = "mother-daughter_352x288_yv12_filtered_gpu.yuv";  /* main.cu:130 */
+	unsigned int width = 352, height = 288, Qp = 35;                             /* main.cu:131-133 */
+	if (argc >= 5) {
+		input_file_name = argv[1];
+		width = (unsigned)std::strtoul(argv[2], nullptr, 10);
+		height = (unsigned)std::strtoul(argv[3], nullptr, 10);
+		Qp = (unsigned)std::strtoul(argv[4], nullptr, 10);
+		output_file_name_gpu = argc >= 6 ? argv[5] : input_file_name + ".filtered_gpu.yuv";
+	}
+	b200::GetGpuDeviceInfo();
+	try {
+		/* the object interface: ctor -> DeblockingFilter -> Save (main.cu:39-43 with the GPU behind it) */
+		b200::ReadYuvFrame frame(input_file_name.c_str(), width, height, Qp);
+		frame.DeblockingFilter();
+		frame.DeblockingFilter();   /* second call on the filtered frame: warm timings; output saved below is from ExecuteGpu */
+		std::cout << "Elapsed Time for B200 implementation behind ReadYuvFrame: "
+			<< frame.Timing().total_ms / 1e3 << "s" << std::endl;
+		/* the function interface (main.cu:138) */
+		b200::ExecuteGpu(input_file_name, output_file_name_gpu, width, height, Qp, 20, 20, 20, 20);
+	} catch (const char *msg) {
+		std::cerr << "error: " << msg << std::endl;
+		return 1;
+	}
+	return 0;
+}
