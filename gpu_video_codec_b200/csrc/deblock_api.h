@@ -33,8 +33,7 @@ constexpr int kSlots = 4;
 
 struct Slot {          /* one slice of a batch in flight */
 	unsigned char *frames = nullptr, *vbs = nullptr, *hbs = nullptr;
-	unsigned *qp = nullptr;
-	size_t frames_cap = 0, vbs_cap = 0, hbs_cap = 0, qp_cap = 0;
+	size_t frames_cap = 0, vbs_cap = 0, hbs_cap = 0;
 	cudaEvent_t h2d_done = nullptr, k_done = nullptr, d2h_done = nullptr;
 	bool ev_ready = false;
 };
@@ -83,7 +82,9 @@ struct hdb_context {
 	size_t generic_scratch_bytes = 0;
 	void *stage_in = nullptr, *stage_out = nullptr;
 	size_t stage_cap = 0;
-	size_t chunk_bytes = (size_t)32 << 20;   /* slice size of the host pipeline */
+	unsigned *qp_dev = nullptr;              /* the QPs of the batch in flight */
+	size_t qp_cap = 0;
+	size_t chunk_bytes = (size_t)128 << 20;  /* full slice size of the host pipeline (HDB_CHUNK_MB) */
 	unsigned long long launches = 0;
 	std::string err;
 	std::mutex mu;

@@ -26,6 +26,7 @@
 
 #include <stdint.h>
 
+
 #if defined(HDB_HOST_EMU)
 #define HDB_FN static inline
 #define HDB_HD static inline
@@ -66,6 +67,7 @@ HDB_FN u32 Prmt(u32 x, u32 y, u32 s) {
 	return r;
 }
 HDB_FN u32 SumHalves(u32 a) { return (a & 0xffffu) + (a >> 16); }
+HDB_FN u32 SumHalvesPlus(u32 a, u32 c) { return (a & 0xffffu) + (a >> 16) + c; }
 #else
 HDB_FN u32 Add2(u32 a, u32 b) { return __vadd2(a, b); }                          /* VIADD.16x2 */
 HDB_FN u32 Max2(u32 a, u32 b) { return __vmaxs2(a, b); }                         /* VIMNMX.S16x2 */
@@ -75,6 +77,7 @@ HDB_FN u32 AddMin2(u32 a, u32 b, u32 c) { return __viaddmin_s16x2(a, b, c); }
 HDB_FN u32 AddMinRelu2(u32 a, u32 b, u32 c) { return __viaddmin_s16x2_relu(a, b, c); }
 HDB_FN u32 Prmt(u32 x, u32 y, u32 s) { return __byte_perm(x, y, s); }            /* PRMT */
 HDB_FN u32 SumHalves(u32 a) { return __dp2a_lo(a, 0x0101u, 0u); }                /* IDP.2A: lo*1 + hi*1 */
+HDB_FN u32 SumHalvesPlus(u32 a, u32 c) { return __dp2a_lo(a, 0x0101u, c); }      /* ... + c, same instruction */
 #endif
 
 /* both halves = v (v may be negative: two's complement per half) */
@@ -87,15 +90,20 @@ struct FilterParams {
 	int beta, tc;
 	/* derived once per frame, all as packed or biased constants */
 	int dE_lim;      /* 2048 + beta            : dE test on the biased sum      cpu.h:1086-1087 */
-	int dEpq_lim;    /* 1024 + 3*beta/16       : dEp / dEq                      cpu.h:1245, 1249 */
+	int dEpq_neg;    /* -(1024 + 3*beta/16)    : dEp / dEq as a sign bit        cpu.h:1245, 1249 */
 	u32 k_b8;        /* (0x8000 + beta/8 - 1) x2 : "< beta/8" on both halves    cpu.h:1099-1105 */
 	u32 k_tc52;      /* (0x8000 + 5*tc/2 - 1) x2 : "< 5*tc/2" on both halves    cpu.h:1109-1110 */
-	u32 c2_neg, c2_pos;       /* -2tc, +2tc replicated                          cpu.h:1191, 1235 */
+	/* strong filter: the +-2tc clip applied before the >> 3 / >> 2 (scaled by 8 / 4)   cpu.h:1191-1211 */
+	u32 s8_neg, s8_pos;   /* -16tc ; 16tc + 7 */
+	u32 s4_neg, s4_pos;   /* -8tc  ; 8tc + 3 */
+	/* normal filter */
+	u32 c2_neg, c2_pos;   /* -2tc, +2tc replicated                              cpu.h:1235 */
 	u32 k_e_lo;      /* (2tc - 256) x2 */
 	u32 k_tc10;      /* (256 + 10tc + 1) x2                                     cpu.h:1254 */
 	u32 k_half;      /* (513 - 4tc) x2 : bias of the merged p1/q1 numerator */
-	u32 h_neg, h_lo, h_2; /* -(tc/2), (tc/2 - 256), 2*(tc/2) replicated         cpu.h:1236 */
-	u32 h_rep, c2_rep4; /* (tc/2) x2 ; (4tc) x2 */
+	u32 h4_lo, h8_hi;     /* 4*(tc/2 - 256) ; 8*(tc/2) + 3 : the +-tc/2 clip before the >> 2   cpu.h:1236 */
+	u32 h_neg, h_rep;     /* -(tc/2) ; (tc/2) */
+	u32 c2_rep4;     /* (4tc) x2 */
 	u32 ct_neg, ct_lo, ct_2; /* chroma, c = tc: -tc, (tc - 256), 2tc replicated cpu.h:1442 */
 };
 
@@ -103,15 +111,18 @@ HDB_FN void MakeFilterParams(FilterParams &fp, int beta, int tc)
 {
 	fp.beta = beta; fp.tc = tc;
 	fp.dE_lim = 2048 + beta;
-	fp.dEpq_lim = 1024 + 3 * beta / 16;
+	fp.dEpq_neg = -(1024 + 3 * beta / 16);
 	fp.k_b8 = Rep2(0x8000 + beta / 8 - 1);
 	fp.k_tc52 = Rep2(0x8000 + 5 * tc / 2 - 1);
+	fp.s8_neg = Rep2(-16 * tc); fp.s8_pos = Rep2(16 * tc + 7);
+	fp.s4_neg = Rep2(-8 * tc); fp.s4_pos = Rep2(8 * tc + 3);
 	fp.c2_neg = Rep2(-2 * tc); fp.c2_pos = Rep2(2 * tc);
 	fp.k_e_lo = Rep2(2 * tc - 256);
 	fp.k_tc10 = Rep2(256 + 10 * tc + 1);
 	fp.k_half = Rep2(513 - 4 * tc);
-	fp.h_neg = Rep2(-(tc / 2)); fp.h_lo = Rep2(tc / 2 - 256); fp.h_2 = Rep2(2 * (tc / 2));
-	fp.h_rep = Rep2(tc / 2); fp.c2_rep4 = Rep2(4 * tc);
+	fp.h4_lo = Rep2(4 * (tc / 2 - 256)); fp.h8_hi = Rep2(8 * (tc / 2) + 3);
+	fp.h_neg = Rep2(-(tc / 2)); fp.h_rep = Rep2(tc / 2);
+	fp.c2_rep4 = Rep2(4 * tc);
 	fp.ct_neg = Rep2(-tc); fp.ct_lo = Rep2(tc - 256); fp.ct_2 = Rep2(2 * tc);
 }
 
@@ -131,28 +142,30 @@ HDB_FN u32 AbsDiff2(u32 a, u32 b) { return Max2(a, b) - Min2(a, b); }
 /*
  * Strong filter on one line pair (cpu.h:1128-1213).  With x + delta_x equal to
  * the all-positive sums below (adding a multiple of 8 commutes with >> 3),
- *   x' = Clip255(x + Clip(-2tc, 2tc, delta_x)) = min(max(F_x, x - 2tc), x + 2tc)
- * and the 0..255 clip is the identity because 0 <= F_x <= 255.
+ *   x' = Clip255(x + Clip(-2tc, 2tc, delta_x)) = min(max(F_x, x - 2tc), x + 2tc),   F_x = T_x >> 3
+ * and the 0..255 clip is the identity because 0 <= F_x <= 255.  The clip is applied to
+ * T_x itself, against 8(x - 2tc) and 8(x + 2tc) + 7 (floor is monotone), so that the
+ * shift comes last: what it drags from the upper half into bits 13..15 of the lower half
+ * needs no mask, because every consumer of a filtered tap takes bytes 0 and 2 only
+ * (StoreVertPair, JoinRow).  FILTERED TAPS THEREFORE CARRY GARBAGE ABOVE BIT 7 OF EACH HALF.
  */
 HDB_FN void StrongPair(LumaPair &t, const FilterParams &fp)
 {
-	const u32 m8 = 0x00ff00ffu;
 	u32 s2 = t.p0 + t.q0 + 0x00020002u;       /* p0 + q0 + 2 */
 	u32 t1p = t.p2 + t.p1 + s2;               /* p2 + p1 + p0 + q0 + 2          -> >>2  cpu.h:1160 */
 	u32 t1q = t.q2 + t.q1 + s2;               /*                                         cpu.h:1179 */
 	u32 m = t.p1 + t.q1 + s2;
-	u32 t0p = t1p + m;                        /* p2 + 2p1 + 2p0 + 2q0 + q1 + 4  -> >>3  cpu.h:1154 */
-	u32 t0q = t1q + m;                        /*                                         cpu.h:1173 */
+	u32 t0p = t1p + m;                      /* p2 + 2p1 + 2p0 + 2q0 + q1 + 4  -> >>3  cpu.h:1154 */
+	u32 t0q = t1q + m;                      /*                                         cpu.h:1173 */
 	u32 t2p = 2u * (t.p3 + t.p2 + 0x00010001u) + t1p; /* 2p3 + 3p2 + p1 + p0 + q0 + 4 -> >>3  cpu.h:1166 */
 	u32 t2q = 2u * (t.q3 + t.q2 + 0x00010001u) + t1q; /*                                       cpu.h:1185 */
-	u32 f0p = (t0p >> 3) & m8, f1p = (t1p >> 2) & m8, f2p = (t2p >> 3) & m8;
-	u32 f0q = (t0q >> 3) & m8, f1q = (t1q >> 2) & m8, f2q = (t2q >> 3) & m8;
-	t.p0 = AddMin2(t.p0, fp.c2_pos, AddMax2(t.p0, fp.c2_neg, f0p)); /* cpu.h:1192-1211 */
-	t.p1 = AddMin2(t.p1, fp.c2_pos, AddMax2(t.p1, fp.c2_neg, f1p));
-	t.p2 = AddMin2(t.p2, fp.c2_pos, AddMax2(t.p2, fp.c2_neg, f2p));
-	t.q0 = AddMin2(t.q0, fp.c2_pos, AddMax2(t.q0, fp.c2_neg, f0q));
-	t.q1 = AddMin2(t.q1, fp.c2_pos, AddMax2(t.q1, fp.c2_neg, f1q));
-	t.q2 = AddMin2(t.q2, fp.c2_pos, AddMax2(t.q2, fp.c2_neg, f2q));
+	u32 a;
+	a = 8u * t.p0; t.p0 = AddMin2(a, fp.s8_pos, AddMax2(a, fp.s8_neg, t0p)) >> 3;   /* cpu.h:1192-1211 */
+	a = 4u * t.p1; t.p1 = AddMin2(a, fp.s4_pos, AddMax2(a, fp.s4_neg, t1p)) >> 2;
+	a = 8u * t.p2; t.p2 = AddMin2(a, fp.s8_pos, AddMax2(a, fp.s8_neg, t2p)) >> 3;
+	a = 8u * t.q0; t.q0 = AddMin2(a, fp.s8_pos, AddMax2(a, fp.s8_neg, t0q)) >> 3;
+	a = 4u * t.q1; t.q1 = AddMin2(a, fp.s4_pos, AddMax2(a, fp.s4_neg, t1q)) >> 2;
+	a = 8u * t.q2; t.q2 = AddMin2(a, fp.s8_pos, AddMax2(a, fp.s8_neg, t2q)) >> 3;
 }
 
 /*
@@ -161,31 +174,31 @@ HDB_FN void StrongPair(LumaPair &t, const FilterParams &fp)
  * |delta| < 10*tc test is per line (cpu.h:1254), hence a per-half mask.  sd_p / sd_q
  * are 512 + (x2 - 2 x1 + x0) per half.  The p1 update uses
  *   (((p2 + p0 + 1) >> 1) - p1 + D) >> 1  ==  (p2 + p0 - 2 p1 + 2 D + 1) >> 2
- * (dropping the parity bit of an even numerator does not change floor(. / 4)).
+ * (dropping the parity bit of an even numerator does not change floor(. / 4)), and its
+ * +-tc/2 clip is applied before the >> 2 like the strong filter's; the bits the shift
+ * drags across the halves are removed by the select that follows (its mask keeps 9 bits).
  */
 HDB_FN void NormalPair(LumaPair &t, const FilterParams &fp, u32 m_p, u32 m_q, u32 sd_p, u32 sd_q)
 {
 	/* 4096 + 9(q0-p0) - 3(q1-p1) + 8, each half in [1044, 7164] */
 	u32 num = 3u * (3u * (t.q0 - t.p0) + t.p1 - t.q1) + 0x10081008u;
 	u32 e = (num >> 4) & 0x01ff01ffu;                  /* 256 + delta              cpu.h:1253 */
-	u32 a = Max2(e, 0x02000200u - e);                  /* 256 + |delta| */
+	u32 a = Max2(e, 0x02000200u - e);                /* 256 + |delta| */
 	u32 on = AddMinRelu2(~a, fp.k_tc10, 0x00010001u);  /* 1 where |delta| < 10tc   cpu.h:1254 */
-	u32 mask = on * 0xffffu;
+	u32 mask = on * 0x01ffu;                           /* 9 bits per half: every value selected below is < 512 */
 	u32 d = AddMinRelu2(e, fp.k_e_lo, fp.c2_rep4);     /* Clip(delta) + 2tc in [0, 4tc]  cpu.h:1256 */
 	d = (d & mask) | (fp.c2_pos & ~mask);              /* lines that are off: delta = 0 */
-	u32 dn = fp.c2_rep4 - d;                           /* 2tc - Clip(delta) */
-	/* 256 + ((x2 + x0 - 2 x1 +- 2D + 1) >> 2), then Clip(., tc/2) + tc/2   cpu.h:1259-1265 */
-	u32 hp = ((sd_p + fp.k_half + 2u * d) >> 2) & 0x01ff01ffu;
-	u32 hq = ((sd_q + fp.k_half + 2u * dn) >> 2) & 0x01ff01ffu;
-	u32 dp = AddMinRelu2(hp, fp.h_lo, fp.h_2);
-	u32 dq = AddMinRelu2(hq, fp.h_lo, fp.h_2);
+	u32 dn = fp.c2_rep4 - d;                         /* 2tc - Clip(delta) */
+	/* Clip(((x2 + x0 - 2 x1 +- 2D + 1) >> 2), tc/2) + tc/2 in [0, 2(tc/2)]   cpu.h:1259-1265 */
+	u32 hp = AddMinRelu2(sd_p + fp.k_half + 2u * d, fp.h4_lo, fp.h8_hi) >> 2;
+	u32 hq = AddMinRelu2(sd_q + fp.k_half + 2u * dn, fp.h4_lo, fp.h8_hi) >> 2;
 	m_p &= mask; m_q &= mask;
-	dp = (dp & m_p) | (fp.h_rep & ~m_p);               /* side or line off: no change */
-	dq = (dq & m_q) | (fp.h_rep & ~m_q);
-	t.p1 = AddMinRelu2(Add2(t.p1, fp.h_neg), dp, 0x00ff00ffu);     /* cpu.h:1272 */
-	t.q1 = AddMinRelu2(Add2(t.q1, fp.h_neg), dq, 0x00ff00ffu);     /* cpu.h:1275 */
-	t.p0 = AddMinRelu2(Add2(t.p0, fp.c2_neg), d, 0x00ff00ffu);     /* cpu.h:1268 */
-	t.q0 = AddMinRelu2(Add2(t.q0, fp.c2_neg), dn, 0x00ff00ffu);    /* cpu.h:1269 */
+	u32 dp = (hp & m_p) | (fp.h_rep & ~m_p);           /* side or line off: no change */
+	u32 dq = (hq & m_q) | (fp.h_rep & ~m_q);
+	t.p1 = AddMinRelu2(t.p1 + dp, fp.h_neg, 0x00ff00ffu);      /* cpu.h:1272 */
+	t.q1 = AddMinRelu2(t.q1 + dq, fp.h_neg, 0x00ff00ffu);      /* cpu.h:1275 */
+	t.p0 = AddMinRelu2(t.p0 + d, fp.c2_neg, 0x00ff00ffu);      /* cpu.h:1268 */
+	t.q0 = AddMinRelu2(t.q0 + dn, fp.c2_neg, 0x00ff00ffu);     /* cpu.h:1269 */
 }
 
 enum { kSegOff = 0, kSegNormal = 1, kSegStrong = 2 };
@@ -200,7 +213,7 @@ HDB_FN int LumaSegment(LumaPair &x, LumaPair &y, const FilterParams &fp)
 	const u32 sdp = SecondDiffSigned(x.p2, x.p1, x.p0), sdq = SecondDiffSigned(x.q2, x.q1, x.q0);
 	const u32 dP = SecondDiffAbs(sdp);                 /* 512 + dp0 | 512 + dp3 */
 	const u32 dQ = SecondDiffAbs(sdq);
-	const u32 s = dP + dQ;                             /* 1024 + dp+dq per line */
+	const u32 s = dP + dQ;                           /* 1024 + dp+dq per line */
 	if (!((int)SumHalves(s) < fp.dE_lim)) return kSegOff;           /* cpu.h:1086-1087 */
 	/* strong decision, lines 0 and 3 at once (cpu.h:1099-1110) */
 	const u32 c3 = AbsDiff2(x.p3, x.p0) + AbsDiff2(x.q0, x.q3);
@@ -212,8 +225,8 @@ HDB_FN int LumaSegment(LumaPair &x, LumaPair &y, const FilterParams &fp)
 		StrongPair(y, fp);
 		return kSegStrong;
 	}
-	const u32 m_p = (int)SumHalves(dP) < fp.dEpq_lim ? 0xffffffffu : 0u;   /* cpu.h:1245 */
-	const u32 m_q = (int)SumHalves(dQ) < fp.dEpq_lim ? 0xffffffffu : 0u;   /* cpu.h:1249 */
+	const u32 m_p = (u32)((int)SumHalvesPlus(dP, (u32)fp.dEpq_neg) >> 31);   /* all ones iff dp0 + dp3 < 3*beta/16  cpu.h:1245 */
+	const u32 m_q = (u32)((int)SumHalvesPlus(dQ, (u32)fp.dEpq_neg) >> 31);   /* cpu.h:1249 */
 	NormalPair(x, fp, m_p, m_q, sdp, sdq);
 	NormalPair(y, fp, m_p, m_q, SecondDiffSigned(y.p2, y.p1, y.p0), SecondDiffSigned(y.q2, y.q1, y.q0));
 	return kSegNormal;
@@ -228,9 +241,9 @@ HDB_FN void ChromaPairFilter(ChromaPair &t, const FilterParams &fp)
 	u32 ep = (np >> 3) & 0x01ff01ffu;                               /* 256 + delta_p */
 	u32 eq = (nq >> 3) & 0x01ff01ffu;                               /* 256 + delta_q */
 	u32 dp = AddMinRelu2(ep, fp.ct_lo, fp.ct_2);                    /* Clip(delta_p) + tc   cpu.h:1464 */
-	u32 dq = fp.ct_2 - AddMinRelu2(eq, fp.ct_lo, fp.ct_2);          /* tc - Clip(delta_q)   cpu.h:1469 */
-	t.p0 = AddMinRelu2(Add2(t.p0, fp.ct_neg), dp, 0x00ff00ffu);     /* cpu.h:1475 */
-	t.q0 = AddMinRelu2(Add2(t.q0, fp.ct_neg), dq, 0x00ff00ffu);     /* cpu.h:1476 */
+	u32 dq = AddMinRelu2(eq, fp.ct_lo, fp.ct_2);                    /* Clip(delta_q) + tc   cpu.h:1469 */
+	t.p0 = AddMinRelu2(t.p0 + dp, fp.ct_neg, 0x00ff00ffu);          /* cpu.h:1475 */
+	t.q0 = AddMinRelu2(t.q0 + fp.ct_2 - dq, fp.ct_neg, 0x00ff00ffu);/* cpu.h:1476 */
 }
 
 /* ------------------------------------------------------------------ */

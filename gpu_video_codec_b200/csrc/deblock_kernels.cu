@@ -39,6 +39,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 
 #ifndef HDB_RB
 #define HDB_RB 1        /* block rows per item */
@@ -137,6 +138,24 @@ __device__ __forceinline__ PlaneInfo MakePlaneInfo(const TiledBatch &b, int plan
 	return p;
 }
 
+/*
+ * The four boundary strengths of the block lane `lane` owns in block row `rb` of item
+ * {frame, desc}, packed as LumaBsOfBlock packs them; 0 for lanes and rows outside the plane
+ * (a block whose four strengths are 0 is left untouched by LumaBlock / ChromaBlock).
+ */
+__device__ __forceinline__ u32 ItemBs(const TiledBatch &b, uint32_t frame, uint32_t desc, int lane, int rb)
+{
+	int plane, bx0, lby0;
+	ItemCoords(desc, plane, bx0, lby0);
+	const bool c = plane != 0;
+	const int bx = bx0 + lane, lby = lby0 + rb;
+	if (bx >= (c ? b.chroma_nbx : b.luma_nbx) || lby >= (c ? b.chroma_rows : b.luma_rows)) return 0;
+	const int gby = (c ? b.chroma_row0 : b.luma_row0) + lby;
+	if (c) return __ldg(b.chroma_bs + gby * b.chroma_nbx + bx);
+	return LumaBsOfBlock(bx, gby, b.width >> 3, b.luma_nbx, b.luma_nby,
+		b.vert_bs + (long long)frame * b.vert_bs_stride, b.hor_bs + (long long)frame * b.hor_bs_stride);
+}
+
 /* ------------------------------------------------------------------ */
 /* the kernel                                                          */
 /* ------------------------------------------------------------------ */
@@ -218,20 +237,11 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_consta
 		/* boundary strengths of this lane's blocks; issued before the tile wait */
 		u32 bs[kRB];
 #pragma unroll
-		for (int rb = 0; rb < kRB; rb++) {
-			const int lby = lby0 + rb;
-			bs[rb] = 0;
-			if (bx < pl.nbx && lby < pl.rows) {
-				const int gby = pl.row0 + lby;
-				if (chroma) bs[rb] = __ldg(b.chroma_bs + gby * b.chroma_nbx + bx);
-				else bs[rb] = LumaBsOfBlock(bx, gby, b.width >> 3, b.luma_nbx, b.luma_nby,
-					b.vert_bs + (long long)frame * b.vert_bs_stride,
-					b.hor_bs + (long long)frame * b.hor_bs_stride);
-			}
-		}
+		for (int rb = 0; rb < kRB; rb++) bs[rb] = ItemBs(b, frame, desc, lane, rb);
 
 		MbarWait(bars_s + 8u * s, parity);
 		u32 *tile = reinterpret_cast<u32 *>(tiles + s * kTileBytes);
+		unsigned char *dst = pl.out + (long long)frame * b.frame_stride;
 #pragma unroll
 		for (int rb = 0; rb < kRB; rb++) {
 			if (bx < pl.nbx && lby0 + rb < pl.rows) {
@@ -252,7 +262,6 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_consta
 		{
 			const int y0 = 8 * lby0 + pl.y_org;
 			const int x_img = 8 * bx0 - 4;
-			unsigned char *dst = pl.out + (long long)frame * b.frame_stride;
 			const unsigned char *tile8 = reinterpret_cast<const unsigned char *>(tile);
 			/* 16-byte vectors: tile bytes 16 .. 255 <-> image columns x_img + 4 .. x_img + 243; two rows per pass */
 			const int j = lane & 15, half = lane >> 4;
@@ -361,6 +370,8 @@ cudaError_t LaunchTiled(const TensorMaps3 &maps, const TiledBatch &b, void *sche
 	/* run length: consecutive items per scheduler request; short when work is scarce */
 	long long per_warp = b.total_items / (ctas * kWarps);
 	uint32_t run_len = (uint32_t)std::max<long long>(1, std::min<long long>(16, per_warp / 8));
+	static const int run_len_env = getenv("HDB_RUN_LEN") ? atoi(getenv("HDB_RUN_LEN")) : 0;   /* measurement knob */
+	if (run_len_env > 0) run_len = (uint32_t)run_len_env;
 	DeblockTiledKernel<<<(unsigned)ctas, kWarps * 32, kSmemBytes, stream>>>(maps, b,
 		reinterpret_cast<SchedWords *>(sched), run_len);
 	return cudaGetLastError();

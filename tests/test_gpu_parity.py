@@ -148,7 +148,7 @@ def test_batch_host_pipeline(dev, n, w, h):
 def test_batch_many_slices_pinned(dev):
     """More slices than pipeline slots, pinned torch buffers (the bench's e2e path)."""
     import torch
-    n, w, h = 64, 1920, 1080  # 32 MiB slices -> 10 frames per slice -> 7 slices over 4 slots
+    n, w, h = 64, 1920, 1080  # slice plan 5,10,17,17,10,5 frames (128 MiB full slices, ramped): 6 slices over 4 slots
     frames, qps, v, hh = synth.make_batch(77, 8, w, h)
     reps = n // 8
     tf = torch.from_numpy(np.tile(frames, (reps, 1))).pin_memory()
