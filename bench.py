@@ -61,12 +61,14 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic(workload):
-    """DRAM bytes per launch from the committed ncu --set full capture, if there is one for this workload."""
+def ncu_traffic(workload, frames_in_launch):
+    """DRAM bytes of one launch over `frames_in_launch` frames, from the committed ncu --set full capture
+    (dram__bytes_read.sum + dram__bytes_write.sum per frame of this workload), or None."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get(workload)
+            per_frame = json.load(open(p)).get(workload + "_per_frame")
+            return None if per_frame is None else int(per_frame * frames_in_launch)
         except Exception:
             return None
     return None
@@ -437,7 +439,7 @@ def run_ours(args, rank, world, local_rank):
                        "l2": "inputs larger than L2 (%.1f GB in + %.1f GB out per GPU)" % (n * fb / 1e9, n * fb / 1e9),
                        "timing": "CUDA events on the launching stream, max over ranks"},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4), "traffic": ncu_traffic(args.workload),
+                         "frac": round(achieved / peak, 4), "traffic": ncu_traffic(args.workload, n),
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
                          "kernel": "DeblockTiledKernel", "mean_launch_ms": round(mean_launch_ms, 4)},
             "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

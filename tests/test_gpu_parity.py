@@ -186,6 +186,33 @@ def test_batch_device_resident(dev, in_place):
     assert np.array_equal(d_in2.cpu().numpy(), orc.deblock_batch(frames, w, h, qps))
 
 
+@pytest.mark.parametrize("size", [(32, 8), (352, 288), (1920, 1080), (24, 40)], ids=lambda s: "%dx%d" % s)
+def test_no_write_outside_the_frames(dev, size):
+    """compute-sanitizer is closed on this pool, so out-of-bounds stores are hunted with canaries: the
+    output batch sits between two 64 KiB guard bands that must come back untouched (tiled path: stores
+    the reference would make into its padding must be dropped; generic path: crop must stay inside)."""
+    import torch
+    w, h = size
+    n, guard = 3, 1 << 16
+    frames, qps, v, hh = synth.make_batch(w + h, n, w, h)
+    fb = frames.shape[1]
+    buf = torch.full((guard + n * fb + guard,), 0xA5, dtype=torch.uint8, device="cuda")
+    d_out = buf[guard:guard + n * fb]
+    d_in = torch.from_numpy(frames).cuda()
+    d_qp = torch.from_numpy(qps.astype(np.int32)).cuda()
+    d_v, d_h = torch.from_numpy(v).cuda(), torch.from_numpy(hh).cuda()
+    dev.deblock_batch_device(d_in, d_out, n, w, h, d_qp, d_v, d_h, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_out.cpu().numpy().reshape(n, fb), orc.deblock_batch(frames, w, h, qps, v, hh))
+    assert bool((buf[:guard] == 0xA5).all()) and bool((buf[guard + n * fb:] == 0xA5).all())
+    # in place inside the same guarded buffer
+    buf[guard:guard + n * fb] = d_in.reshape(-1)
+    dev.deblock_batch_device(d_out, d_out, n, w, h, d_qp, d_v, d_h, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_out.cpu().numpy().reshape(n, fb), orc.deblock_batch(frames, w, h, qps, v, hh))
+    assert bool((buf[:guard] == 0xA5).all()) and bool((buf[guard + n * fb:] == 0xA5).all())
+
+
 def test_repeated_launches_reset_scheduler(dev):
     """The work counter is reset by the kernel itself; many back-to-back launches must all be complete."""
     import torch
