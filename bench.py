@@ -257,7 +257,7 @@ def run_reference_arm(args, rank):
     from tests import synth
     w, h, total, desc = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
-    n = max(1, min(total, args.cpu_sample or min(max(cores, 16), 256)))
+    n = max(1, min(total, args.cpu_sample or 256))
     distinct = min(n, 8)   # a few distinct synthetic frames, tiled: numpy generation of 4K frames is slow
     frames, qps, vbs, hbs = synth.make_batch(2024, distinct, w, h)
     reps = (n + distinct - 1) // distinct
@@ -419,8 +419,36 @@ def run_ours(args, rank, world, local_rank):
     h2d = int(tm.h2d_bytes)
     d2h = int(tm.d2h_bytes)
     if rank == 0:
-        got = h_out[:1].numpy()
-        assert np.array_equal(got, out[:1].cpu().numpy()), "e2e output differs from the device-resident output"
+        # every frame of this rank's shard, as delivered to the host by the e2e path, against the CPU
+        # checker (the unmodified reference on all host cores when oracle/_ref is there, else the port)
+        from oracle import oracle_py as orc
+        cores = os.cpu_count() or 1
+        np_in, np_out = h_in.numpy(), h_out.numpy()
+        np_qp = h_qp.numpy().astype(np.uint32)
+        np_v = None if h_v is None else h_v.numpy()
+        np_h = None if h_h is None else h_h.numpy()
+        bad, t_chk = 0, time.perf_counter()
+        for f0 in range(0, n, 64):
+            f1 = min(n, f0 + 64)
+            vv = None if np_v is None else np_v[f0:f1]
+            hv = None if np_h is None else np_h[f0:f1]
+            if orc.have_ref():
+                want, _ = orc.ref_deblock_batch(np_in[f0:f1], w, h, np_qp[f0:f1], vv, hv, min(cores, f1 - f0), 1)
+            else:
+                want = orc.deblock_batch(np_in[f0:f1], w, h, np_qp[f0:f1], vv, hv)
+            bad += sum(0 if np.array_equal(np_out[f0 + i], want[i]) else 1 for i in range(f1 - f0))
+        # and the output of the kernel-only (timed) launch must be that same output, frame for frame
+        for f0 in range(0, n, 64):
+            f1 = min(n, f0 + 64)
+            if not torch.equal(out[f0:f1], h_out[f0:f1].cuda(non_blocking=False)):
+                raise SystemExit("PARITY FAILURE: device-resident output differs from the e2e output in frames %d..%d" % (f0, f1))
+        parity["e2e_frames_checked"] = n
+        parity["e2e_frames_differing"] = bad
+        parity["checker"] = "reference (oracle/_ref)" if orc.have_ref() else "port (oracle/deblock_oracle.c)"
+        parity["check_seconds"] = round(time.perf_counter() - t_chk, 1)
+        parity["bit_exact"] = parity["bit_exact"] and bad == 0
+        if bad:
+            raise SystemExit("PARITY FAILURE: %d of %d e2e frames differ from the CPU checker; no number is reported" % (bad, n))
     if dist is not None:
         t = torch.tensor([h2d, d2h, kernel_launches, e2e_launches], dtype=torch.int64, device="cuda")
         dist.all_reduce(t)
@@ -451,7 +479,7 @@ def run_ours(args, rank, world, local_rank):
         }
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
-            ns = max(1, min(n, args.cpu_sample or min(max(cores, 16), 256)))
+            ns = max(1, min(n, args.cpu_sample or 256))
             sel = torch.arange(ns, device="cuda")
             src = frames[sel].cpu().numpy()
             q = qp[sel].cpu().numpy().astype(np.uint32)
@@ -475,7 +503,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="4k_batch1024", choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-sample", type=int, default=0, help="frames in the CPU sample (default: max(cores, 16))")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="frames in the CPU sample (default 256)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
