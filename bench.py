@@ -38,6 +38,8 @@ WORKLOADS = {
     "4k_batch1024": (3840, 2160, 1024, "synthetic 3840x2160 YV12 batch of 1024 frames, random QP/BS maps, sharded by frame"),
     "1080p_batch256": (1920, 1080, 256, "synthetic 1920x1080 YV12 batch of 256 frames, random QP/BS maps"),
     "image2_single": (768, 576, 1, "single 768x576 frame, QP 30, default BS (latency case)"),
+    # BASELINE.json configs[4]: one process drives all GPUs (hdb_multi_deblock_frame_strips); not a torchrun workload
+    "8k_strips": (7680, 4320, 16, "stream of single 7680x4320 frames, each split into CTU-row strips across the GPUs, P2P halos"),
 }
 METRIC = "deblocked Mpixel/s"
 UNIT = "Mpixel/s"
@@ -496,6 +498,70 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_strips(args):
+    """BASELINE configs[4]: a stream of 8K frames, each cut into CTU-row strips over --gpus devices of this
+    process (logical shards on device 0 when the box has fewer).  One step = the whole stream, frame by
+    frame, host buffers in and out (the strip path has no device-resident form: its point is latency of
+    one frame that arrives on the host).  Beside it: the same stream through one GPU unsplit."""
+    import torch
+    import gpu_video_codec_b200 as hdb
+    from oracle import oracle_py as orc
+    from tests import synth
+    quiet_stdout()
+    w, h, total, desc = WORKLOADS[args.workload]
+    have = torch.cuda.device_count()
+    devices = list(range(args.gpus)) if have >= args.gpus else [i % have for i in range(args.gpus)]
+    m = hdb.MultiDeblocker(devices)
+    one = hdb.Deblocker(0)
+    distinct = 4
+    frames, qps, v, hh = synth.make_batch(77, distinct, w, h)
+    h_in = torch.from_numpy(frames).pin_memory()
+    h_out = torch.empty_like(h_in).pin_memory()
+    np_in, np_out = h_in.numpy(), h_out.numpy()
+    want, _ = orc.ref_deblock_batch(frames, w, h, qps, v, hh, distinct, 1) if orc.have_ref() else (orc.deblock_batch(frames, w, h, qps, v, hh), 0)
+    tm = hdb.Timing()
+
+    def stream(fn):
+        k = 0.0
+        for f in range(total):
+            i = f % distinct
+            fn(np_in[i], w, h, int(qps[i]), v[i], hh[i], out=np_out[i], timing=tm)
+            k += tm.kernel_ms
+        return k
+
+    res = {}
+    for name, fn in (("strips", m.deblock_frame_strips), ("unsplit_1gpu", one.deblock_frame)):
+        for _ in range(max(args.warmup, 3)):
+            stream(fn)
+        ok = all(np.array_equal(np_out[i], want[i]) for i in range(distinct))
+        if not ok:
+            raise SystemExit("PARITY FAILURE (%s): output differs from the CPU checker" % name)
+        np_out[:] = 0
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        kms = 0.0
+        for _ in range(args.steps):
+            kms += stream(fn)
+        dt = time.perf_counter() - t0
+        res[name] = {"mpixel_s": round(args.steps * total * w * h / 1e6 / dt, 1), "ms_per_frame": round(dt * 1e3 / (args.steps * total), 4),
+                     "kernel_ms_per_frame": round(kms / (args.steps * total), 4)}
+    fb = 3 * w * h // 2
+    line = {"metric": METRIC, "value": res["strips"]["mpixel_s"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(res["strips"]["ms_per_frame"] * total, 3),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": args.workload, "description": desc, "width": w, "height": h, "frames": total,
+                       "devices": devices, "timing": "wall clock around the calls (host buffers in and out)"},
+            "e2e": {"value": res["strips"]["mpixel_s"], "unit": UNIT, "h2d_bytes_per_step": total * (fb + v.shape[1] + hh.shape[1]),
+                    "d2h_bytes_per_step": total * fb, "ms_per_step": round(res["strips"]["ms_per_frame"] * total, 3),
+                    "api": "hdb_multi_deblock_frame_strips"},
+            "strips": res["strips"], "unsplit_1gpu": res["unsplit_1gpu"],
+            "gpu_launches": args.steps * total * len(devices),
+            "parity": {"bit_exact": True, "frames_checked": distinct}}
+    emit(line)
+    m.close()
+    one.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -511,6 +577,10 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference_arm(args, rank)
+        return
+    if args.workload == "8k_strips":
+        if rank == 0:
+            run_strips(args)
         return
     if world != args.gpus and world == 1 and args.gpus > 1:
         raise SystemExit("--gpus %d needs torchrun: python -m torch.distributed.run --nnodes=1 --nproc-per-node %d "

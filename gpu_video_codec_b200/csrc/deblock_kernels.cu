@@ -175,17 +175,29 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_consta
 	const uint32_t total = (uint32_t)b.total_items;
 
 	/* lane 0 is the warp's producer: scheduler state, TMA issue */
-	uint32_t run_next = 0, run_end = 0, run_pending = 0;
+	uint32_t run_next = 0, run_end = 0, run_pending = 0, pending_len = 0;
+	/*
+	 * Guided self-scheduling: a request takes (items still unassigned) / (2 x warps in the grid)
+	 * consecutive items, at most run_len and at least 1.  Long runs keep the scheduler atomic and
+	 * the cursor decode cheap while there is plenty of work; towards the end the runs shrink to
+	 * single items, so the last warp finishes one item after the others instead of run_len items.
+	 */
+	const uint32_t two_grid_warps = 2u * gridDim.x * kWarps;
+	auto next_len = [&](uint32_t seen) -> uint32_t {
+		const uint32_t left = total > seen ? total - seen : 0u;
+		return min(max(left / two_grid_warps, 1u), run_len);
+	};
 	ItemCursor cur;
 	cur.frame = cur.plane = cur.grp = cur.chunk = 0; cur.chunks = cur.groups = 1;
 
 	auto issue_load = [&](int s) {         /* lane 0 only */
 		if (run_next == run_end) {
 			run_next = run_pending;
-			run_end = run_pending + run_len;
+			run_end = run_pending + pending_len;
 			if (run_next < total) {
-				/* ask for the run after this one now; it is not needed for run_len items */
-				run_pending = atomicAdd(&sched->next, run_len);
+				/* ask for the run after this one now; it is not needed before this one is used up */
+				pending_len = next_len(run_end);
+				run_pending = atomicAdd(&sched->next, pending_len);
 				cur.Seek(b, run_next);
 			}
 		} else {
@@ -204,7 +216,8 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_consta
 	if (lane == 0) {
 		for (int s = 0; s < kStages; s++) MbarInit(bars_s + 8u * s, 1);
 		FenceMbarInit();
-		run_pending = atomicAdd(&sched->next, run_len);
+		pending_len = next_len(0u);
+		run_pending = atomicAdd(&sched->next, pending_len);
 		for (int s = 0; s < kStages; s++) issue_load(s);
 	}
 	__syncwarp();
@@ -367,9 +380,8 @@ cudaError_t LaunchTiled(const TensorMaps3 &maps, const TiledBatch &b, void *sche
 	const long long warps_wanted = b.total_items;
 	long long ctas = std::min<long long>((long long)sm_count * g_tiled_ctas_per_sm, (warps_wanted + kWarps - 1) / kWarps);
 	ctas = std::max<long long>(ctas, 1);
-	/* run length: consecutive items per scheduler request; short when work is scarce */
-	long long per_warp = b.total_items / (ctas * kWarps);
-	uint32_t run_len = (uint32_t)std::max<long long>(1, std::min<long long>(16, per_warp / 8));
+	/* consecutive items per scheduler request: an upper bound, the kernel shortens the runs as the work runs out */
+	uint32_t run_len = 8;
 	static const int run_len_env = getenv("HDB_RUN_LEN") ? atoi(getenv("HDB_RUN_LEN")) : 0;   /* measurement knob */
 	if (run_len_env > 0) run_len = (uint32_t)run_len_env;
 	DeblockTiledKernel<<<(unsigned)ctas, kWarps * 32, kSmemBytes, stream>>>(maps, b,
