@@ -204,32 +204,53 @@ HDB_FN void NormalPair(LumaPair &t, const FilterParams &fp, u32 m_p, u32 m_q, u3
 enum { kSegOff = 0, kSegNormal = 1, kSegStrong = 2 };
 
 /*
- * One luma edge segment (cpu.h:1359-1429).  x = lines (0,3), y = lines (1,2).
- * Returns which taps may have changed: kSegOff none, kSegNormal p1,p0,q0,q1,
- * kSegStrong p2..q2.
+ * The decisions of one luma edge segment (cpu.h:1359-1429 with 1074-1114), taken once per
+ * segment from pair x = lines (0,3): off (dE false), strong, or normal together with the side
+ * masks dEp / dEq and the signed second differences of x the normal filter reuses.
  */
-HDB_FN int LumaSegment(LumaPair &x, LumaPair &y, const FilterParams &fp)
+HDB_FN int LumaDecide(const LumaPair &x, const FilterParams &fp, u32 &m_p, u32 &m_q, u32 &sdp, u32 &sdq)
 {
-	const u32 sdp = SecondDiffSigned(x.p2, x.p1, x.p0), sdq = SecondDiffSigned(x.q2, x.q1, x.q0);
+	sdp = SecondDiffSigned(x.p2, x.p1, x.p0); sdq = SecondDiffSigned(x.q2, x.q1, x.q0);
 	const u32 dP = SecondDiffAbs(sdp);                 /* 512 + dp0 | 512 + dp3 */
 	const u32 dQ = SecondDiffAbs(sdq);
-	const u32 s = dP + dQ;                           /* 1024 + dp+dq per line */
+	const u32 s = dP + dQ;                             /* 1024 + dp+dq per line */
+	m_p = m_q = 0u;
 	if (!((int)SumHalves(s) < fp.dE_lim)) return kSegOff;           /* cpu.h:1086-1087 */
 	/* strong decision, lines 0 and 3 at once (cpu.h:1099-1110) */
 	const u32 c3 = AbsDiff2(x.p3, x.p0) + AbsDiff2(x.q0, x.q3);
 	const u32 c4 = AbsDiff2(x.p0, x.q0);
 	const u32 m1 = Max2(s - 0x04000400u, c3);
 	const u32 ok = (fp.k_b8 - m1) & (fp.k_tc52 - c4) & 0x80008000u;
-	if (ok == 0x80008000u) {
-		StrongPair(x, fp);
-		StrongPair(y, fp);
-		return kSegStrong;
-	}
-	const u32 m_p = (u32)((int)SumHalvesPlus(dP, (u32)fp.dEpq_neg) >> 31);   /* all ones iff dp0 + dp3 < 3*beta/16  cpu.h:1245 */
-	const u32 m_q = (u32)((int)SumHalvesPlus(dQ, (u32)fp.dEpq_neg) >> 31);   /* cpu.h:1249 */
+	if (ok == 0x80008000u) return kSegStrong;
+	m_p = (u32)((int)SumHalvesPlus(dP, (u32)fp.dEpq_neg) >> 31);   /* all ones iff dp0 + dp3 < 3*beta/16  cpu.h:1245 */
+	m_q = (u32)((int)SumHalvesPlus(dQ, (u32)fp.dEpq_neg) >> 31);   /* cpu.h:1249 */
+	return kSegNormal;
+}
+
+HDB_FN void LumaNormal(LumaPair &x, LumaPair &y, const FilterParams &fp, u32 m_p, u32 m_q, u32 sdp, u32 sdq)
+{
 	NormalPair(x, fp, m_p, m_q, sdp, sdq);
 	NormalPair(y, fp, m_p, m_q, SecondDiffSigned(y.p2, y.p1, y.p0), SecondDiffSigned(y.q2, y.q1, y.q0));
-	return kSegNormal;
+}
+
+HDB_FN void LumaStrong(LumaPair &x, LumaPair &y, const FilterParams &fp)
+{
+	StrongPair(x, fp);
+	StrongPair(y, fp);
+}
+
+/*
+ * One luma edge segment (cpu.h:1359-1429).  x = lines (0,3), y = lines (1,2).
+ * Returns which taps may have changed: kSegOff none, kSegNormal p1,p0,q0,q1,
+ * kSegStrong p2..q2.
+ */
+HDB_FN int LumaSegment(LumaPair &x, LumaPair &y, const FilterParams &fp)
+{
+	u32 m_p, m_q, sdp, sdq;
+	const int kind = LumaDecide(x, fp, m_p, m_q, sdp, sdq);
+	if (kind == kSegStrong) LumaStrong(x, y, fp);
+	else if (kind == kSegNormal) LumaNormal(x, y, fp, m_p, m_q, sdp, sdq);
+	return kind;
 }
 
 /* One chroma line pair (cpu.h:1431-1488); only p0 and q0 change. */
