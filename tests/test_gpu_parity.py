@@ -129,6 +129,28 @@ def test_error_behaviour(dev):
     assert np.array_equal(dev.deblock_frame(frame, 16, 16, 30), orc.deblock_frame(frame, 16, 16, 30))
 
 
+def test_random_geometry_fuzz(dev):
+    """Random frame sizes (every multiple of 8 up to 1280 x 384, both kernel paths), QPs, contents and
+    boundary-strength maps against the oracle: chunk, row-group and plane-border handling off the
+    beaten sizes."""
+    rng = np.random.default_rng(20261018)
+    kinds = ["blocky", "random", "steps", "saturated", "ramp"]
+    bs_kinds = [None, "uniform012", "wide", "twos", "zeros"]
+    for case in range(60):
+        w = 8 * int(rng.integers(1, 161))
+        h = 8 * int(rng.integers(1, 49))
+        if case % 3 == 0:
+            w = 32 * max(1, w // 32)          # make sure the tiled path gets its share
+        qp = int(rng.integers(16, 56))
+        kind = kinds[int(rng.integers(len(kinds)))]
+        bs_kind = bs_kinds[int(rng.integers(len(bs_kinds)))]
+        frame = synth.make_frame(rng, w, h, kind)
+        v, hh = (None, None) if bs_kind is None else synth.make_bs(rng, w, h, bs_kind)
+        got = dev.deblock_frame(frame, w, h, qp, v, hh)
+        want = orc.deblock_frame(frame, w, h, qp, v, hh)
+        assert np.array_equal(got, want), (case, w, h, qp, kind, bs_kind, int((got != want).sum()))
+
+
 # ---- batches: host pipeline and device-resident -------------------------------------------
 @pytest.mark.parametrize("n,w,h", [(1, 352, 288), (9, 352, 288), (40, 1920, 1080), (5, 24, 40), (3, 3840, 2160)])
 def test_batch_host_pipeline(dev, n, w, h):
