@@ -70,6 +70,8 @@ static int CreateContext(hdb_context **out, int device)
 		return Fail(nullptr, HDB_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
 	}
 	ctx->encode = reinterpret_cast<EncodeTiledFn>(fn);
+	/* measurement knob: HDB_ZERO_COPY=0 sends single-slice calls through the copy engines too */
+	if (const char *z = getenv("HDB_ZERO_COPY")) ctx->zero_copy = atoi(z) != 0;
 	/* tuning knob for measurements: slice size of the host pipeline in MB */
 	if (const char *mb = getenv("HDB_CHUNK_MB")) {
 		const long v = strtol(mb, nullptr, 10);
@@ -289,6 +291,18 @@ static int EnsureSlots(hdb_context *ctx, size_t frame_bytes, int chunk, unsigned
 	return HDB_OK;
 }
 
+constexpr size_t kZeroCopyMaxBytes = (size_t)4 << 20;
+
+/* device-side address of a host buffer that is page-locked and mapped, or false */
+static bool MappedDevicePointer(const void *host, unsigned char **dev)
+{
+	cudaPointerAttributes a;
+	if (cudaPointerGetAttributes(&a, host) != cudaSuccess) { cudaGetLastError(); return false; }
+	if (a.type != cudaMemoryTypeHost || !a.devicePointer) return false;
+	*dev = static_cast<unsigned char *>(a.devicePointer);
+	return true;
+}
+
 /*
  * Slice plan of a batch of n frames, max_f frames per full slice.  Slices grow geometrically
  * from max_f/8 at the head and shrink again at the tail: the first H2D copy and the last D2H
@@ -369,6 +383,48 @@ int BatchHost(hdb_context *ctx, const unsigned char *in, unsigned char *out, uns
 	/* every frame's QP in one copy, ahead of the first slice on the same stream */
 	if (!uniform_qp)
 		HDB_CUDA(ctx, cudaMemcpyAsync(ctx->qp_dev, qp, sizeof(unsigned) * n, cudaMemcpyHostToDevice, s_h2d));
+
+	/*
+	 * One slice: there is no second slice to overlap a copy with, so H2D, kernel and D2H would run
+	 * back to back.  When both host buffers are page-locked and mapped, the kernel works on them
+	 * directly instead -- TMA loads and vector stores over the link -- and the two transfers and
+	 * the arithmetic overlap inside the one launch.  (Boundary strengths still go through a copy:
+	 * the kernel reads them bytewise.)  Measured on B200 / PCIe Gen5 (tools/latency.py): 75 -> 47 us
+	 * for 352x288, 109 -> 67 us for 768x576, 233 -> 178 us for 1080p; but SM-issued transfers reach
+	 * only ~19 GB/s per direction against the copy engines' ~50, so a 4K frame loses (523 -> 668 us):
+	 * hence the size limit.
+	 */
+	unsigned char *z_in = nullptr, *z_out = nullptr;
+	if (single && ctx->zero_copy && fb * n <= kZeroCopyMaxBytes
+		&& MappedDevicePointer(in, &z_in) && MappedDevicePointer(out, &z_out)) {
+		Slot &sl = ctx->slots[0];
+		if (vbs) {
+			HDB_CUDA(ctx, cudaMemcpyAsync(sl.vbs, vbs, (size_t)nv * n, cudaMemcpyHostToDevice, s_k));
+			HDB_CUDA(ctx, cudaMemcpyAsync(sl.hbs, hbs, (size_t)nh * n, cudaMemcpyHostToDevice, s_k));
+		}
+		cudaEvent_t *ev = timed ? &ctx->event_pool[0] : nullptr;
+		if (timed) HDB_CUDA(ctx, cudaEventRecord(ev[0], s_k));
+		rc = EnqueueFilter(ctx, view, z_in, z_out, (int)n, uniform_qp ? nullptr : ctx->qp_dev, qp[0],
+			vbs ? sl.vbs : nullptr, nv, vbs ? sl.hbs : nullptr, nh, s_k, &path);
+		if (rc) { cudaDeviceSynchronize(); return rc; }
+		if (timed) HDB_CUDA(ctx, cudaEventRecord(ev[1], s_k));
+		HDB_CUDA(ctx, cudaStreamSynchronize(s_k));
+		const auto t_done = std::chrono::steady_clock::now();
+		if (timed) {
+			memset(timing, 0, sizeof *timing);
+			float k = 0;
+			cudaEventElapsedTime(&k, ev[0], ev[1]);
+			timing->kernel_ms = k;                       /* includes both transfers: they happen inside the kernel */
+			timing->copy_ms = 0;
+			timing->total_ms = std::chrono::duration<double, std::milli>(t_done - t_begin).count();
+			timing->h2d_bytes = (unsigned long long)fb * n + (n == 1 ? 0 : sizeof(unsigned) * (unsigned long long)n)
+				+ (vbs ? (unsigned long long)(nv + nh) * n : 0);
+			timing->d2h_bytes = (unsigned long long)fb * n;
+			timing->kernel_launches = (int)(ctx->launches - launches0);
+			timing->path = path;
+		}
+		return HDB_OK;
+	}
 	unsigned f0 = 0;
 	for (int c = 0; c < nchunks; f0 += (unsigned)slices[c], c++) {
 		Slot &sl = ctx->slots[c % kSlots];

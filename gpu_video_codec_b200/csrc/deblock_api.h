@@ -85,6 +85,7 @@ struct hdb_context {
 	unsigned *qp_dev = nullptr;              /* the QPs of the batch in flight */
 	size_t qp_cap = 0;
 	size_t chunk_bytes = (size_t)128 << 20;  /* full slice size of the host pipeline (HDB_CHUNK_MB) */
+	bool zero_copy = true;                   /* single-slice calls on mapped pinned buffers skip the copy engines */
 	unsigned long long launches = 0;
 	std::string err;
 	std::mutex mu;

@@ -167,6 +167,26 @@ def test_batch_host_pipeline(dev, n, w, h):
     assert np.array_equal(buf, orc.deblock_batch(frames, w, h, qps))
 
 
+@pytest.mark.parametrize("n,w,h", [(1, 352, 288), (5, 768, 576), (3, 24, 40), (1, 1920, 1080)])
+def test_single_slice_on_mapped_pinned_buffers(dev, n, w, h):
+    """One small slice in page-locked mapped memory: the kernel reads and writes the host buffers itself
+    (no copy-engine legs); same bytes as the oracle, with caller strengths, defaults and in place."""
+    import torch
+    frames, qps, v, hh = synth.make_batch(n * 7 + w, n, w, h)
+    t_in = torch.from_numpy(frames).pin_memory()
+    t_out = torch.zeros_like(t_in).pin_memory()
+    t_qp = torch.from_numpy(qps.astype(np.int32)).pin_memory()
+    tm = hdb.Timing()
+    dev.deblock_batch(t_in, w, h, t_qp, v, hh, out=t_out, timing=tm, n_frames=n)
+    assert np.array_equal(t_out.numpy(), orc.deblock_batch(frames, w, h, qps, v, hh))
+    assert tm.d2h_bytes == frames.nbytes
+    if n == 1:
+        assert tm.copy_ms == 0.0 and tm.kernel_launches >= 1         # one slice: the transfers happened inside the kernel
+    assert np.array_equal(t_in.numpy(), frames)                      # input untouched
+    dev.deblock_batch(t_in, w, h, t_qp, out=t_in, n_frames=n)        # defaults, in place
+    assert np.array_equal(t_in.numpy(), orc.deblock_batch(frames, w, h, qps))
+
+
 def test_batch_many_slices_pinned(dev):
     """More slices than pipeline slots, pinned torch buffers (the bench's e2e path)."""
     import torch
