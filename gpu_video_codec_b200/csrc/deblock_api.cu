@@ -80,8 +80,9 @@ static int CreateContext(hdb_context **out, int device)
 	bool ok = cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking) == cudaSuccess
 		&& cudaStreamCreateWithFlags(&ctx->s_k, cudaStreamNonBlocking) == cudaSuccess
 		&& cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking) == cudaSuccess
-		&& cudaMalloc(&ctx->sched, TiledSchedBytes()) == cudaSuccess
-		&& cudaMemset(ctx->sched, 0, TiledSchedBytes()) == cudaSuccess;
+		&& PrepareTiled(&ctx->tiled_ctas_per_sm) == cudaSuccess
+		&& cudaMalloc(&ctx->sched, TiledSchedBytes() * kSchedSlots) == cudaSuccess
+		&& cudaMemset(ctx->sched, 0, TiledSchedBytes() * kSchedSlots) == cudaSuccess;
 	if (!ok) {
 		e = cudaGetLastError();
 		DestroyContext(ctx);
@@ -236,7 +237,10 @@ int EnqueueFilter(hdb_context *ctx, const FrameView &view, const unsigned char *
 			if ((rc = EncodePlaneMap(ctx, &maps.in[p], in0 + off[p], pw[p], ph[p], nf, fs, 8 * cfg.block_rows_per_item))) return rc;
 			b.out_plane[p] = out0 + off[p];
 		}
-		HDB_CUDA(ctx, LaunchTiled(maps, b, ctx->sched, ctx->prop.multiProcessorCount, stream));
+		/* launches take the scheduler words in turn: two launches that overlap on the device (different
+		 * streams) must not share a work counter, and each launch leaves its own words zeroed */
+		void *sched = static_cast<char *>(ctx->sched) + TiledSchedBytes() * (ctx->launches % kSchedSlots);
+		HDB_CUDA(ctx, LaunchTiled(maps, b, sched, ctx->prop.multiProcessorCount, ctx->tiled_ctas_per_sm, stream));
 		ctx->launches += 1;
 	}
 	return HDB_OK;

@@ -30,6 +30,7 @@ struct SizeState {     /* device tables that depend on the frame size only */
 };
 
 constexpr int kSlots = 4;
+constexpr int kSchedSlots = 64;      /* scheduler-word sets handed to successive launches in turn */
 
 struct Slot {          /* one slice of a batch in flight */
 	unsigned char *frames = nullptr, *vbs = nullptr, *hbs = nullptr;
@@ -75,6 +76,7 @@ struct hdb_context {
 	hdb::EncodeTiledFn encode = nullptr;
 	cudaStream_t s_h2d = nullptr, s_k = nullptr, s_d2h = nullptr;
 	void *sched = nullptr;
+	int tiled_ctas_per_sm = 1;               /* resident CTAs per SM of the tiled kernel on this device */
 	std::vector<hdb::SizeState> sizes;
 	hdb::Slot slots[hdb::kSlots];
 	std::vector<cudaEvent_t> event_pool;

@@ -362,23 +362,24 @@ void FinalizeTiledBatch(TiledBatch &b)
 	b.div_items_chroma.Init((uint32_t)std::max(b.items_chroma, 1));
 }
 
-static int g_tiled_ctas_per_sm = 0;
+cudaError_t PrepareTiled(int *ctas_per_sm)
+{
+	cudaError_t err = cudaFuncSetAttribute(DeblockTiledKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+	if (err != cudaSuccess) return err;
+	int n = 0;
+	err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, DeblockTiledKernel, kWarps * 32, kSmemBytes);
+	if (err != cudaSuccess) return err;
+	*ctas_per_sm = std::max(n, 1);
+	return cudaSuccess;
+}
 
-cudaError_t LaunchTiled(const TensorMaps3 &maps, const TiledBatch &b, void *sched, int sm_count, cudaStream_t stream)
+cudaError_t LaunchTiled(const TensorMaps3 &maps, const TiledBatch &b, void *sched, int sm_count, int ctas_per_sm,
+	cudaStream_t stream)
 {
 	if (b.total_items <= 0) return cudaSuccess;
 	if (b.total_items >= (1ll << 31)) return cudaErrorInvalidValue;
-	cudaError_t err;
-	if (g_tiled_ctas_per_sm == 0) {
-		err = cudaFuncSetAttribute(DeblockTiledKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-		if (err != cudaSuccess) return err;
-		int n = 0;
-		err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, DeblockTiledKernel, kWarps * 32, kSmemBytes);
-		if (err != cudaSuccess) return err;
-		g_tiled_ctas_per_sm = std::max(n, 1);
-	}
 	const long long warps_wanted = b.total_items;
-	long long ctas = std::min<long long>((long long)sm_count * g_tiled_ctas_per_sm, (warps_wanted + kWarps - 1) / kWarps);
+	long long ctas = std::min<long long>((long long)sm_count * std::max(ctas_per_sm, 1), (warps_wanted + kWarps - 1) / kWarps);
 	ctas = std::max<long long>(ctas, 1);
 	/* consecutive items per scheduler request: an upper bound, the kernel shortens the runs as the work runs out */
 	uint32_t run_len = 8;

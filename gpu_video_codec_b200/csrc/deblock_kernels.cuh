@@ -73,8 +73,11 @@ TiledConfig GetTiledConfig();
 /* Fill the work-decomposition fields from the geometry fields. */
 void FinalizeTiledBatch(TiledBatch &b);
 
+/* Once per device (the current one): function attributes; returns the resident CTAs per SM the grid is sized with. */
+cudaError_t PrepareTiled(int *ctas_per_sm);
 /* Persistent tiled kernel: one launch filters Y, U and V of every frame of the batch. */
-cudaError_t LaunchTiled(const TensorMaps3 &maps, const TiledBatch &b, void *sched, int sm_count, cudaStream_t stream);
+cudaError_t LaunchTiled(const TensorMaps3 &maps, const TiledBatch &b, void *sched, int sm_count, int ctas_per_sm,
+	cudaStream_t stream);
 /* bytes of zero-initialised device memory the scheduler needs (one per context) */
 size_t TiledSchedBytes();
 

@@ -255,6 +255,28 @@ def test_no_write_outside_the_frames(dev, size):
     assert bool((buf[:guard] == 0xA5).all()) and bool((buf[guard + n * fb:] == 0xA5).all())
 
 
+def test_launches_overlapping_on_two_streams(dev):
+    """Two streams, one context: launches that overlap on the device must not share a work counter."""
+    import torch
+    n, w, h = 24, 1920, 1080
+    frames, qps, v, hh = synth.make_batch(11, 6, w, h)
+    reps = n // 6
+    want = torch.from_numpy(orc.deblock_batch(frames, w, h, qps, v, hh)).cuda()
+    d_in = torch.from_numpy(frames).cuda().repeat(reps, 1)
+    d_qp = torch.from_numpy(qps.astype(np.int32)).cuda().repeat(reps)
+    d_v, d_h = torch.from_numpy(v).cuda().repeat(reps, 1), torch.from_numpy(hh).cuda().repeat(reps, 1)
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    outs = [[torch.empty_like(d_in) for _ in range(6)] for _ in streams]
+    torch.cuda.synchronize()
+    for i in range(6):
+        for st, o in zip(streams, outs):
+            dev.deblock_batch_device(d_in, o[i], n, w, h, d_qp, d_v, d_h, stream=st.cuda_stream)
+    torch.cuda.synchronize()
+    for o in outs:
+        for t in o:
+            assert bool((t.view(reps, 6, -1) == want.unsqueeze(0)).all())
+
+
 def test_repeated_launches_reset_scheduler(dev):
     """The work counter is reset by the kernel itself; many back-to-back launches must all be complete."""
     import torch
