@@ -208,8 +208,8 @@ int EnqueueFilter(hdb_context *ctx, const FrameView &view, const unsigned char *
 	b.chroma_nbx = (cw + 8) / 8; b.chroma_nby = (ch + 8) / 8;
 	b.luma_row0 = view.luma_row0; b.luma_rows = view.luma_rows;
 	b.chroma_row0 = view.chroma_row0; b.chroma_rows = view.chroma_rows;
-	b.luma_y_org = view.luma_row0 == 0 ? -4 : 0;
-	b.chroma_y_org = view.chroma_row0 == 0 ? -4 : 0;
+	b.luma_y_org = view.luma_y_org;
+	b.chroma_y_org = view.chroma_y_org;
 	b.vert_bs_stride = vbs_stride; b.hor_bs_stride = hbs_stride;
 	b.chroma_bs = ss->chroma_bs;
 	b.qp_value = qp_value;
@@ -253,6 +253,7 @@ FrameView WholeFrameView(int w, int h)
 	v.luma_row0 = 0; v.luma_rows = (h + 8) / 8;
 	v.chroma_row0 = 0; v.chroma_rows = (h / 2 + 8) / 8;
 	v.luma_buf_rows = h; v.chroma_buf_rows = h / 2;
+	v.luma_y_org = -4; v.chroma_y_org = -4;
 	v.u_offset = (long long)w * h; v.v_offset = (long long)w * h + (long long)(w / 2) * (h / 2);
 	v.frame_stride = (long long)w * h * 3 / 2;
 	return v;

@@ -64,6 +64,7 @@ struct FrameView {
 	int luma_row0, luma_rows;      /* padded-block rows to filter, frame-global numbering */
 	int chroma_row0, chroma_rows;
 	int luma_buf_rows, chroma_buf_rows;   /* sample rows present in the buffers */
+	int luma_y_org, chroma_y_org;  /* buffer row of the first sample row of block row *_row0 (-4: the buffer starts at image row 0) */
 	long long u_offset, v_offset;  /* byte offsets of the chroma planes inside one frame's buffer */
 	long long frame_stride;        /* bytes between frames */
 };

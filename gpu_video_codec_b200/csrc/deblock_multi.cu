@@ -283,6 +283,8 @@ int hdb_multi_deblock_frame_strips(hdb_multi *m, const unsigned char *yuv_in, un
 		v.chroma_row0 = s.y0 / 16;
 		v.chroma_rows = (d == g - 1 ? (ch + 8) / 8 : s.y1 / 16 + 1) - v.chroma_row0;
 		v.luma_buf_rows = L.lrows; v.chroma_buf_rows = L.crows;
+		/* the buffer starts 4 rows above the strip's first block row, except at the top of the frame */
+		v.luma_y_org = v.luma_row0 == 0 ? -4 : 0; v.chroma_y_org = v.chroma_row0 == 0 ? -4 : 0;
 		v.u_offset = (long long)L.u_off; v.v_offset = (long long)L.v_off;
 		v.frame_stride = (long long)((L.bytes + 15) & ~(size_t)15);
 		if (timing) {

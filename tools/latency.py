@@ -36,5 +36,5 @@ for (w, h) in [(352, 288), (768, 576), (1920, 1080), (3840, 2160), (7680, 4320)]
                 dev.deblock_frame(h_in.numpy(), w, h, 35, *args, out=h_out.numpy(), timing=tm)
                 ts.append(time.perf_counter() - t0)
             res.append("%s BS: median %.1f us (kernel %.1f us) %s" % ("caller" if bs else "default", np.median(ts) * 1e6, tm.kernel_ms * 1e3, "ok" if ok else "MISMATCH"))
-        print("%dx%d zero_copy=%s | %s | %s" % (w, h, zc, res[0], res[1]), flush=True)
+        print("%dx%d %s | %s | %s" % (w, h, "zero-copy where it applies (<= 4 MB)" if zc == "1" else "plain H2D, kernel, D2H", res[0], res[1]), flush=True)
         dev.close()
