@@ -53,6 +53,9 @@
 #ifndef HDB_MIN_CTAS
 #define HDB_MIN_CTAS 5
 #endif
+#ifndef HDB_TRACE
+#define HDB_TRACE 0     /* 1: development build that records per-warp timestamps (tools/trace_tail.py) */
+#endif
 
 namespace hdb {
 
@@ -66,6 +69,17 @@ constexpr int kTileH = 8 * kRB;
 constexpr int kTileBytes = kTileW * kTileH;     /* 2176 * kRB: a multiple of 128 */
 constexpr int kSmemBytes = kWarps * kStages * (kTileBytes + 8 + 8);
 constexpr uint32_t kNoItem = 0xffffffffu;
+
+#if HDB_TRACE
+/* development builds only (tools/trace_tail.py): per warp {kernel entry, first tile ready, loop exit} in ns and the item count */
+__device__ unsigned long long g_trace[8192][4];
+__device__ __forceinline__ unsigned long long GlobalTimerNs()
+{
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+	return t;
+}
+#endif
 
 /* scheduler words in global memory: [0] next item, [1] CTAs done */
 struct SchedWords { unsigned int next; unsigned int done; };
@@ -213,6 +227,10 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_consta
 			8 * kRB * (int)cur.grp + (cur.plane ? b.chroma_y_org : b.luma_y_org), (int)cur.frame, bar);
 	};
 
+#if HDB_TRACE
+	const unsigned long long t_entry = GlobalTimerNs();
+	unsigned long long t_first = 0, n_done = 0;
+#endif
 	if (lane == 0) {
 		for (int s = 0; s < kStages; s++) MbarInit(bars_s + 8u * s, 1);
 		FenceMbarInit();
@@ -253,6 +271,9 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_consta
 		for (int rb = 0; rb < kRB; rb++) bs[rb] = ItemBs(b, frame, desc, lane, rb);
 
 		MbarWait(bars_s + 8u * s, parity);
+#if HDB_TRACE
+		if (n_done++ == 0) t_first = GlobalTimerNs();
+#endif
 		u32 *tile = reinterpret_cast<u32 *>(tiles + s * kTileBytes);
 		unsigned char *dst = pl.out + (long long)frame * b.frame_stride;
 #pragma unroll
@@ -323,6 +344,10 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_consta
 	if (lane == 0) {
 		/* the last run request must have returned before the counter may be reset */
 		asm volatile("" :: "r"(run_pending) : "memory");
+#if HDB_TRACE
+		const unsigned w = blockIdx.x * kWarps + warp;
+		if (w < 8192) { g_trace[w][0] = t_entry; g_trace[w][1] = t_first; g_trace[w][2] = GlobalTimerNs(); g_trace[w][3] = n_done; }
+#endif
 	}
 	__syncthreads();
 	if (threadIdx.x == 0) {
@@ -334,6 +359,13 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_consta
 		}
 	}
 }
+
+#if HDB_TRACE
+extern "C" int hdb_debug_read_trace(unsigned long long *dst, int n_warps)
+{
+	return (int)cudaMemcpyFromSymbol(dst, g_trace, sizeof(unsigned long long) * 4 * (size_t)std::min(n_warps, 8192));
+}
+#endif
 
 int HostBeta(unsigned qp) { return BetaOf(qp); }
 int HostTc(unsigned qp) { return TcOf(qp); }
