@@ -42,10 +42,10 @@
 #include <cstdlib>
 
 #ifndef HDB_RB
-#define HDB_RB 1        /* block rows per item */
+#define HDB_RB 2        /* block rows per item */
 #endif
 #ifndef HDB_STAGES
-#define HDB_STAGES 3
+#define HDB_STAGES 2
 #endif
 /*
  * One warp per CTA.  Warps share nothing -- each runs its own pipeline -- so the CTA is only the
@@ -283,14 +283,18 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_consta
 #endif
 		u32 *tile = reinterpret_cast<u32 *>(tiles + s * kTileBytes);
 		unsigned char *dst = pl.out + (long long)frame * b.frame_stride;
-#pragma unroll
+		/* not unrolled: one copy of the block code, or the kernel outgrows the instruction cache
+		 * (unrolled, two block rows per item run 25 % slower than one) */
+#pragma unroll 1
 		for (int rb = 0; rb < kRB; rb++) {
 			if (bx < pl.nbx && lby0 + rb < pl.rows) {
 				u32 *base = tile + rb * 8 * kTileWords + kLead / 4 + 2 * lane;
 				u32 lo[8], hi[8];
 #pragma unroll
 				for (int r = 0; r < 8; r++) { lo[r] = base[r * kTileWords]; hi[r] = base[r * kTileWords + 1]; }
-				const u32 s4 = bs[rb];
+				u32 s4 = bs[0];          /* select instead of indexing: bs[] stays in registers */
+#pragma unroll
+				for (int k = 1; k < kRB; k++) if (rb == k) s4 = bs[k];
 				if (chroma) ChromaBlock(lo, hi, s4 & 0xff, (s4 >> 8) & 0xff, (s4 >> 16) & 0xff, s4 >> 24, fp);
 				else LumaBlock(lo, hi, s4 & 0xff, (s4 >> 8) & 0xff, (s4 >> 16) & 0xff, s4 >> 24, fp);
 #pragma unroll
@@ -421,7 +425,7 @@ cudaError_t LaunchTiled(const TensorMaps3 &maps, const TiledBatch &b, void *sche
 	long long ctas = std::min<long long>((long long)sm_count * std::max(ctas_per_sm, 1), (warps_wanted + kWarps - 1) / kWarps);
 	ctas = std::max<long long>(ctas, 1);
 	/* consecutive items per scheduler request: an upper bound, the kernel shortens the runs as the work runs out */
-	uint32_t run_len = 8;
+	uint32_t run_len = 4;
 	static const int run_len_env = getenv("HDB_RUN_LEN") ? atoi(getenv("HDB_RUN_LEN")) : 0;   /* measurement knob */
 	if (run_len_env > 0) run_len = (uint32_t)run_len_env;
 	DeblockTiledKernel<<<(unsigned)ctas, kWarps * 32, kSmemBytes, stream>>>(maps, b,
