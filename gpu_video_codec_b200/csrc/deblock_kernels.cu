@@ -76,6 +76,7 @@ constexpr int kTileH = 8 * kRB;
 constexpr int kTileBytes = kTileW * kTileH;     /* 2176 * kRB: a multiple of 128 */
 constexpr int kSmemBytes = kWarps * kStages * (kTileBytes + 8 + 8);
 constexpr uint32_t kNoItem = 0xffffffffu;
+static_assert(kStages >= 2, "the stage after the current one holds the next item (boundary-strength prefetch)");
 
 #if HDB_TRACE
 /* development builds only (tools/trace_tail.py): per warp {kernel entry, first tile ready, loop exit} in ns and the item count */
@@ -160,21 +161,40 @@ __device__ __forceinline__ PlaneInfo MakePlaneInfo(const TiledBatch &b, int plan
 }
 
 /*
- * The four boundary strengths of the block lane `lane` owns in block row `rb` of item
- * {frame, desc}, packed as LumaBsOfBlock packs them; 0 for lanes and rows outside the plane
- * (a block whose four strengths are 0 is left untouched by LumaBlock / ChromaBlock).
+ * The boundary strengths of the block lane `lane` owns in block row `rb` of item {frame, desc}, as
+ * loaded and not yet looked at: four bytes for a luma block (cpu.h:159-163, 223-227, 287-291,
+ * 368-372), one packed word of the per-size table for a chroma block; all 0 for lanes and rows
+ * outside the plane (a block whose four strengths are 0 is left untouched).  Loads and use are
+ * taken apart on purpose: the loads of item i+1 are issued while item i is filtered and nothing
+ * waits on them until PackBs() one item later (+1 % on long launches, +1.7 % on short ones).
  */
-__device__ __forceinline__ u32 ItemBs(const TiledBatch &b, uint32_t frame, uint32_t desc, int lane, int rb)
+struct BsRaw { u32 a, b, c, d; };
+
+__device__ __forceinline__ BsRaw ItemBsRaw(const TiledBatch &b, uint32_t frame, uint32_t desc, int lane, int rb)
 {
+	BsRaw r = { 0u, 0u, 0u, 0u };
+	if (desc == kNoItem) return r;
 	int plane, bx0, lby0;
 	ItemCoords(desc, plane, bx0, lby0);
 	const bool c = plane != 0;
 	const int bx = bx0 + lane, lby = lby0 + rb;
-	if (bx >= (c ? b.chroma_nbx : b.luma_nbx) || lby >= (c ? b.chroma_rows : b.luma_rows)) return 0;
-	const int gby = (c ? b.chroma_row0 : b.luma_row0) + lby;
-	if (c) return __ldg(b.chroma_bs + gby * b.chroma_nbx + bx);
-	return LumaBsOfBlock(bx, gby, b.width >> 3, b.luma_nbx, b.luma_nby,
-		b.vert_bs + (long long)frame * b.vert_bs_stride, b.hor_bs + (long long)frame * b.hor_bs_stride);
+	if (bx >= (c ? b.chroma_nbx : b.luma_nbx) || lby >= (c ? b.chroma_rows : b.luma_rows)) return r;
+	const int by = (c ? b.chroma_row0 : b.luma_row0) + lby;
+	if (c) { r.a = __ldg(b.chroma_bs + by * b.chroma_nbx + bx); return r; }
+	const int w8 = b.width >> 3;
+	const unsigned char *vert_bs = b.vert_bs + (long long)frame * b.vert_bs_stride;
+	const unsigned char *hor_bs = b.hor_bs + (long long)frame * b.hor_bs_stride;
+	if (by > 0) r.a = __ldg(vert_bs + (by - 1) * (w8 + 1) + bx);
+	if (by < b.luma_nby - 1) r.b = __ldg(vert_bs + by * (w8 + 1) + bx);
+	if (bx > 0) r.c = __ldg(hor_bs + by * w8 + bx - 1);
+	if (bx < b.luma_nbx - 1) r.d = __ldg(hor_bs + by * w8 + bx);
+	return r;
+}
+
+/* BS_ver1 | BS_ver2 << 8 | BS_hor1 << 16 | BS_hor2 << 24 */
+__device__ __forceinline__ u32 PackBs(const BsRaw &r, bool chroma)
+{
+	return chroma ? r.a : (r.a | (r.b << 8) | (r.c << 16) | (r.d << 24));
 }
 
 /* ------------------------------------------------------------------ */
@@ -255,6 +275,13 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_consta
 	PlaneInfo pl;
 	MakeFilterParams(fp, 0, 0);
 	pl = MakePlaneInfo(b, 0);
+	/* boundary strengths travel one item ahead of the samples */
+	BsRaw bs_raw[kRB];
+	{
+		const uint2 it0 = held[0];
+#pragma unroll
+		for (int rb = 0; rb < kRB; rb++) bs_raw[rb] = ItemBsRaw(b, it0.x, it0.y, lane, rb);
+	}
 	for (;;) {
 		const uint2 it = held[s];
 		const uint32_t frame = it.x, desc = it.y;
@@ -272,10 +299,15 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_consta
 		if (plane != cur_plane) { cur_plane = plane; pl = MakePlaneInfo(b, plane); }
 		const int bx = bx0 + lane;
 
-		/* boundary strengths of this lane's blocks; issued before the tile wait */
+		/* this item's boundary strengths were loaded during the previous item; start the next item's loads */
 		u32 bs[kRB];
+		{
+			const uint2 it_next = held[s + 1 == kStages ? 0 : s + 1];
 #pragma unroll
-		for (int rb = 0; rb < kRB; rb++) bs[rb] = ItemBs(b, frame, desc, lane, rb);
+			for (int rb = 0; rb < kRB; rb++) bs[rb] = PackBs(bs_raw[rb], chroma);
+#pragma unroll
+			for (int rb = 0; rb < kRB; rb++) bs_raw[rb] = ItemBsRaw(b, it_next.x, it_next.y, lane, rb);
+		}
 
 		MbarWait(bars_s + 8u * s, parity);
 #if HDB_TRACE
