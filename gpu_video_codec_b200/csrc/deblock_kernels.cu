@@ -456,8 +456,10 @@ cudaError_t LaunchTiled(const TensorMaps3 &maps, const TiledBatch &b, void *sche
 	const long long warps_wanted = b.total_items;
 	long long ctas = std::min<long long>((long long)sm_count * std::max(ctas_per_sm, 1), (warps_wanted + kWarps - 1) / kWarps);
 	ctas = std::max<long long>(ctas, 1);
-	/* consecutive items per scheduler request: an upper bound, the kernel shortens the runs as the work runs out */
-	uint32_t run_len = 4;
+	/* consecutive items per scheduler request: an upper bound, the kernel shortens the runs as the work runs
+	 * out.  Longer runs re-read fewer tile-edge sectors (neighbouring items share one per row); shorter runs
+	 * level the end of a short launch out better. */
+	uint32_t run_len = b.total_items / (ctas * kWarps) >= 512 ? 8 : 4;
 	static const int run_len_env = getenv("HDB_RUN_LEN") ? atoi(getenv("HDB_RUN_LEN")) : 0;   /* measurement knob */
 	if (run_len_env > 0) run_len = (uint32_t)run_len_env;
 	DeblockTiledKernel<<<(unsigned)ctas, kWarps * 32, kSmemBytes, stream>>>(maps, b,
