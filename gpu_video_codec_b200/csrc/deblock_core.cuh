@@ -80,6 +80,13 @@ HDB_FN u32 SumHalves(u32 a) { return __dp2a_lo(a, 0x0101u, 0u); }               
 HDB_FN u32 SumHalvesPlus(u32 a, u32 c) { return __dp2a_lo(a, 0x0101u, c); }      /* ... + c, same instruction */
 #endif
 
+/* keep v as a value of its own: stops the compiler from folding its definition into every use */
+#if defined(HDB_HOST_EMU)
+HDB_FN void Materialise(u32 &) {}
+#else
+HDB_FN void Materialise(u32 &v) { asm volatile("" : "+r"(v)); }
+#endif
+
 /* both halves = v (v may be negative: two's complement per half) */
 HDB_FN u32 Rep2(int v) { return ((u32)v & 0xffffu) * 0x10001u; }
 
@@ -99,7 +106,7 @@ struct FilterParams {
 	/* normal filter */
 	u32 c2_neg, c2_pos;   /* -2tc, +2tc replicated                              cpu.h:1235 */
 	u32 k_e_lo;      /* (2tc - 256) x2 */
-	u32 k_tc10;      /* (256 + 10tc + 1) x2                                     cpu.h:1254 */
+	u32 k_tc10;      /* (10tc - 256) x2                                         cpu.h:1254 */
 	u32 k_half;      /* (513 - 4tc) x2 : bias of the merged p1/q1 numerator */
 	u32 h4_lo, h8_hi;     /* 4*(tc/2 - 256) ; 8*(tc/2) + 3 : the +-tc/2 clip before the >> 2   cpu.h:1236 */
 	u32 h_neg, h_rep;     /* -(tc/2) ; (tc/2) */
@@ -118,7 +125,7 @@ HDB_FN void MakeFilterParams(FilterParams &fp, int beta, int tc)
 	fp.s4_neg = Rep2(-8 * tc); fp.s4_pos = Rep2(8 * tc + 3);
 	fp.c2_neg = Rep2(-2 * tc); fp.c2_pos = Rep2(2 * tc);
 	fp.k_e_lo = Rep2(2 * tc - 256);
-	fp.k_tc10 = Rep2(256 + 10 * tc + 1);
+	fp.k_tc10 = Rep2(10 * tc - 256);
 	fp.k_half = Rep2(513 - 4 * tc);
 	fp.h4_lo = Rep2(4 * (tc / 2 - 256)); fp.h8_hi = Rep2(8 * (tc / 2) + 3);
 	fp.h_neg = Rep2(-(tc / 2)); fp.h_rep = Rep2(tc / 2);
@@ -136,8 +143,15 @@ HDB_FN u32 SecondDiffSigned(u32 a2, u32 a1, u32 a0) { return a2 + a0 + 0x0200020
 /* 512 + |a2 - 2*a1 + a0| per half from the signed form (cpu.h:1086: the second-derivative terms) */
 HDB_FN u32 SecondDiffAbs(u32 sd) { return Max2(sd, 0x04000400u - sd); }
 
-/* |a - b| per half for unsigned halves */
+/*
+ * |a - b| per half for halves that hold a sample (0..255, upper byte zero): the byte-wise
+ * absolute difference does it in one instruction (VABSDIFF4.U8; the upper bytes give |0 - 0|).
+ */
+#if defined(HDB_HOST_EMU)
 HDB_FN u32 AbsDiff2(u32 a, u32 b) { return Max2(a, b) - Min2(a, b); }
+#else
+HDB_FN u32 AbsDiff2(u32 a, u32 b) { return __vabsdiffu4(a, b); }
+#endif
 
 /*
  * Strong filter on one line pair (cpu.h:1128-1213).  With x + delta_x equal to
@@ -183,8 +197,8 @@ HDB_FN void NormalPair(LumaPair &t, const FilterParams &fp, u32 m_p, u32 m_q, u3
 	/* 4096 + 9(q0-p0) - 3(q1-p1) + 8, each half in [1044, 7164] */
 	u32 num = 3u * (3u * (t.q0 - t.p0) + t.p1 - t.q1) + 0x10081008u;
 	u32 e = (num >> 4) & 0x01ff01ffu;                  /* 256 + delta              cpu.h:1253 */
-	u32 a = Max2(e, 0x02000200u - e);                /* 256 + |delta| */
-	u32 on = AddMinRelu2(~a, fp.k_tc10, 0x00010001u);  /* 1 where |delta| < 10tc   cpu.h:1254 */
+	u32 na = Min2(e, 0x02000200u - e);                 /* 256 - |delta| */
+	u32 on = AddMinRelu2(na, fp.k_tc10, 0x00010001u);  /* 1 where |delta| < 10tc   cpu.h:1254 */
 	u32 mask = on * 0x01ffu;                           /* 9 bits per half: every value selected below is < 512 */
 	u32 d = AddMinRelu2(e, fp.k_e_lo, fp.c2_rep4);     /* Clip(delta) + 2tc in [0, 4tc]  cpu.h:1256 */
 	d = (d & mask) | (fp.c2_pos & ~mask);              /* lines that are off: delta = 0 */
@@ -193,6 +207,7 @@ HDB_FN void NormalPair(LumaPair &t, const FilterParams &fp, u32 m_p, u32 m_q, u3
 	u32 hp = AddMinRelu2(sd_p + fp.k_half + 2u * d, fp.h4_lo, fp.h8_hi) >> 2;
 	u32 hq = AddMinRelu2(sd_q + fp.k_half + 2u * dn, fp.h4_lo, fp.h8_hi) >> 2;
 	m_p &= mask; m_q &= mask;
+	Materialise(m_p); Materialise(m_q);                /* two 3-input selects below, not three 2-input steps each */
 	u32 dp = (hp & m_p) | (fp.h_rep & ~m_p);           /* side or line off: no change */
 	u32 dq = (hq & m_q) | (fp.h_rep & ~m_q);
 	t.p1 = AddMinRelu2(t.p1 + dp, fp.h_neg, 0x00ff00ffu);      /* cpu.h:1272 */
