@@ -80,13 +80,6 @@ HDB_FN u32 SumHalves(u32 a) { return __dp2a_lo(a, 0x0101u, 0u); }               
 HDB_FN u32 SumHalvesPlus(u32 a, u32 c) { return __dp2a_lo(a, 0x0101u, c); }      /* ... + c, same instruction */
 #endif
 
-/* keep v as a value of its own: stops the compiler from folding its definition into every use */
-#if defined(HDB_HOST_EMU)
-HDB_FN void Materialise(u32 &) {}
-#else
-HDB_FN void Materialise(u32 &v) { asm volatile("" : "+r"(v)); }
-#endif
-
 /* both halves = v (v may be negative: two's complement per half) */
 HDB_FN u32 Rep2(int v) { return ((u32)v & 0xffffu) * 0x10001u; }
 
@@ -109,6 +102,7 @@ struct FilterParams {
 	u32 k_tc10;      /* (10tc - 256) x2                                         cpu.h:1254 */
 	u32 k_half;      /* (513 - 4tc) x2 : bias of the merged p1/q1 numerator */
 	u32 h4_lo, h8_hi;     /* 4*(tc/2 - 256) ; 8*(tc/2) + 3 : the +-tc/2 clip before the >> 2   cpu.h:1236 */
+	u32 h4_mid;           /* 4*(tc/2) + 3 : upper bound of the window of a side that is off */
 	u32 h_neg, h_rep;     /* -(tc/2) ; (tc/2) */
 	u32 c2_rep4;     /* (4tc) x2 */
 	u32 ct_neg, ct_lo, ct_2; /* chroma, c = tc: -tc, (tc - 256), 2tc replicated cpu.h:1442 */
@@ -128,6 +122,7 @@ HDB_FN void MakeFilterParams(FilterParams &fp, int beta, int tc)
 	fp.k_tc10 = Rep2(10 * tc - 256);
 	fp.k_half = Rep2(513 - 4 * tc);
 	fp.h4_lo = Rep2(4 * (tc / 2 - 256)); fp.h8_hi = Rep2(8 * (tc / 2) + 3);
+	fp.h4_mid = Rep2(4 * (tc / 2) + 3);
 	fp.h_neg = Rep2(-(tc / 2)); fp.h_rep = Rep2(tc / 2);
 	fp.c2_rep4 = Rep2(4 * tc);
 	fp.ct_neg = Rep2(-tc); fp.ct_lo = Rep2(tc - 256); fp.ct_2 = Rep2(2 * tc);
@@ -183,16 +178,17 @@ HDB_FN void StrongPair(LumaPair &t, const FilterParams &fp)
 }
 
 /*
- * Normal filter on one line pair (cpu.h:1215-1357).  m_p / m_q are the segment-wide
- * side decisions dEp / dEq (cpu.h:1243-1249) as all-ones / all-zeros words; the
- * |delta| < 10*tc test is per line (cpu.h:1254), hence a per-half mask.  sd_p / sd_q
+ * Normal filter on one line pair (cpu.h:1215-1357).  [lo_p, hi_p] / [lo_q, hi_q] are the
+ * clip windows of the p1 / q1 corrections, which carry the segment-wide side decisions
+ * dEp / dEq (cpu.h:1243-1249, see LumaNormal); the |delta| < 10*tc test is per line
+ * (cpu.h:1254), hence a per-half mask.  sd_p / sd_q
  * are 512 + (x2 - 2 x1 + x0) per half.  The p1 update uses
  *   (((p2 + p0 + 1) >> 1) - p1 + D) >> 1  ==  (p2 + p0 - 2 p1 + 2 D + 1) >> 2
  * (dropping the parity bit of an even numerator does not change floor(. / 4)), and its
  * +-tc/2 clip is applied before the >> 2 like the strong filter's; the bits the shift
  * drags across the halves are removed by the select that follows (its mask keeps 9 bits).
  */
-HDB_FN void NormalPair(LumaPair &t, const FilterParams &fp, u32 m_p, u32 m_q, u32 sd_p, u32 sd_q)
+HDB_FN void NormalPair(LumaPair &t, const FilterParams &fp, u32 lo_p, u32 hi_p, u32 lo_q, u32 hi_q, u32 sd_p, u32 sd_q)
 {
 	/* 4096 + 9(q0-p0) - 3(q1-p1) + 8, each half in [1044, 7164] */
 	u32 num = 3u * (3u * (t.q0 - t.p0) + t.p1 - t.q1) + 0x10081008u;
@@ -204,12 +200,10 @@ HDB_FN void NormalPair(LumaPair &t, const FilterParams &fp, u32 m_p, u32 m_q, u3
 	d = (d & mask) | (fp.c2_pos & ~mask);              /* lines that are off: delta = 0 */
 	u32 dn = fp.c2_rep4 - d;                         /* 2tc - Clip(delta) */
 	/* Clip(((x2 + x0 - 2 x1 +- 2D + 1) >> 2), tc/2) + tc/2 in [0, 2(tc/2)]   cpu.h:1259-1265 */
-	u32 hp = AddMinRelu2(sd_p + fp.k_half + 2u * d, fp.h4_lo, fp.h8_hi) >> 2;
-	u32 hq = AddMinRelu2(sd_q + fp.k_half + 2u * dn, fp.h4_lo, fp.h8_hi) >> 2;
-	m_p &= mask; m_q &= mask;
-	Materialise(m_p); Materialise(m_q);                /* two 3-input selects below, not three 2-input steps each */
-	u32 dp = (hp & m_p) | (fp.h_rep & ~m_p);           /* side or line off: no change */
-	u32 dq = (hq & m_q) | (fp.h_rep & ~m_q);
+	u32 hp = AddMinRelu2(sd_p + fp.k_half + 2u * d, lo_p, hi_p) >> 2;
+	u32 hq = AddMinRelu2(sd_q + fp.k_half + 2u * dn, lo_q, hi_q) >> 2;
+	u32 dp = (hp & mask) | (fp.h_rep & ~mask);         /* line off: no change */
+	u32 dq = (hq & mask) | (fp.h_rep & ~mask);
 	t.p1 = AddMinRelu2(t.p1 + dp, fp.h_neg, 0x00ff00ffu);      /* cpu.h:1272 */
 	t.q1 = AddMinRelu2(t.q1 + dq, fp.h_neg, 0x00ff00ffu);      /* cpu.h:1275 */
 	t.p0 = AddMinRelu2(t.p0 + d, fp.c2_neg, 0x00ff00ffu);      /* cpu.h:1268 */
@@ -244,8 +238,14 @@ HDB_FN int LumaDecide(const LumaPair &x, const FilterParams &fp, u32 &m_p, u32 &
 
 HDB_FN void LumaNormal(LumaPair &x, LumaPair &y, const FilterParams &fp, u32 m_p, u32 m_q, u32 sdp, u32 sdq)
 {
-	NormalPair(x, fp, m_p, m_q, sdp, sdq);
-	NormalPair(y, fp, m_p, m_q, SecondDiffSigned(y.p2, y.p1, y.p0), SecondDiffSigned(y.q2, y.q1, y.q0));
+	/* The side decisions dEp / dEq hold for the whole segment, so they go into the window the p1 / q1
+	 * correction is clipped to, once per segment, instead of into a select per line pair: a side that
+	 * is off gets the window [tc/2, tc/2] -- whatever the numerator, the correction comes out as "no
+	 * change" -- by an offset no numerator can stay below and an upper bound of 4*(tc/2) + 3. */
+	const u32 lo_p = (fp.h4_lo & m_p) | (0x40004000u & ~m_p), hi_p = (fp.h8_hi & m_p) | (fp.h4_mid & ~m_p);
+	const u32 lo_q = (fp.h4_lo & m_q) | (0x40004000u & ~m_q), hi_q = (fp.h8_hi & m_q) | (fp.h4_mid & ~m_q);
+	NormalPair(x, fp, lo_p, hi_p, lo_q, hi_q, sdp, sdq);
+	NormalPair(y, fp, lo_p, hi_p, lo_q, hi_q, SecondDiffSigned(y.p2, y.p1, y.p0), SecondDiffSigned(y.q2, y.q1, y.q0));
 }
 
 HDB_FN void LumaStrong(LumaPair &x, LumaPair &y, const FilterParams &fp)
