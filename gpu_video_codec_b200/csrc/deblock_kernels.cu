@@ -1,9 +1,11 @@
 /*
  * deblock_kernels.cu -- sm_100a kernels of the deblocking path.
  *
- * DeblockTiledKernel: persistent, warp-autonomous.  Every warp runs its own
- * TMA -> registers -> 128-bit-store pipeline over "items" = 32 horizontally
- * adjacent padded 8x8 blocks x kRB block rows of one plane of one frame.
+ * DeblockTiledKernel: persistent, warp-autonomous, one warp per CTA.  Every warp
+ * runs its own TMA -> registers -> 128-bit-store pipeline over "items" = 32
+ * horizontally adjacent padded 8x8 blocks x kRB (= 2) block rows of one plane of
+ * one frame; the block rows of an item go through one rolled copy of the block
+ * code, their boundary strengths are fetched one item ahead.
  *
  * Geometry.  The reference pads every plane by 4 samples (cpu.h:55-82), so padded
  * block (bx, by) covers image columns 8bx-4 .. 8bx+3 and rows 8by-4 .. 8by+3: it
@@ -25,11 +27,12 @@
  * fill a vector on their own; writes the reference would make into its padding
  * are dropped by the bounds predicate.  Each output byte is written by exactly
  * one item and only bytes an item owns are consumed, so filtering in place
- * (out == in) is safe.  No CTA-wide barrier exists in the kernel.
+ * (out == in) is safe.
  *
  * Work is handed out dynamically in runs of consecutive items from one global
- * counter (luma items cost ~4x chroma items, so a static split would be
- * unbalanced); the last CTA to leave resets the counter for the next launch.
+ * counter (luma items cost ~3x chroma items, so a static split would be
+ * unbalanced); the runs shrink as the work runs out, and the last CTA to leave
+ * resets the counter for the next launch.
  *
  * The generic kernels at the end cover frame sizes TMA cannot describe.
  */
