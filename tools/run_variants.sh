@@ -4,5 +4,5 @@
 cd "$(dirname "$0")/.."
 N=${1:-256}; shift
 for so in build_variants/libhdb_*.so; do
-	env "$@" HDB_LIBRARY=$PWD/$so timeout 300 python tools/quick_time.py --n $N --iters 10 2>&1 | tail -1
+	env "$@" HDB_LIBRARY=$PWD/$so timeout 300 python tools/quick_time.py --n $N --iters ${ITERS:-10} 2>&1 | tail -1
 done

@@ -30,7 +30,7 @@ for n in [int(x) for x in (sys.argv[1:] or ["16", "128"])]:
     dev.deblock_batch_device(frames, out, n, w, h, qp, vbs, hbs, stream=st)
     e1.record()
     torch.cuda.synchronize()
-    nw = 148 * 28
+    nw = 148 * 23
     buf = np.zeros((nw, 4), np.uint64)
     rc = lib.hdb_debug_read_trace(buf.ctypes.data_as(C.c_void_p), nw)
     assert rc == 0
