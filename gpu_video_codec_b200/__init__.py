@@ -11,6 +11,7 @@ from .binding import (  # noqa: F401
     Deblocker,
     DeblockError,
     MultiDeblocker,
+    Surfaces,
     Timing,
     build_library,
     default_boundary_strength,

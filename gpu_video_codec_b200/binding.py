@@ -37,6 +37,13 @@ class Timing(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class Surfaces(C.Structure):
+    """hdb_surfaces: three device planes with row pitches."""
+    _fields_ = [("y", C.c_void_p), ("u", C.c_void_p), ("v", C.c_void_p),
+                ("pitch_y", C.c_size_t), ("pitch_c", C.c_size_t),
+                ("frame_stride_y", C.c_size_t), ("frame_stride_c", C.c_size_t)]
+
+
 class DeviceInfo(C.Structure):
     _fields_ = [("name", C.c_char * 256), ("cc_major", C.c_int), ("cc_minor", C.c_int),
                 ("sm_count", C.c_int), ("warp_size", C.c_int), ("max_threads_per_block", C.c_int),
@@ -106,6 +113,8 @@ def load_library():
     batch_args = [vp, vp, C.c_uint, C.c_uint, C.c_uint, vp, vp, vp]
     lib.hdb_deblock_batch.argtypes = [vp] + batch_args + [C.POINTER(Timing)]
     lib.hdb_deblock_batch_device.argtypes = [vp] + batch_args + [vp]
+    lib.hdb_deblock_surfaces_device.argtypes = [vp, C.POINTER(Surfaces), C.POINTER(Surfaces), C.c_uint, C.c_uint, C.c_uint,
+                                                vp, vp, vp, vp]
     lib.hdb_kernel_launch_count.argtypes = [vp]
     lib.hdb_kernel_launch_count.restype = C.c_ulonglong
     lib.hdb_multi_create.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), C.c_int]
@@ -235,6 +244,13 @@ class Deblocker:
         """Device pointers (torch CUDA tensors or ints); enqueues on `stream` and returns."""
         self._check(self._lib.hdb_deblock_batch_device(self._ctx, _addr(d_in), _addr(d_out), n_frames, width, height,
                                                        _addr(d_qp), _addr(d_vert_bs), _addr(d_hor_bs), stream))
+
+
+    def deblock_surfaces_device(self, src, dst, n_frames, width, height, d_qp, d_vert_bs=None, d_hor_bs=None,
+                                stream=None):
+        """src / dst: Surfaces (device planes with pitches); enqueues on `stream` and returns."""
+        self._check(self._lib.hdb_deblock_surfaces_device(self._ctx, C.byref(src), C.byref(dst), n_frames, width, height,
+                                                          _addr(d_qp), _addr(d_vert_bs), _addr(d_hor_bs), stream))
 
 
 class MultiDeblocker:

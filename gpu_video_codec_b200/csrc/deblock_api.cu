@@ -132,11 +132,11 @@ int GetSizeState(hdb_context *ctx, int w, int h, SizeState **out)
 }
 
 static int EncodePlaneMap(hdb_context *ctx, CUtensorMap *map, const void *base, int pw, int ph, int n,
-	long long frame_stride, int box_rows)
+	long long pitch, long long frame_stride, int box_rows)
 {
 	/* 32-bit elements: a box may then be 272 bytes wide (a box dimension is limited to 256 elements) */
 	cuuint64_t dims[3] = { (cuuint64_t)pw / 4, (cuuint64_t)ph, (cuuint64_t)n };
-	cuuint64_t strides[2] = { (cuuint64_t)pw, (cuuint64_t)frame_stride };
+	cuuint64_t strides[2] = { (cuuint64_t)pitch, (cuuint64_t)frame_stride };
 	cuuint32_t box[3] = { 68u, (cuuint32_t)box_rows, 1u };
 	cuuint32_t estr[3] = { 1u, 1u, 1u };
 	CUresult r = ctx->encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<void *>(base), dims, strides, box, estr,
@@ -217,7 +217,7 @@ int EnqueueFilter(hdb_context *ctx, const FrameView &view, const unsigned char *
 	b.n_frames = 1;
 	FinalizeTiledBatch(b);
 	const long long max_frames = std::max<long long>(1, ((1ll << 31) - (1 << 20)) / std::max(b.items_per_frame, 1));
-	const long long fs = view.frame_stride;
+	const long long fs = view.frame_stride, cfs = view.chroma_frame_stride;
 	for (long long f0 = 0; f0 < n; f0 += max_frames) {
 		const int nf = (int)std::min<long long>(max_frames, n - f0);
 		b.n_frames = nf;
@@ -226,16 +226,18 @@ int EnqueueFilter(hdb_context *ctx, const FrameView &view, const unsigned char *
 		b.vert_bs = d_vbs + f0 * vbs_stride;
 		b.hor_bs = d_hbs + f0 * hbs_stride;
 		TensorMaps3 maps;
-		const unsigned char *in0 = d_in + f0 * fs;
-		unsigned char *out0 = d_out + f0 * fs;
-		b.frame_stride = fs;
+		b.frame_stride = fs; b.chroma_frame_stride = cfs;
+		b.luma_pitch = view.luma_pitch; b.chroma_pitch = view.chroma_pitch;
 		b.luma_buf_rows = view.luma_buf_rows; b.chroma_buf_rows = view.chroma_buf_rows;
-		const long long off[3] = { 0, view.u_offset, view.v_offset };
+		const long long off_in[3] = { 0, view.u_offset, view.v_offset };
+		const long long off_out[3] = { 0, view.u_offset_out, view.v_offset_out };
 		const int pw[3] = { w, cw, cw };
 		const int ph[3] = { view.luma_buf_rows, view.chroma_buf_rows, view.chroma_buf_rows };
 		for (int p = 0; p < 3; p++) {
-			if ((rc = EncodePlaneMap(ctx, &maps.in[p], in0 + off[p], pw[p], ph[p], nf, fs, 8 * cfg.block_rows_per_item))) return rc;
-			b.out_plane[p] = out0 + off[p];
+			const long long pfs = p ? cfs : fs;
+			if ((rc = EncodePlaneMap(ctx, &maps.in[p], d_in + off_in[p] + f0 * pfs, pw[p], ph[p], nf,
+					p ? view.chroma_pitch : view.luma_pitch, pfs, 8 * cfg.block_rows_per_item))) return rc;
+			b.out_plane[p] = d_out + off_out[p] + f0 * pfs;
 		}
 		/* launches take the scheduler words in turn: two launches that overlap on the device (different
 		 * streams) must not share a work counter, and each launch leaves its own words zeroed */
@@ -255,7 +257,9 @@ FrameView WholeFrameView(int w, int h)
 	v.luma_buf_rows = h; v.chroma_buf_rows = h / 2;
 	v.luma_y_org = -4; v.chroma_y_org = -4;
 	v.u_offset = (long long)w * h; v.v_offset = (long long)w * h + (long long)(w / 2) * (h / 2);
-	v.frame_stride = (long long)w * h * 3 / 2;
+	v.u_offset_out = v.u_offset; v.v_offset_out = v.v_offset;
+	v.luma_pitch = w; v.chroma_pitch = w / 2;
+	v.frame_stride = v.chroma_frame_stride = (long long)w * h * 3 / 2;
 	return v;
 }
 
@@ -642,6 +646,46 @@ int hdb_deblock_batch_device(hdb_context *ctx, const void *d_frames_in, void *d_
 	const FrameView view = WholeFrameView((int)width, (int)height);
 	return EnqueueFilter(ctx, view, static_cast<const unsigned char *>(d_frames_in),
 		static_cast<unsigned char *>(d_frames_out), (int)n_frames, d_qp, 0,
+		d_vert_bs, hdb_num_vert_bs(width, height), d_hor_bs, hdb_num_hor_bs(width, height),
+		static_cast<cudaStream_t>(stream), nullptr);
+}
+
+int hdb_deblock_surfaces_device(hdb_context *ctx, const hdb_surfaces *in, const hdb_surfaces *out,
+	unsigned n_frames, unsigned width, unsigned height, const unsigned *d_qp,
+	const unsigned char *d_vert_bs, const unsigned char *d_hor_bs, void *stream)
+{
+	if (!ctx) return HDB_ERR_INVALID_ARG;
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	if (!in || !out || !d_qp || n_frames == 0 || !in->y || !in->u || !in->v || !out->y || !out->u || !out->v)
+		return Fail(ctx, HDB_ERR_INVALID_ARG, "NULL surface, plane or QP pointer, or empty batch");
+	int rc = ValidateFrameArgs(ctx, width, height, d_vert_bs, 0, d_hor_bs, 0, false);
+	if (rc) return rc;
+	if (width % 32 != 0) return Fail(ctx, HDB_ERR_DIMENSIONS, "pitched surfaces need a width that is a multiple of 32");
+	const hdb_surfaces *both[2] = { in, out };
+	for (const hdb_surfaces *s : both) {
+		const uintptr_t a = (uintptr_t)s->y | (uintptr_t)s->u | (uintptr_t)s->v | s->pitch_y | s->pitch_c
+			| (n_frames > 1 ? s->frame_stride_y | s->frame_stride_c : 0);
+		if (a % 16 != 0) return Fail(ctx, HDB_ERR_INVALID_ARG, "surface addresses, pitches and frame strides must be multiples of 16 bytes");
+		if (s->pitch_y < width || s->pitch_c < width / 2 || s->pitch_y > (1u << 30) || s->pitch_c > (1u << 30))
+			return Fail(ctx, HDB_ERR_INVALID_ARG, "pitch smaller than the plane width");
+	}
+	if (in->pitch_y != out->pitch_y || in->pitch_c != out->pitch_c
+		|| (n_frames > 1 && (in->frame_stride_y != out->frame_stride_y || in->frame_stride_c != out->frame_stride_c)))
+		return Fail(ctx, HDB_ERR_INVALID_ARG, "input and output surfaces must share pitches and frame strides");
+	DeviceGuard guard(ctx->device);
+	FrameView view = WholeFrameView((int)width, (int)height);
+	const unsigned char *iy = static_cast<const unsigned char *>(in->y);
+	unsigned char *oy = static_cast<unsigned char *>(out->y);
+	view.u_offset = static_cast<const unsigned char *>(in->u) - iy;
+	view.v_offset = static_cast<const unsigned char *>(in->v) - iy;
+	view.u_offset_out = static_cast<unsigned char *>(out->u) - oy;
+	view.v_offset_out = static_cast<unsigned char *>(out->v) - oy;
+	view.luma_pitch = (int)in->pitch_y; view.chroma_pitch = (int)in->pitch_c;
+	/* one frame: any 16-byte multiple serves as the (unused) stride of the frame dimension */
+	view.frame_stride = n_frames > 1 ? (long long)in->frame_stride_y : (long long)in->pitch_y * height;
+	view.chroma_frame_stride = n_frames > 1 ? (long long)in->frame_stride_c : (long long)in->pitch_c * (height / 2);
+	view.whole_frame = false;   /* pitched planes have no generic path: the checks above admit the tiled kernel only */
+	return EnqueueFilter(ctx, view, iy, oy, (int)n_frames, d_qp, 0,
 		d_vert_bs, hdb_num_vert_bs(width, height), d_hor_bs, hdb_num_hor_bs(width, height),
 		static_cast<cudaStream_t>(stream), nullptr);
 }

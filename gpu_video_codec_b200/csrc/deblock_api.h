@@ -65,8 +65,10 @@ struct FrameView {
 	int chroma_row0, chroma_rows;
 	int luma_buf_rows, chroma_buf_rows;   /* sample rows present in the buffers */
 	int luma_y_org, chroma_y_org;  /* buffer row of the first sample row of block row *_row0 (-4: the buffer starts at image row 0) */
-	long long u_offset, v_offset;  /* byte offsets of the chroma planes inside one frame's buffer */
-	long long frame_stride;        /* bytes between frames */
+	long long u_offset, v_offset;  /* byte offsets of the input chroma planes from the input luma plane */
+	long long u_offset_out, v_offset_out;   /* the same for the output planes */
+	int luma_pitch, chroma_pitch;  /* bytes between rows */
+	long long frame_stride, chroma_frame_stride;   /* bytes between frames, luma plane / chroma planes */
 };
 
 } // namespace hdb

@@ -145,7 +145,8 @@ struct ItemCursor {
 
 /* what the consumer needs to know about the plane an item belongs to */
 struct PlaneInfo {
-	int nbx, rows, row0, pw, buf_rows, y_org;
+	int nbx, rows, row0, pw, pitch, buf_rows, y_org;
+	long long frame_stride;
 	unsigned char *out;
 };
 
@@ -157,6 +158,8 @@ __device__ __forceinline__ PlaneInfo MakePlaneInfo(const TiledBatch &b, int plan
 	p.rows = c ? b.chroma_rows : b.luma_rows;
 	p.row0 = c ? b.chroma_row0 : b.luma_row0;
 	p.pw = c ? (b.width >> 1) : b.width;
+	p.pitch = c ? b.chroma_pitch : b.luma_pitch;
+	p.frame_stride = c ? b.chroma_frame_stride : b.frame_stride;
 	p.buf_rows = c ? b.chroma_buf_rows : b.luma_buf_rows;
 	p.y_org = c ? b.chroma_y_org : b.luma_y_org;
 	p.out = plane == 0 ? b.out_plane[0] : (plane == 1 ? b.out_plane[1] : b.out_plane[2]);
@@ -317,7 +320,7 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_consta
 		if (n_done++ == 0) t_first = GlobalTimerNs();
 #endif
 		u32 *tile = reinterpret_cast<u32 *>(tiles + s * kTileBytes);
-		unsigned char *dst = pl.out + (long long)frame * b.frame_stride;
+		unsigned char *dst = pl.out + (long long)frame * pl.frame_stride;
 		/* not unrolled: one copy of the block code, or the kernel outgrows the instruction cache
 		 * (unrolled, two block rows per item run 25 % slower than one) */
 #pragma unroll 1
@@ -348,8 +351,8 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_consta
 			const int vcol = x_img + 4 + 16 * j;
 			const bool vec_lane = j < 15 && vcol < pl.pw;
 			const unsigned char *vsrc = tile8 + half * kTileW + 16 + 16 * j;
-			unsigned char *vdst = dst + (long long)(y0 + half) * pl.pw + vcol;
-			const long long pitch2 = 2ll * pl.pw;
+			unsigned char *vdst = dst + (long long)(y0 + half) * pl.pitch + vcol;
+			const long long pitch2 = 2ll * pl.pitch;
 			/* fringe words: tile word 3 (image column x_img) and words 64..66 (x_img + 244 ..): 4 per row */
 			const int ftr = lane >> 2, k = lane & 3;
 			const int fword = k == 0 ? 3 : 63 + k;
@@ -364,7 +367,7 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_consta
 				}
 #pragma unroll
 				for (int rr = 0; rr < kTileH; rr += 8)
-					if (f_lane) *reinterpret_cast<u32 *>(dst + (long long)(y0 + rr + ftr) * pl.pw + fcol) = tile[(rr + ftr) * kTileWords + fword];
+					if (f_lane) *reinterpret_cast<u32 *>(dst + (long long)(y0 + rr + ftr) * pl.pitch + fcol) = tile[(rr + ftr) * kTileWords + fword];
 			} else {
 				/* first / last rows of a plane: the reference writes these into its padding; drop them */
 #pragma unroll
@@ -376,7 +379,7 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_consta
 #pragma unroll
 				for (int rr = 0; rr < kTileH; rr += 8) {
 					const int y = y0 + rr + ftr;
-					if (f_lane && y >= 0 && y < pl.buf_rows) *reinterpret_cast<u32 *>(dst + (long long)y * pl.pw + fcol) = tile[(rr + ftr) * kTileWords + fword];
+					if (f_lane && y >= 0 && y < pl.buf_rows) *reinterpret_cast<u32 *>(dst + (long long)y * pl.pitch + fcol) = tile[(rr + ftr) * kTileWords + fword];
 				}
 			}
 		}

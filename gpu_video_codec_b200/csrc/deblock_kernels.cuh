@@ -61,7 +61,8 @@ struct TiledBatch {
 	/* output: plane base pointers of frame 0 (may equal the input's), rows present, frame pitch */
 	unsigned char *out_plane[3];
 	int luma_buf_rows, chroma_buf_rows;
-	long long frame_stride;
+	int luma_pitch, chroma_pitch;                      /* bytes between rows (>= plane width, multiple of 16) */
+	long long frame_stride, chroma_frame_stride;       /* bytes between frames, luma plane / chroma planes */
 };
 
 struct TensorMaps3 { CUtensorMap in[3]; };   /* Y, U, V input planes, 32-bit elements */

@@ -285,8 +285,9 @@ int hdb_multi_deblock_frame_strips(hdb_multi *m, const unsigned char *yuv_in, un
 		v.luma_buf_rows = L.lrows; v.chroma_buf_rows = L.crows;
 		/* the buffer starts 4 rows above the strip's first block row, except at the top of the frame */
 		v.luma_y_org = v.luma_row0 == 0 ? -4 : 0; v.chroma_y_org = v.chroma_row0 == 0 ? -4 : 0;
-		v.u_offset = (long long)L.u_off; v.v_offset = (long long)L.v_off;
-		v.frame_stride = (long long)((L.bytes + 15) & ~(size_t)15);
+		v.u_offset = v.u_offset_out = (long long)L.u_off; v.v_offset = v.v_offset_out = (long long)L.v_off;
+		v.luma_pitch = W; v.chroma_pitch = cw;
+		v.frame_stride = v.chroma_frame_stride = (long long)((L.bytes + 15) & ~(size_t)15);
 		if (timing) {
 			M_CUDA(cudaEventCreate(&k0[d])); M_CUDA(cudaEventCreate(&k1[d]));
 			M_CUDA(cudaEventRecord(k0[d], st));

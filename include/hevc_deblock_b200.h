@@ -141,6 +141,27 @@ int hdb_deblock_batch_device(hdb_context *ctx, const void *d_frames_in, void *d_
 	unsigned n_frames, unsigned width, unsigned height, const unsigned *d_qp,
 	const unsigned char *d_vert_bs, const unsigned char *d_hor_bs, void *stream);
 
+/* ---- decoder-style surfaces in device memory ---------------------------- */
+/*
+ * Three separately addressed planes with row pitches, as a hardware decoder or a frame pool hands
+ * them over (the reference only knows tight planes, cpu.h:55-82; this is the first of the data
+ * formats on the caller's side of the path).  Plane p of frame f starts at
+ * base_p + f * frame_stride_{y|c}; row r of it at + r * pitch_{y|c}.  Pitches, frame strides and
+ * base addresses must be multiples of 16 bytes, pitches at least the plane width, and the width a
+ * multiple of 32 (HDB_ERR_DIMENSIONS otherwise).  Bytes between the plane width and the pitch are
+ * neither read into the result nor written.  out may equal in (in place).  Asynchronous on `stream`
+ * like hdb_deblock_batch_device; d_qp, d_vert_bs, d_hor_bs as there.
+ */
+typedef struct hdb_surfaces {
+	void *y, *u, *v;                        /* device pointers to frame 0 of each plane */
+	size_t pitch_y, pitch_c;                /* bytes between rows of the luma plane / of each chroma plane */
+	size_t frame_stride_y, frame_stride_c;  /* bytes between frames; ignored when n_frames == 1 */
+} hdb_surfaces;
+
+int hdb_deblock_surfaces_device(hdb_context *ctx, const hdb_surfaces *in, const hdb_surfaces *out,
+	unsigned n_frames, unsigned width, unsigned height, const unsigned *d_qp,
+	const unsigned char *d_vert_bs, const unsigned char *d_hor_bs, void *stream);
+
 /* number of filter-kernel launches made through ctx since creation */
 unsigned long long hdb_kernel_launch_count(const hdb_context *ctx);
 

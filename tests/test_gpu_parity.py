@@ -255,6 +255,53 @@ def test_no_write_outside_the_frames(dev, size):
     assert bool((buf[:guard] == 0xA5).all()) and bool((buf[guard + n * fb:] == 0xA5).all())
 
 
+@pytest.mark.parametrize("case", [(1, 352, 288, 64, 32), (3, 1920, 1080, 128, 64), (2, 3840, 2160, 0, 0), (4, 64, 48, 16, 48)],
+                         ids=lambda c: "%dx%dx%d+%d" % c[:4])
+def test_pitched_surfaces_in_device_memory(dev, case):
+    """Decoder-style surfaces: three separate planes with row pitches above the width.  Same bytes as the
+    oracle on the samples, pitch padding untouched, out of place and in place."""
+    import torch
+    n, w, h, pad_y, pad_c = case
+    cw, ch = w // 2, h // 2
+    frames, qps, v, hh = synth.make_batch(w + n, n, w, h)
+    want = orc.deblock_batch(frames, w, h, qps, v, hh)
+    py, pc = w + pad_y, cw + pad_c
+
+    def planes(fill):
+        return (torch.full((n, h, py), fill, dtype=torch.uint8, device="cuda"),
+                torch.full((n, ch, pc), fill, dtype=torch.uint8, device="cuda"),
+                torch.full((n, ch, pc), fill, dtype=torch.uint8, device="cuda"))
+
+    def surf(p):
+        return hdb.Surfaces(p[0].data_ptr(), p[1].data_ptr(), p[2].data_ptr(), py, pc, h * py, ch * pc)
+
+    src, dst = planes(0x5A), planes(0xA5)
+    t = torch.from_numpy(frames).cuda()
+    src[0][:, :, :w] = t[:, :w * h].view(n, h, w)
+    src[1][:, :, :cw] = t[:, w * h:w * h + cw * ch].view(n, ch, cw)
+    src[2][:, :, :cw] = t[:, w * h + cw * ch:].view(n, ch, cw)
+    d_qp = torch.from_numpy(qps.astype(np.int32)).cuda()
+    d_v, d_h = torch.from_numpy(v).cuda(), torch.from_numpy(hh).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+
+    def gather(p):
+        return torch.cat([p[0][:, :, :w].reshape(n, -1), p[1][:, :, :cw].reshape(n, -1), p[2][:, :, :cw].reshape(n, -1)], 1).cpu().numpy()
+
+    dev.deblock_surfaces_device(surf(src), surf(dst), n, w, h, d_qp, d_v, d_h, stream=st)
+    torch.cuda.synchronize()
+    assert np.array_equal(gather(dst), want)
+    assert np.array_equal(gather(src), frames)                                    # input untouched
+    for p, width in zip(dst, (w, cw, cw)):
+        assert bool((p[:, :, width:] == 0xA5).all())                              # pitch padding untouched
+    dev.deblock_surfaces_device(surf(src), surf(src), n, w, h, d_qp, d_v, d_h, stream=st)   # in place
+    torch.cuda.synchronize()
+    assert np.array_equal(gather(src), want)
+    for p, width in zip(src, (w, cw, cw)):
+        assert bool((p[:, :, width:] == 0x5A).all())
+    with pytest.raises(hdb.DeblockError):
+        dev.deblock_surfaces_device(surf(src), surf(dst), n, w + 8, h, d_qp, stream=st)      # width not a multiple of 32
+
+
 def test_launches_overlapping_on_two_streams(dev):
     """Two streams, one context: launches that overlap on the device must not share a work counter."""
     import torch

@@ -55,6 +55,8 @@ def main():
         e1.record()
     torch.cuda.synchronize()
     ms = np.array([e0.elapsed_time(e1) for e0, e1 in evs])
+    if os.environ.get("QT_VERBOSE"):
+        print(" ".join("%.3f" % x for x in ms))
     cw, ch = w // 2, h // 2
     alg = 3 * w * h + nv + nh + hdb.num_vert_bs(cw, ch) + hdb.num_hor_bs(cw, ch)
     pix = n * w * h
