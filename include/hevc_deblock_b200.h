@@ -56,6 +56,11 @@ typedef struct hdb_multi hdb_multi;       /* several GPUs of one box */
  * Timing of one call, the three figures the reference prints (gpu.cu:1292, 1302-1303)
  * plus byte counts.  Device times come from CUDA events.
  */
+/*
+ * A call that fits one small slice (<= 4 MB) on page-locked, mapped host buffers is served without
+ * the copy engines: the kernel reads and writes host memory itself.  copy_ms is then 0 and kernel_ms
+ * covers the transfers as well, because they happen inside the kernel.
+ */
 typedef struct hdb_timing {
 	double kernel_ms;          /* "Execution Time without copy on GPU"  gpu.cu:1266-1292 */
 	double copy_ms;            /* "Copy Operation Time"  (H2D + D2H busy time)  gpu.cu:1246-1258, 1294-1303 */
