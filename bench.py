@@ -40,6 +40,8 @@ WORKLOADS = {
     "image2_single": (768, 576, 1, "single 768x576 frame, QP 30, default BS (latency case)"),
     # BASELINE.json configs[4]: one process drives all GPUs (hdb_multi_deblock_frame_strips); not a torchrun workload
     "8k_strips": (7680, 4320, 16, "stream of single 7680x4320 frames, each split into CTU-row strips across the GPUs, P2P halos"),
+    # block data -> edge maps (bs | qp << 2) -> per-edge-QP filter; one GPU
+    "4k_edges512": (3840, 2160, 512, "synthetic 3840x2160 YV12 batch of 512 frames, per-8x8-block decoder data -> derived edge maps -> per-edge-QP filter"),
 }
 METRIC = "deblocked Mpixel/s"
 UNIT = "Mpixel/s"
@@ -578,6 +580,140 @@ def run_strips(args):
     one.close()
 
 
+def device_block_info(torch, n, w, h, seed, device="cuda"):
+    """hdb_block_info[n, h/8, w/8] on the device as int32[n, h/8 * w/8, 3] words (deblock_core.cuh: BlockWords):
+    16x16 coding units with their own motion, QP, coded flag; a fifth intra; a third bi-predicted."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    h8, w8 = h // 8, w // 8
+    ch, cw = (h8 + 1) // 2, (w8 + 1) // 2
+    R = lambda lo, hi, shape: torch.randint(lo, hi, shape, device=device, generator=g, dtype=torch.int32)
+    up = lambda a: a.repeat_interleave(2, 1).repeat_interleave(2, 2)[:, :h8, :w8]
+    cand = R(-24, 25, (n, 6, 4))
+    pick = R(0, 6, (n, ch, cw)).long()
+    mv = torch.gather(cand, 1, pick.view(n, -1, 1).expand(-1, -1, 4)).view(n, ch, cw, 4)
+    mv = mv + (R(0, 10, (n, ch, cw, 1)) < 3) * R(-5, 6, (n, ch, cw, 4))
+    ref0 = R(0, 2, (n, ch, cw))
+    bi = R(0, 3, (n, ch, cw)) == 0
+    ref1 = torch.where(bi, R(0, 3, (n, ch, cw)), torch.full_like(ref0, -1))
+    intra = R(0, 5, (n, ch, cw)) == 0
+    cbf = R(0, 2, (n, ch, cw)) == 1
+    split = R(0, 4, (n, ch, cw)) == 0
+    qp = (R(24, 40, (n, 1, 1)) + R(-6, 7, (n, ch, cw))).clamp_(0, 51)
+    ref0 = torch.where(intra, torch.full_like(ref0, -1), ref0)
+    ref1 = torch.where(intra, torch.full_like(ref1, -1), ref1)
+    yy = torch.arange(h8, device=device).view(1, h8, 1)
+    xx = torch.arange(w8, device=device).view(1, 1, w8)
+    sp = up(split.int()).bool()
+    flags = up(intra.int()) * 1 + up(cbf.int()) * 2 + ((xx % 2 == 0) | sp).int() * 4 + ((yy % 2 == 0) | sp).int() * 8 \
+        + (xx % 2 == 0).int() * 16 + (yy % 2 == 0).int() * 32
+    m = [up(mv[..., i]) & 0xffff for i in range(4)]
+    w0 = m[0] | (m[1] << 16)
+    w1 = m[2] | (m[3] << 16)
+    w2 = (up(ref0) & 0xff) | ((up(ref1) & 0xff) << 8) | (flags << 16) | (up(qp) << 24)
+    return torch.stack([w0, w1, w2], dim=-1).reshape(n, h8 * w8, 3).contiguous()
+
+
+def run_edges(args):
+    """SURVEY.md section 8(f) rank 1 on one GPU: DeriveEdgesKernel and DeblockTiledKernel<true> (per-edge QP),
+    with the plain kernel on the same frames beside them; e2e through hdb_deblock_batch_edges."""
+    import torch
+    import gpu_video_codec_b200 as hdb
+    from oracle import oracle_py as orc
+    quiet_stdout()
+    torch.cuda.set_device(0)
+    w, h, n, desc = WORKLOADS[args.workload]
+    fb = 3 * w * h // 2
+    dev = hdb.Deblocker(0)
+    stream = torch.cuda.current_stream().cuda_stream
+    frames, qp, vbs, hbs = device_batch(torch, n, w, h, seed=4242)
+    info = device_block_info(torch, n, w, h, seed=99)
+    nv, nh = hdb.num_vert_bs(w, h), hdb.num_hor_bs(w, h)
+    d_v = torch.empty((n, nv), dtype=torch.uint8, device="cuda")
+    d_h = torch.empty((n, nh), dtype=torch.uint8, device="cuda")
+    out = torch.empty_like(frames)
+    out_plain = torch.empty_like(frames)
+
+    def timed(fn, reps):
+        for _ in range(max(args.warmup, 3)):
+            fn()
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+        ev[0].record()
+        for i in range(reps):
+            fn()
+            ev[i + 1].record()
+        torch.cuda.synchronize()
+        return ev[0].elapsed_time(ev[-1]) / reps
+
+    sampler = ClockSampler(0)
+    sampler.start()
+    l0 = dev.kernel_launch_count()
+    ms_derive = timed(lambda: dev.derive_edges_device(info, n, w, h, d_v, d_h, stream=stream), args.steps)
+    ms_edges = timed(lambda: dev.deblock_batch_edges_device(frames, out, n, w, h, qp, d_v, d_h, stream=stream), args.steps)
+    # the plain kernel on the same frames with the derived strengths alone and one QP per frame
+    bs_v, bs_h = d_v & 3, d_h & 3
+    ms_plain = timed(lambda: dev.deblock_batch_device(frames, out_plain, n, w, h, qp, bs_v, bs_h, stream=stream), args.steps)
+    ms_both = timed(lambda: (dev.derive_edges_device(info, n, w, h, d_v, d_h, stream=stream),
+                             dev.deblock_batch_edges_device(frames, out, n, w, h, qp, d_v, d_h, stream=stream)), args.steps)
+    launches = dev.kernel_launch_count() - l0
+    sampler.pause()
+
+    # parity: derivation and filter of a strided sample against the oracle
+    idx = [0, n // 3, (2 * n) // 3, n - 1]
+    np_info = info[idx].cpu().numpy().view(np.uint8).reshape(len(idx), h // 8, w // 8, 12).copy().view(orc.BLOCK_INFO).reshape(len(idx), h // 8, w // 8)
+    for k, f in enumerate(idx):
+        ov, oh = orc.derive_edges(np_info[k], w, h)
+        if not (np.array_equal(d_v[f].cpu().numpy(), ov) and np.array_equal(d_h[f].cpu().numpy(), oh)):
+            raise SystemExit("PARITY FAILURE: derived edge maps of frame %d differ from the oracle" % f)
+        want = orc.deblock_frame_edges(frames[f].cpu().numpy(), w, h, int(qp[f]), ov, oh)
+        if not np.array_equal(out[f].cpu().numpy(), want):
+            raise SystemExit("PARITY FAILURE: per-edge-QP output of frame %d differs from the oracle" % f)
+    hist = torch.bincount((d_v[idx].reshape(-1) & 3).long(), minlength=4).tolist()
+
+    # e2e: host buffers through hdb_deblock_batch_edges (edge maps travel with the frames)
+    h_in = torch.empty((n, fb), dtype=torch.uint8).pin_memory()
+    h_out = torch.empty((n, fb), dtype=torch.uint8).pin_memory()
+    h_in.copy_(frames)
+    h_qp, h_v, h_h = qp.cpu().pin_memory(), d_v.cpu().pin_memory(), d_h.cpu().pin_memory()
+    tm = hdb.Timing()
+    e2e = lambda: dev.deblock_batch_edges(h_in, w, h, h_qp, h_v, h_h, out=h_out, timing=tm, n_frames=n)
+    e2e()
+    sampler.resume(0.05)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    clocks = sampler.stop()
+    if not torch.equal(h_out[::37].cuda(), out[::37]):
+        raise SystemExit("PARITY FAILURE: e2e output differs from the device-resident output")
+
+    peak, peak_src = measured_peak()
+    alg = alg_bytes_per_frame(w, h) * n
+    blocks = (w // 8) * (h // 8) * n
+    alg_derive = 12 * blocks + (nv + nh) * n
+    mpix = n * w * h / 1e6
+    line = {"metric": METRIC, "value": round(mpix / (ms_edges / 1e3), 1), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_edges, 4), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": args.workload, "description": desc, "width": w, "height": h, "frames": n,
+                       "l2": "inputs larger than L2 (%.1f GB in + %.1f GB out)" % (n * fb / 1e9, n * fb / 1e9),
+                       "timing": "CUDA events on the launching stream", "derived_bs_histogram_0123": hist},
+            "roofline": {"bound": "hbm", "achieved": round(alg / (ms_edges / 1e3) / 1e9, 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(alg / (ms_edges / 1e3) / 1e9 / peak, 4), "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg, "kernel": "DeblockTiledKernel<true>", "mean_launch_ms": round(ms_edges, 4)},
+            "plain_kernel_same_frames": {"ms": round(ms_plain, 4), "mpixel_s": round(mpix / (ms_plain / 1e3), 1),
+                                         "achieved_gbs": round(alg / (ms_plain / 1e3) / 1e9, 1)},
+            "derive_kernel": {"ms": round(ms_derive, 4), "algorithmic_bytes": alg_derive,
+                              "achieved_gbs": round(alg_derive / (ms_derive / 1e3) / 1e9, 1), "frac": round(alg_derive / (ms_derive / 1e3) / 1e9 / peak, 4)},
+            "derive_plus_filter": {"ms": round(ms_both, 4), "mpixel_s": round(mpix / (ms_both / 1e3), 1)},
+            "e2e": {"value": round(mpix / e2e_s, 1), "unit": UNIT, "h2d_bytes_per_step": int(tm.h2d_bytes), "d2h_bytes_per_step": int(tm.d2h_bytes),
+                    "ms_per_step": round(e2e_s * 1e3, 3), "api": "hdb_deblock_batch_edges (pinned host buffers, 3-stream pipeline)"},
+            "gpu_launches": launches, "clocks": clocks,
+            "parity": {"bit_exact": True, "frames_checked": len(idx), "changed_fraction": round(float((out[idx] != frames[idx]).float().mean()), 4)}}
+    emit(line)
+    dev.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -597,6 +733,10 @@ def main():
     if args.workload == "8k_strips":
         if rank == 0:
             run_strips(args)
+        return
+    if args.workload == "4k_edges512":
+        if rank == 0:
+            run_edges(args)
         return
     if world != args.gpus and world == 1 and args.gpus > 1:
         raise SystemExit("--gpus %d needs torchrun: python -m torch.distributed.run --nnodes=1 --nproc-per-node %d "

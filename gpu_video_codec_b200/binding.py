@@ -115,6 +115,11 @@ def load_library():
     lib.hdb_deblock_batch_device.argtypes = [vp] + batch_args + [vp]
     lib.hdb_deblock_surfaces_device.argtypes = [vp, C.POINTER(Surfaces), C.POINTER(Surfaces), C.c_uint, C.c_uint, C.c_uint,
                                                 vp, vp, vp, vp]
+    lib.hdb_deblock_frame_edges.argtypes = [vp, vp, vp] + frame_args
+    lib.hdb_deblock_batch_edges.argtypes = [vp] + batch_args + [C.POINTER(Timing)]
+    lib.hdb_deblock_batch_edges_device.argtypes = [vp] + batch_args + [vp]
+    lib.hdb_derive_edges_device.argtypes = [vp, vp, C.c_uint, C.c_uint, C.c_uint, vp, vp, vp]
+    lib.hdb_derive_edges.argtypes = [vp, vp, C.c_uint, C.c_uint, C.c_uint, vp, vp]
     lib.hdb_kernel_launch_count.argtypes = [vp]
     lib.hdb_kernel_launch_count.restype = C.c_ulonglong
     lib.hdb_multi_create.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), C.c_int]
@@ -146,6 +151,16 @@ def default_boundary_strength(width, height):
     if rc:
         raise DeblockError(rc, lib.hdb_status_string(rc).decode())
     return v, h
+
+
+# hdb_block_info: what a decoder knows about one 8x8 luma block (12 bytes)
+BLOCK_INFO = np.dtype([("mv", np.int16, (2, 2)), ("ref", np.int8, (2,)), ("flags", np.uint8), ("qp", np.uint8)])
+BLK_INTRA, BLK_CBF, BLK_TU_LEFT, BLK_TU_TOP, BLK_PU_LEFT, BLK_PU_TOP = 1, 2, 4, 8, 16, 32
+
+
+def edge_bytes(bs, qp):
+    """HDB_EDGE(bs, qp) = bs | qp << 2, elementwise."""
+    return ((np.asarray(bs, np.uint32) & 3) | (np.minimum(np.asarray(qp, np.uint32), 51) << 2)).astype(np.uint8)
 
 
 def _addr(a):
@@ -244,7 +259,48 @@ class Deblocker:
         """Device pointers (torch CUDA tensors or ints); enqueues on `stream` and returns."""
         self._check(self._lib.hdb_deblock_batch_device(self._ctx, _addr(d_in), _addr(d_out), n_frames, width, height,
                                                        _addr(d_qp), _addr(d_vert_bs), _addr(d_hor_bs), stream))
+    # --- edge maps: per-edge QP (edge byte = bs | qp << 2) and their derivation from block data ---
+    def deblock_frame_edges(self, yuv, width, height, qp, vert_edges, hor_edges, out=None, timing=None):
+        yuv = np.ascontiguousarray(yuv, np.uint8).reshape(-1)
+        if yuv.size != 3 * width * height // 2:
+            raise DeblockError(2, "Incorrect file size")
+        out = np.empty_like(yuv) if out is None else out
+        v = None if vert_edges is None else np.ascontiguousarray(vert_edges, np.uint8)
+        h = None if hor_edges is None else np.ascontiguousarray(hor_edges, np.uint8)
+        self._check(self._lib.hdb_deblock_frame_edges(self._ctx, _addr(yuv), _addr(out), width, height, qp,
+                                                      _addr(v), 0 if v is None else v.size,
+                                                      _addr(h), 0 if h is None else h.size,
+                                                      None if timing is None else C.byref(timing)))
+        return out
 
+    def deblock_batch_edges(self, frames, width, height, qps, vert_edges, hor_edges, out=None, timing=None,
+                            n_frames=None):
+        n = n_frames if n_frames is not None else int(frames.shape[0])
+        if out is None:
+            out = np.empty_like(frames)
+        self._check(self._lib.hdb_deblock_batch_edges(self._ctx, _addr(frames), _addr(out), n, width, height,
+                                                      _addr(qps), _addr(vert_edges), _addr(hor_edges),
+                                                      None if timing is None else C.byref(timing)))
+        return out
+
+    def deblock_batch_edges_device(self, d_in, d_out, n_frames, width, height, d_qp, d_vert_edges, d_hor_edges,
+                                   stream=None):
+        self._check(self._lib.hdb_deblock_batch_edges_device(self._ctx, _addr(d_in), _addr(d_out), n_frames, width,
+                                                             height, _addr(d_qp), _addr(d_vert_edges),
+                                                             _addr(d_hor_edges), stream))
+
+    def derive_edges(self, info, width, height):
+        """info: BLOCK_INFO[n, H/8, W/8] (host) -> (vert_edges[n, nV], hor_edges[n, nH]), computed on the GPU."""
+        info = np.ascontiguousarray(info, BLOCK_INFO)
+        n = info.size // ((width // 8) * (height // 8))
+        v = np.empty((n, num_vert_bs(width, height)), np.uint8)
+        h = np.empty((n, num_hor_bs(width, height)), np.uint8)
+        self._check(self._lib.hdb_derive_edges(self._ctx, _addr(info), n, width, height, _addr(v), _addr(h)))
+        return v, h
+
+    def derive_edges_device(self, d_info, n_frames, width, height, d_vert_edges, d_hor_edges, stream=None):
+        self._check(self._lib.hdb_derive_edges_device(self._ctx, _addr(d_info), n_frames, width, height,
+                                                      _addr(d_vert_edges), _addr(d_hor_edges), stream))
 
     def deblock_surfaces_device(self, src, dst, n_frames, width, height, d_qp, d_vert_bs=None, d_hor_bs=None,
                                 stream=None):

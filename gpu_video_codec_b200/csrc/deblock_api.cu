@@ -100,6 +100,7 @@ void DestroyContext(hdb_context *ctx)
 	for (auto &s : ctx->sizes) { cudaFree(s.chroma_bs); cudaFree(s.def_vbs); cudaFree(s.def_hbs); }
 	for (auto &sl : ctx->slots) { cudaFree(sl.frames); cudaFree(sl.vbs); cudaFree(sl.hbs); }
 	cudaFree(ctx->qp_dev);
+	cudaFree(ctx->derive_dev);
 	for (auto ev : ctx->event_pool) cudaEventDestroy(ev);
 	cudaFree(ctx->generic_scratch);
 	cudaFree(ctx->sched);
@@ -162,12 +163,13 @@ bool TiledPathUsable(int w, int h, const void *d_in, const void *d_out)
  */
 int EnqueueFilter(hdb_context *ctx, const FrameView &view, const unsigned char *d_in, unsigned char *d_out,
 	int n, const unsigned *d_qp, unsigned qp_value, const unsigned char *d_vbs, long long vbs_stride,
-	const unsigned char *d_hbs, long long hbs_stride, cudaStream_t stream, int *path)
+	const unsigned char *d_hbs, long long hbs_stride, cudaStream_t stream, int *path, bool edge_qp)
 {
 	const int w = view.width, h = view.height;
 	SizeState *ss = nullptr;
 	int rc = GetSizeState(ctx, w, h, &ss);
 	if (rc) return rc;
+	if (edge_qp && (!d_vbs || !d_hbs)) return Fail(ctx, HDB_ERR_INVALID_ARG, "edge maps are required: there is no default for them");
 	if (!d_vbs || !d_hbs) { d_vbs = ss->def_vbs; d_hbs = ss->def_hbs; vbs_stride = hbs_stride = 0; }
 	const TiledConfig cfg = GetTiledConfig();
 
@@ -194,6 +196,7 @@ int EnqueueFilter(hdb_context *ctx, const FrameView &view, const unsigned char *
 			g.qp = d_qp ? d_qp + f0 : nullptr; g.qp_value = qp_value;
 			g.vert_bs = d_vbs + f0 * vbs_stride; g.hor_bs = d_hbs + f0 * hbs_stride;
 			g.vert_bs_stride = vbs_stride; g.hor_bs_stride = hbs_stride;
+			g.edge_qp = edge_qp;
 			HDB_CUDA(ctx, LaunchGeneric(g, stream));
 			ctx->launches += 3;
 		}
@@ -242,7 +245,7 @@ int EnqueueFilter(hdb_context *ctx, const FrameView &view, const unsigned char *
 		/* launches take the scheduler words in turn: two launches that overlap on the device (different
 		 * streams) must not share a work counter, and each launch leaves its own words zeroed */
 		void *sched = static_cast<char *>(ctx->sched) + TiledSchedBytes() * (ctx->launches % kSchedSlots);
-		HDB_CUDA(ctx, LaunchTiled(maps, b, sched, ctx->prop.multiProcessorCount, ctx->tiled_ctas_per_sm, stream));
+		HDB_CUDA(ctx, LaunchTiled(maps, b, sched, ctx->prop.multiProcessorCount, ctx->tiled_ctas_per_sm, stream, edge_qp));
 		ctx->launches += 1;
 	}
 	return HDB_OK;
@@ -356,11 +359,12 @@ static int GetEvents(hdb_context *ctx, size_t n)
  * single slice runs on one stream.
  */
 int BatchHost(hdb_context *ctx, const unsigned char *in, unsigned char *out, unsigned n, unsigned w, unsigned h,
-	const unsigned *qp, const unsigned char *vbs, const unsigned char *hbs, hdb_timing *timing)
+	const unsigned *qp, const unsigned char *vbs, const unsigned char *hbs, hdb_timing *timing, bool edge_qp)
 {
 	if (!ctx) return HDB_ERR_INVALID_ARG;
 	std::lock_guard<std::mutex> lock(ctx->mu);
 	if (!in || !out || !qp || n == 0) return Fail(ctx, HDB_ERR_INVALID_ARG, "NULL buffer or empty batch");
+	if (edge_qp && (!vbs || !hbs)) return Fail(ctx, HDB_ERR_INVALID_ARG, "edge maps are required: there is no default for them");
 	int rc = ValidateFrameArgs(ctx, w, h, vbs, 0, hbs, 0, false);
 	if (rc) return rc;
 	DeviceGuard guard(ctx->device);
@@ -414,7 +418,7 @@ int BatchHost(hdb_context *ctx, const unsigned char *in, unsigned char *out, uns
 		cudaEvent_t *ev = timed ? &ctx->event_pool[0] : nullptr;
 		if (timed) HDB_CUDA(ctx, cudaEventRecord(ev[0], s_k));
 		rc = EnqueueFilter(ctx, view, z_in, z_out, (int)n, uniform_qp ? nullptr : ctx->qp_dev, qp[0],
-			vbs ? sl.vbs : nullptr, nv, vbs ? sl.hbs : nullptr, nh, s_k, &path);
+			vbs ? sl.vbs : nullptr, nv, vbs ? sl.hbs : nullptr, nh, s_k, &path, edge_qp);
 		if (rc) { cudaDeviceSynchronize(); return rc; }
 		if (timed) HDB_CUDA(ctx, cudaEventRecord(ev[1], s_k));
 		HDB_CUDA(ctx, cudaStreamSynchronize(s_k));
@@ -460,7 +464,7 @@ int BatchHost(hdb_context *ctx, const unsigned char *in, unsigned char *out, uns
 		}
 		if (timed) HDB_CUDA(ctx, cudaEventRecord(ev[2], s_k));
 		rc = EnqueueFilter(ctx, view, sl.frames, sl.frames, nf, uniform_qp ? nullptr : ctx->qp_dev + f0, qp[0],
-			vbs ? sl.vbs : nullptr, nv, vbs ? sl.hbs : nullptr, nh, s_k, &path);
+			vbs ? sl.vbs : nullptr, nv, vbs ? sl.hbs : nullptr, nh, s_k, &path, edge_qp);
 		if (rc) { cudaDeviceSynchronize(); return rc; }
 		if (timed) HDB_CUDA(ctx, cudaEventRecord(ev[3], s_k));
 		if (!single) {
@@ -688,6 +692,93 @@ int hdb_deblock_surfaces_device(hdb_context *ctx, const hdb_surfaces *in, const 
 	return EnqueueFilter(ctx, view, iy, oy, (int)n_frames, d_qp, 0,
 		d_vert_bs, hdb_num_vert_bs(width, height), d_hor_bs, hdb_num_hor_bs(width, height),
 		static_cast<cudaStream_t>(stream), nullptr);
+}
+
+/* ---- edge maps: per-edge QP and boundary-strength derivation ---- */
+
+int hdb_deblock_frame_edges(hdb_context *ctx, const unsigned char *yuv_in, unsigned char *yuv_out,
+	unsigned width, unsigned height, unsigned qp, const unsigned char *vert_edges, unsigned num_vert_edges,
+	const unsigned char *hor_edges, unsigned num_hor_edges, hdb_timing *timing)
+{
+	if (!ctx) return HDB_ERR_INVALID_ARG;
+	if (!vert_edges || !hor_edges) return Fail(ctx, HDB_ERR_INVALID_ARG, "edge maps are required: there is no default for them");
+	int rc = ValidateFrameArgs(ctx, width, height, vert_edges, num_vert_edges, hor_edges, num_hor_edges, true);
+	if (rc) return rc;
+	return BatchHost(ctx, yuv_in, yuv_out, 1, width, height, &qp, vert_edges, hor_edges, timing, true);
+}
+
+int hdb_deblock_batch_edges(hdb_context *ctx, const unsigned char *frames_in, unsigned char *frames_out,
+	unsigned n_frames, unsigned width, unsigned height, const unsigned *qp,
+	const unsigned char *vert_edges, const unsigned char *hor_edges, hdb_timing *timing)
+{
+	return BatchHost(ctx, frames_in, frames_out, n_frames, width, height, qp, vert_edges, hor_edges, timing, true);
+}
+
+int hdb_deblock_batch_edges_device(hdb_context *ctx, const void *d_frames_in, void *d_frames_out,
+	unsigned n_frames, unsigned width, unsigned height, const unsigned *d_qp,
+	const unsigned char *d_vert_edges, const unsigned char *d_hor_edges, void *stream)
+{
+	if (!ctx) return HDB_ERR_INVALID_ARG;
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	if (!d_frames_in || !d_frames_out || !d_qp || !d_vert_edges || !d_hor_edges || n_frames == 0)
+		return Fail(ctx, HDB_ERR_INVALID_ARG, "NULL buffer or empty batch");
+	int rc = ValidateFrameArgs(ctx, width, height, d_vert_edges, 0, d_hor_edges, 0, false);
+	if (rc) return rc;
+	DeviceGuard guard(ctx->device);
+	const FrameView view = WholeFrameView((int)width, (int)height);
+	return EnqueueFilter(ctx, view, static_cast<const unsigned char *>(d_frames_in),
+		static_cast<unsigned char *>(d_frames_out), (int)n_frames, d_qp, 0,
+		d_vert_edges, hdb_num_vert_bs(width, height), d_hor_edges, hdb_num_hor_bs(width, height),
+		static_cast<cudaStream_t>(stream), nullptr, true);
+}
+
+/* caller holds ctx->mu */
+static int DeriveEdgesLocked(hdb_context *ctx, const hdb_block_info *d_info, unsigned n_frames,
+	unsigned width, unsigned height, unsigned char *d_vert_edges, unsigned char *d_hor_edges, cudaStream_t stream)
+{
+	if ((uintptr_t)d_info % 4 != 0) return Fail(ctx, HDB_ERR_INVALID_ARG, "block data must be 4-byte aligned");
+	DeviceGuard guard(ctx->device);
+	HDB_CUDA(ctx, LaunchDeriveEdges(d_info, (int)width, (int)height, (int)n_frames, d_vert_edges, d_hor_edges, stream));
+	ctx->launches += 1;
+	return HDB_OK;
+}
+
+int hdb_derive_edges_device(hdb_context *ctx, const hdb_block_info *d_info, unsigned n_frames,
+	unsigned width, unsigned height, unsigned char *d_vert_edges, unsigned char *d_hor_edges, void *stream)
+{
+	if (!ctx) return HDB_ERR_INVALID_ARG;
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	if (!d_info || !d_vert_edges || !d_hor_edges || n_frames == 0) return Fail(ctx, HDB_ERR_INVALID_ARG, "NULL buffer or empty batch");
+	int rc = ValidateFrameArgs(ctx, width, height, nullptr, 0, nullptr, 0, false);
+	if (rc) return rc;
+	return DeriveEdgesLocked(ctx, d_info, n_frames, width, height, d_vert_edges, d_hor_edges, static_cast<cudaStream_t>(stream));
+}
+
+int hdb_derive_edges(hdb_context *ctx, const hdb_block_info *info, unsigned n_frames,
+	unsigned width, unsigned height, unsigned char *vert_edges, unsigned char *hor_edges)
+{
+	if (!ctx) return HDB_ERR_INVALID_ARG;
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	if (!info || !vert_edges || !hor_edges || n_frames == 0) return Fail(ctx, HDB_ERR_INVALID_ARG, "NULL buffer or empty batch");
+	int rc = ValidateFrameArgs(ctx, width, height, nullptr, 0, nullptr, 0, false);
+	if (rc) return rc;
+	const size_t ni = sizeof(hdb_block_info) * (size_t)(width / 8) * (height / 8) * n_frames;
+	const size_t nv = (size_t)hdb_num_vert_bs(width, height) * n_frames, nh = (size_t)hdb_num_hor_bs(width, height) * n_frames;
+	const size_t off_v = (ni + 255) & ~(size_t)255, off_h = (off_v + nv + 255) & ~(size_t)255, total = off_h + nh;
+	DeviceGuard guard(ctx->device);
+	if (ctx->derive_cap < total) {
+		cudaFree(ctx->derive_dev); ctx->derive_dev = nullptr; ctx->derive_cap = 0;
+		HDB_CUDA(ctx, cudaMalloc(&ctx->derive_dev, total));
+		ctx->derive_cap = total;
+	}
+	unsigned char *d = static_cast<unsigned char *>(ctx->derive_dev);
+	HDB_CUDA(ctx, cudaMemcpyAsync(d, info, ni, cudaMemcpyHostToDevice, ctx->s_k));
+	rc = DeriveEdgesLocked(ctx, reinterpret_cast<const hdb_block_info *>(d), n_frames, width, height, d + off_v, d + off_h, ctx->s_k);
+	if (rc) return rc;
+	HDB_CUDA(ctx, cudaMemcpyAsync(vert_edges, d + off_v, nv, cudaMemcpyDeviceToHost, ctx->s_k));
+	HDB_CUDA(ctx, cudaMemcpyAsync(hor_edges, d + off_h, nh, cudaMemcpyDeviceToHost, ctx->s_k));
+	HDB_CUDA(ctx, cudaStreamSynchronize(ctx->s_k));
+	return HDB_OK;
 }
 
 unsigned long long hdb_kernel_launch_count(const hdb_context *ctx) { return ctx ? ctx->launches : 0; }

@@ -87,6 +87,8 @@ struct hdb_context {
 	size_t generic_scratch_bytes = 0;
 	void *stage_in = nullptr, *stage_out = nullptr;
 	size_t stage_cap = 0;
+	void *derive_dev = nullptr;              /* block data and edge maps of a host-side hdb_derive_edges call */
+	size_t derive_cap = 0;
 	unsigned *qp_dev = nullptr;              /* the QPs of the batch in flight */
 	size_t qp_cap = 0;
 	size_t chunk_bytes = (size_t)128 << 20;  /* full slice size of the host pipeline (HDB_CHUNK_MB) */
@@ -108,9 +110,9 @@ int ValidateFrameArgs(hdb_context *ctx, unsigned w, unsigned h, const unsigned c
 	const unsigned char *hbs, unsigned nh, bool sizes_given);
 int EnqueueFilter(hdb_context *ctx, const FrameView &view, const unsigned char *d_in, unsigned char *d_out,
 	int n, const unsigned *d_qp, unsigned qp_value, const unsigned char *d_vbs, long long vbs_stride,
-	const unsigned char *d_hbs, long long hbs_stride, cudaStream_t stream, int *path);
+	const unsigned char *d_hbs, long long hbs_stride, cudaStream_t stream, int *path, bool edge_qp = false);
 int BatchHost(hdb_context *ctx, const unsigned char *in, unsigned char *out, unsigned n, unsigned w, unsigned h,
-	const unsigned *qp, const unsigned char *vbs, const unsigned char *hbs, hdb_timing *timing);
+	const unsigned *qp, const unsigned char *vbs, const unsigned char *hbs, hdb_timing *timing, bool edge_qp = false);
 
 /* beta / tc on the host (cpu.h:1021-1033, 1064-1072); defined in deblock_kernels.cu next to the device tables */
 int HostBeta(unsigned qp);

@@ -434,21 +434,61 @@ HDB_FN u32 ChromaBsOfBlock(int bx, int by, unsigned cw, unsigned ch, int luma_nb
 /* ------------------------------------------------------------------ */
 
 /*
- * Luma block, cpu.h:158-446.  bs[0..3] = BS_ver1, BS_ver2, BS_hor1, BS_hor2 as
- * resolved by the caller (zero where the reference's guards skip the lookup).
+ * Edge maps (no reference counterpart -- the reference has one QP per
+ * frame, cpu.h:35-37).  An edge byte is  bs | qp << 2  in the reference's own array layouts; a luma
+ * segment then takes beta / tc from its own entry.  The 6-bit qp indexes a 64-entry table of
+ * beta | tc << 8 whose entries 52..63 repeat entry 51 (the clamp of cpu.h:1064-1072).  On the device
+ * the table sits in one 128-byte line of global memory: the index differs from lane to lane, which a
+ * constant-bank access would serialise.
  */
-HDB_FN void LumaBlock(u32 (&lo)[8], u32 (&hi)[8], u32 bs_ver1, u32 bs_ver2, u32 bs_hor1, u32 bs_hor2,
+#define HDB_BT(b, t) (uint16_t)((b) | ((t) << 8))
+#define HDB_BETA_TC_TABLE { \
+	HDB_BT(0, 0), HDB_BT(0, 0), HDB_BT(0, 0), HDB_BT(0, 0), HDB_BT(0, 0), HDB_BT(0, 0), HDB_BT(0, 0), HDB_BT(0, 0), \
+	HDB_BT(0, 0), HDB_BT(0, 0), HDB_BT(0, 0), HDB_BT(0, 0), HDB_BT(0, 0), HDB_BT(0, 0), HDB_BT(0, 0), HDB_BT(0, 0), \
+	HDB_BT(6, 0), HDB_BT(7, 0), HDB_BT(8, 1), HDB_BT(9, 1), HDB_BT(10, 1), HDB_BT(11, 1), HDB_BT(12, 1), HDB_BT(13, 1), \
+	HDB_BT(14, 1), HDB_BT(15, 1), HDB_BT(16, 1), HDB_BT(17, 2), HDB_BT(18, 2), HDB_BT(20, 2), HDB_BT(22, 2), HDB_BT(24, 3), \
+	HDB_BT(26, 3), HDB_BT(28, 3), HDB_BT(30, 3), HDB_BT(32, 4), HDB_BT(34, 4), HDB_BT(36, 4), HDB_BT(38, 5), HDB_BT(40, 5), \
+	HDB_BT(42, 6), HDB_BT(44, 6), HDB_BT(46, 7), HDB_BT(48, 8), HDB_BT(50, 9), HDB_BT(52, 10), HDB_BT(54, 11), HDB_BT(56, 13), \
+	HDB_BT(58, 14), HDB_BT(60, 16), HDB_BT(62, 18), HDB_BT(64, 20), HDB_BT(64, 20), HDB_BT(64, 20), HDB_BT(64, 20), HDB_BT(64, 20), \
+	HDB_BT(64, 20), HDB_BT(64, 20), HDB_BT(64, 20), HDB_BT(64, 20), HDB_BT(64, 20), HDB_BT(64, 20), HDB_BT(64, 20), HDB_BT(64, 20) }
+#if defined(HDB_HOST_EMU)
+static const uint16_t g_beta_tc_of_qp6[64] = HDB_BETA_TC_TABLE;
+HDB_FN u32 BetaTcOfQp6(u32 qp6) { return g_beta_tc_of_qp6[qp6 & 63u]; }
+#else
+static __device__ __align__(128) const uint16_t g_beta_tc_of_qp6[64] = HDB_BETA_TC_TABLE;
+HDB_FN u32 BetaTcOfQp6(u32 qp6) { return __ldg(g_beta_tc_of_qp6 + (qp6 & 63u)); }
+#endif
+
+HDB_HD u32 EdgeByte(u32 bs, u32 qp) { return (bs & 3u) | ((qp > 51u ? 51u : qp) << 2); }
+
+/*
+ * Luma block, cpu.h:158-446.  The four arguments are BS_ver1, BS_ver2, BS_hor1, BS_hor2 as
+ * resolved by the caller (zero where the reference's guards skip the lookup): boundary
+ * strengths when kEdgeQp is false -- every segment then uses the frame's parameters fp --
+ * and edge bytes when it is true.
+ */
+template <bool kEdgeQp>
+HDB_FN void LumaBlockT(u32 (&lo)[8], u32 (&hi)[8], u32 bs_ver1, u32 bs_ver2, u32 bs_hor1, u32 bs_hor2,
 	const FilterParams &fp)
 {
+	FilterParams fpe;
+	u32 bt_ver1 = 0, bt_ver2 = 0, bt_hor1 = 0, bt_hor2 = 0;
+	if (kEdgeQp) {
+		/* the four table reads first, so that they are in flight together */
+		bt_ver1 = BetaTcOfQp6(bs_ver1 >> 2); bt_ver2 = BetaTcOfQp6(bs_ver2 >> 2);
+		bt_hor1 = BetaTcOfQp6(bs_hor1 >> 2); bt_hor2 = BetaTcOfQp6(bs_hor2 >> 2);
+		bs_ver1 &= 3u; bs_ver2 &= 3u; bs_hor1 &= 3u; bs_hor2 &= 3u;
+	}
 	/* upper (rows 0-3) and lower (rows 4-7) vertical edge segments */
 #pragma unroll
 	for (int s = 0; s < 2; s++) {
 		const int r = 4 * s;
 		if ((s == 0 ? bs_ver1 : bs_ver2) > 0) {                     /* cpu.h:164, 228 */
+			if (kEdgeQp) { const u32 bt = s == 0 ? bt_ver1 : bt_ver2; MakeFilterParams(fpe, (int)(bt & 0xffu), (int)(bt >> 8)); }
 			LumaPair x, y;
 			LoadVertPair(x, lo[r], lo[r + 3], hi[r], hi[r + 3]);
 			LoadVertPair(y, lo[r + 1], lo[r + 2], hi[r + 1], hi[r + 2]);
-			int kind = LumaSegment(x, y, fp);
+			int kind = LumaSegment(x, y, kEdgeQp ? fpe : fp);
 			if (kind != kSegOff) {
 				StoreVertPair(x, kind, lo[r], lo[r + 3], hi[r], hi[r + 3]);
 				StoreVertPair(y, kind, lo[r + 1], lo[r + 2], hi[r + 1], hi[r + 2]);
@@ -457,12 +497,13 @@ HDB_FN void LumaBlock(u32 (&lo)[8], u32 (&hi)[8], u32 bs_ver1, u32 bs_ver2, u32 
 	}
 	/* left horizontal edge segment: columns 0-3, p rows 3..0, q rows 4..7 (cpu.h:287-365) */
 	if (bs_hor1 > 0) {
+		if (kEdgeQp) MakeFilterParams(fpe, (int)(bt_hor1 & 0xffu), (int)(bt_hor1 >> 8));
 		LumaPair x, y;
 		SplitRow(lo[0], x.p3, y.p3); SplitRow(lo[1], x.p2, y.p2);
 		SplitRow(lo[2], x.p1, y.p1); SplitRow(lo[3], x.p0, y.p0);
 		SplitRow(lo[4], x.q0, y.q0); SplitRow(lo[5], x.q1, y.q1);
 		SplitRow(lo[6], x.q2, y.q2); SplitRow(lo[7], x.q3, y.q3);
-		int kind = LumaSegment(x, y, fp);
+		int kind = LumaSegment(x, y, kEdgeQp ? fpe : fp);
 		if (kind != kSegOff) {
 			lo[2] = JoinRow(x.p1, y.p1); lo[3] = JoinRow(x.p0, y.p0);
 			lo[4] = JoinRow(x.q0, y.q0); lo[5] = JoinRow(x.q1, y.q1);
@@ -472,18 +513,25 @@ HDB_FN void LumaBlock(u32 (&lo)[8], u32 (&hi)[8], u32 bs_ver1, u32 bs_ver2, u32 
 	/* right horizontal edge segment: p = columns 4-7 of rows 3..0, q = columns 0-3 of
 	 * rows 4..7 -- the reference's pairing (cpu.h:383-445), reproduced as is */
 	if (bs_hor2 > 0) {
+		if (kEdgeQp) MakeFilterParams(fpe, (int)(bt_hor2 & 0xffu), (int)(bt_hor2 >> 8));
 		LumaPair x, y;
 		SplitRow(hi[0], x.p3, y.p3); SplitRow(hi[1], x.p2, y.p2);
 		SplitRow(hi[2], x.p1, y.p1); SplitRow(hi[3], x.p0, y.p0);
 		SplitRow(lo[4], x.q0, y.q0); SplitRow(lo[5], x.q1, y.q1);
 		SplitRow(lo[6], x.q2, y.q2); SplitRow(lo[7], x.q3, y.q3);
-		int kind = LumaSegment(x, y, fp);
+		int kind = LumaSegment(x, y, kEdgeQp ? fpe : fp);
 		if (kind != kSegOff) {
 			hi[2] = JoinRow(x.p1, y.p1); hi[3] = JoinRow(x.p0, y.p0);
 			lo[4] = JoinRow(x.q0, y.q0); lo[5] = JoinRow(x.q1, y.q1);
 			if (kind == kSegStrong) { hi[1] = JoinRow(x.p2, y.p2); lo[6] = JoinRow(x.q2, y.q2); }
 		}
 	}
+}
+
+HDB_FN void LumaBlock(u32 (&lo)[8], u32 (&hi)[8], u32 bs_ver1, u32 bs_ver2, u32 bs_hor1, u32 bs_hor2,
+	const FilterParams &fp)
+{
+	LumaBlockT<false>(lo, hi, bs_ver1, bs_ver2, bs_hor1, bs_hor2, fp);
 }
 
 /* Chroma block, cpu.h:453-721 (and 724-992): same geometry, taps k = 0,1, BS == 2 only. */
@@ -519,6 +567,62 @@ HDB_FN void ChromaBlock(u32 (&lo)[8], u32 (&hi)[8], u32 bs_ver1, u32 bs_ver2, u3
 		ChromaPairFilter(y, fp);
 		hi[3] = JoinRow(x.p0, y.p0); lo[4] = JoinRow(x.q0, y.q0);
 	}
+}
+
+/* ------------------------------------------------------------------ */
+/* boundary-strength and edge-QP derivation                            */
+/* ------------------------------------------------------------------ */
+
+/*
+ * What a decoder knows about one 8x8 luma block; binary layout of hdb_block_info
+ * (include/hevc_deblock_b200.h), read as three 32-bit words:
+ *   w0 = mv[0] (x | y << 16)   w1 = mv[1]   w2 = ref[0] | ref[1] << 8 | flags << 16 | qp << 24
+ * The reference has nothing upstream of its filter -- strengths are constants (cpu.h:91-99) -- so
+ * the rule is the published one, H.265 8.7.2.4: an edge that is neither a transform nor a
+ * prediction edge is off; intra on either side -> 2; a transform edge with coded coefficients on
+ * either side -> 1; different reference pictures or a different number of motion vectors -> 1; a
+ * motion-vector difference of four quarter samples or more in either component -> 1; else 0.
+ */
+struct BlockWords { u32 mv0, mv1, meta; };
+enum { kBlkIntra = 1, kBlkCbf = 2, kBlkTuLeft = 4, kBlkTuTop = 8, kBlkPuLeft = 16, kBlkPuTop = 32 };
+
+HDB_HD int MvFar(u32 a, u32 b)
+{
+	int dx = (int)(int16_t)(a & 0xffffu) - (int)(int16_t)(b & 0xffffu);
+	int dy = (int)(int16_t)(a >> 16) - (int)(int16_t)(b >> 16);
+	if (dx < 0) dx = -dx;
+	if (dy < 0) dy = -dy;
+	return dx >= 4 || dy >= 4;
+}
+
+HDB_HD u32 DeriveBs(const BlockWords &p, const BlockWords &q, bool tu_edge, bool pu_edge)
+{
+	if (!tu_edge && !pu_edge) return 0u;
+	const u32 flags = (p.meta | q.meta) >> 16;
+	if (flags & kBlkIntra) return 2u;
+	if (tu_edge && (flags & kBlkCbf)) return 1u;
+	const int p0 = (int)(int8_t)(p.meta & 0xffu), p1 = (int)(int8_t)((p.meta >> 8) & 0xffu);
+	const int q0 = (int)(int8_t)(q.meta & 0xffu), q1 = (int)(int8_t)((q.meta >> 8) & 0xffu);
+	const int np = (p0 >= 0) + (p1 >= 0), nq = (q0 >= 0) + (q1 >= 0);
+	if (np != nq) return 1u;
+	if (np == 1) {
+		if ((p0 >= 0 ? p0 : p1) != (q0 >= 0 ? q0 : q1)) return 1u;
+		return (u32)MvFar(p0 >= 0 ? p.mv0 : p.mv1, q0 >= 0 ? q.mv0 : q.mv1);
+	}
+	if (np == 2) {
+		if (!((p0 == q0 && p1 == q1) || (p0 == q1 && p1 == q0))) return 1u;
+		const int straight = MvFar(p.mv0, q.mv0) || MvFar(p.mv1, q.mv1);
+		const int crossed = MvFar(p.mv0, q.mv1) || MvFar(p.mv1, q.mv0);
+		if (p0 != p1) return (u32)(p0 == q0 ? straight : crossed);
+		return (u32)(straight && crossed);
+	}
+	return 0u;
+}
+
+/* edge byte between block p (left / above) and block q: strength by the rule above, QP = (QpP + QpQ + 1) >> 1 */
+HDB_HD u32 DeriveEdge(const BlockWords &p, const BlockWords &q, bool tu_edge, bool pu_edge)
+{
+	return EdgeByte(DeriveBs(p, q, tu_edge, pu_edge), ((p.meta >> 24) + (q.meta >> 24) + 1u) >> 1);
 }
 
 } // namespace hdb

@@ -206,6 +206,9 @@ __device__ __forceinline__ u32 PackBs(const BsRaw &r, bool chroma)
 /* ------------------------------------------------------------------ */
 /* the kernel                                                          */
 /* ------------------------------------------------------------------ */
+/* kEdgeQp: the luma boundary-strength arrays hold edge bytes (bs | qp << 2, deblock_core.cuh) and every
+ * luma segment takes beta / tc from its own entry; chroma is untouched by it (frame QP, cpu.h:110-117) */
+template <bool kEdgeQp>
 __global__ void __launch_bounds__(kWarps * 32, HDB_MIN_CTAS)
 DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_constant__ TiledBatch b,
 	SchedWords *sched, const uint32_t run_len)
@@ -334,7 +337,7 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_consta
 #pragma unroll
 				for (int k = 1; k < kRB; k++) if (rb == k) s4 = bs[k];
 				if (chroma) ChromaBlock(lo, hi, s4 & 0xff, (s4 >> 8) & 0xff, (s4 >> 16) & 0xff, s4 >> 24, fp);
-				else LumaBlock(lo, hi, s4 & 0xff, (s4 >> 8) & 0xff, (s4 >> 16) & 0xff, s4 >> 24, fp);
+				else LumaBlockT<kEdgeQp>(lo, hi, s4 & 0xff, (s4 >> 8) & 0xff, (s4 >> 16) & 0xff, s4 >> 24, fp);
 #pragma unroll
 				for (int r = 0; r < 8; r++) { base[r * kTileWords] = lo[r]; base[r * kTileWords + 1] = hi[r]; }
 			}
@@ -445,17 +448,22 @@ void FinalizeTiledBatch(TiledBatch &b)
 
 cudaError_t PrepareTiled(int *ctas_per_sm)
 {
-	cudaError_t err = cudaFuncSetAttribute(DeblockTiledKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+	cudaError_t err = cudaFuncSetAttribute(DeblockTiledKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
 	if (err != cudaSuccess) return err;
-	int n = 0;
-	err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, DeblockTiledKernel, kWarps * 32, kSmemBytes);
+	err = cudaFuncSetAttribute(DeblockTiledKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
 	if (err != cudaSuccess) return err;
-	*ctas_per_sm = std::max(n, 1);
+	/* both instantiations are built to the same launch bounds: one grid size serves both */
+	int n = 0, n_edge = 0;
+	err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, DeblockTiledKernel<false>, kWarps * 32, kSmemBytes);
+	if (err != cudaSuccess) return err;
+	err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n_edge, DeblockTiledKernel<true>, kWarps * 32, kSmemBytes);
+	if (err != cudaSuccess) return err;
+	*ctas_per_sm = std::max(std::min(n, n_edge), 1);
 	return cudaSuccess;
 }
 
 cudaError_t LaunchTiled(const TensorMaps3 &maps, const TiledBatch &b, void *sched, int sm_count, int ctas_per_sm,
-	cudaStream_t stream)
+	cudaStream_t stream, bool edge_qp)
 {
 	if (b.total_items <= 0) return cudaSuccess;
 	if (b.total_items >= (1ll << 31)) return cudaErrorInvalidValue;
@@ -468,8 +476,12 @@ cudaError_t LaunchTiled(const TensorMaps3 &maps, const TiledBatch &b, void *sche
 	uint32_t run_len = b.total_items / (ctas * kWarps) >= 512 ? 8 : 4;
 	static const int run_len_env = getenv("HDB_RUN_LEN") ? atoi(getenv("HDB_RUN_LEN")) : 0;   /* measurement knob */
 	if (run_len_env > 0) run_len = (uint32_t)run_len_env;
-	DeblockTiledKernel<<<(unsigned)ctas, kWarps * 32, kSmemBytes, stream>>>(maps, b,
-		reinterpret_cast<SchedWords *>(sched), run_len);
+	if (edge_qp)
+		DeblockTiledKernel<true><<<(unsigned)ctas, kWarps * 32, kSmemBytes, stream>>>(maps, b,
+			reinterpret_cast<SchedWords *>(sched), run_len);
+	else
+		DeblockTiledKernel<false><<<(unsigned)ctas, kWarps * 32, kSmemBytes, stream>>>(maps, b,
+			reinterpret_cast<SchedWords *>(sched), run_len);
 	return cudaGetLastError();
 }
 
@@ -509,6 +521,45 @@ cudaError_t LaunchDefaultLumaBs(unsigned char *vert_bs, unsigned char *hor_bs, i
 	const unsigned n = std::max(NumVertBs(width, height), NumHorBs(width, height));
 	if (n == 0) return cudaSuccess;
 	DefaultLumaBsKernel<<<(n + 255) / 256, 256, 0, stream>>>(vert_bs, hor_bs, width, height);
+	return cudaGetLastError();
+}
+
+/*
+ * Edge maps from block data (deblock_core.cuh: DeriveEdge).  One thread per point (r, x) of the
+ * (H/8 + 1) x (W/8 + 1) grid of block corners: it writes the vertical entry [r][x] -- the edge
+ * between blocks (r, x-1) and (r, x) -- and the horizontal entry [r][x] -- between (r-1, x) and
+ * (r, x).  Entries on the picture's four sides are 0 (H.265 does not filter them).  Per 8x8 block
+ * 12 bytes are read (the neighbours come out of L1 / L2) and 2 written, against 192 the filter moves.
+ */
+__global__ void DeriveEdgesKernel(const uint32_t *info, int w8, int h8, int n_frames,
+	unsigned char *vert_edges, unsigned char *hor_edges)
+{
+	const int x = blockIdx.x * blockDim.x + threadIdx.x;
+	const int r = blockIdx.y;
+	if (x > w8) return;
+	const long long nv = (long long)(w8 + 1) * h8, nh = (long long)(h8 + 1) * w8;
+	for (int f = blockIdx.z; f < n_frames; f += gridDim.z) {
+		const uint32_t *fi = info + 3ll * f * w8 * h8;
+		auto blk = [&](int rr, int xx) { const uint32_t *p = fi + 3ll * ((long long)rr * w8 + xx); return BlockWords{ __ldg(p), __ldg(p + 1), __ldg(p + 2) }; };
+		u32 ev = 0, eh = 0;
+		if (r < h8 && x < w8) {
+			const BlockWords q = blk(r, x);
+			const u32 fl = q.meta >> 16;
+			if (x > 0) ev = DeriveEdge(blk(r, x - 1), q, fl & kBlkTuLeft, fl & kBlkPuLeft);
+			if (r > 0) eh = DeriveEdge(blk(r - 1, x), q, fl & kBlkTuTop, fl & kBlkPuTop);
+		}
+		if (r < h8) vert_edges[f * nv + (long long)r * (w8 + 1) + x] = (unsigned char)ev;
+		if (x < w8) hor_edges[f * nh + (long long)r * w8 + x] = (unsigned char)eh;
+	}
+}
+
+cudaError_t LaunchDeriveEdges(const void *info, int width, int height, int n_frames,
+	unsigned char *vert_edges, unsigned char *hor_edges, cudaStream_t stream)
+{
+	const int w8 = width / 8, h8 = height / 8;
+	if (n_frames <= 0 || w8 <= 0 || h8 <= 0) return cudaSuccess;
+	const dim3 grid((w8 + 1 + 127) / 128, h8 + 1, (unsigned)std::min(n_frames, 4096));
+	DeriveEdgesKernel<<<grid, 128, 0, stream>>>(static_cast<const uint32_t *>(info), w8, h8, n_frames, vert_edges, hor_edges);
 	return cudaGetLastError();
 }
 
@@ -559,6 +610,7 @@ __global__ void GenericPadKernel(GenericBatch b, long long scratch_per_frame)
 }
 
 /* one thread per padded block, addressing pitch nbx * 8 as in cpu.h:169-172 / 469-471 */
+template <bool kEdgeQp>
 __global__ void GenericFilterKernel(GenericBatch b, long long scratch_per_frame)
 {
 	const int plane = blockIdx.y, frame = blockIdx.z;
@@ -582,7 +634,7 @@ __global__ void GenericFilterKernel(GenericBatch b, long long scratch_per_frame)
 	if (plane == 0) {
 		const u32 s4 = LumaBsOfBlock(bx, by, b.width >> 3, g.nbx, g.nby,
 			b.vert_bs + frame * b.vert_bs_stride, b.hor_bs + frame * b.hor_bs_stride);
-		LumaBlock(lo, hi, s4 & 0xff, (s4 >> 8) & 0xff, (s4 >> 16) & 0xff, s4 >> 24, fp);
+		LumaBlockT<kEdgeQp>(lo, hi, s4 & 0xff, (s4 >> 8) & 0xff, (s4 >> 16) & 0xff, s4 >> 24, fp);
 	} else {
 		const u32 s4 = ChromaBsOfBlock(bx, by, (unsigned)g.w, (unsigned)g.h, luma_nbx, luma_nby);
 		ChromaBlock(lo, hi, s4 & 0xff, (s4 >> 8) & 0xff, (s4 >> 16) & 0xff, s4 >> 24, fp);
@@ -623,7 +675,9 @@ cudaError_t LaunchGeneric(const GenericBatch &b, cudaStream_t stream)
 		part.hor_bs = b.hor_bs + (long long)f0 * b.hor_bs_stride;
 		const dim3 gpix((unsigned)std::min<long long>((ypix + 255) / 256, 1024), 3, (unsigned)part.n_frames);
 		GenericPadKernel<<<gpix, 256, 0, stream>>>(part, spf);
-		GenericFilterKernel<<<dim3((nblk + 127) / 128, 3, (unsigned)part.n_frames), 128, 0, stream>>>(part, spf);
+		const dim3 gblk((nblk + 127) / 128, 3, (unsigned)part.n_frames);
+		if (b.edge_qp) GenericFilterKernel<true><<<gblk, 128, 0, stream>>>(part, spf);
+		else GenericFilterKernel<false><<<gblk, 128, 0, stream>>>(part, spf);
 		GenericCropKernel<<<gpix, 256, 0, stream>>>(part, spf);
 	}
 	return cudaGetLastError();

@@ -78,7 +78,7 @@ void FinalizeTiledBatch(TiledBatch &b);
 cudaError_t PrepareTiled(int *ctas_per_sm);
 /* Persistent tiled kernel: one launch filters Y, U and V of every frame of the batch. */
 cudaError_t LaunchTiled(const TensorMaps3 &maps, const TiledBatch &b, void *sched, int sm_count, int ctas_per_sm,
-	cudaStream_t stream);
+	cudaStream_t stream, bool edge_qp = false);
 /* bytes of zero-initialised device memory the scheduler needs (one per context) */
 size_t TiledSchedBytes();
 
@@ -103,8 +103,16 @@ struct GenericBatch {
 	unsigned qp_value;
 	const unsigned char *vert_bs, *hor_bs;
 	long long vert_bs_stride, hor_bs_stride;
+	bool edge_qp;                                  /* vert_bs / hor_bs hold edge bytes (bs | qp << 2) */
 };
 size_t GenericScratchBytes(int width, int height);
 cudaError_t LaunchGeneric(const GenericBatch &b, cudaStream_t stream);
+
+/*
+ * Edge maps (bs | qp << 2 per entry, reference array layouts) from per-8x8-block decoder data:
+ * info = hdb_block_info[n_frames][H/8][W/8] (12 bytes each, 4-byte aligned) in device memory.
+ */
+cudaError_t LaunchDeriveEdges(const void *info, int width, int height, int n_frames,
+	unsigned char *vert_edges, unsigned char *hor_edges, cudaStream_t stream);
 
 } // namespace hdb

@@ -167,6 +167,63 @@ int hdb_deblock_surfaces_device(hdb_context *ctx, const hdb_surfaces *in, const 
 	unsigned n_frames, unsigned width, unsigned height, const unsigned *d_qp,
 	const unsigned char *d_vert_bs, const unsigned char *d_hor_bs, void *stream);
 
+/* ---- edge maps: per-edge QP and boundary-strength derivation ------------------------------ */
+/*
+ * The first of the components upstream of the filter.  The reference stubs both: one QP per frame
+ * (cpu.h:35-37, 136-137) and constant boundary strengths (cpu.h:91-99); its setter takes strengths
+ * only (cpu.h:120-132).  An EDGE BYTE carries both for one 8-sample edge:
+ *     e = bs | qp << 2          bs 0..3 (0 = off, luma filters when > 0 as cpu.h:164), qp 0..51
+ * in the reference's own two array layouts (vert[(H/8)][W/8 + 1], hor[(H/8 + 1)][W/8], sizes
+ * hdb_num_vert_bs / hdb_num_hor_bs, exact-size check as cpu.h:122-123).  With edge maps every luma
+ * edge segment takes beta / tc (cpu.h:1064-1072) from its own entry's qp; geometry, order, decisions
+ * and filters are unchanged, and with one QP in every entry the result equals hdb_deblock_frame's.
+ * The chroma planes follow the reference as before: the frame's qp and the constructor's chroma
+ * strengths (cpu.h:110-117), which are not caller-settable there either.
+ */
+#define HDB_EDGE(bs, qp) ((unsigned char)(((bs) & 3u) | ((qp) << 2)))
+
+int hdb_deblock_frame_edges(hdb_context *ctx, const unsigned char *yuv_in, unsigned char *yuv_out,
+	unsigned width, unsigned height, unsigned qp,
+	const unsigned char *vert_edges, unsigned num_vert_edges,
+	const unsigned char *hor_edges, unsigned num_hor_edges, hdb_timing *timing);
+
+/* batch forms of the same: hdb_deblock_batch / hdb_deblock_batch_device with edge maps (required) */
+int hdb_deblock_batch_edges(hdb_context *ctx, const unsigned char *frames_in, unsigned char *frames_out,
+	unsigned n_frames, unsigned width, unsigned height, const unsigned *qp,
+	const unsigned char *vert_edges, const unsigned char *hor_edges, hdb_timing *timing);
+int hdb_deblock_batch_edges_device(hdb_context *ctx, const void *d_frames_in, void *d_frames_out,
+	unsigned n_frames, unsigned width, unsigned height, const unsigned *d_qp,
+	const unsigned char *d_vert_edges, const unsigned char *d_hor_edges, void *stream);
+
+/*
+ * What a decoder knows about one 8x8 luma block.  hdb_derive_edges turns info[n_frames][H/8][W/8]
+ * into edge maps by the published H.265 rule (8.7.2.4), which the reference leaves out: an edge that
+ * is neither a transform nor a prediction edge is off; intra on either side -> 2; transform edge
+ * with coded coefficients on either side -> 1; different reference pictures or motion-vector count,
+ * or a motion-vector difference of >= 4 quarter samples in a component -> 1; else 0; the edge's qp
+ * is (QpP + QpQ + 1) >> 1, above 51 acting as 51; the four sides of the picture are off.  All-intra
+ * blocks with every edge a transform edge give the reference's "2 everywhere" on the inner edges.
+ */
+typedef struct hdb_block_info {
+	short mv[2][2];          /* [list][x, y], quarter samples */
+	signed char ref[2];      /* reference picture per list, < 0 = list unused */
+	unsigned char flags;     /* HDB_BLK_* */
+	unsigned char qp;        /* QpY */
+} hdb_block_info;            /* 12 bytes */
+#define HDB_BLK_INTRA   1u   /* intra-predicted */
+#define HDB_BLK_CBF     2u   /* the transform block covering it has non-zero coefficients */
+#define HDB_BLK_TU_LEFT 4u   /* its left edge is a transform-block edge */
+#define HDB_BLK_TU_TOP  8u
+#define HDB_BLK_PU_LEFT 16u  /* its left edge is a prediction-block edge */
+#define HDB_BLK_PU_TOP  32u
+
+/* device pointers; asynchronous on `stream`; the maps of frame f start at + f * hdb_num_*_bs */
+int hdb_derive_edges_device(hdb_context *ctx, const hdb_block_info *d_info, unsigned n_frames,
+	unsigned width, unsigned height, unsigned char *d_vert_edges, unsigned char *d_hor_edges, void *stream);
+/* host pointers (runs on the GPU all the same: copy in, kernel, copy out) */
+int hdb_derive_edges(hdb_context *ctx, const hdb_block_info *info, unsigned n_frames,
+	unsigned width, unsigned height, unsigned char *vert_edges, unsigned char *hor_edges);
+
 /* number of filter-kernel launches made through ctx since creation */
 unsigned long long hdb_kernel_launch_count(const hdb_context *ctx);
 

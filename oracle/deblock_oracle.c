@@ -161,7 +161,7 @@ static unsigned bs_at(const uint8_t *bs, unsigned n, unsigned idx)
  */
 static void filter_plane(uint8_t *pl, int nbx, int nby, ptrdiff_t pitch, unsigned bw,
 	int lim_x, int lim_y, const uint8_t *vbs, unsigned nv, const uint8_t *hbs, unsigned nh,
-	int beta, int tc, int chroma)
+	int beta, int tc, int chroma, int edges)
 {
 	int bx, by;
 	for (bx = 0; bx < nbx; bx++) {
@@ -184,15 +184,19 @@ static void filter_plane(uint8_t *pl, int nbx, int nby, ptrdiff_t pitch, unsigne
 			sg[3].pb = b + 3 * pitch + 4; sg[3].qb = b + 4 * pitch; sg[3].ts = pitch; sg[3].ls = 1;
 			for (e = 0; e < 4; e++) {
 				if (chroma) { if (bs[e] == 2) chroma_segment(&sg[e], tc); } /* cpu.h:463 */
+				else if (edges) {
+					/* edge byte = bs | qp << 2: the segment's own beta / tc (deblock_oracle.h) */
+					if ((bs[e] & 3u) > 0) luma_segment(&sg[e], hdbo_beta(bs[e] >> 2), hdbo_tc(bs[e] >> 2));
+				}
 				else { if (bs[e] > 0) luma_segment(&sg[e], beta, tc); }     /* cpu.h:164 */
 			}
 		}
 	}
 }
 
-int hdbo_deblock_frame(const uint8_t *in, uint8_t *out, unsigned width, unsigned height,
+static int deblock_frame(const uint8_t *in, uint8_t *out, unsigned width, unsigned height,
 	unsigned qp, const uint8_t *vert_bs, unsigned num_vert_bs,
-	const uint8_t *hor_bs, unsigned num_hor_bs)
+	const uint8_t *hor_bs, unsigned num_hor_bs, int edges)
 {
 	unsigned cw = width / 2, ch = height / 2;                    /* cpu.h:59-60 */
 	unsigned nw = width + S, nh = height + S;                    /* cpu.h:55-56 */
@@ -225,7 +229,7 @@ int hdbo_deblock_frame(const uint8_t *in, uint8_t *out, unsigned width, unsigned
 	for (r = 0; r < height; r++)
 		memcpy(Y + (size_t)(r + S / 2) * nw + S / 2, in + (size_t)r * width, width);
 	filter_plane(Y, nbx, nby, (ptrdiff_t)nbx * S, width / S, nbx, nby,
-		vbs, nV, hbs, nH, beta, tc, 0);
+		vbs, nV, hbs, nH, beta, tc, 0, edges);
 	for (r = 0; r < height; r++)                                 /* cpu.h:1000-1004 */
 		memcpy(out + (size_t)r * width, Y + (size_t)(r + S / 2) * nw + S / 2, width);
 
@@ -239,12 +243,90 @@ int hdbo_deblock_frame(const uint8_t *in, uint8_t *out, unsigned width, unsigned
 		/* addressing pitch is cnbx*8 (cpu.h:469-471), "last block" limits are the
 		 * luma counts (cpu.h:515, 645) */
 		filter_plane(C, cnbx, cnby, (ptrdiff_t)cnbx * S, cw / S, nbx, nby,
-			cvbs, ncV, chbs, ncH, beta, tc, 1);
+			cvbs, ncV, chbs, ncH, beta, tc, 1, 0);
 		for (r = 0; r < ch; r++)
 			memcpy(dst + (size_t)r * cw, C + (size_t)(r + S / 2) * ncw + S / 2, cw);
 	}
 	free(Y); free(C); free(vbs); free(hbs); free(cvbs); free(chbs);
 	return HDBO_OK;
+}
+
+int hdbo_deblock_frame(const uint8_t *in, uint8_t *out, unsigned width, unsigned height,
+	unsigned qp, const uint8_t *vert_bs, unsigned num_vert_bs,
+	const uint8_t *hor_bs, unsigned num_hor_bs)
+{
+	return deblock_frame(in, out, width, height, qp, vert_bs, num_vert_bs, hor_bs, num_hor_bs, 0);
+}
+
+/* cpu.h unchanged except that a luma segment takes beta / tc from its own edge byte */
+int hdbo_deblock_frame_edges(const uint8_t *in, uint8_t *out, unsigned width, unsigned height,
+	unsigned qp, const uint8_t *vert_edges, unsigned num_vert, const uint8_t *hor_edges, unsigned num_hor)
+{
+	if (!vert_edges || !hor_edges) return HDBO_ERR_BS_SIZE;
+	return deblock_frame(in, out, width, height, qp, vert_edges, num_vert, hor_edges, num_hor, 1);
+}
+
+/* ------------------------------------------------------------------ */
+/* boundary-strength and edge-QP derivation (H.265 8.7.2.4; no reference counterpart) */
+/* ------------------------------------------------------------------ */
+static int mv_far(const int16_t *a, const int16_t *b)
+{
+	return iabs((int)a[0] - (int)b[0]) >= 4 || iabs((int)a[1] - (int)b[1]) >= 4;
+}
+
+static unsigned derive_bs(const hdbo_block_info *p, const hdbo_block_info *q, int tu_edge, int pu_edge)
+{
+	int np, nq;
+	if (!tu_edge && !pu_edge) return 0;
+	if ((p->flags | q->flags) & HDBO_BLK_INTRA) return 2;
+	if (tu_edge && ((p->flags | q->flags) & HDBO_BLK_CBF)) return 1;
+	np = (p->ref[0] >= 0) + (p->ref[1] >= 0);
+	nq = (q->ref[0] >= 0) + (q->ref[1] >= 0);
+	if (np != nq) return 1;
+	if (np == 1) {
+		int a = p->ref[0] >= 0 ? 0 : 1, b = q->ref[0] >= 0 ? 0 : 1;
+		if (p->ref[a] != q->ref[b]) return 1;
+		return (unsigned)mv_far(p->mv[a], q->mv[b]);
+	}
+	if (np == 2) {
+		if (!((p->ref[0] == q->ref[0] && p->ref[1] == q->ref[1]) || (p->ref[0] == q->ref[1] && p->ref[1] == q->ref[0])))
+			return 1;
+		if (p->ref[0] != p->ref[1]) {
+			if (p->ref[0] == q->ref[0]) return (unsigned)(mv_far(p->mv[0], q->mv[0]) || mv_far(p->mv[1], q->mv[1]));
+			return (unsigned)(mv_far(p->mv[0], q->mv[1]) || mv_far(p->mv[1], q->mv[0]));
+		}
+		return (unsigned)((mv_far(p->mv[0], q->mv[0]) || mv_far(p->mv[1], q->mv[1]))
+			&& (mv_far(p->mv[0], q->mv[1]) || mv_far(p->mv[1], q->mv[0])));
+	}
+	return 0;
+}
+
+static uint8_t derive_edge(const hdbo_block_info *p, const hdbo_block_info *q, int tu_edge, int pu_edge)
+{
+	unsigned qp = ((unsigned)p->qp + q->qp + 1) >> 1;
+	if (qp > 51) qp = 51;
+	return HDBO_EDGE(derive_bs(p, q, tu_edge, pu_edge), qp);
+}
+
+void hdbo_derive_edges(const hdbo_block_info *info, unsigned width, unsigned height,
+	uint8_t *vert_edges, uint8_t *hor_edges)
+{
+	unsigned w8 = width / S, h8 = height / S, r, x;
+	/* vertical edges: [h8 rows][w8 + 1 edges] (cpu.h:86, 88); edge 0 and edge w8 are the picture's
+	 * sides, which H.265 does not filter */
+	for (r = 0; r < h8; r++)
+		for (x = 0; x <= w8; x++) {
+			const hdbo_block_info *q = info + (size_t)r * w8 + x;
+			vert_edges[(size_t)r * (w8 + 1) + x] = (x == 0 || x == w8) ? 0
+				: derive_edge(q - 1, q, q->flags & HDBO_BLK_TU_LEFT, q->flags & HDBO_BLK_PU_LEFT);
+		}
+	/* horizontal edges: [h8 + 1 edge rows][w8] (cpu.h:87, 89) */
+	for (r = 0; r <= h8; r++)
+		for (x = 0; x < w8; x++) {
+			const hdbo_block_info *q = info + (size_t)r * w8 + x;
+			hor_edges[(size_t)r * w8 + x] = (r == 0 || r == h8) ? 0
+				: derive_edge(q - w8, q, q->flags & HDBO_BLK_TU_TOP, q->flags & HDBO_BLK_PU_TOP);
+		}
 }
 
 int hdbo_deblock_batch(const uint8_t *in, uint8_t *out, unsigned n, unsigned width,

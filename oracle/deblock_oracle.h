@@ -65,6 +65,58 @@ int hdbo_deblock_frame(const uint8_t *in, uint8_t *out, unsigned width, unsigned
 int hdbo_deblock_batch(const uint8_t *in, uint8_t *out, unsigned n, unsigned width,
 	unsigned height, const unsigned *qp, const uint8_t *vert_bs, const uint8_t *hor_bs);
 
+/* ---------------------------------------------------------------------------
+ * Edge maps: SURVEY.md section 8(f) rank 1 (per-block QP and boundary-strength
+ * derivation upstream of the filter).  The reference stubs both: one QP per
+ * frame (cpu.h:35-37, 136-137) and constant strengths (cpu.h:91-99).
+ *
+ * An edge byte is  e = bs | qp << 2  (bs 0..3, qp 0..51), stored in the
+ * reference's own luma array layouts (cpu.h:86-89).  The luma filter of an
+ * edge segment then takes beta / tc from that entry's qp instead of the frame
+ * QP; everything else (geometry, order, decisions, filters, chroma with the
+ * frame QP and the constructor's chroma strengths) is cpu.h unchanged.
+ *
+ * Parity status of hdbo_deblock_frame_edges: PINNED through the unmodified
+ * reference.  tests/test_edges.py checks it (a) with one QP in every entry
+ * against the reference itself, (b) with arbitrary per-entry QPs against a
+ * chain of reference runs over the luma plane, each at one QP with only that
+ * QP's edges enabled (oracle_py.ref_compose_edges: vertical edges by QP, then
+ * horizontal edges column by column, which reproduces each block's segment
+ * order exactly; maps with the left and bottom picture edges off, since plane
+ * padding written by one run is not seen by the next), and (c) against golden hashes of such chains
+ * (tests/golden/edges.json, made by oracle/make_golden_edges.py).
+ *
+ * Parity status of hdbo_derive_edges: UNPINNED against the reference -- it has
+ * no counterpart there.  It restates the published H.265 rule (8.7.2.4: intra
+ * -> 2; transform edge with coded coefficients -> 1; different reference
+ * pictures / motion-vector count, or a motion-vector difference of >= 4
+ * quarter samples -> 1; else 0; QP of an edge = (QpP + QpQ + 1) >> 1) and is
+ * anchored only on the cases the reference does define: all-intra input gives
+ * the reference's "every inner edge 2" at one QP.
+ */
+#define HDBO_EDGE(bs, qp) ((uint8_t)(((bs) & 3u) | ((qp) << 2)))
+
+int hdbo_deblock_frame_edges(const uint8_t *in, uint8_t *out, unsigned width, unsigned height,
+	unsigned qp, const uint8_t *vert_edges, unsigned num_vert, const uint8_t *hor_edges, unsigned num_hor);
+
+/* what a decoder knows about one 8x8 luma block (12 bytes) */
+typedef struct hdbo_block_info {
+	int16_t mv[2][2];   /* [list][x, y] in quarter samples */
+	int8_t ref[2];      /* reference picture id per list, < 0 = list unused */
+	uint8_t flags;      /* HDBO_BLK_* */
+	uint8_t qp;         /* QpY of the block */
+} hdbo_block_info;
+#define HDBO_BLK_INTRA   1u   /* intra-predicted */
+#define HDBO_BLK_CBF     2u   /* its transform block has non-zero coefficients */
+#define HDBO_BLK_TU_LEFT 4u   /* its left edge is a transform-block edge */
+#define HDBO_BLK_TU_TOP  8u
+#define HDBO_BLK_PU_LEFT 16u  /* its left edge is a prediction-block edge */
+#define HDBO_BLK_PU_TOP  32u
+
+/* info[(height/8)][(width/8)] -> vert_edges[hdbo_num_vert_bs], hor_edges[hdbo_num_hor_bs] */
+void hdbo_derive_edges(const hdbo_block_info *info, unsigned width, unsigned height,
+	uint8_t *vert_edges, uint8_t *hor_edges);
+
 #ifdef __cplusplus
 }
 #endif

@@ -49,6 +49,10 @@ def _load_port():
                                        _u8p, C.c_uint, _u8p, C.c_uint]
     lib.hdbo_deblock_batch.argtypes = [_u8p, _u8p, C.c_uint, C.c_uint, C.c_uint,
                                        _u32p, _u8p, _u8p]
+    lib.hdbo_deblock_frame_edges.argtypes = [_u8p, _u8p, C.c_uint, C.c_uint, C.c_uint,
+                                             _u8p, C.c_uint, _u8p, C.c_uint]
+    lib.hdbo_derive_edges.argtypes = [C.c_void_p, C.c_uint, C.c_uint, _u8p, _u8p]
+    lib.hdbo_derive_edges.restype = None
     return lib
 
 
@@ -172,3 +176,83 @@ def ref_deblock_batch(frames, w, h, qps, vert_bs=None, hor_bs=None, outer_thread
     if rc:
         raise RuntimeError("reference batch failed rc=%d" % rc)
     return out, sec.value
+
+
+# ---------------------------------------------------------------------------
+# edge maps: edge byte = bs | qp << 2
+# ---------------------------------------------------------------------------
+BLOCK_INFO = np.dtype([("mv", np.int16, (2, 2)), ("ref", np.int8, (2,)), ("flags", np.uint8), ("qp", np.uint8)])
+assert BLOCK_INFO.itemsize == 12
+BLK_INTRA, BLK_CBF, BLK_TU_LEFT, BLK_TU_TOP, BLK_PU_LEFT, BLK_PU_TOP = 1, 2, 4, 8, 16, 32
+
+
+def edge_bytes(bs, qp):
+    return ((np.asarray(bs, np.uint32) & 3) | (np.asarray(qp, np.uint32) << 2)).astype(np.uint8)
+
+
+def deblock_frame_edges(frame, w, h, qp, vert_edges, hor_edges):
+    """Restatement with per-edge QP for luma (deblock_oracle.h); chroma as the reference (frame qp)."""
+    frame = _check_frame(frame, w, h)
+    out = np.empty_like(frame)
+    v = np.ascontiguousarray(vert_edges, np.uint8)
+    hh = np.ascontiguousarray(hor_edges, np.uint8)
+    rc = port().hdbo_deblock_frame_edges(_ptr(frame), _ptr(out), w, h, qp, _ptr(v), v.size, _ptr(hh), hh.size)
+    if rc:
+        raise OracleError({1: "Width and height of image must be multiplier of sample block size",
+                           2: "Incorrect size of input boundary strenght array"}[rc])
+    return out
+
+
+def derive_edges(info, w, h):
+    """info: BLOCK_INFO[h/8, w/8] -> (vert_edges, hor_edges) by the H.265 rule (deblock_oracle.h)."""
+    info = np.ascontiguousarray(info, BLOCK_INFO)
+    assert info.size == (w // 8) * (h // 8)
+    v = np.empty(num_vert_bs(w, h), np.uint8)
+    hh = np.empty(num_hor_bs(w, h), np.uint8)
+    port().hdbo_derive_edges(info.ctypes.data, w, h, _ptr(v), _ptr(hh))
+    return v, hh
+
+
+def ref_compose_edges(frame, w, h, qp, vert_edges, hor_edges):
+    """Per-edge QP through the UNMODIFIED reference, as a chain of reference runs over the luma plane,
+    each with one QP and with only that QP's edges enabled (all other strengths 0):
+      1. one run per distinct QP of the vertical map (vertical segments never touch each other's
+         samples, so their order does not matter);
+      2. horizontal entries column by column in increasing order, one run per distinct QP of the
+         column: entry (by, c) is the right-hand segment of block c and the left-hand segment of
+         block c + 1 (cpu.h:287-291, 368-372), so increasing columns reproduce each block's own
+         order left segment -> right segment (cpu.h:287-446), and within one column all segments
+         lie in different blocks.
+    Blocks are independent and every block runs its vertical segments first (cpu.h:158-284), so the
+    chain equals the per-edge-QP filter exactly -- provided no segment reads plane padding an earlier
+    segment of its block wrote, because padding does not survive from one run to the next.  That
+    happens in two places only: the left picture edge (vert[:, 0]; its p samples are padding that
+    the right-hand horizontal segment of block column 0 reads as q) and the bottom picture edge
+    (hor[H/8, :]).  Maps with those two off -- the H.265 convention, and what derive_edges produces --
+    are pinned exactly; for the others the restatement stands on its uniform-QP pin, which covers the
+    padding paths.  The chroma planes come from one run at the frame QP."""
+    frame = np.ascontiguousarray(frame, np.uint8).reshape(-1)
+    v = np.ascontiguousarray(vert_edges, np.uint8)
+    hh = np.ascontiguousarray(hor_edges, np.uint8)
+    ysz = w * h
+    chroma, _ = ref_deblock_frame(frame, w, h, qp)
+    cur = frame.copy()
+    zero_v, zero_h = np.zeros_like(v), np.zeros_like(hh)
+
+    def run(q, mv, mh):
+        out, _ = ref_deblock_frame(cur, w, h, int(q), mv, mh)
+        cur[:ysz] = out[:ysz]
+
+    on = (v & 3) > 0
+    for q in np.unique(v[on] >> 2):
+        run(q, np.where(on & ((v >> 2) == q), v & 3, 0).astype(np.uint8), zero_h)
+    h2 = hh.reshape(h // 8 + 1, w // 8)
+    for c in range(w // 8):
+        col = h2[:, c]
+        on = (col & 3) > 0
+        for q in np.unique(col[on] >> 2):
+            m = np.zeros_like(h2)
+            m[:, c] = np.where(on & ((col >> 2) == q), col & 3, 0)
+            run(q, zero_v, m.reshape(-1))
+    cur[ysz:] = chroma[ysz:]
+    return cur

@@ -19,7 +19,7 @@ using namespace hdb;
 
 static void FilterPlane(uint8_t *pl, int nbx, int nby, size_t pitch, bool chroma,
 	unsigned w, unsigned h, int luma_nbx, int luma_nby,
-	const uint8_t *vbs, const uint8_t *hbs, const FilterParams &fp)
+	const uint8_t *vbs, const uint8_t *hbs, const FilterParams &fp, bool edges = false)
 {
 	for (int by = 0; by < nby; by++)
 		for (int bx = 0; bx < nbx; bx++) {
@@ -32,6 +32,7 @@ static void FilterPlane(uint8_t *pl, int nbx, int nby, size_t pitch, bool chroma
 			u32 bs = chroma ? ChromaBsOfBlock(bx, by, w, h, luma_nbx, luma_nby)
 				: LumaBsOfBlock(bx, by, (int)(w / 8), nbx, nby, vbs, hbs);
 			if (chroma) ChromaBlock(lo, hi, bs & 0xff, (bs >> 8) & 0xff, (bs >> 16) & 0xff, bs >> 24, fp);
+			else if (edges) LumaBlockT<true>(lo, hi, bs & 0xff, (bs >> 8) & 0xff, (bs >> 16) & 0xff, bs >> 24, fp);
 			else LumaBlock(lo, hi, bs & 0xff, (bs >> 8) & 0xff, (bs >> 16) & 0xff, bs >> 24, fp);
 			for (int r = 0; r < 8; r++) {
 				memcpy(b + r * pitch, &lo[r], 4);
@@ -43,8 +44,8 @@ static void FilterPlane(uint8_t *pl, int nbx, int nby, size_t pitch, bool chroma
 extern "C" int emu_beta(unsigned qp) { return BetaOf(qp); }
 extern "C" int emu_tc(unsigned qp) { return TcOf(qp); }
 
-extern "C" int emu_deblock_frame(const uint8_t *in, uint8_t *out, unsigned w, unsigned h, unsigned qp,
-	const uint8_t *vbs, const uint8_t *hbs)
+static int DeblockFrame(const uint8_t *in, uint8_t *out, unsigned w, unsigned h, unsigned qp,
+	const uint8_t *vbs, const uint8_t *hbs, bool edges)
 {
 	if (w % 8 || h % 8) return 1;
 	unsigned cw = w / 2, ch = h / 2;
@@ -61,7 +62,7 @@ extern "C" int emu_deblock_frame(const uint8_t *in, uint8_t *out, unsigned w, un
 	}
 	std::vector<uint8_t> Y((size_t)nw * nh, 0), C((size_t)ncw * nch);
 	for (unsigned r = 0; r < h; r++) memcpy(&Y[(size_t)(r + 4) * nw + 4], in + (size_t)r * w, w);
-	FilterPlane(Y.data(), nbx, nby, (size_t)nbx * 8, false, w, h, nbx, nby, vbs, hbs, fp);
+	FilterPlane(Y.data(), nbx, nby, (size_t)nbx * 8, false, w, h, nbx, nby, vbs, hbs, fp, edges);
 	for (unsigned r = 0; r < h; r++) memcpy(out + (size_t)r * w, &Y[(size_t)(r + 4) * nw + 4], w);
 	for (int p = 0; p < 2; p++) {
 		const uint8_t *src = in + (size_t)w * h + (size_t)p * cw * ch;
@@ -72,4 +73,38 @@ extern "C" int emu_deblock_frame(const uint8_t *in, uint8_t *out, unsigned w, un
 		for (unsigned r = 0; r < ch; r++) memcpy(dst + (size_t)r * cw, &C[(size_t)(r + 4) * ncw + 4], cw);
 	}
 	return 0;
+}
+
+extern "C" int emu_deblock_frame(const uint8_t *in, uint8_t *out, unsigned w, unsigned h, unsigned qp,
+	const uint8_t *vbs, const uint8_t *hbs)
+{
+	return DeblockFrame(in, out, w, h, qp, vbs, hbs, false);
+}
+
+/* edge bytes (bs | qp << 2) instead of strengths: LumaBlockT<true> */
+extern "C" int emu_deblock_frame_edges(const uint8_t *in, uint8_t *out, unsigned w, unsigned h, unsigned qp,
+	const uint8_t *vert_edges, const uint8_t *hor_edges)
+{
+	if (!vert_edges || !hor_edges) return 2;
+	return DeblockFrame(in, out, w, h, qp, vert_edges, hor_edges, true);
+}
+
+/* DeriveEdge over one frame, indexed exactly as DeriveEdgesKernel does */
+extern "C" void emu_derive_edges(const uint32_t *info, unsigned w, unsigned h, uint8_t *vert, uint8_t *hor)
+{
+	const unsigned w8 = w / 8, h8 = h / 8;
+	auto blk = [&](unsigned r, unsigned x) { const uint32_t *p = info + 3 * ((size_t)r * w8 + x); return BlockWords{ p[0], p[1], p[2] }; };
+	for (unsigned r = 0; r <= h8; r++)
+		for (unsigned x = 0; x <= w8; x++) {
+			if (r < h8) {
+				uint8_t e = 0;
+				if (x > 0 && x < w8) { const BlockWords q = blk(r, x); e = (uint8_t)DeriveEdge(blk(r, x - 1), q, (q.meta >> 16) & kBlkTuLeft, (q.meta >> 16) & kBlkPuLeft); }
+				vert[(size_t)r * (w8 + 1) + x] = e;
+			}
+			if (x < w8) {
+				uint8_t e = 0;
+				if (r > 0 && r < h8) { const BlockWords q = blk(r, x); e = (uint8_t)DeriveEdge(blk(r - 1, x), q, (q.meta >> 16) & kBlkTuTop, (q.meta >> 16) & kBlkPuTop); }
+				hor[(size_t)r * w8 + x] = e;
+			}
+		}
 }

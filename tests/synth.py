@@ -90,3 +90,97 @@ def make_batch(seed, n, w, h, kind="blocky", bs_kind="uniform012", qp_lo=18, qp_
         qps[6] = 60
     bs = [make_bs(rng, w, h, bs_kind) for _ in range(n)]
     return frames, qps, np.stack([b[0] for b in bs]), np.stack([b[1] for b in bs])
+
+
+# ---------------------------------------------------------------------------------------------
+# edge maps (edge byte = bs | qp << 2) and the per-8x8-block decoder data they are derived from
+# ---------------------------------------------------------------------------------------------
+BLOCK_INFO = np.dtype([("mv", np.int16, (2, 2)), ("ref", np.int8, (2,)), ("flags", np.uint8), ("qp", np.uint8)])
+BLK_INTRA, BLK_CBF, BLK_TU_LEFT, BLK_TU_TOP, BLK_PU_LEFT, BLK_PU_TOP = 1, 2, 4, 8, 16, 32
+
+
+def edge_bytes(bs, qp):
+    return ((np.asarray(bs, np.uint32) & 3) | (np.asarray(qp, np.uint32) << 2)).astype(np.uint8)
+
+
+def make_edge_maps(rng, w, h, kind="random", picture_edges=False):
+    """(vert_edges[nV], hor_edges[nH]).  kind: "random" (bs U{0..2}, qp U{14..51} per entry),
+    "wide" (bs U{0..3}, qp U{0..63}: the six qp bits past 51 act as 51), "smooth" (qp varies slowly, as
+    in a rate-controlled picture), "uniform" (one qp everywhere).  Unless picture_edges, the left
+    and bottom picture edges are off (the H.265 convention; see oracle_py.ref_compose_edges)."""
+    h8, w8 = h // 8, w // 8
+    shape_v, shape_h = (h8, w8 + 1), (h8 + 1, w8)
+    if kind == "random":
+        bs = [rng.integers(0, 3, s) for s in (shape_v, shape_h)]
+        qp = [rng.integers(14, 52, s) for s in (shape_v, shape_h)]
+    elif kind == "wide":
+        bs = [rng.integers(0, 4, s) for s in (shape_v, shape_h)]
+        qp = [rng.integers(0, 64, s) for s in (shape_v, shape_h)]
+    elif kind == "smooth":
+        bs = [rng.integers(0, 3, s) for s in (shape_v, shape_h)]
+        base = rng.integers(22, 46)
+        qp = []
+        for s in (shape_v, shape_h):
+            yy, xx = np.mgrid[0:s[0], 0:s[1]]
+            qp.append(np.clip(base + np.round(6 * np.sin(xx / 9.0) + 5 * np.cos(yy / 7.0)).astype(np.int64)
+                              + rng.integers(-1, 2, s), 0, 51))
+    elif kind == "uniform":
+        q = int(rng.integers(18, 52))
+        bs = [rng.integers(0, 3, s) for s in (shape_v, shape_h)]
+        qp = [np.full(s, q) for s in (shape_v, shape_h)]
+    else:
+        raise ValueError(kind)
+    v, hh = edge_bytes(bs[0], qp[0]), edge_bytes(bs[1], qp[1])
+    if not picture_edges:
+        v[:, 0] &= 0xfc
+        hh[-1, :] &= 0xfc
+    return v.reshape(-1), hh.reshape(-1)
+
+
+def make_block_info(rng, w, h, kind="cu16"):
+    """BLOCK_INFO[h/8, w/8].  "intra": every block intra, every edge a transform edge; "random":
+    every field random per block; "cu16": 16x16 coding units with their own motion, QP and coded
+    flag, a fifth of them intra, a third bi-predicted, transform / prediction edges on the CU grid
+    plus some inner transform splits -- neighbours that share motion give strength 0."""
+    h8, w8 = h // 8, w // 8
+    info = np.zeros((h8, w8), BLOCK_INFO)
+    if kind == "intra":
+        info["flags"] = BLK_INTRA | BLK_TU_LEFT | BLK_TU_TOP | BLK_PU_LEFT | BLK_PU_TOP
+        info["ref"] = -1
+        info["qp"] = rng.integers(20, 45)
+    elif kind == "random":
+        info["mv"] = rng.integers(-9, 10, info["mv"].shape)
+        info["ref"] = rng.integers(-1, 3, info["ref"].shape)
+        info["flags"] = rng.integers(0, 64, info.shape) & np.where(rng.random(info.shape) < 0.15, 63, 62)
+        info["qp"] = rng.integers(0, 70, info.shape)
+    elif kind == "cu16":
+        ch, cw = (h8 + 1) // 2, (w8 + 1) // 2
+        up = lambda a: np.kron(a, np.ones((2, 2), a.dtype))[:h8, :w8]
+        # motion drawn from a few candidates so that neighbouring units often agree
+        cand = rng.integers(-24, 25, (6, 2, 2))
+        pick = rng.integers(0, 6, (ch, cw))
+        mv = cand[pick] + (rng.random((ch, cw, 1, 1)) < 0.3) * rng.integers(-5, 6, (ch, cw, 2, 2))
+        for l in range(2):
+            for c in range(2):
+                info["mv"][:, :, l, c] = up(mv[:, :, l, c])
+        ref0 = rng.integers(0, 2, (ch, cw))
+        bi = rng.random((ch, cw)) < 0.33
+        ref1 = np.where(bi, rng.integers(0, 3, (ch, cw)), -1)
+        only_l1 = (~bi) & (rng.random((ch, cw)) < 0.2)
+        ref1 = np.where(only_l1, ref0, ref1)
+        ref0 = np.where(only_l1, -1, ref0)
+        info["ref"][:, :, 0] = up(ref0.astype(np.int64))
+        info["ref"][:, :, 1] = up(ref1.astype(np.int64))
+        intra = up((rng.random((ch, cw)) < 0.2).astype(np.int64)).astype(bool)
+        cbf = up((rng.random((ch, cw)) < 0.5).astype(np.int64)).astype(bool)
+        info["qp"] = up(np.clip(rng.integers(24, 40) + rng.integers(-6, 7, (ch, cw)), 0, 51))
+        yy, xx = np.mgrid[0:h8, 0:w8]
+        split = up((rng.random((ch, cw)) < 0.25).astype(np.int64)).astype(bool)   # units split into four 8x8 transforms
+        flags = intra * BLK_INTRA + cbf * BLK_CBF
+        flags = flags + ((xx % 2 == 0) | split) * BLK_TU_LEFT + ((yy % 2 == 0) | split) * BLK_TU_TOP
+        flags = flags + (xx % 2 == 0) * BLK_PU_LEFT + (yy % 2 == 0) * BLK_PU_TOP
+        info["flags"] = flags
+        info["ref"][intra] = -1
+    else:
+        raise ValueError(kind)
+    return info
