@@ -10,7 +10,10 @@ capability 10.x device, every filtering call raises.
 from .binding import (  # noqa: F401
     Deblocker,
     DeblockError,
+    FLAG_EDGE_MAPS,
+    FLAG_NV12,
     MultiDeblocker,
+    Nv12Surfaces,
     Surfaces,
     Timing,
     build_library,

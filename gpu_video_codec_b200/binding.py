@@ -44,6 +44,15 @@ class Surfaces(C.Structure):
                 ("frame_stride_y", C.c_size_t), ("frame_stride_c", C.c_size_t)]
 
 
+class Nv12Surfaces(C.Structure):
+    """hdb_nv12_surfaces: device Y plane and interleaved UV plane with row pitches."""
+    _fields_ = [("y", C.c_void_p), ("uv", C.c_void_p), ("pitch_y", C.c_size_t), ("pitch_uv", C.c_size_t),
+                ("frame_stride_y", C.c_size_t), ("frame_stride_uv", C.c_size_t)]
+
+
+FLAG_EDGE_MAPS, FLAG_NV12 = 1, 2
+
+
 class DeviceInfo(C.Structure):
     _fields_ = [("name", C.c_char * 256), ("cc_major", C.c_int), ("cc_minor", C.c_int),
                 ("sm_count", C.c_int), ("warp_size", C.c_int), ("max_threads_per_block", C.c_int),
@@ -120,6 +129,10 @@ def load_library():
     lib.hdb_deblock_batch_edges_device.argtypes = [vp] + batch_args + [vp]
     lib.hdb_derive_edges_device.argtypes = [vp, vp, C.c_uint, C.c_uint, C.c_uint, vp, vp, vp]
     lib.hdb_derive_edges.argtypes = [vp, vp, C.c_uint, C.c_uint, C.c_uint, vp, vp]
+    lib.hdb_deblock_batch_ex.argtypes = [vp] + batch_args + [C.c_uint, C.POINTER(Timing)]
+    lib.hdb_deblock_batch_device_ex.argtypes = [vp] + batch_args + [C.c_uint, vp]
+    lib.hdb_deblock_nv12_surfaces_device.argtypes = [vp, C.POINTER(Nv12Surfaces), C.POINTER(Nv12Surfaces), C.c_uint, C.c_uint,
+                                                     C.c_uint, vp, vp, vp, C.c_uint, vp]
     lib.hdb_kernel_launch_count.argtypes = [vp]
     lib.hdb_kernel_launch_count.restype = C.c_ulonglong
     lib.hdb_multi_create.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), C.c_int]
@@ -301,6 +314,28 @@ class Deblocker:
     def derive_edges_device(self, d_info, n_frames, width, height, d_vert_edges, d_hor_edges, stream=None):
         self._check(self._lib.hdb_derive_edges_device(self._ctx, _addr(d_info), n_frames, width, height,
                                                       _addr(d_vert_edges), _addr(d_hor_edges), stream))
+
+    # --- flagged general forms: FLAG_EDGE_MAPS, FLAG_NV12 ---
+    def deblock_batch_ex(self, frames, width, height, qps, vert=None, hor=None, flags=0, out=None, timing=None,
+                         n_frames=None):
+        n = n_frames if n_frames is not None else int(frames.shape[0])
+        if out is None:
+            out = np.empty_like(frames)
+        self._check(self._lib.hdb_deblock_batch_ex(self._ctx, _addr(frames), _addr(out), n, width, height,
+                                                   _addr(qps), _addr(vert), _addr(hor), flags,
+                                                   None if timing is None else C.byref(timing)))
+        return out
+
+    def deblock_batch_device_ex(self, d_in, d_out, n_frames, width, height, d_qp, d_vert=None, d_hor=None, flags=0,
+                                stream=None):
+        self._check(self._lib.hdb_deblock_batch_device_ex(self._ctx, _addr(d_in), _addr(d_out), n_frames, width, height,
+                                                          _addr(d_qp), _addr(d_vert), _addr(d_hor), flags, stream))
+
+    def deblock_nv12_surfaces_device(self, src, dst, n_frames, width, height, d_qp, d_vert=None, d_hor=None, flags=0,
+                                     stream=None):
+        self._check(self._lib.hdb_deblock_nv12_surfaces_device(self._ctx, C.byref(src), C.byref(dst), n_frames, width,
+                                                               height, _addr(d_qp), _addr(d_vert), _addr(d_hor), flags,
+                                                               stream))
 
     def deblock_surfaces_device(self, src, dst, n_frames, width, height, d_qp, d_vert_bs=None, d_hor_bs=None,
                                 stream=None):

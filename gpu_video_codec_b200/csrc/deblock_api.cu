@@ -80,7 +80,7 @@ static int CreateContext(hdb_context **out, int device)
 	bool ok = cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking) == cudaSuccess
 		&& cudaStreamCreateWithFlags(&ctx->s_k, cudaStreamNonBlocking) == cudaSuccess
 		&& cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking) == cudaSuccess
-		&& PrepareTiled(&ctx->tiled_ctas_per_sm) == cudaSuccess
+		&& PrepareTiled(ctx->tiled_ctas_per_sm) == cudaSuccess
 		&& cudaMalloc(&ctx->sched, TiledSchedBytes() * kSchedSlots) == cudaSuccess
 		&& cudaMemset(ctx->sched, 0, TiledSchedBytes() * kSchedSlots) == cudaSuccess;
 	if (!ok) {
@@ -173,6 +173,8 @@ int EnqueueFilter(hdb_context *ctx, const FrameView &view, const unsigned char *
 	if (!d_vbs || !d_hbs) { d_vbs = ss->def_vbs; d_hbs = ss->def_hbs; vbs_stride = hbs_stride = 0; }
 	const TiledConfig cfg = GetTiledConfig();
 
+	if (view.nv12 && !TiledPathUsable(w, h, d_in, d_out))
+		return Fail(ctx, HDB_ERR_DIMENSIONS, "NV12 frames need a width that is a multiple of 32 and 16-byte aligned buffers");
 	if (view.whole_frame && !TiledPathUsable(w, h, d_in, d_out)) {
 		/* generic path: explicit padded planes in scratch memory */
 		if (path) *path = 2;
@@ -216,6 +218,7 @@ int EnqueueFilter(hdb_context *ctx, const FrameView &view, const unsigned char *
 	b.vert_bs_stride = vbs_stride; b.hor_bs_stride = hbs_stride;
 	b.chroma_bs = ss->chroma_bs;
 	b.qp_value = qp_value;
+	b.nv12 = view.nv12 ? 1 : 0;
 	/* frames per launch bounded by the 31-bit item counter */
 	b.n_frames = 1;
 	FinalizeTiledBatch(b);
@@ -234,9 +237,10 @@ int EnqueueFilter(hdb_context *ctx, const FrameView &view, const unsigned char *
 		b.luma_buf_rows = view.luma_buf_rows; b.chroma_buf_rows = view.chroma_buf_rows;
 		const long long off_in[3] = { 0, view.u_offset, view.v_offset };
 		const long long off_out[3] = { 0, view.u_offset_out, view.v_offset_out };
-		const int pw[3] = { w, cw, cw };
+		const int pw[3] = { w, view.nv12 ? w : cw, cw };     /* bytes per row: the interleaved UV plane is as wide as luma */
 		const int ph[3] = { view.luma_buf_rows, view.chroma_buf_rows, view.chroma_buf_rows };
-		for (int p = 0; p < 3; p++) {
+		memset(&maps, 0, sizeof maps);
+		for (int p = 0; p < (view.nv12 ? 2 : 3); p++) {
 			const long long pfs = p ? cfs : fs;
 			if ((rc = EncodePlaneMap(ctx, &maps.in[p], d_in + off_in[p] + f0 * pfs, pw[p], ph[p], nf,
 					p ? view.chroma_pitch : view.luma_pitch, pfs, 8 * cfg.block_rows_per_item))) return rc;
@@ -251,9 +255,10 @@ int EnqueueFilter(hdb_context *ctx, const FrameView &view, const unsigned char *
 	return HDB_OK;
 }
 
-FrameView WholeFrameView(int w, int h)
+FrameView WholeFrameView(int w, int h, bool nv12)
 {
 	FrameView v{};
+	v.nv12 = nv12;
 	v.width = w; v.height = h; v.whole_frame = true;
 	v.luma_row0 = 0; v.luma_rows = (h + 8) / 8;
 	v.chroma_row0 = 0; v.chroma_rows = (h / 2 + 8) / 8;
@@ -261,7 +266,7 @@ FrameView WholeFrameView(int w, int h)
 	v.luma_y_org = -4; v.chroma_y_org = -4;
 	v.u_offset = (long long)w * h; v.v_offset = (long long)w * h + (long long)(w / 2) * (h / 2);
 	v.u_offset_out = v.u_offset; v.v_offset_out = v.v_offset;
-	v.luma_pitch = w; v.chroma_pitch = w / 2;
+	v.luma_pitch = w; v.chroma_pitch = nv12 ? w : w / 2;
 	v.frame_stride = v.chroma_frame_stride = (long long)w * h * 3 / 2;
 	return v;
 }
@@ -359,9 +364,10 @@ static int GetEvents(hdb_context *ctx, size_t n)
  * single slice runs on one stream.
  */
 int BatchHost(hdb_context *ctx, const unsigned char *in, unsigned char *out, unsigned n, unsigned w, unsigned h,
-	const unsigned *qp, const unsigned char *vbs, const unsigned char *hbs, hdb_timing *timing, bool edge_qp)
+	const unsigned *qp, const unsigned char *vbs, const unsigned char *hbs, hdb_timing *timing, unsigned flags)
 {
 	if (!ctx) return HDB_ERR_INVALID_ARG;
+	const bool edge_qp = (flags & HDB_FLAG_EDGE_MAPS) != 0, nv12 = (flags & HDB_FLAG_NV12) != 0;
 	std::lock_guard<std::mutex> lock(ctx->mu);
 	if (!in || !out || !qp || n == 0) return Fail(ctx, HDB_ERR_INVALID_ARG, "NULL buffer or empty batch");
 	if (edge_qp && (!vbs || !hbs)) return Fail(ctx, HDB_ERR_INVALID_ARG, "edge maps are required: there is no default for them");
@@ -381,7 +387,8 @@ int BatchHost(hdb_context *ctx, const unsigned char *in, unsigned char *out, uns
 		HDB_CUDA(ctx, cudaMalloc(&ctx->qp_dev, sizeof(unsigned) * n));
 		ctx->qp_cap = n;
 	}
-	const FrameView view = WholeFrameView((int)w, (int)h);
+	const FrameView view = WholeFrameView((int)w, (int)h, nv12);
+	if (nv12 && w % 32 != 0) return Fail(ctx, HDB_ERR_DIMENSIONS, "NV12 frames need a width that is a multiple of 32");
 
 	PinHostRange pin_in(in, fb * n), pin_out(out != in ? out : nullptr, fb * n);
 	PinHostRange pin_v(vbs, (size_t)nv * n), pin_h(hbs, (size_t)nh * n);
@@ -704,14 +711,14 @@ int hdb_deblock_frame_edges(hdb_context *ctx, const unsigned char *yuv_in, unsig
 	if (!vert_edges || !hor_edges) return Fail(ctx, HDB_ERR_INVALID_ARG, "edge maps are required: there is no default for them");
 	int rc = ValidateFrameArgs(ctx, width, height, vert_edges, num_vert_edges, hor_edges, num_hor_edges, true);
 	if (rc) return rc;
-	return BatchHost(ctx, yuv_in, yuv_out, 1, width, height, &qp, vert_edges, hor_edges, timing, true);
+	return BatchHost(ctx, yuv_in, yuv_out, 1, width, height, &qp, vert_edges, hor_edges, timing, HDB_FLAG_EDGE_MAPS);
 }
 
 int hdb_deblock_batch_edges(hdb_context *ctx, const unsigned char *frames_in, unsigned char *frames_out,
 	unsigned n_frames, unsigned width, unsigned height, const unsigned *qp,
 	const unsigned char *vert_edges, const unsigned char *hor_edges, hdb_timing *timing)
 {
-	return BatchHost(ctx, frames_in, frames_out, n_frames, width, height, qp, vert_edges, hor_edges, timing, true);
+	return BatchHost(ctx, frames_in, frames_out, n_frames, width, height, qp, vert_edges, hor_edges, timing, HDB_FLAG_EDGE_MAPS);
 }
 
 int hdb_deblock_batch_edges_device(hdb_context *ctx, const void *d_frames_in, void *d_frames_out,
@@ -779,6 +786,73 @@ int hdb_derive_edges(hdb_context *ctx, const hdb_block_info *info, unsigned n_fr
 	HDB_CUDA(ctx, cudaMemcpyAsync(hor_edges, d + off_h, nh, cudaMemcpyDeviceToHost, ctx->s_k));
 	HDB_CUDA(ctx, cudaStreamSynchronize(ctx->s_k));
 	return HDB_OK;
+}
+
+/* ---- NV12 and the flagged general forms ---- */
+
+int hdb_deblock_batch_ex(hdb_context *ctx, const unsigned char *frames_in, unsigned char *frames_out,
+	unsigned n_frames, unsigned width, unsigned height, const unsigned *qp,
+	const unsigned char *vert, const unsigned char *hor, unsigned flags, hdb_timing *timing)
+{
+	if (flags & ~(HDB_FLAG_EDGE_MAPS | HDB_FLAG_NV12)) return ctx ? Fail(ctx, HDB_ERR_INVALID_ARG, "unknown flag") : HDB_ERR_INVALID_ARG;
+	return BatchHost(ctx, frames_in, frames_out, n_frames, width, height, qp, vert, hor, timing, flags);
+}
+
+int hdb_deblock_batch_device_ex(hdb_context *ctx, const void *d_frames_in, void *d_frames_out,
+	unsigned n_frames, unsigned width, unsigned height, const unsigned *d_qp,
+	const unsigned char *d_vert, const unsigned char *d_hor, unsigned flags, void *stream)
+{
+	if (!ctx) return HDB_ERR_INVALID_ARG;
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	if (flags & ~(HDB_FLAG_EDGE_MAPS | HDB_FLAG_NV12)) return Fail(ctx, HDB_ERR_INVALID_ARG, "unknown flag");
+	if (!d_frames_in || !d_frames_out || !d_qp || n_frames == 0) return Fail(ctx, HDB_ERR_INVALID_ARG, "NULL buffer or empty batch");
+	int rc = ValidateFrameArgs(ctx, width, height, d_vert, 0, d_hor, 0, false);
+	if (rc) return rc;
+	DeviceGuard guard(ctx->device);
+	const FrameView view = WholeFrameView((int)width, (int)height, (flags & HDB_FLAG_NV12) != 0);
+	return EnqueueFilter(ctx, view, static_cast<const unsigned char *>(d_frames_in),
+		static_cast<unsigned char *>(d_frames_out), (int)n_frames, d_qp, 0,
+		d_vert, hdb_num_vert_bs(width, height), d_hor, hdb_num_hor_bs(width, height),
+		static_cast<cudaStream_t>(stream), nullptr, (flags & HDB_FLAG_EDGE_MAPS) != 0);
+}
+
+int hdb_deblock_nv12_surfaces_device(hdb_context *ctx, const hdb_nv12_surfaces *in, const hdb_nv12_surfaces *out,
+	unsigned n_frames, unsigned width, unsigned height, const unsigned *d_qp,
+	const unsigned char *d_vert, const unsigned char *d_hor, unsigned flags, void *stream)
+{
+	if (!ctx) return HDB_ERR_INVALID_ARG;
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	if (flags & ~HDB_FLAG_EDGE_MAPS) return Fail(ctx, HDB_ERR_INVALID_ARG, "unknown flag");
+	if (!in || !out || !d_qp || n_frames == 0 || !in->y || !in->uv || !out->y || !out->uv)
+		return Fail(ctx, HDB_ERR_INVALID_ARG, "NULL surface, plane or QP pointer, or empty batch");
+	int rc = ValidateFrameArgs(ctx, width, height, d_vert, 0, d_hor, 0, false);
+	if (rc) return rc;
+	if (width % 32 != 0) return Fail(ctx, HDB_ERR_DIMENSIONS, "NV12 surfaces need a width that is a multiple of 32");
+	const hdb_nv12_surfaces *both[2] = { in, out };
+	for (const hdb_nv12_surfaces *s : both) {
+		const uintptr_t a = (uintptr_t)s->y | (uintptr_t)s->uv | s->pitch_y | s->pitch_uv
+			| (n_frames > 1 ? s->frame_stride_y | s->frame_stride_uv : 0);
+		if (a % 16 != 0) return Fail(ctx, HDB_ERR_INVALID_ARG, "surface addresses, pitches and frame strides must be multiples of 16 bytes");
+		if (s->pitch_y < width || s->pitch_uv < width || s->pitch_y > (1u << 30) || s->pitch_uv > (1u << 30))
+			return Fail(ctx, HDB_ERR_INVALID_ARG, "pitch smaller than the plane width");
+	}
+	if (in->pitch_y != out->pitch_y || in->pitch_uv != out->pitch_uv
+		|| (n_frames > 1 && (in->frame_stride_y != out->frame_stride_y || in->frame_stride_uv != out->frame_stride_uv)))
+		return Fail(ctx, HDB_ERR_INVALID_ARG, "input and output surfaces must share pitches and frame strides");
+	DeviceGuard guard(ctx->device);
+	FrameView view = WholeFrameView((int)width, (int)height, true);
+	const unsigned char *iy = static_cast<const unsigned char *>(in->y);
+	unsigned char *oy = static_cast<unsigned char *>(out->y);
+	view.u_offset = static_cast<const unsigned char *>(in->uv) - iy;
+	view.u_offset_out = static_cast<unsigned char *>(out->uv) - oy;
+	view.v_offset = view.u_offset; view.v_offset_out = view.u_offset_out;
+	view.luma_pitch = (int)in->pitch_y; view.chroma_pitch = (int)in->pitch_uv;
+	view.frame_stride = n_frames > 1 ? (long long)in->frame_stride_y : (long long)in->pitch_y * height;
+	view.chroma_frame_stride = n_frames > 1 ? (long long)in->frame_stride_uv : (long long)in->pitch_uv * (height / 2);
+	view.whole_frame = false;
+	return EnqueueFilter(ctx, view, iy, oy, (int)n_frames, d_qp, 0,
+		d_vert, hdb_num_vert_bs(width, height), d_hor, hdb_num_hor_bs(width, height),
+		static_cast<cudaStream_t>(stream), nullptr, (flags & HDB_FLAG_EDGE_MAPS) != 0);
 }
 
 unsigned long long hdb_kernel_launch_count(const hdb_context *ctx) { return ctx ? ctx->launches : 0; }

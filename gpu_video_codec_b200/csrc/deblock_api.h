@@ -69,6 +69,7 @@ struct FrameView {
 	long long u_offset_out, v_offset_out;   /* the same for the output planes */
 	int luma_pitch, chroma_pitch;  /* bytes between rows */
 	long long frame_stride, chroma_frame_stride;   /* bytes between frames, luma plane / chroma planes */
+	bool nv12;                     /* two planes: Y and interleaved UV at u_offset (v_offset unused) */
 };
 
 } // namespace hdb
@@ -79,7 +80,7 @@ struct hdb_context {
 	hdb::EncodeTiledFn encode = nullptr;
 	cudaStream_t s_h2d = nullptr, s_k = nullptr, s_d2h = nullptr;
 	void *sched = nullptr;
-	int tiled_ctas_per_sm = 1;               /* resident CTAs per SM of the tiled kernel on this device */
+	int tiled_ctas_per_sm[4] = { 1, 1, 1, 1 };   /* resident CTAs per SM of the tiled kernel's variants on this device */
 	std::vector<hdb::SizeState> sizes;
 	hdb::Slot slots[hdb::kSlots];
 	std::vector<cudaEvent_t> event_pool;
@@ -104,7 +105,7 @@ int Fail(hdb_context *ctx, int status, const std::string &msg);
 int FailCuda(hdb_context *ctx, cudaError_t e, const char *what);
 void DestroyContext(hdb_context *ctx);
 int GetSizeState(hdb_context *ctx, int w, int h, SizeState **out);
-FrameView WholeFrameView(int w, int h);
+FrameView WholeFrameView(int w, int h, bool nv12 = false);
 bool TiledPathUsable(int w, int h, const void *d_in, const void *d_out);
 int ValidateFrameArgs(hdb_context *ctx, unsigned w, unsigned h, const unsigned char *vbs, unsigned nv,
 	const unsigned char *hbs, unsigned nh, bool sizes_given);
@@ -112,7 +113,7 @@ int EnqueueFilter(hdb_context *ctx, const FrameView &view, const unsigned char *
 	int n, const unsigned *d_qp, unsigned qp_value, const unsigned char *d_vbs, long long vbs_stride,
 	const unsigned char *d_hbs, long long hbs_stride, cudaStream_t stream, int *path, bool edge_qp = false);
 int BatchHost(hdb_context *ctx, const unsigned char *in, unsigned char *out, unsigned n, unsigned w, unsigned h,
-	const unsigned *qp, const unsigned char *vbs, const unsigned char *hbs, hdb_timing *timing, bool edge_qp = false);
+	const unsigned *qp, const unsigned char *vbs, const unsigned char *hbs, hdb_timing *timing, unsigned flags = 0);
 
 /* beta / tc on the host (cpu.h:1021-1033, 1064-1072); defined in deblock_kernels.cu next to the device tables */
 int HostBeta(unsigned qp);

@@ -350,6 +350,22 @@ HDB_FN void StoreVertPairChroma(const ChromaPair &t, u32 &la, u32 &lb, u32 &ha, 
 	hb = Prmt(hb, t.q0, 0x3216);
 }
 
+/*
+ * NV12: the two chroma planes arrive interleaved, U0 V0 U1 V1 ...; the
+ * reference only knows planar YV12 (cpu.h:73-82) and treats both chroma planes alike (cpu.h:453-992).
+ * A row of an interleaved 8-sample block is four words; SplitUv picks one plane's eight samples out of
+ * them as the (lo, hi) pair ChromaBlock works on, JoinUv interleaves four samples of each plane again.
+ */
+HDB_FN void SplitUv(u32 w0, u32 w1, u32 w2, u32 w3, bool v_plane, u32 &lo, u32 &hi)
+{
+	const u32 sel = v_plane ? 0x7531u : 0x6420u;
+	lo = Prmt(w0, w1, sel); hi = Prmt(w2, w3, sel);
+}
+HDB_FN void JoinUv(u32 u, u32 v, u32 &w_first, u32 &w_second)
+{
+	w_first = Prmt(u, v, 0x5140u); w_second = Prmt(u, v, 0x7362u);
+}
+
 /* ------------------------------------------------------------------ */
 /* tables and boundary-strength resolution                             */
 /* ------------------------------------------------------------------ */

@@ -99,10 +99,12 @@ struct SchedWords { unsigned int next; unsigned int done; };
 /* item bookkeeping                                                    */
 /* ------------------------------------------------------------------ */
 
+/* kNv12: plane 1 is the interleaved UV plane; one of its items holds 16 block columns of U and of V */
+template <bool kNv12>
 __device__ __forceinline__ void ItemCoords(uint32_t desc, int &plane, int &bx0, int &lby0)
 {
 	plane = (int)(desc & 3u);
-	bx0 = (int)((desc >> 2) & 0x3ffu) * 32;
+	bx0 = (int)((desc >> 2) & 0x3ffu) * ((kNv12 && plane) ? 16 : 32);
 	lby0 = (int)(desc >> 12) * kRB;
 }
 
@@ -130,13 +132,14 @@ struct ItemCursor {
 		}
 		chunk = r - grp * chunks;
 	}
+	template <bool kNv12>
 	__device__ __forceinline__ void Next(const TiledBatch &b)
 	{
 		if (++chunk < chunks) return;
 		chunk = 0;
 		if (++grp < groups) return;
 		grp = 0;
-		if (++plane == 3) { plane = 0; frame++; }
+		if (++plane == (kNv12 ? 2 : 3)) { plane = 0; frame++; }
 		chunks = (uint32_t)(plane ? b.chroma_chunks : b.luma_chunks);
 		groups = (uint32_t)(plane ? b.chroma_groups : b.luma_groups);
 	}
@@ -150,6 +153,7 @@ struct PlaneInfo {
 	unsigned char *out;
 };
 
+template <bool kNv12>
 __device__ __forceinline__ PlaneInfo MakePlaneInfo(const TiledBatch &b, int plane)
 {
 	PlaneInfo p;
@@ -157,7 +161,7 @@ __device__ __forceinline__ PlaneInfo MakePlaneInfo(const TiledBatch &b, int plan
 	p.nbx = c ? b.chroma_nbx : b.luma_nbx;
 	p.rows = c ? b.chroma_rows : b.luma_rows;
 	p.row0 = c ? b.chroma_row0 : b.luma_row0;
-	p.pw = c ? (b.width >> 1) : b.width;
+	p.pw = (c && !kNv12) ? (b.width >> 1) : b.width;      /* bytes per row of the plane: the UV plane is as wide as luma */
 	p.pitch = c ? b.chroma_pitch : b.luma_pitch;
 	p.frame_stride = c ? b.chroma_frame_stride : b.frame_stride;
 	p.buf_rows = c ? b.chroma_buf_rows : b.luma_buf_rows;
@@ -176,14 +180,15 @@ __device__ __forceinline__ PlaneInfo MakePlaneInfo(const TiledBatch &b, int plan
  */
 struct BsRaw { u32 a, b, c, d; };
 
+template <bool kNv12>
 __device__ __forceinline__ BsRaw ItemBsRaw(const TiledBatch &b, uint32_t frame, uint32_t desc, int lane, int rb)
 {
 	BsRaw r = { 0u, 0u, 0u, 0u };
 	if (desc == kNoItem) return r;
 	int plane, bx0, lby0;
-	ItemCoords(desc, plane, bx0, lby0);
+	ItemCoords<kNv12>(desc, plane, bx0, lby0);
 	const bool c = plane != 0;
-	const int bx = bx0 + lane, lby = lby0 + rb;
+	const int bx = bx0 + ((kNv12 && c) ? (lane & 15) : lane), lby = lby0 + rb;
 	if (bx >= (c ? b.chroma_nbx : b.luma_nbx) || lby >= (c ? b.chroma_rows : b.luma_rows)) return r;
 	const int by = (c ? b.chroma_row0 : b.luma_row0) + lby;
 	if (c) { r.a = __ldg(b.chroma_bs + by * b.chroma_nbx + bx); return r; }
@@ -208,8 +213,11 @@ __device__ __forceinline__ u32 PackBs(const BsRaw &r, bool chroma)
 /* ------------------------------------------------------------------ */
 /* kEdgeQp: the luma boundary-strength arrays hold edge bytes (bs | qp << 2, deblock_core.cuh) and every
  * luma segment takes beta / tc from its own entry; chroma is untouched by it (frame QP, cpu.h:110-117) */
-template <bool kEdgeQp>
-__global__ void __launch_bounds__(kWarps * 32, HDB_MIN_CTAS)
+/* kNv12: two planes, Y and interleaved UV (lanes 0-15 filter the U blocks of a UV item, lanes 16-31 the V blocks) */
+/* (the two-plane variants hold the interleaved-chroma code as well and are given 96 registers, which
+ * still leaves 21 resident CTAs per SM; at 80 they spill 420 bytes) */
+template <bool kEdgeQp, bool kNv12>
+__global__ void __launch_bounds__(kWarps * 32, kNv12 ? HDB_MIN_CTAS - 1 : HDB_MIN_CTAS)
 DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_constant__ TiledBatch b,
 	SchedWords *sched, const uint32_t run_len)
 {
@@ -251,7 +259,7 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_consta
 				cur.Seek(b, run_next);
 			}
 		} else {
-			cur.Next(b);
+			cur.template Next<kNv12>(b);
 		}
 		if (run_next >= total) { held[s] = make_uint2(0u, kNoItem); return; }
 		run_next++;
@@ -283,20 +291,20 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_consta
 	FilterParams fp;
 	PlaneInfo pl;
 	MakeFilterParams(fp, 0, 0);
-	pl = MakePlaneInfo(b, 0);
+	pl = MakePlaneInfo<kNv12>(b, 0);
 	/* boundary strengths travel one item ahead of the samples */
 	BsRaw bs_raw[kRB];
 	{
 		const uint2 it0 = held[0];
 #pragma unroll
-		for (int rb = 0; rb < kRB; rb++) bs_raw[rb] = ItemBsRaw(b, it0.x, it0.y, lane, rb);
+		for (int rb = 0; rb < kRB; rb++) bs_raw[rb] = ItemBsRaw<kNv12>(b, it0.x, it0.y, lane, rb);
 	}
 	for (;;) {
 		const uint2 it = held[s];
 		const uint32_t frame = it.x, desc = it.y;
 		if (desc == kNoItem) break;
 		int plane, bx0, lby0;
-		ItemCoords(desc, plane, bx0, lby0);
+		ItemCoords<kNv12>(desc, plane, bx0, lby0);
 		const bool chroma = plane != 0;
 		/* beta / tc once per frame (cpu.h:136-137); plane constants once per plane.  Runs of
 		 * consecutive items share both, so these two branches are rarely taken. */
@@ -305,8 +313,8 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_consta
 			const unsigned qp = b.qp ? __ldg(b.qp + frame) : b.qp_value;
 			MakeFilterParams(fp, BetaOf(qp), TcOf(qp));
 		}
-		if (plane != cur_plane) { cur_plane = plane; pl = MakePlaneInfo(b, plane); }
-		const int bx = bx0 + lane;
+		if (plane != cur_plane) { cur_plane = plane; pl = MakePlaneInfo<kNv12>(b, plane); }
+		const int bx = bx0 + ((kNv12 && chroma) ? (lane & 15) : lane);
 
 		/* this item's boundary strengths were loaded during the previous item; start the next item's loads */
 		u32 bs[kRB];
@@ -315,7 +323,7 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_consta
 #pragma unroll
 			for (int rb = 0; rb < kRB; rb++) bs[rb] = PackBs(bs_raw[rb], chroma);
 #pragma unroll
-			for (int rb = 0; rb < kRB; rb++) bs_raw[rb] = ItemBsRaw(b, it_next.x, it_next.y, lane, rb);
+			for (int rb = 0; rb < kRB; rb++) bs_raw[rb] = ItemBsRaw<kNv12>(b, it_next.x, it_next.y, lane, rb);
 		}
 
 		MbarWait(bars_s + 8u * s, parity);
@@ -328,7 +336,37 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_consta
 		 * (unrolled, two block rows per item run 25 % slower than one) */
 #pragma unroll 1
 		for (int rb = 0; rb < kRB; rb++) {
-			if (bx < pl.nbx && lby0 + rb < pl.rows) {
+			if (kNv12 && chroma) {
+				u32 s4 = bs[0];
+#pragma unroll
+				for (int k = 1; k < kRB; k++) if (rb == k) s4 = bs[k];
+				/* interleaved UV: the block pair of column l = lane & 15 is 16 bytes per row, 8 bytes after the
+				 * box origin; lane l filters its U samples, lane l + 16 its V samples, then the two swap
+				 * halves and each writes two of the row's four words */
+				const bool live = bx < pl.nbx && lby0 + rb < pl.rows;
+				const unsigned pairs = __ballot_sync(0xffffffffu, live);
+				if (live) {
+					const bool v_plane = lane >= 16;
+					u32 *base = tile + rb * 8 * kTileWords + 2 + 4 * (lane & 15);
+					u32 lo[8], hi[8];
+#pragma unroll
+					for (int r = 0; r < 8; r++) {
+						const u32 *w = base + r * kTileWords;
+						SplitUv(w[0], w[1], w[2], w[3], v_plane, lo[r], hi[r]);
+					}
+					ChromaBlock(lo, hi, s4 & 0xff, (s4 >> 8) & 0xff, (s4 >> 16) & 0xff, s4 >> 24, fp);
+#pragma unroll
+					for (int r = 0; r < 8; r++) {
+						/* the U lane needs the other plane's lo, the V lane the other plane's hi */
+						const u32 other = __shfl_xor_sync(pairs, v_plane ? lo[r] : hi[r], 16);
+						u32 w_first, w_second;
+						if (v_plane) JoinUv(other, hi[r], w_first, w_second);
+						else JoinUv(lo[r], other, w_first, w_second);
+						u32 *w = base + r * kTileWords + (v_plane ? 2 : 0);
+						w[0] = w_first; w[1] = w_second;
+					}
+				}
+			} else if (bx < pl.nbx && lby0 + rb < pl.rows) {
 				u32 *base = tile + rb * 8 * kTileWords + kLead / 4 + 2 * lane;
 				u32 lo[8], hi[8];
 #pragma unroll
@@ -336,7 +374,7 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_consta
 				u32 s4 = bs[0];          /* select instead of indexing: bs[] stays in registers */
 #pragma unroll
 				for (int k = 1; k < kRB; k++) if (rb == k) s4 = bs[k];
-				if (chroma) ChromaBlock(lo, hi, s4 & 0xff, (s4 >> 8) & 0xff, (s4 >> 16) & 0xff, s4 >> 24, fp);
+				if (!kNv12 && chroma) ChromaBlock(lo, hi, s4 & 0xff, (s4 >> 8) & 0xff, (s4 >> 16) & 0xff, s4 >> 24, fp);
 				else LumaBlockT<kEdgeQp>(lo, hi, s4 & 0xff, (s4 >> 8) & 0xff, (s4 >> 16) & 0xff, s4 >> 24, fp);
 #pragma unroll
 				for (int r = 0; r < 8; r++) { base[r * kTileWords] = lo[r]; base[r * kTileWords + 1] = hi[r]; }
@@ -347,7 +385,10 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_consta
 		/* stream the item's own columns out: image columns x_img .. x_img + 251 start at tile byte kLead */
 		{
 			const int y0 = 8 * lby0 + pl.y_org;
-			const int x_img = 8 * bx0 - 4;
+			/* plane byte of tile byte kLead; a UV item starts 8 bytes into the box instead of 12 but covers the
+			 * same 256 plane bytes per row relative to the box, four bytes further left */
+			const bool uv = kNv12 && chroma;
+			const int x_img = uv ? 16 * bx0 - 4 : 8 * bx0 - 4;
 			const unsigned char *tile8 = reinterpret_cast<const unsigned char *>(tile);
 			/* 16-byte vectors: tile bytes 16 .. 255 <-> image columns x_img + 4 .. x_img + 243; two rows per pass */
 			const int j = lane & 15, half = lane >> 4;
@@ -358,7 +399,7 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_consta
 			const long long pitch2 = 2ll * pl.pitch;
 			/* fringe words: tile word 3 (image column x_img) and words 64..66 (x_img + 244 ..): 4 per row */
 			const int ftr = lane >> 2, k = lane & 3;
-			const int fword = k == 0 ? 3 : 63 + k;
+			const int fword = uv ? (k < 2 ? 2 + k : 62 + k) : (k == 0 ? 3 : 63 + k);
 			const int fcol = x_img + 4 * (fword - 3);
 			const bool f_lane = fcol >= 0 && fcol < pl.pw;
 			if (y0 >= 0 && y0 + kTileH <= pl.buf_rows) {
@@ -433,12 +474,12 @@ TiledConfig GetTiledConfig()
 void FinalizeTiledBatch(TiledBatch &b)
 {
 	b.luma_chunks = (b.luma_nbx + 31) / 32;
-	b.chroma_chunks = (b.chroma_nbx + 31) / 32;
+	b.chroma_chunks = b.nv12 ? (b.chroma_nbx + 15) / 16 : (b.chroma_nbx + 31) / 32;
 	b.luma_groups = (b.luma_rows + kRB - 1) / kRB;
 	b.chroma_groups = (b.chroma_rows + kRB - 1) / kRB;
 	b.items_luma = b.luma_chunks * b.luma_groups;
 	b.items_chroma = b.chroma_chunks * b.chroma_groups;
-	b.items_per_frame = b.items_luma + 2 * b.items_chroma;
+	b.items_per_frame = b.items_luma + (b.nv12 ? 1 : 2) * b.items_chroma;
 	b.total_items = (long long)b.items_per_frame * b.n_frames;
 	b.div_items_per_frame.Init((uint32_t)b.items_per_frame);
 	b.div_luma_chunks.Init((uint32_t)b.luma_chunks);
@@ -446,29 +487,36 @@ void FinalizeTiledBatch(TiledBatch &b)
 	b.div_items_chroma.Init((uint32_t)std::max(b.items_chroma, 1));
 }
 
-cudaError_t PrepareTiled(int *ctas_per_sm)
+typedef void (*TiledKernelFn)(const TensorMaps3, const TiledBatch, SchedWords *, const uint32_t);
+
+static TiledKernelFn TiledKernelOf(bool edge_qp, bool nv12)
 {
-	cudaError_t err = cudaFuncSetAttribute(DeblockTiledKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-	if (err != cudaSuccess) return err;
-	err = cudaFuncSetAttribute(DeblockTiledKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-	if (err != cudaSuccess) return err;
-	/* both instantiations are built to the same launch bounds: one grid size serves both */
-	int n = 0, n_edge = 0;
-	err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, DeblockTiledKernel<false>, kWarps * 32, kSmemBytes);
-	if (err != cudaSuccess) return err;
-	err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n_edge, DeblockTiledKernel<true>, kWarps * 32, kSmemBytes);
-	if (err != cudaSuccess) return err;
-	*ctas_per_sm = std::max(std::min(n, n_edge), 1);
+	if (nv12) return edge_qp ? DeblockTiledKernel<true, true> : DeblockTiledKernel<false, true>;
+	return edge_qp ? DeblockTiledKernel<true, false> : DeblockTiledKernel<false, false>;
+}
+
+cudaError_t PrepareTiled(int ctas_per_sm[4])
+{
+	for (int v = 0; v < 4; v++) {
+		const TiledKernelFn fn = TiledKernelOf(v & 1, v & 2);
+		cudaError_t err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+		if (err != cudaSuccess) return err;
+		int n = 0;
+		err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, kWarps * 32, kSmemBytes);
+		if (err != cudaSuccess) return err;
+		ctas_per_sm[v] = std::max(n, 1);
+	}
 	return cudaSuccess;
 }
 
-cudaError_t LaunchTiled(const TensorMaps3 &maps, const TiledBatch &b, void *sched, int sm_count, int ctas_per_sm,
+cudaError_t LaunchTiled(const TensorMaps3 &maps, const TiledBatch &b, void *sched, int sm_count, const int ctas_per_sm[4],
 	cudaStream_t stream, bool edge_qp)
 {
 	if (b.total_items <= 0) return cudaSuccess;
 	if (b.total_items >= (1ll << 31)) return cudaErrorInvalidValue;
 	const long long warps_wanted = b.total_items;
-	long long ctas = std::min<long long>((long long)sm_count * std::max(ctas_per_sm, 1), (warps_wanted + kWarps - 1) / kWarps);
+	const int resident = std::max(ctas_per_sm[(edge_qp ? 1 : 0) | (b.nv12 ? 2 : 0)], 1);
+	long long ctas = std::min<long long>((long long)sm_count * resident, (warps_wanted + kWarps - 1) / kWarps);
 	ctas = std::max<long long>(ctas, 1);
 	/* consecutive items per scheduler request: an upper bound, the kernel shortens the runs as the work runs
 	 * out.  Longer runs re-read fewer tile-edge sectors (neighbouring items share one per row); shorter runs
@@ -476,12 +524,8 @@ cudaError_t LaunchTiled(const TensorMaps3 &maps, const TiledBatch &b, void *sche
 	uint32_t run_len = b.total_items / (ctas * kWarps) >= 512 ? 8 : 4;
 	static const int run_len_env = getenv("HDB_RUN_LEN") ? atoi(getenv("HDB_RUN_LEN")) : 0;   /* measurement knob */
 	if (run_len_env > 0) run_len = (uint32_t)run_len_env;
-	if (edge_qp)
-		DeblockTiledKernel<true><<<(unsigned)ctas, kWarps * 32, kSmemBytes, stream>>>(maps, b,
-			reinterpret_cast<SchedWords *>(sched), run_len);
-	else
-		DeblockTiledKernel<false><<<(unsigned)ctas, kWarps * 32, kSmemBytes, stream>>>(maps, b,
-			reinterpret_cast<SchedWords *>(sched), run_len);
+	TiledKernelOf(edge_qp, b.nv12 != 0)<<<(unsigned)ctas, kWarps * 32, kSmemBytes, stream>>>(maps, b,
+		reinterpret_cast<SchedWords *>(sched), run_len);
 	return cudaGetLastError();
 }
 
@@ -525,31 +569,66 @@ cudaError_t LaunchDefaultLumaBs(unsigned char *vert_bs, unsigned char *hor_bs, i
 }
 
 /*
- * Edge maps from block data (deblock_core.cuh: DeriveEdge).  One thread per point (r, x) of the
- * (H/8 + 1) x (W/8 + 1) grid of block corners: it writes the vertical entry [r][x] -- the edge
- * between blocks (r, x-1) and (r, x) -- and the horizontal entry [r][x] -- between (r-1, x) and
- * (r, x).  Entries on the picture's four sides are 0 (H.265 does not filter them).  Per 8x8 block
- * 12 bytes are read (the neighbours come out of L1 / L2) and 2 written, against 192 the filter moves.
+ * Edge maps from block data (deblock_core.cuh: DeriveEdge).  Point (r, x) of the (H/8 + 1) x (W/8 + 1)
+ * grid of block corners owns the vertical entry [r][x] -- the edge between blocks (r, x-1) and (r, x) --
+ * and the horizontal entry [r][x] -- between (r-1, x) and (r, x).  Entries on the picture's four sides
+ * are 0 (H.265 does not filter them).  A CTA takes kDeriveCols x kDeriveRows points of one frame: the
+ * block data of those rows plus the row above and the column to the left go to shared memory first, as
+ * consecutive 32-bit words (a 12-byte record read by its owner would cost three cache lines per warp
+ * instruction, and every record is needed by three points), then one thread per column walks down the
+ * rows.  Per 8x8 block 12 bytes are read (+ 1/kDeriveRows for the row above) and 2 written, against the
+ * 192 the filter moves.
  */
-__global__ void DeriveEdgesKernel(const uint32_t *info, int w8, int h8, int n_frames,
-	unsigned char *vert_edges, unsigned char *hor_edges)
+constexpr int kDeriveCols = 128, kDeriveRows = 8;
+
+__global__ void __launch_bounds__(kDeriveCols)
+DeriveEdgesKernel(const uint32_t *info, int w8, int h8, int n_frames, unsigned char *vert_edges, unsigned char *hor_edges)
 {
-	const int x = blockIdx.x * blockDim.x + threadIdx.x;
-	const int r = blockIdx.y;
-	if (x > w8) return;
+	/* tile[rr][3c + k]: word k of block (r0 - 1 + rr, x0 - 1 + c) */
+	__shared__ uint32_t tile[kDeriveRows + 1][3 * (kDeriveCols + 1)];
+	const int t = threadIdx.x;
+	const int x0 = blockIdx.x * kDeriveCols, r0 = blockIdx.y * kDeriveRows;
+	const int x = x0 + t;
 	const long long nv = (long long)(w8 + 1) * h8, nh = (long long)(h8 + 1) * w8;
 	for (int f = blockIdx.z; f < n_frames; f += gridDim.z) {
 		const uint32_t *fi = info + 3ll * f * w8 * h8;
-		auto blk = [&](int rr, int xx) { const uint32_t *p = fi + 3ll * ((long long)rr * w8 + xx); return BlockWords{ __ldg(p), __ldg(p + 1), __ldg(p + 2) }; };
-		u32 ev = 0, eh = 0;
-		if (r < h8 && x < w8) {
-			const BlockWords q = blk(r, x);
-			const u32 fl = q.meta >> 16;
-			if (x > 0) ev = DeriveEdge(blk(r, x - 1), q, fl & kBlkTuLeft, fl & kBlkPuLeft);
-			if (r > 0) eh = DeriveEdge(blk(r - 1, x), q, fl & kBlkTuTop, fl & kBlkPuTop);
+#pragma unroll 1
+		for (int rr = 0; rr <= kDeriveRows; rr++) {
+			const int r = r0 - 1 + rr;
+			if (r < 0 || r >= h8) continue;
+			const uint32_t *row = fi + 3ll * r * w8;
+			for (int i = t; i < 3 * (kDeriveCols + 1); i += kDeriveCols) {
+				const int wi = 3 * (x0 - 1) + i;
+				if (wi >= 0 && wi < 3 * w8) tile[rr][i] = __ldg(row + wi);
+			}
 		}
-		if (r < h8) vert_edges[f * nv + (long long)r * (w8 + 1) + x] = (unsigned char)ev;
-		if (x < w8) hor_edges[f * nh + (long long)r * w8 + x] = (unsigned char)eh;
+		__syncthreads();
+		if (x <= w8) {
+			unsigned char *vf = vert_edges + f * nv, *hf = hor_edges + f * nh;
+#pragma unroll 2
+			for (int rr = 1; rr <= kDeriveRows; rr++) {
+				const int r = r0 - 1 + rr;
+				if (r > h8) break;
+				u32 ev = 0, eh = 0;
+				if (r < h8 && x < w8) {
+					const uint32_t *qw = &tile[rr][3 * (t + 1)];
+					const BlockWords q = { qw[0], qw[1], qw[2] };
+					const u32 fl = q.meta >> 16;
+					if (x > 0) {
+						const BlockWords p = { qw[-3], qw[-2], qw[-1] };
+						ev = DeriveEdge(p, q, fl & kBlkTuLeft, fl & kBlkPuLeft);
+					}
+					if (r > 0) {
+						const uint32_t *pw = &tile[rr - 1][3 * (t + 1)];
+						const BlockWords p = { pw[0], pw[1], pw[2] };
+						eh = DeriveEdge(p, q, fl & kBlkTuTop, fl & kBlkPuTop);
+					}
+				}
+				if (r < h8) vf[(long long)r * (w8 + 1) + x] = (unsigned char)ev;
+				if (x < w8) hf[(long long)r * w8 + x] = (unsigned char)eh;
+			}
+		}
+		__syncthreads();
 	}
 }
 
@@ -558,8 +637,8 @@ cudaError_t LaunchDeriveEdges(const void *info, int width, int height, int n_fra
 {
 	const int w8 = width / 8, h8 = height / 8;
 	if (n_frames <= 0 || w8 <= 0 || h8 <= 0) return cudaSuccess;
-	const dim3 grid((w8 + 1 + 127) / 128, h8 + 1, (unsigned)std::min(n_frames, 4096));
-	DeriveEdgesKernel<<<grid, 128, 0, stream>>>(static_cast<const uint32_t *>(info), w8, h8, n_frames, vert_edges, hor_edges);
+	const dim3 grid((w8 + kDeriveCols) / kDeriveCols, (h8 + kDeriveRows) / kDeriveRows, (unsigned)std::min(n_frames, 32768));
+	DeriveEdgesKernel<<<grid, kDeriveCols, 0, stream>>>(static_cast<const uint32_t *>(info), w8, h8, n_frames, vert_edges, hor_edges);
 	return cudaGetLastError();
 }
 

@@ -36,6 +36,7 @@ struct FastDiv {
  */
 struct TiledBatch {
 	int n_frames;
+	int nv12;                       /* 1: two planes, Y and interleaved UV (maps.in[1], out_plane[1]); else Y, U, V */
 	/* frame-global geometry */
 	int width, height;              /* luma */
 	int luma_nbx, luma_nby;         /* (W+8)/8, (H+8)/8 */
@@ -74,10 +75,11 @@ TiledConfig GetTiledConfig();
 /* Fill the work-decomposition fields from the geometry fields. */
 void FinalizeTiledBatch(TiledBatch &b);
 
-/* Once per device (the current one): function attributes; returns the resident CTAs per SM the grid is sized with. */
-cudaError_t PrepareTiled(int *ctas_per_sm);
+/* Once per device (the current one): function attributes; returns the resident CTAs per SM the grid is sized
+ * with, per kernel variant: index = (edge maps ? 1 : 0) | (NV12 ? 2 : 0). */
+cudaError_t PrepareTiled(int ctas_per_sm[4]);
 /* Persistent tiled kernel: one launch filters Y, U and V of every frame of the batch. */
-cudaError_t LaunchTiled(const TensorMaps3 &maps, const TiledBatch &b, void *sched, int sm_count, int ctas_per_sm,
+cudaError_t LaunchTiled(const TensorMaps3 &maps, const TiledBatch &b, void *sched, int sm_count, const int ctas_per_sm[4],
 	cudaStream_t stream, bool edge_qp = false);
 /* bytes of zero-initialised device memory the scheduler needs (one per context) */
 size_t TiledSchedBytes();

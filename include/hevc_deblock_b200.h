@@ -224,6 +224,38 @@ int hdb_derive_edges_device(hdb_context *ctx, const hdb_block_info *d_info, unsi
 int hdb_derive_edges(hdb_context *ctx, const hdb_block_info *info, unsigned n_frames,
 	unsigned width, unsigned height, unsigned char *vert_edges, unsigned char *hor_edges);
 
+/* ---- NV12 (a hardware decoder's surface format) and the flagged general forms -------------- */
+/*
+ * The second of the data formats on the caller's side: Y plane followed by one plane of interleaved
+ * chroma, U0 V0 U1 V1 ..., width bytes per row, height / 2 rows.  The reference reads planar YV12
+ * only (cpu.h:66-82) and filters its two chroma planes identically (cpu.h:453-992); an NV12 frame
+ * gives, sample for sample, what the reference gives on the same frame stored as YV12.  A tight NV12
+ * frame has the size of a YV12 one (3 * width * height / 2), so the batch entry points take it as
+ * is.  NV12 needs a width that is a multiple of 32 (HDB_ERR_DIMENSIONS otherwise: there is no
+ * second kernel path for it).
+ */
+#define HDB_FLAG_EDGE_MAPS 1u   /* vert / hor hold edge bytes (HDB_EDGE) and are required */
+#define HDB_FLAG_NV12      2u   /* frames are NV12 instead of YV12 */
+
+/* hdb_deblock_batch / hdb_deblock_batch_device with flags (0 = exactly those two) */
+int hdb_deblock_batch_ex(hdb_context *ctx, const unsigned char *frames_in, unsigned char *frames_out,
+	unsigned n_frames, unsigned width, unsigned height, const unsigned *qp,
+	const unsigned char *vert, const unsigned char *hor, unsigned flags, hdb_timing *timing);
+int hdb_deblock_batch_device_ex(hdb_context *ctx, const void *d_frames_in, void *d_frames_out,
+	unsigned n_frames, unsigned width, unsigned height, const unsigned *d_qp,
+	const unsigned char *d_vert, const unsigned char *d_hor, unsigned flags, void *stream);
+
+/* pitched NV12 surfaces in device memory, as hdb_deblock_surfaces_device; flags: HDB_FLAG_EDGE_MAPS or 0 */
+typedef struct hdb_nv12_surfaces {
+	void *y, *uv;                            /* device pointers to frame 0 of each plane */
+	size_t pitch_y, pitch_uv;                /* bytes between rows (>= width for both) */
+	size_t frame_stride_y, frame_stride_uv;  /* bytes between frames; ignored when n_frames == 1 */
+} hdb_nv12_surfaces;
+
+int hdb_deblock_nv12_surfaces_device(hdb_context *ctx, const hdb_nv12_surfaces *in, const hdb_nv12_surfaces *out,
+	unsigned n_frames, unsigned width, unsigned height, const unsigned *d_qp,
+	const unsigned char *d_vert, const unsigned char *d_hor, unsigned flags, void *stream);
+
 /* number of filter-kernel launches made through ctx since creation */
 unsigned long long hdb_kernel_launch_count(const hdb_context *ctx);
 

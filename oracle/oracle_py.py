@@ -256,3 +256,36 @@ def ref_compose_edges(frame, w, h, qp, vert_edges, hor_edges):
             run(q, zero_v, m.reshape(-1))
     cur[ysz:] = chroma[ysz:]
     return cur
+
+
+# ---------------------------------------------------------------------------
+# NV12: Y plane, then one plane of interleaved U0 V0 U1 V1 ...
+# The reference reads planar frames only (cpu.h:66-82) and filters its two chroma planes alike,
+# so the NV12 oracle is the YV12 one between two byte permutations.
+# ---------------------------------------------------------------------------
+def yv12_to_nv12(frame, w, h):
+    frame = np.ascontiguousarray(frame, np.uint8).reshape(-1)
+    ysz, csz = w * h, (w // 2) * (h // 2)
+    out = np.empty_like(frame)
+    out[:ysz] = frame[:ysz]
+    uv = out[ysz:].reshape(h // 2, w // 2, 2)
+    uv[:, :, 0] = frame[ysz:ysz + csz].reshape(h // 2, w // 2)
+    uv[:, :, 1] = frame[ysz + csz:].reshape(h // 2, w // 2)
+    return out
+
+
+def nv12_to_yv12(frame, w, h):
+    frame = np.ascontiguousarray(frame, np.uint8).reshape(-1)
+    ysz, csz = w * h, (w // 2) * (h // 2)
+    out = np.empty_like(frame)
+    out[:ysz] = frame[:ysz]
+    uv = frame[ysz:].reshape(h // 2, w // 2, 2)
+    out[ysz:ysz + csz] = uv[:, :, 0].reshape(-1)
+    out[ysz + csz:] = uv[:, :, 1].reshape(-1)
+    return out
+
+
+def deblock_frame_nv12(frame, w, h, qp, vert=None, hor=None, edges=False):
+    planar = nv12_to_yv12(frame, w, h)
+    y = deblock_frame_edges(planar, w, h, qp, vert, hor) if edges else deblock_frame(planar, w, h, qp, vert, hor)
+    return yv12_to_nv12(y, w, h)

@@ -108,3 +108,42 @@ extern "C" void emu_derive_edges(const uint32_t *info, unsigned w, unsigned h, u
 			}
 		}
 }
+
+/*
+ * The interleaved-chroma block code of DeblockTiledKernel<., true>, lane pair by lane pair: the "U lane"
+ * and the "V lane" each pick their samples out of the four words of a row (SplitUv), filter, swap halves
+ * and write two words each (JoinUv).  uv: tight interleaved plane, w bytes x h/2 rows (w, h = luma size).
+ */
+extern "C" int emu_deblock_uv_plane(const uint8_t *uv_in, uint8_t *uv_out, unsigned w, unsigned h, unsigned qp)
+{
+	if (w % 8 || h % 8) return 1;
+	const unsigned cw = w / 2, ch = h / 2;
+	const int nbx = (w + 8) / 8, nby = (h + 8) / 8, cnbx = (cw + 8) / 8, cnby = (ch + 8) / 8;
+	const size_t pitch = (size_t)cnbx * 16;     /* bytes per padded interleaved row */
+	FilterParams fp;
+	MakeFilterParams(fp, BetaOf(qp), TcOf(qp));
+	std::vector<uint8_t> P(pitch * cnby * 8, 0);
+	for (unsigned r = 0; r < ch; r++) memcpy(&P[(size_t)(r + 4) * pitch + 8], uv_in + (size_t)r * w, w);
+	for (int by = 0; by < cnby; by++)
+		for (int bx = 0; bx < cnbx; bx++) {
+			uint8_t *b = &P[(size_t)by * 8 * pitch + (size_t)bx * 16];
+			const u32 bs = ChromaBsOfBlock(bx, by, cw, ch, nbx, nby);
+			u32 lo[2][8], hi[2][8];
+			for (int v = 0; v < 2; v++) {
+				for (int r = 0; r < 8; r++) {
+					u32 wd[4];
+					memcpy(wd, b + r * pitch, 16);
+					SplitUv(wd[0], wd[1], wd[2], wd[3], v != 0, lo[v][r], hi[v][r]);
+				}
+				ChromaBlock(lo[v], hi[v], bs & 0xff, (bs >> 8) & 0xff, (bs >> 16) & 0xff, bs >> 24, fp);
+			}
+			for (int r = 0; r < 8; r++) {
+				u32 wd[4];
+				JoinUv(lo[0][r], lo[1][r], wd[0], wd[1]);   /* written by the U lane */
+				JoinUv(hi[0][r], hi[1][r], wd[2], wd[3]);   /* written by the V lane */
+				memcpy(b + r * pitch, wd, 16);
+			}
+		}
+	for (unsigned r = 0; r < ch; r++) memcpy(uv_out + (size_t)r * w, &P[(size_t)(r + 4) * pitch + 8], w);
+	return 0;
+}

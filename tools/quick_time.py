@@ -33,11 +33,16 @@ def main():
     ap.add_argument("--n", type=int, default=64)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--inplace", action="store_true")
+    ap.add_argument("--nv12", action="store_true", help="the same frames stored as NV12 (DeblockTiledKernel<., true>)")
     a = ap.parse_args()
     dev = hdb.Deblocker(0)
     w, h, n = a.w, a.h, a.n
     g = torch.Generator(device="cuda").manual_seed(1)
     frames = device_blocky(n, w, h)
+    if a.nv12:
+        ysz, csz = w * h, (w // 2) * (h // 2)
+        frames[:, ysz:] = torch.stack([frames[:, ysz:ysz + csz], frames[:, ysz + csz:]], dim=2).reshape(n, -1)
+    flags = hdb.FLAG_NV12 if a.nv12 else 0
     out = frames.clone() if a.inplace else torch.empty_like(frames)
     qp = torch.randint(18, 52, (n,), device="cuda", generator=g, dtype=torch.int32)
     nv, nh = hdb.num_vert_bs(w, h), hdb.num_hor_bs(w, h)
@@ -46,12 +51,12 @@ def main():
     stream = torch.cuda.current_stream().cuda_stream
     src = out if a.inplace else frames
     for _ in range(3):
-        dev.deblock_batch_device(src, out, n, w, h, qp, vbs, hbs, stream=stream)
+        dev.deblock_batch_device_ex(src, out, n, w, h, qp, vbs, hbs, flags=flags, stream=stream)
     torch.cuda.synchronize()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.iters)]
     for e0, e1 in evs:
         e0.record()
-        dev.deblock_batch_device(src, out, n, w, h, qp, vbs, hbs, stream=stream)
+        dev.deblock_batch_device_ex(src, out, n, w, h, qp, vbs, hbs, flags=flags, stream=stream)
         e1.record()
     torch.cuda.synchronize()
     ms = np.array([e0.elapsed_time(e1) for e0, e1 in evs])
@@ -62,8 +67,8 @@ def main():
     pix = n * w * h
     chk = int(out.view(torch.int64).sum().item()) & 0xffffffffffff
     print("[%s] chk=%012x " % (os.path.basename(hdb.library_path()), chk), end="")
-    print("%dx%d n=%d inplace=%s: median %.3f ms  min %.3f ms | %.1f Mpixel/s | %.1f GB/s algorithmic | changed %.1f%%" % (
-        w, h, n, a.inplace, np.median(ms), ms.min(), pix / np.median(ms) / 1e3, n * alg / np.median(ms) / 1e6,
+    print("%s%dx%d n=%d inplace=%s: median %.3f ms  min %.3f ms | %.1f Mpixel/s | %.1f GB/s algorithmic | changed %.1f%%" % (
+        "NV12 " if a.nv12 else "", w, h, n, a.inplace, np.median(ms), ms.min(), pix / np.median(ms) / 1e3, n * alg / np.median(ms) / 1e6,
         100.0 * float((out != frames).float().mean()) if not a.inplace else -1))
 
 
