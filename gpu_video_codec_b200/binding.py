@@ -133,6 +133,8 @@ def load_library():
     lib.hdb_deblock_batch_device_ex.argtypes = [vp] + batch_args + [C.c_uint, vp]
     lib.hdb_deblock_nv12_surfaces_device.argtypes = [vp, C.POINTER(Nv12Surfaces), C.POINTER(Nv12Surfaces), C.c_uint, C.c_uint,
                                                      C.c_uint, vp, vp, vp, C.c_uint, vp]
+    lib.hdb_execute_gpu_sequence.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_uint, C.c_uint, C.c_uint, C.c_uint,
+                                             C.POINTER(C.c_uint), C.POINTER(Timing)]
     lib.hdb_kernel_launch_count.argtypes = [vp]
     lib.hdb_kernel_launch_count.restype = C.c_ulonglong
     lib.hdb_multi_create.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), C.c_int]
@@ -142,6 +144,7 @@ def load_library():
     lib.hdb_multi_last_error.argtypes = [vp]
     lib.hdb_multi_last_error.restype = C.c_char_p
     lib.hdb_multi_deblock_batch.argtypes = [vp] + batch_args + [C.POINTER(Timing)]
+    lib.hdb_multi_deblock_batch_ex.argtypes = [vp] + batch_args + [C.c_uint, C.POINTER(Timing)]
     lib.hdb_multi_deblock_frame_strips.argtypes = [vp, vp, vp] + frame_args
     _lib = lib
     return lib
@@ -254,6 +257,14 @@ class Deblocker:
         """ExecuteGpu(input_file_name, output_file_name, width, height, Qp) of main.cu:87-90."""
         self._check(self._lib.hdb_execute_gpu(self._ctx, os.fsencode(input_file_name), os.fsencode(output_file_name),
                                               width, height, qp, None if timing is None else C.byref(timing)))
+
+    def execute_gpu_sequence(self, input_file_name, output_file_name, width, height, qp, flags=0, timing=None):
+        """A raw sequence file with any number of frames; returns the frame count."""
+        n = C.c_uint(0)
+        self._check(self._lib.hdb_execute_gpu_sequence(self._ctx, os.fsencode(input_file_name), os.fsencode(output_file_name),
+                                                       width, height, qp, flags, C.byref(n),
+                                                       None if timing is None else C.byref(timing)))
+        return int(n.value)
 
     # --- batches ---
     def deblock_batch(self, frames, width, height, qps, vert_bs=None, hor_bs=None, out=None, timing=None,
@@ -383,6 +394,15 @@ class MultiDeblocker:
         self._check(self._lib.hdb_multi_deblock_batch(self._m, _addr(frames), _addr(out), n, width, height,
                                                       _addr(qps), _addr(vert_bs), _addr(hor_bs),
                                                       None if timing is None else C.byref(timing)))
+        return out
+
+    def deblock_batch_ex(self, frames, width, height, qps, vert=None, hor=None, flags=0, out=None, timing=None):
+        n = int(frames.shape[0])
+        if out is None:
+            out = np.empty_like(frames)
+        self._check(self._lib.hdb_multi_deblock_batch_ex(self._m, _addr(frames), _addr(out), n, width, height,
+                                                         _addr(qps), _addr(vert), _addr(hor), flags,
+                                                         None if timing is None else C.byref(timing)))
         return out
 
     def deblock_frame_strips(self, yuv, width, height, qp, vert_bs=None, hor_bs=None, out=None, timing=None):

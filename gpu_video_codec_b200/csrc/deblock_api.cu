@@ -855,6 +855,52 @@ int hdb_deblock_nv12_surfaces_device(hdb_context *ctx, const hdb_nv12_surfaces *
 		static_cast<cudaStream_t>(stream), nullptr, (flags & HDB_FLAG_EDGE_MAPS) != 0);
 }
 
+/*
+ * A raw YUV sequence: the file holds any number of frames back to back (rank 4 of SURVEY.md section 8(f);
+ * the reference's reader takes exactly one, cpu.h:43).  Frames go through the batch pipeline a bounded
+ * chunk at a time, so the file may be larger than host or device memory.
+ */
+int hdb_execute_gpu_sequence(hdb_context *ctx, const char *input_file_name, const char *output_file_name,
+	unsigned width, unsigned height, unsigned qp, unsigned flags, unsigned *n_frames_out, hdb_timing *timing)
+{
+	if (!ctx || !input_file_name || !output_file_name) return HDB_ERR_INVALID_ARG;
+	if (flags & ~HDB_FLAG_NV12) return Fail(ctx, HDB_ERR_INVALID_ARG, "unknown flag");
+	FILE *f = fopen(input_file_name, "rb");
+	if (!f) return Fail(ctx, HDB_ERR_IO, std::string("cannot open ") + input_file_name);
+	fseeko(f, 0, SEEK_END);
+	const long long length = ftello(f);
+	fseeko(f, 0, SEEK_SET);
+	const size_t fb = (size_t)3 * width * height / 2;
+	/* the reference's order: length first (cpu.h:43), then the dimensions (cpu.h:46) */
+	if (fb == 0 || length <= 0 || (size_t)length % fb != 0) { fclose(f); return Fail(ctx, HDB_ERR_FILE_SIZE, kMsgFileSize); }
+	if (width % 8 != 0 || height % 8 != 0) { fclose(f); return Fail(ctx, HDB_ERR_DIMENSIONS, kMsgDims); }
+	const unsigned long long total = (unsigned long long)length / fb;
+	const unsigned chunk = (unsigned)std::min<unsigned long long>(total, std::max<size_t>(1, ((size_t)512 << 20) / fb));
+	unsigned char *buf = static_cast<unsigned char *>(hdb_host_alloc(fb * chunk));
+	if (!buf) { fclose(f); return Fail(ctx, HDB_ERR_NO_MEMORY, "cudaMallocHost failed"); }
+	FILE *o = fopen(output_file_name, "wb");
+	int rc = o ? HDB_OK : Fail(ctx, HDB_ERR_IO, std::string("cannot write ") + output_file_name);
+	std::vector<unsigned> qps(chunk, qp);
+	hdb_timing sum{}, t{};
+	for (unsigned long long f0 = 0; !rc && f0 < total; f0 += chunk) {
+		const unsigned n = (unsigned)std::min<unsigned long long>(chunk, total - f0);
+		if (fread(buf, 1, fb * n, f) != fb * n) { rc = Fail(ctx, HDB_ERR_IO, "short read"); break; }
+		rc = BatchHost(ctx, buf, buf, n, width, height, qps.data(), nullptr, nullptr, &t, flags);
+		if (rc) break;
+		if (fwrite(buf, 1, fb * n, o) != fb * n) { rc = Fail(ctx, HDB_ERR_IO, std::string("cannot write ") + output_file_name); break; }
+		sum.kernel_ms += t.kernel_ms; sum.copy_ms += t.copy_ms; sum.total_ms += t.total_ms;
+		sum.h2d_bytes += t.h2d_bytes; sum.d2h_bytes += t.d2h_bytes; sum.kernel_launches += t.kernel_launches; sum.path = t.path;
+	}
+	fclose(f);
+	if (o) fclose(o);
+	hdb_host_free(buf);
+	if (!rc) {
+		if (timing) *timing = sum;
+		if (n_frames_out) *n_frames_out = (unsigned)total;
+	}
+	return rc;
+}
+
 unsigned long long hdb_kernel_launch_count(const hdb_context *ctx) { return ctx ? ctx->launches : 0; }
 
 } // extern "C"

@@ -68,6 +68,8 @@ HDB_FN u32 Prmt(u32 x, u32 y, u32 s) {
 }
 HDB_FN u32 SumHalves(u32 a) { return (a & 0xffffu) + (a >> 16); }
 HDB_FN u32 SumHalvesPlus(u32 a, u32 c) { return (a & 0xffffu) + (a >> 16) + c; }
+HDB_FN u32 MaxU2(u32 a, u32 b) { return (Mx(a & 0xffffu, b & 0xffffu)) | ((u32)Mx(a >> 16, b >> 16) << 16); }
+HDB_FN u32 MinU2(u32 a, u32 b) { return (Mn(a & 0xffffu, b & 0xffffu)) | ((u32)Mn(a >> 16, b >> 16) << 16); }
 #else
 HDB_FN u32 Add2(u32 a, u32 b) { return __vadd2(a, b); }                          /* VIADD.16x2 */
 HDB_FN u32 Max2(u32 a, u32 b) { return __vmaxs2(a, b); }                         /* VIMNMX.S16x2 */
@@ -78,6 +80,8 @@ HDB_FN u32 AddMinRelu2(u32 a, u32 b, u32 c) { return __viaddmin_s16x2_relu(a, b,
 HDB_FN u32 Prmt(u32 x, u32 y, u32 s) { return __byte_perm(x, y, s); }            /* PRMT */
 HDB_FN u32 SumHalves(u32 a) { return __dp2a_lo(a, 0x0101u, 0u); }                /* IDP.2A: lo*1 + hi*1 */
 HDB_FN u32 SumHalvesPlus(u32 a, u32 c) { return __dp2a_lo(a, 0x0101u, c); }      /* ... + c, same instruction */
+HDB_FN u32 MaxU2(u32 a, u32 b) { return __vmaxu2(a, b); }                         /* VIMNMX.U16x2 */
+HDB_FN u32 MinU2(u32 a, u32 b) { return __vminu2(a, b); }
 #endif
 
 /* both halves = v (v may be negative: two's complement per half) */
@@ -602,41 +606,48 @@ HDB_FN void ChromaBlock(u32 (&lo)[8], u32 (&hi)[8], u32 bs_ver1, u32 bs_ver2, u3
 struct BlockWords { u32 mv0, mv1, meta; };
 enum { kBlkIntra = 1, kBlkCbf = 2, kBlkTuLeft = 4, kBlkTuTop = 8, kBlkPuLeft = 16, kBlkPuTop = 32 };
 
-HDB_HD int MvFar(u32 a, u32 b)
+/* non-zero iff the two vectors (x | y << 16, signed halves) differ by 4 or more in a component: flip the
+ * sign bits (signed order -> unsigned order), |a - b| per half as max - min (no borrow between the
+ * halves, exact up to 65535), then any bit above bit 1 */
+HDB_FN u32 MvFarBits(u32 a, u32 b)
 {
-	int dx = (int)(int16_t)(a & 0xffffu) - (int)(int16_t)(b & 0xffffu);
-	int dy = (int)(int16_t)(a >> 16) - (int)(int16_t)(b >> 16);
-	if (dx < 0) dx = -dx;
-	if (dy < 0) dy = -dy;
-	return dx >= 4 || dy >= 4;
+	a ^= 0x80008000u; b ^= 0x80008000u;
+	return (MaxU2(a, b) - MinU2(a, b)) & 0xfffcfffcu;
 }
 
-HDB_HD u32 DeriveBs(const BlockWords &p, const BlockWords &q, bool tu_edge, bool pu_edge)
+/* both reference bytes of a block with every negative value turned into 0xff ("list unused") */
+HDB_FN u32 RefPair(u32 meta)
 {
-	if (!tu_edge && !pu_edge) return 0u;
+	const u32 r = meta & 0xffffu;
+	return r | (((r >> 7) & 0x0101u) * 0xffu);
+}
+
+/*
+ * Straight-line form of the rule (the kernel evaluates two edges per thread with lane-varying data:
+ * branches would diverge on every one of them).  With pr / qr the two reference bytes of each side,
+ * "same pictures, same vector count" is exactly  pr == qr  (lists pair up straight) or  pr == swap(qr)
+ * (lists pair up crossed); both hold when all used references are one picture, and then -- as in the
+ * standard -- the motion differs only if it differs under both pairings.  A pairing skips the lists
+ * that are unused (reference 0xff on both sides of it).
+ */
+HDB_FN u32 DeriveBs(const BlockWords &p, const BlockWords &q, bool tu_edge, bool pu_edge)
+{
 	const u32 flags = (p.meta | q.meta) >> 16;
-	if (flags & kBlkIntra) return 2u;
-	if (tu_edge && (flags & kBlkCbf)) return 1u;
-	const int p0 = (int)(int8_t)(p.meta & 0xffu), p1 = (int)(int8_t)((p.meta >> 8) & 0xffu);
-	const int q0 = (int)(int8_t)(q.meta & 0xffu), q1 = (int)(int8_t)((q.meta >> 8) & 0xffu);
-	const int np = (p0 >= 0) + (p1 >= 0), nq = (q0 >= 0) + (q1 >= 0);
-	if (np != nq) return 1u;
-	if (np == 1) {
-		if ((p0 >= 0 ? p0 : p1) != (q0 >= 0 ? q0 : q1)) return 1u;
-		return (u32)MvFar(p0 >= 0 ? p.mv0 : p.mv1, q0 >= 0 ? q.mv0 : q.mv1);
-	}
-	if (np == 2) {
-		if (!((p0 == q0 && p1 == q1) || (p0 == q1 && p1 == q0))) return 1u;
-		const int straight = MvFar(p.mv0, q.mv0) || MvFar(p.mv1, q.mv1);
-		const int crossed = MvFar(p.mv0, q.mv1) || MvFar(p.mv1, q.mv0);
-		if (p0 != p1) return (u32)(p0 == q0 ? straight : crossed);
-		return (u32)(straight && crossed);
-	}
-	return 0u;
+	const u32 pr = RefPair(p.meta), qr = RefPair(q.meta);
+	const u32 qr_swapped = Prmt(qr, 0u, 0x4401);
+	const bool straight = pr == qr, crossed = pr == qr_swapped;
+	const u32 use0 = (pr & 0x80u) ? 0u : 0xffffffffu, use1 = (pr & 0x8000u) ? 0u : 0xffffffffu;
+	const bool far_straight = ((MvFarBits(p.mv0, q.mv0) & use0) | (MvFarBits(p.mv1, q.mv1) & use1)) != 0u;
+	const bool far_crossed = ((MvFarBits(p.mv0, q.mv1) & use0) | (MvFarBits(p.mv1, q.mv0) & use1)) != 0u;
+	const u32 motion = straight ? (u32)(crossed ? (far_straight && far_crossed) : far_straight)
+		: (crossed ? (u32)far_crossed : 1u);
+	const u32 inter = (tu_edge && (flags & kBlkCbf)) ? 1u : motion;
+	const u32 bs = (flags & kBlkIntra) ? 2u : inter;
+	return (tu_edge || pu_edge) ? bs : 0u;
 }
 
 /* edge byte between block p (left / above) and block q: strength by the rule above, QP = (QpP + QpQ + 1) >> 1 */
-HDB_HD u32 DeriveEdge(const BlockWords &p, const BlockWords &q, bool tu_edge, bool pu_edge)
+HDB_FN u32 DeriveEdge(const BlockWords &p, const BlockWords &q, bool tu_edge, bool pu_edge)
 {
 	return EdgeByte(DeriveBs(p, q, tu_edge, pu_edge), ((p.meta >> 24) + (q.meta >> 24) + 1u) >> 1);
 }

@@ -133,7 +133,15 @@ int hdb_multi_deblock_batch(hdb_multi *m, const unsigned char *frames_in, unsign
 	unsigned n_frames, unsigned width, unsigned height, const unsigned *qp,
 	const unsigned char *vert_bs, const unsigned char *hor_bs, hdb_timing *timing)
 {
+	return hdb_multi_deblock_batch_ex(m, frames_in, frames_out, n_frames, width, height, qp, vert_bs, hor_bs, 0, timing);
+}
+
+int hdb_multi_deblock_batch_ex(hdb_multi *m, const unsigned char *frames_in, unsigned char *frames_out,
+	unsigned n_frames, unsigned width, unsigned height, const unsigned *qp,
+	const unsigned char *vert_bs, const unsigned char *hor_bs, unsigned flags, hdb_timing *timing)
+{
 	if (!m || m->ctx.empty()) return HDB_ERR_INVALID_ARG;
+	if (flags & ~(HDB_FLAG_EDGE_MAPS | HDB_FLAG_NV12)) return MFail(m, HDB_ERR_INVALID_ARG, "unknown flag");
 	if (!frames_in || !frames_out || !qp || n_frames == 0) return MFail(m, HDB_ERR_INVALID_ARG, "NULL buffer or empty batch");
 	const int g = (int)std::min<size_t>(m->ctx.size(), n_frames);
 	const size_t fb = (size_t)width * height * 3 / 2;
@@ -150,7 +158,7 @@ int hdb_multi_deblock_batch(hdb_multi *m, const unsigned char *frames_in, unsign
 		pool.emplace_back([=, &rcs, &tms]() {
 			rcs[d] = BatchHost(m->ctx[d], frames_in + first * fb, frames_out + first * fb, nf, width, height,
 				qp + first, vert_bs ? vert_bs + (size_t)first * nv : nullptr,
-				hor_bs ? hor_bs + (size_t)first * nh : nullptr, &tms[d]);
+				hor_bs ? hor_bs + (size_t)first * nh : nullptr, &tms[d], flags);
 		});
 		f0 += nf;
 	}

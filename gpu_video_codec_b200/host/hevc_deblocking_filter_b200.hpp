@@ -155,4 +155,31 @@ inline void ExecuteGpu(std::string const &input_file_name, std::string const &ou
 	hdb_destroy(ctx);
 }
 
+/*
+ * ExecuteGpu for a raw sequence: the file may hold any number of frames (the reference's driver runs
+ * one single-frame file per build, main.cu:111-133).  Prints the frame count and the same three lines.
+ */
+inline void ExecuteGpuSequence(std::string const &input_file_name, std::string const &output_file_name,
+	unsigned int width, unsigned int height, unsigned int Qp)
+{
+	hdb_context *ctx = nullptr;
+	if (hdb_create(&ctx, 0) != HDB_OK) { std::printf("Error: %s\n", hdb_last_error(nullptr)); return; }
+	hdb_timing t{};
+	unsigned frames = 0;
+	int rc = hdb_execute_gpu_sequence(ctx, input_file_name.c_str(), output_file_name.c_str(), width, height, Qp, 0, &frames, &t);
+	if (rc != HDB_OK) {
+		std::string msg = hdb_last_error(ctx);
+		hdb_destroy(ctx);
+		if (rc == HDB_ERR_FILE_SIZE) throw "Incorrect file size";
+		if (rc == HDB_ERR_DIMENSIONS) throw "Width and height of image must be multiplier of sample block size";
+		std::printf("Error: %s\n", msg.c_str());
+		return;
+	}
+	std::cout << "Frames: " << frames << std::endl;
+	std::cout << "Execution Time without copy on GPU: " << t.kernel_ms / 1e3 << "s" << std::endl;
+	std::cout << "Execution Time with copy on GPU: " << t.total_ms / 1e3 << "s" << std::endl;
+	std::cout << "Copy Operation Time with GPU buffers: " << t.copy_ms / 1e3 << "s" << std::endl;
+	hdb_destroy(ctx);
+}
+
 } // namespace b200

@@ -256,6 +256,16 @@ int hdb_deblock_nv12_surfaces_device(hdb_context *ctx, const hdb_nv12_surfaces *
 	unsigned n_frames, unsigned width, unsigned height, const unsigned *d_qp,
 	const unsigned char *d_vert, const unsigned char *d_hor, unsigned flags, void *stream);
 
+/*
+ * File in, file out for a raw sequence: any number of frames back to back in one file (the reference's
+ * reader takes exactly one, cpu.h:43; its driver names one file per run, main.cu:111-133).  Same
+ * checks and messages as hdb_execute_gpu, the length check becoming "a whole number of frames".
+ * One qp for all frames, default strengths; flags: HDB_FLAG_NV12 or 0.  The file is processed a
+ * bounded chunk at a time through the batch pipeline; timings are summed over the chunks.
+ */
+int hdb_execute_gpu_sequence(hdb_context *ctx, const char *input_file_name, const char *output_file_name,
+	unsigned width, unsigned height, unsigned qp, unsigned flags, unsigned *n_frames, hdb_timing *timing);
+
 /* number of filter-kernel launches made through ctx since creation */
 unsigned long long hdb_kernel_launch_count(const hdb_context *ctx);
 
@@ -270,6 +280,11 @@ const char *hdb_multi_last_error(const hdb_multi *m);
 int hdb_multi_deblock_batch(hdb_multi *m, const unsigned char *frames_in, unsigned char *frames_out,
 	unsigned n_frames, unsigned width, unsigned height, const unsigned *qp,
 	const unsigned char *vert_bs, const unsigned char *hor_bs, hdb_timing *timing);
+
+/* the same with HDB_FLAG_EDGE_MAPS / HDB_FLAG_NV12 (declared further up) */
+int hdb_multi_deblock_batch_ex(hdb_multi *m, const unsigned char *frames_in, unsigned char *frames_out,
+	unsigned n_frames, unsigned width, unsigned height, const unsigned *qp,
+	const unsigned char *vert, const unsigned char *hor, unsigned flags, hdb_timing *timing);
 
 /*
  * One large frame split into strips of CTU rows (64 luma lines), one strip per GPU.

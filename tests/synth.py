@@ -153,6 +153,13 @@ def make_block_info(rng, w, h, kind="cu16"):
         info["ref"] = rng.integers(-1, 3, info["ref"].shape)
         info["flags"] = rng.integers(0, 64, info.shape) & np.where(rng.random(info.shape) < 0.15, 63, 62)
         info["qp"] = rng.integers(0, 70, info.shape)
+    elif kind == "extreme":
+        # vectors at the ends of the 16-bit range and around the threshold of 4; few distinct pictures
+        vals = np.array([-32768, -32767, -32765, -32764, -5, -4, -3, 0, 3, 4, 5, 32763, 32764, 32766, 32767])
+        info["mv"] = vals[rng.integers(0, vals.size, info["mv"].shape)]
+        info["ref"] = rng.integers(-2, 2, info["ref"].shape)
+        info["flags"] = rng.integers(0, 64, info.shape) & 60
+        info["qp"] = rng.integers(0, 256, info.shape)
     elif kind == "cu16":
         ch, cw = (h8 + 1) // 2, (w8 + 1) // 2
         up = lambda a: np.kron(a, np.ones((2, 2), a.dtype))[:h8, :w8]

@@ -116,7 +116,7 @@ def _emu_derive(lib, info, w, h):
 
 
 @pytest.mark.parametrize("size", [(8, 8), (16, 24), (64, 48), (352, 288), (1920, 1080)])
-@pytest.mark.parametrize("kind", ["intra", "random", "cu16"])
+@pytest.mark.parametrize("kind", ["intra", "random", "cu16", "extreme"])
 def test_emu_derive_matches_oracle(emu, size, kind):  # noqa: F811
     w, h = size
     rng = np.random.default_rng(w + 7 * h)

@@ -117,7 +117,7 @@ def test_edge_batch_device_resident(dev, in_place):
 
 # ---- derivation ---------------------------------------------------------------------------------
 @pytest.mark.parametrize("size", [(8, 8), (16, 24), (64, 48), (352, 288), (1920, 1080), (3840, 2160)], ids=lambda s: "%dx%d" % s)
-@pytest.mark.parametrize("kind", ["intra", "random", "cu16"])
+@pytest.mark.parametrize("kind", ["intra", "random", "cu16", "extreme"])
 def test_derive_edges_vs_oracle(dev, size, kind):
     w, h = size
     rng = np.random.default_rng(w * 3 + h)

@@ -63,3 +63,19 @@ def test_strips_golden_8k():
     y = m.deblock_frame_strips(frame, 7680, 4320, case["qp"], v, hh)
     assert common.md5(y) == case["md5"]
     m.close()
+
+
+@pytest.mark.parametrize("devices", _device_sets()[1:], ids=lambda d: "dev" + "".join(map(str, d)))
+def test_frame_sharded_batch_nv12_with_edge_maps(devices):
+    """The flagged batch form across devices: NV12 frames with per-edge QP maps, sharded by frame."""
+    m = hdb.MultiDeblocker(devices)
+    n, w, h = 13, 768, 576
+    rng = np.random.default_rng(41)
+    frames = np.stack([orc.yv12_to_nv12(synth.make_frame(rng, w, h, "blocky"), w, h) for _ in range(n)])
+    qps = rng.integers(18, 52, n).astype(np.uint32)
+    maps = [synth.make_edge_maps(rng, w, h, "smooth", picture_edges=bool(f & 1)) for f in range(n)]
+    v, hh = np.stack([a for a, _ in maps]), np.stack([b for _, b in maps])
+    got = m.deblock_batch_ex(frames, w, h, qps, v, hh, flags=hdb.FLAG_NV12 | hdb.FLAG_EDGE_MAPS)
+    for f in range(n):
+        assert np.array_equal(got[f], orc.deblock_frame_nv12(frames[f], w, h, int(qps[f]), v[f], hh[f], edges=True)), f
+    m.close()

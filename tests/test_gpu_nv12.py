@@ -178,3 +178,30 @@ def test_nv12_equals_yv12_at_full_size(dev):
     uv = out_n[:, ysz:].view(n, cw * ch, 2)
     assert bool((uv[:, :, 0] == out_p[:, ysz:ysz + cw * ch]).all()) and bool((uv[:, :, 1] == out_p[:, ysz + cw * ch:]).all())
     assert float((out_p != planar).float().mean()) > 0.02
+
+
+@pytest.mark.parametrize("nv12", [False, True])
+def test_sequence_file(dev, tmp_path, nv12):
+    """hdb_execute_gpu_sequence: a raw file with several frames, YV12 and NV12, and the reference's two file errors."""
+    n, w, h, qp = 7, 352, 288, 35
+    rng = np.random.default_rng(12)
+    frames = np.stack([synth.make_frame(rng, w, h, "blocky") for _ in range(n)])
+    frames[0] = common.fixture("mother-daughter_352x288_yv12.yuv")
+    stored = np.stack([orc.yv12_to_nv12(f, w, h) for f in frames]) if nv12 else frames
+    fin, fout = tmp_path / "seq.yuv", tmp_path / "seq_out.yuv"
+    stored.tofile(fin)
+    t = hdb.Timing()
+    assert dev.execute_gpu_sequence(str(fin), str(fout), w, h, qp, flags=hdb.FLAG_NV12 if nv12 else 0, timing=t) == n
+    got = np.fromfile(fout, np.uint8).reshape(n, -1)
+    for f in range(n):
+        want = orc.deblock_frame(frames[f], w, h, qp)
+        assert np.array_equal(orc.nv12_to_yv12(got[f], w, h) if nv12 else got[f], want), f
+    case = [c for c in common.golden()["bundled"] if c["file"].startswith("mother") and c["qp"] == 35][0]
+    assert common.md5(orc.nv12_to_yv12(got[0], w, h) if nv12 else got[0]) == case["md5"]
+    assert t.d2h_bytes == frames.nbytes
+    stored.reshape(-1)[:-5].tofile(fin)
+    with pytest.raises(hdb.DeblockError, match="Incorrect file size"):
+        dev.execute_gpu_sequence(str(fin), str(fout), w, h, qp)
+    np.zeros(2 * 3 * 12 * 8 // 2, np.uint8).tofile(fin)
+    with pytest.raises(hdb.DeblockError, match="multiplier of sample block size"):
+        dev.execute_gpu_sequence(str(fin), str(fout), 12, 8, qp)
