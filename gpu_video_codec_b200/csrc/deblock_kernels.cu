@@ -63,6 +63,9 @@
 #ifndef HDB_MIN_CTAS
 #define HDB_MIN_CTAS 21
 #endif
+#ifndef HDB_NV12_MIN_CTAS
+#define HDB_NV12_MIN_CTAS (HDB_MIN_CTAS - 1)    /* the two-plane variants: see DeblockTiledKernel */
+#endif
 #ifndef HDB_TRACE
 #define HDB_TRACE 0     /* 1: development build that records per-warp timestamps (tools/trace_tail.py) */
 #endif
@@ -217,7 +220,7 @@ __device__ __forceinline__ u32 PackBs(const BsRaw &r, bool chroma)
 /* (the two-plane variants hold the interleaved-chroma code as well and are given 96 registers, which
  * still leaves 21 resident CTAs per SM; at 80 they spill 420 bytes) */
 template <bool kEdgeQp, bool kNv12>
-__global__ void __launch_bounds__(kWarps * 32, kNv12 ? HDB_MIN_CTAS - 1 : HDB_MIN_CTAS)
+__global__ void __launch_bounds__(kWarps * 32, kNv12 ? HDB_NV12_MIN_CTAS : HDB_MIN_CTAS)
 DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_constant__ TiledBatch b,
 	SchedWords *sched, const uint32_t run_len)
 {
@@ -351,19 +354,20 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_consta
 					u32 lo[8], hi[8];
 #pragma unroll
 					for (int r = 0; r < 8; r++) {
-						const u32 *w = base + r * kTileWords;
-						SplitUv(w[0], w[1], w[2], w[3], v_plane, lo[r], hi[r]);
+						/* the pair's 16 bytes of a row start 8 bytes into a 16-byte unit: two 64-bit accesses */
+						const uint2 *w = reinterpret_cast<const uint2 *>(base + r * kTileWords);
+						const uint2 a = w[0], c = w[1];
+						SplitUv(a.x, a.y, c.x, c.y, v_plane, lo[r], hi[r]);
 					}
 					ChromaBlock(lo, hi, s4 & 0xff, (s4 >> 8) & 0xff, (s4 >> 16) & 0xff, s4 >> 24, fp);
 #pragma unroll
 					for (int r = 0; r < 8; r++) {
 						/* the U lane needs the other plane's lo, the V lane the other plane's hi */
 						const u32 other = __shfl_xor_sync(pairs, v_plane ? lo[r] : hi[r], 16);
-						u32 w_first, w_second;
-						if (v_plane) JoinUv(other, hi[r], w_first, w_second);
-						else JoinUv(lo[r], other, w_first, w_second);
-						u32 *w = base + r * kTileWords + (v_plane ? 2 : 0);
-						w[0] = w_first; w[1] = w_second;
+						uint2 o;
+						if (v_plane) JoinUv(other, hi[r], o.x, o.y);
+						else JoinUv(lo[r], other, o.x, o.y);
+						*reinterpret_cast<uint2 *>(base + r * kTileWords + (v_plane ? 2 : 0)) = o;
 					}
 				}
 			} else if (bx < pl.nbx && lby0 + rb < pl.rows) {
@@ -580,52 +584,74 @@ cudaError_t LaunchDefaultLumaBs(unsigned char *vert_bs, unsigned char *hor_bs, i
  * 192 the filter moves.
  */
 constexpr int kDeriveCols = 128, kDeriveRows = 8;
+constexpr int kDeriveTileWords = 3 * kDeriveCols + 4;     /* 388: the 128 records, the one to their left, one word of slack in front */
 
 __global__ void __launch_bounds__(kDeriveCols)
 DeriveEdgesKernel(const uint32_t *info, int w8, int h8, int n_frames, unsigned char *vert_edges, unsigned char *hor_edges)
 {
-	/* tile[rr][3c + k]: word k of block (r0 - 1 + rr, x0 - 1 + c) */
-	__shared__ uint32_t tile[kDeriveRows + 1][3 * (kDeriveCols + 1)];
+	/* tile[rr][i]: word 3 * x0 - 4 + i of block row r0 - 1 + rr, so that record x0 - 1 + c starts at word 3c + 1
+	 * and the tile starts on a 16-byte boundary of the row (x0 is a multiple of 128) */
+	__shared__ __align__(16) uint32_t tile[kDeriveRows + 1][kDeriveTileWords];
 	const int t = threadIdx.x;
 	const int x0 = blockIdx.x * kDeriveCols, r0 = blockIdx.y * kDeriveRows;
 	const int x = x0 + t;
+	const int row_words = 3 * w8;
 	const long long nv = (long long)(w8 + 1) * h8, nh = (long long)(h8 + 1) * w8;
+	/* rows and frames start on 16-byte boundaries when W/8 is a multiple of 4 (every size the tiled filter takes) */
+	const bool vec = (w8 & 3) == 0 && (reinterpret_cast<uintptr_t>(info) & 15) == 0;
+	const int rr_first = r0 == 0 ? 1 : 0;
+	const int rr_last = min(kDeriveRows, h8 - r0);          /* last tile row that exists in the frame */
 	for (int f = blockIdx.z; f < n_frames; f += gridDim.z) {
 		const uint32_t *fi = info + 3ll * f * w8 * h8;
+		const int w_first = 3 * x0 - 4;
+		if (vec) {
+			if (t < kDeriveTileWords / 4) {
+				const int wi = w_first + 4 * t;
+				if (wi >= 0 && wi + 4 <= row_words) {
+					const uint4 *src = reinterpret_cast<const uint4 *>(fi + (long long)(r0 - 1 + rr_first) * row_words + wi);
+#pragma unroll
+					for (int rr = 0; rr <= kDeriveRows; rr++)
+						if (rr >= rr_first && rr <= rr_last)
+							*reinterpret_cast<uint4 *>(&tile[rr][4 * t]) = __ldg(src + (long long)(rr - rr_first) * (row_words / 4));
+				}
+			}
+		} else {
 #pragma unroll 1
-		for (int rr = 0; rr <= kDeriveRows; rr++) {
-			const int r = r0 - 1 + rr;
-			if (r < 0 || r >= h8) continue;
-			const uint32_t *row = fi + 3ll * r * w8;
-			for (int i = t; i < 3 * (kDeriveCols + 1); i += kDeriveCols) {
-				const int wi = 3 * (x0 - 1) + i;
-				if (wi >= 0 && wi < 3 * w8) tile[rr][i] = __ldg(row + wi);
+			for (int rr = rr_first; rr <= rr_last; rr++) {
+				const uint32_t *row = fi + (long long)(r0 - 1 + rr) * row_words;
+				for (int i = t; i < kDeriveTileWords; i += kDeriveCols) {
+					const int wi = w_first + i;
+					if (wi >= 0 && wi < row_words) tile[rr][i] = __ldg(row + wi);
+				}
 			}
 		}
 		__syncthreads();
 		if (x <= w8) {
-			unsigned char *vf = vert_edges + f * nv, *hf = hor_edges + f * nh;
+			unsigned char *vf = vert_edges + f * nv + (long long)r0 * (w8 + 1) + x;
+			unsigned char *hf = hor_edges + f * nh + (long long)r0 * w8 + x;
+			const bool has_q = x < w8, has_left = x > 0;
 #pragma unroll 2
 			for (int rr = 1; rr <= kDeriveRows; rr++) {
 				const int r = r0 - 1 + rr;
 				if (r > h8) break;
 				u32 ev = 0, eh = 0;
-				if (r < h8 && x < w8) {
-					const uint32_t *qw = &tile[rr][3 * (t + 1)];
+				if (r < h8 && has_q) {
+					const uint32_t *qw = &tile[rr][3 * t + 4];
 					const BlockWords q = { qw[0], qw[1], qw[2] };
 					const u32 fl = q.meta >> 16;
-					if (x > 0) {
+					if (has_left) {
 						const BlockWords p = { qw[-3], qw[-2], qw[-1] };
 						ev = DeriveEdge(p, q, fl & kBlkTuLeft, fl & kBlkPuLeft);
 					}
 					if (r > 0) {
-						const uint32_t *pw = &tile[rr - 1][3 * (t + 1)];
+						const uint32_t *pw = &tile[rr - 1][3 * t + 4];
 						const BlockWords p = { pw[0], pw[1], pw[2] };
 						eh = DeriveEdge(p, q, fl & kBlkTuTop, fl & kBlkPuTop);
 					}
 				}
-				if (r < h8) vf[(long long)r * (w8 + 1) + x] = (unsigned char)ev;
-				if (x < w8) hf[(long long)r * w8 + x] = (unsigned char)eh;
+				if (r < h8) *vf = (unsigned char)ev;
+				if (has_q) *hf = (unsigned char)eh;
+				vf += w8 + 1; hf += w8;
 			}
 		}
 		__syncthreads();

@@ -1,6 +1,8 @@
 """Development aid: a longer randomised parity soak than the test suite affords (run on the GPU box).
 Random geometry, QP, content, boundary strengths; single frames, host batches, device batches (in place and
-out of place), pitched surfaces and logical-shard strips, all against the oracle."""
+out of place), pitched surfaces and logical-shard strips, all against the oracle; and the widened entry
+points: edge maps (per-edge QP) on host and device batches, NV12 frames with and without edge maps,
+pitched NV12 surfaces, boundary-strength derivation."""
 import sys
 import os
 import time
@@ -23,10 +25,10 @@ bs_kinds = [None, "uniform012", "wide", "twos", "zeros", "ones"]
 t0, n_cases, fails = time.time(), 0, 0
 st = torch.cuda.current_stream().cuda_stream
 while time.time() - t0 < budget:
-    mode = int(rng.integers(5))
+    mode = int(rng.integers(9))
     w = 8 * int(rng.integers(1, 200))
     h = 8 * int(rng.integers(1, 80))
-    if mode in (2, 3, 4) or rng.integers(2):
+    if mode in (2, 3, 4, 6, 7) or rng.integers(2):
         w = 32 * max(1, w // 32)
     n = int(rng.integers(1, 7))
     kind = kinds[int(rng.integers(len(kinds)))]
@@ -38,13 +40,71 @@ while time.time() - t0 < budget:
     else:
         vs, hs = zip(*[synth.make_bs(rng, w, h, bs_kind) for _ in range(n)])
         v, hh = np.stack(vs), np.stack(hs)
-    want = orc.deblock_batch(frames, w, h, qps, v, hh)
+    if mode >= 5:
+        # edge maps (bs | qp << 2) for modes 5, 6 (odd cases of 6), 7; derivation for mode 8
+        edge_kind = ["random", "wide", "smooth", "uniform"][int(rng.integers(4))]
+        maps = [synth.make_edge_maps(rng, w, h, edge_kind, picture_edges=bool(rng.integers(2))) for _ in range(n)]
+        ev, eh = np.stack([m[0] for m in maps]), np.stack([m[1] for m in maps])
     try:
-        if mode == 0:
+        if mode == 5:      # edge maps, YV12: host batch or device batch, both kernel paths
+            want = np.stack([orc.deblock_frame_edges(frames[i], w, h, int(qps[i]), ev[i], eh[i]) for i in range(n)])
+            if rng.integers(2):
+                got = dev.deblock_batch_edges(frames, w, h, qps, ev, eh)
+            else:
+                d = torch.from_numpy(frames).cuda()
+                dev.deblock_batch_edges_device(d, d, n, w, h, torch.from_numpy(qps.astype(np.int32)).cuda(),
+                                               torch.from_numpy(ev).cuda(), torch.from_numpy(eh).cuda(), stream=st)
+                torch.cuda.synchronize()
+                got = d.cpu().numpy()
+        elif mode == 6:    # NV12 frames, with strengths / defaults / edge maps, host or device
+            nv = np.stack([orc.yv12_to_nv12(f, w, h) for f in frames])
+            edges = bool(rng.integers(2))
+            a, b = (ev, eh) if edges else (v, hh)
+            want = np.stack([orc.deblock_frame_nv12(nv[i], w, h, int(qps[i]), None if a is None else a[i],
+                                                    None if b is None else b[i], edges=edges) for i in range(n)])
+            fl = hdb.FLAG_NV12 | (hdb.FLAG_EDGE_MAPS if edges else 0)
+            if rng.integers(2):
+                got = dev.deblock_batch_ex(nv, w, h, qps, a, b, flags=fl)
+            else:
+                d = torch.from_numpy(nv).cuda()
+                o = d if rng.integers(2) else torch.empty_like(d)
+                dev.deblock_batch_device_ex(d, o, n, w, h, torch.from_numpy(qps.astype(np.int32)).cuda(),
+                                            None if a is None else torch.from_numpy(a).cuda(),
+                                            None if b is None else torch.from_numpy(b).cuda(), flags=fl, stream=st)
+                torch.cuda.synchronize()
+                got = o.cpu().numpy()
+        elif mode == 7:    # pitched NV12 surfaces, in place
+            nv = np.stack([orc.yv12_to_nv12(f, w, h) for f in frames])
+            want = np.stack([orc.deblock_frame_nv12(nv[i], w, h, int(qps[i]), ev[i], eh[i], edges=True) for i in range(n)])
+            ch = h // 2
+            py, puv = w + 16 * int(rng.integers(0, 5)), w + 16 * int(rng.integers(0, 5))
+            t = torch.from_numpy(nv).cuda()
+            P = [torch.zeros((n, h, py), dtype=torch.uint8, device="cuda"), torch.zeros((n, ch, puv), dtype=torch.uint8, device="cuda")]
+            P[0][:, :, :w] = t[:, :w * h].view(n, h, w)
+            P[1][:, :, :w] = t[:, w * h:].view(n, ch, w)
+            s = hdb.Nv12Surfaces(P[0].data_ptr(), P[1].data_ptr(), py, puv, h * py, ch * puv)
+            dev.deblock_nv12_surfaces_device(s, s, n, w, h, torch.from_numpy(qps.astype(np.int32)).cuda(),
+                                             torch.from_numpy(ev).cuda(), torch.from_numpy(eh).cuda(),
+                                             flags=hdb.FLAG_EDGE_MAPS, stream=st)
+            torch.cuda.synchronize()
+            got = torch.cat([P[0][:, :, :w].reshape(n, -1), P[1][:, :, :w].reshape(n, -1)], 1).cpu().numpy()
+        elif mode == 8:    # derivation: block data -> edge maps, then the filter with them
+            ik = ["intra", "random", "cu16", "extreme"][int(rng.integers(4))]
+            info = np.stack([synth.make_block_info(rng, w, h, ik) for _ in range(n)])
+            gv, gh = dev.derive_edges(info, w, h)
+            ov, oh = zip(*[orc.derive_edges(info[i], w, h) for i in range(n)])
+            want = np.concatenate([np.stack(ov), np.stack(oh)], 1)
+            got = np.concatenate([gv, gh], 1)
+        if mode >= 5:
+            pass
+        elif mode == 0:
+            want = orc.deblock_batch(frames, w, h, qps, v, hh)
             got = np.stack([dev.deblock_frame(frames[i], w, h, int(qps[i]), None if v is None else v[i], None if hh is None else hh[i]) for i in range(n)])
         elif mode == 1:
+            want = orc.deblock_batch(frames, w, h, qps, v, hh)
             got = dev.deblock_batch(frames, w, h, qps, v, hh)
         elif mode == 2:
+            want = orc.deblock_batch(frames, w, h, qps, v, hh)
             d = torch.from_numpy(frames).cuda()
             o = d if rng.integers(2) else torch.empty_like(d)
             dq = torch.from_numpy(qps.astype(np.int32)).cuda()
@@ -54,6 +114,7 @@ while time.time() - t0 < budget:
             torch.cuda.synchronize()
             got = o.cpu().numpy()
         elif mode == 3:
+            want = orc.deblock_batch(frames, w, h, qps, v, hh)
             cw, ch = w // 2, h // 2
             py, pc = w + 16 * int(rng.integers(0, 5)), cw + 16 * int(rng.integers(0, 5))
             t = torch.from_numpy(frames).cuda()
@@ -70,6 +131,7 @@ while time.time() - t0 < budget:
             torch.cuda.synchronize()
             got = torch.cat([P[0][:, :, :w].reshape(n, -1), P[1][:, :, :cw].reshape(n, -1), P[2][:, :, :cw].reshape(n, -1)], 1).cpu().numpy()
         else:
+            want = orc.deblock_batch(frames, w, h, qps, v, hh)
             got = np.stack([multi.deblock_frame_strips(frames[i], w, h, int(qps[i]), None if v is None else v[i], None if hh is None else hh[i]) for i in range(n)])
         ok = np.array_equal(got, want)
     except Exception as e:  # noqa: BLE001
