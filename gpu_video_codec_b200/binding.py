@@ -146,6 +146,7 @@ def load_library():
     lib.hdb_multi_deblock_batch.argtypes = [vp] + batch_args + [C.POINTER(Timing)]
     lib.hdb_multi_deblock_batch_ex.argtypes = [vp] + batch_args + [C.c_uint, C.POINTER(Timing)]
     lib.hdb_multi_deblock_frame_strips.argtypes = [vp, vp, vp] + frame_args
+    lib.hdb_multi_deblock_frame_strips_ex.argtypes = [vp, vp, vp] + frame_args[:-1] + [C.c_uint, C.POINTER(Timing)]
     _lib = lib
     return lib
 
@@ -405,13 +406,13 @@ class MultiDeblocker:
                                                          None if timing is None else C.byref(timing)))
         return out
 
-    def deblock_frame_strips(self, yuv, width, height, qp, vert_bs=None, hor_bs=None, out=None, timing=None):
+    def deblock_frame_strips(self, yuv, width, height, qp, vert_bs=None, hor_bs=None, out=None, timing=None, flags=0):
         if out is None:
             out = np.empty_like(yuv)
         v = None if vert_bs is None else np.ascontiguousarray(vert_bs, np.uint8)
         h = None if hor_bs is None else np.ascontiguousarray(hor_bs, np.uint8)
-        self._check(self._lib.hdb_multi_deblock_frame_strips(self._m, _addr(yuv), _addr(out), width, height, qp,
-                                                             _addr(v), 0 if v is None else v.size,
-                                                             _addr(h), 0 if h is None else h.size,
-                                                             None if timing is None else C.byref(timing)))
+        self._check(self._lib.hdb_multi_deblock_frame_strips_ex(self._m, _addr(yuv), _addr(out), width, height, qp,
+                                                                _addr(v), 0 if v is None else v.size,
+                                                                _addr(h), 0 if h is None else h.size, flags,
+                                                                None if timing is None else C.byref(timing)))
         return out

@@ -214,6 +214,46 @@ __device__ __forceinline__ u32 PackBs(const BsRaw &r, bool chroma)
 /* ------------------------------------------------------------------ */
 /* the kernel                                                          */
 /* ------------------------------------------------------------------ */
+/*
+ * One block row of an interleaved-UV item (NV12), all 32 lanes: lane l & 15 names the block pair, lanes
+ * 0-15 filter its U samples, lanes 16-31 its V samples.  Only the three chroma constants of the frame's
+ * parameters are passed.  (HDB_UV_NOINLINE=1 keeps it out of line: that does not bring the two-plane
+ * kernels under 80 registers either -- what is live across the call spills instead.)
+ */
+#ifndef HDB_UV_NOINLINE
+#define HDB_UV_NOINLINE 0
+#endif
+#if HDB_UV_NOINLINE
+__device__ __noinline__
+#else
+__device__ __forceinline__
+#endif
+void UvBlockRow(u32 *base, u32 s4, u32 ct_neg, u32 ct_lo, u32 ct_2, bool live, bool v_plane)
+{
+	const unsigned pairs = __ballot_sync(0xffffffffu, live);
+	if (!live) return;
+	FilterParams fp;
+	fp.ct_neg = ct_neg; fp.ct_lo = ct_lo; fp.ct_2 = ct_2;
+	u32 lo[8], hi[8];
+#pragma unroll
+	for (int r = 0; r < 8; r++) {
+		/* the pair's 16 bytes of a row start 8 bytes into a 16-byte unit: two 64-bit accesses */
+		const uint2 *w = reinterpret_cast<const uint2 *>(base + r * kTileWords);
+		const uint2 a = w[0], c = w[1];
+		SplitUv(a.x, a.y, c.x, c.y, v_plane, lo[r], hi[r]);
+	}
+	ChromaBlock(lo, hi, s4 & 0xff, (s4 >> 8) & 0xff, (s4 >> 16) & 0xff, s4 >> 24, fp);
+#pragma unroll
+	for (int r = 0; r < 8; r++) {
+		/* the U lane needs the other plane's lo, the V lane the other plane's hi */
+		const u32 other = __shfl_xor_sync(pairs, v_plane ? lo[r] : hi[r], 16);
+		uint2 o;
+		if (v_plane) JoinUv(other, hi[r], o.x, o.y);
+		else JoinUv(lo[r], other, o.x, o.y);
+		*reinterpret_cast<uint2 *>(base + r * kTileWords + (v_plane ? 2 : 0)) = o;
+	}
+}
+
 /* kEdgeQp: the luma boundary-strength arrays hold edge bytes (bs | qp << 2, deblock_core.cuh) and every
  * luma segment takes beta / tc from its own entry; chroma is untouched by it (frame QP, cpu.h:110-117) */
 /* kNv12: two planes, Y and interleaved UV (lanes 0-15 filter the U blocks of a UV item, lanes 16-31 the V blocks) */
@@ -346,30 +386,8 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_consta
 				/* interleaved UV: the block pair of column l = lane & 15 is 16 bytes per row, 8 bytes after the
 				 * box origin; lane l filters its U samples, lane l + 16 its V samples, then the two swap
 				 * halves and each writes two of the row's four words */
-				const bool live = bx < pl.nbx && lby0 + rb < pl.rows;
-				const unsigned pairs = __ballot_sync(0xffffffffu, live);
-				if (live) {
-					const bool v_plane = lane >= 16;
-					u32 *base = tile + rb * 8 * kTileWords + 2 + 4 * (lane & 15);
-					u32 lo[8], hi[8];
-#pragma unroll
-					for (int r = 0; r < 8; r++) {
-						/* the pair's 16 bytes of a row start 8 bytes into a 16-byte unit: two 64-bit accesses */
-						const uint2 *w = reinterpret_cast<const uint2 *>(base + r * kTileWords);
-						const uint2 a = w[0], c = w[1];
-						SplitUv(a.x, a.y, c.x, c.y, v_plane, lo[r], hi[r]);
-					}
-					ChromaBlock(lo, hi, s4 & 0xff, (s4 >> 8) & 0xff, (s4 >> 16) & 0xff, s4 >> 24, fp);
-#pragma unroll
-					for (int r = 0; r < 8; r++) {
-						/* the U lane needs the other plane's lo, the V lane the other plane's hi */
-						const u32 other = __shfl_xor_sync(pairs, v_plane ? lo[r] : hi[r], 16);
-						uint2 o;
-						if (v_plane) JoinUv(other, hi[r], o.x, o.y);
-						else JoinUv(lo[r], other, o.x, o.y);
-						*reinterpret_cast<uint2 *>(base + r * kTileWords + (v_plane ? 2 : 0)) = o;
-					}
-				}
+				UvBlockRow(tile + rb * 8 * kTileWords + 2 + 4 * (lane & 15), s4, fp.ct_neg, fp.ct_lo, fp.ct_2,
+					bx < pl.nbx && lby0 + rb < pl.rows, lane >= 16);
 			} else if (bx < pl.nbx && lby0 + rb < pl.rows) {
 				u32 *base = tile + rb * 8 * kTileWords + kLead / 4 + 2 * lane;
 				u32 lo[8], hi[8];

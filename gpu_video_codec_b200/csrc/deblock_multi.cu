@@ -188,7 +188,17 @@ int hdb_multi_deblock_frame_strips(hdb_multi *m, const unsigned char *yuv_in, un
 	unsigned width, unsigned height, unsigned qp, const unsigned char *vert_bs, unsigned num_vert_bs,
 	const unsigned char *hor_bs, unsigned num_hor_bs, hdb_timing *timing)
 {
+	return hdb_multi_deblock_frame_strips_ex(m, yuv_in, yuv_out, width, height, qp, vert_bs, num_vert_bs, hor_bs, num_hor_bs, 0, timing);
+}
+
+int hdb_multi_deblock_frame_strips_ex(hdb_multi *m, const unsigned char *yuv_in, unsigned char *yuv_out,
+	unsigned width, unsigned height, unsigned qp, const unsigned char *vert_bs, unsigned num_vert_bs,
+	const unsigned char *hor_bs, unsigned num_hor_bs, unsigned flags, hdb_timing *timing)
+{
 	if (!m || m->ctx.empty()) return HDB_ERR_INVALID_ARG;
+	if (flags & ~HDB_FLAG_EDGE_MAPS) return MFail(m, HDB_ERR_INVALID_ARG, "the strip split takes HDB_FLAG_EDGE_MAPS or 0");
+	const bool edge_qp = (flags & HDB_FLAG_EDGE_MAPS) != 0;
+	if (edge_qp && (!vert_bs || !hor_bs)) return MFail(m, HDB_ERR_INVALID_ARG, "edge maps are required: there is no default for them");
 	if (!yuv_in || !yuv_out) return MFail(m, HDB_ERR_INVALID_ARG, "NULL buffer");
 	int rc = ValidateFrameArgs(m->ctx[0], width, height, vert_bs, num_vert_bs, hor_bs, num_hor_bs, true);
 	if (rc) return MFail(m, rc, m->ctx[0]->err);
@@ -196,8 +206,11 @@ int hdb_multi_deblock_frame_strips(hdb_multi *m, const unsigned char *yuv_in, un
 	const std::vector<Strip> strips = MakeStrips(H, (int)m->ctx.size());
 	const int g = (int)strips.size();
 	/* strips need the tensor-map path; a frame it cannot describe, or a single strip, goes to one GPU whole */
-	if (g == 1 || W % 32 != 0)
-		return hdb_deblock_frame(m->ctx[0], yuv_in, yuv_out, width, height, qp, vert_bs, num_vert_bs, hor_bs, num_hor_bs, timing);
+	if (g == 1 || W % 32 != 0) {
+		rc = edge_qp ? hdb_deblock_frame_edges(m->ctx[0], yuv_in, yuv_out, width, height, qp, vert_bs, num_vert_bs, hor_bs, num_hor_bs, timing)
+			: hdb_deblock_frame(m->ctx[0], yuv_in, yuv_out, width, height, qp, vert_bs, num_vert_bs, hor_bs, num_hor_bs, timing);
+		return rc ? MFail(m, rc, m->ctx[0]->err) : HDB_OK;
+	}
 
 	const auto t0 = std::chrono::steady_clock::now();
 	const unsigned nv = hdb_num_vert_bs(width, height), nh = hdb_num_hor_bs(width, height);
@@ -303,7 +316,7 @@ int hdb_multi_deblock_frame_strips(hdb_multi *m, const unsigned char *yuv_in, un
 		{
 			std::lock_guard<std::mutex> lock(c->mu);
 			rc = EnqueueFilter(c, v, L.y, L.y, 1, nullptr, qp, vert_bs ? m->vbs[d] : nullptr, 0,
-				vert_bs ? m->hbs[d] : nullptr, 0, st, nullptr);
+				vert_bs ? m->hbs[d] : nullptr, 0, st, nullptr, edge_qp);
 		}
 		if (rc) return MFail(m, rc, c->err);
 		if (timing) M_CUDA(cudaEventRecord(k1[d], st));

@@ -295,6 +295,11 @@ int hdb_multi_deblock_frame_strips(hdb_multi *m, const unsigned char *yuv_in, un
 	unsigned width, unsigned height, unsigned qp,
 	const unsigned char *vert_bs, unsigned num_vert_bs,
 	const unsigned char *hor_bs, unsigned num_hor_bs, hdb_timing *timing);
+/* the same with edge maps: flags = HDB_FLAG_EDGE_MAPS (or 0); the maps keep their frame-global indexing */
+int hdb_multi_deblock_frame_strips_ex(hdb_multi *m, const unsigned char *yuv_in, unsigned char *yuv_out,
+	unsigned width, unsigned height, unsigned qp,
+	const unsigned char *vert, unsigned num_vert,
+	const unsigned char *hor, unsigned num_hor, unsigned flags, hdb_timing *timing);
 
 #ifdef __cplusplus
 }

@@ -79,3 +79,20 @@ def test_frame_sharded_batch_nv12_with_edge_maps(devices):
     for f in range(n):
         assert np.array_equal(got[f], orc.deblock_frame_nv12(frames[f], w, h, int(qps[f]), v[f], hh[f], edges=True)), f
     m.close()
+
+
+@pytest.mark.parametrize("devices", _device_sets()[1:], ids=lambda d: "dev" + "".join(map(str, d)))
+@pytest.mark.parametrize("size", [(1920, 1080), (3840, 2160), (256, 136), (200, 120)], ids=lambda s: "%dx%d" % s)
+def test_strip_split_with_edge_maps(devices, size):
+    """The strip split with per-edge QP: the maps keep their frame-global indexing on every device."""
+    w, h = size
+    m = hdb.MultiDeblocker(devices)
+    rng = np.random.default_rng(w * 5 + h)
+    frame = synth.make_frame(rng, w, h, "blocky")
+    v, hh = synth.make_edge_maps(rng, w, h, "random", picture_edges=True)
+    got = m.deblock_frame_strips(frame, w, h, 37, v, hh, flags=hdb.FLAG_EDGE_MAPS)
+    want = orc.deblock_frame_edges(frame, w, h, 37, v, hh)
+    assert np.array_equal(got, want), int((got != want).sum())
+    with pytest.raises(hdb.DeblockError):
+        m.deblock_frame_strips(frame, w, h, 37, flags=hdb.FLAG_EDGE_MAPS)       # maps are required
+    m.close()
