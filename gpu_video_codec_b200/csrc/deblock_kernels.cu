@@ -64,7 +64,7 @@
 #define HDB_MIN_CTAS 21
 #endif
 #ifndef HDB_NV12_MIN_CTAS
-#define HDB_NV12_MIN_CTAS (HDB_MIN_CTAS - 1)    /* the two-plane variants: see DeblockTiledKernel */
+#define HDB_NV12_MIN_CTAS HDB_MIN_CTAS          /* the two-plane variants (measurement knob) */
 #endif
 #ifndef HDB_TRACE
 #define HDB_TRACE 0     /* 1: development build that records per-warp timestamps (tools/trace_tail.py) */
@@ -216,24 +216,14 @@ __device__ __forceinline__ u32 PackBs(const BsRaw &r, bool chroma)
 /* ------------------------------------------------------------------ */
 /*
  * One block row of an interleaved-UV item (NV12), all 32 lanes: lane l & 15 names the block pair, lanes
- * 0-15 filter its U samples, lanes 16-31 its V samples.  Only the three chroma constants of the frame's
- * parameters are passed.  (HDB_UV_NOINLINE=1 keeps it out of line: that does not bring the two-plane
- * kernels under 80 registers either -- what is live across the call spills instead.)
+ * 0-15 filter its U samples, lanes 16-31 its V samples, then the two swap one word per row and each
+ * writes two of the row's four words.  Every lane runs the whole sequence, also those whose block lies
+ * outside the plane (their strengths are 0, nothing is filtered, nothing is written back): the exchange
+ * then sits outside divergent control flow with a full mask.  Under `if (live)` with a ballot mask the
+ * two-plane kernels needed 96 registers (80 spilled 424 bytes) and lost three resident warps per SM.
  */
-#ifndef HDB_UV_NOINLINE
-#define HDB_UV_NOINLINE 0
-#endif
-#if HDB_UV_NOINLINE
-__device__ __noinline__
-#else
-__device__ __forceinline__
-#endif
-void UvBlockRow(u32 *base, u32 s4, u32 ct_neg, u32 ct_lo, u32 ct_2, bool live, bool v_plane)
+__device__ __forceinline__ void UvBlockRow(u32 *base, u32 s4, const FilterParams &fp, bool live, bool v_plane)
 {
-	const unsigned pairs = __ballot_sync(0xffffffffu, live);
-	if (!live) return;
-	FilterParams fp;
-	fp.ct_neg = ct_neg; fp.ct_lo = ct_lo; fp.ct_2 = ct_2;
 	u32 lo[8], hi[8];
 #pragma unroll
 	for (int r = 0; r < 8; r++) {
@@ -246,19 +236,17 @@ void UvBlockRow(u32 *base, u32 s4, u32 ct_neg, u32 ct_lo, u32 ct_2, bool live, b
 #pragma unroll
 	for (int r = 0; r < 8; r++) {
 		/* the U lane needs the other plane's lo, the V lane the other plane's hi */
-		const u32 other = __shfl_xor_sync(pairs, v_plane ? lo[r] : hi[r], 16);
+		const u32 other = __shfl_xor_sync(0xffffffffu, v_plane ? lo[r] : hi[r], 16);
 		uint2 o;
 		if (v_plane) JoinUv(other, hi[r], o.x, o.y);
 		else JoinUv(lo[r], other, o.x, o.y);
-		*reinterpret_cast<uint2 *>(base + r * kTileWords + (v_plane ? 2 : 0)) = o;
+		if (live) *reinterpret_cast<uint2 *>(base + r * kTileWords + (v_plane ? 2 : 0)) = o;
 	}
 }
 
 /* kEdgeQp: the luma boundary-strength arrays hold edge bytes (bs | qp << 2, deblock_core.cuh) and every
  * luma segment takes beta / tc from its own entry; chroma is untouched by it (frame QP, cpu.h:110-117) */
 /* kNv12: two planes, Y and interleaved UV (lanes 0-15 filter the U blocks of a UV item, lanes 16-31 the V blocks) */
-/* (the two-plane variants hold the interleaved-chroma code as well and are given 96 registers, which
- * still leaves 21 resident CTAs per SM; at 80 they spill 420 bytes) */
 template <bool kEdgeQp, bool kNv12>
 __global__ void __launch_bounds__(kWarps * 32, kNv12 ? HDB_NV12_MIN_CTAS : HDB_MIN_CTAS)
 DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_constant__ TiledBatch b,
@@ -386,8 +374,7 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_consta
 				/* interleaved UV: the block pair of column l = lane & 15 is 16 bytes per row, 8 bytes after the
 				 * box origin; lane l filters its U samples, lane l + 16 its V samples, then the two swap
 				 * halves and each writes two of the row's four words */
-				UvBlockRow(tile + rb * 8 * kTileWords + 2 + 4 * (lane & 15), s4, fp.ct_neg, fp.ct_lo, fp.ct_2,
-					bx < pl.nbx && lby0 + rb < pl.rows, lane >= 16);
+				UvBlockRow(tile + rb * 8 * kTileWords + 2 + 4 * (lane & 15), s4, fp, bx < pl.nbx && lby0 + rb < pl.rows, lane >= 16);
 			} else if (bx < pl.nbx && lby0 + rb < pl.rows) {
 				u32 *base = tile + rb * 8 * kTileWords + kLead / 4 + 2 * lane;
 				u32 lo[8], hi[8];
