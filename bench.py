@@ -40,6 +40,8 @@ WORKLOADS = {
     "image2_single": (768, 576, 1, "single 768x576 frame, QP 30, default BS (latency case)"),
     # BASELINE.json configs[4]: one process drives all GPUs (hdb_multi_deblock_frame_strips); not a torchrun workload
     "8k_strips": (7680, 4320, 16, "stream of single 7680x4320 frames, each split into CTU-row strips across the GPUs, P2P halos"),
+    # the same kind of batch stored as NV12 (Y + interleaved UV), one GPU
+    "4k_nv12_512": (3840, 2160, 512, "synthetic 3840x2160 NV12 batch of 512 frames, random QP/BS maps"),
     # block data -> edge maps (bs | qp << 2) -> per-edge-QP filter; one GPU
     "4k_edges512": (3840, 2160, 512, "synthetic 3840x2160 YV12 batch of 512 frames, per-8x8-block decoder data -> derived edge maps -> per-edge-QP filter"),
 }
@@ -365,11 +367,29 @@ def run_ours(args, rank, world, local_rank):
         n = 1
     else:
         frames, qp, vbs, hbs = device_batch(torch, n, w, h, seed=1000 + first)
+    nv12 = "nv12" in args.workload
+    flags = hdb.FLAG_NV12 if nv12 else 0
+    ysz, csz = w * h, (w // 2) * (h // 2)
+
+    def to_nv12(t):      # [k, 3wh/2] planar -> NV12, on whatever device t lives
+        r = t.clone()
+        r[:, ysz:] = torch.stack([t[:, ysz:ysz + csz], t[:, ysz + csz:]], dim=2).reshape(t.shape[0], -1)
+        return r
+
+    def to_yv12(t):
+        r = t.clone()
+        uv = t[:, ysz:].reshape(t.shape[0], csz, 2)
+        r[:, ysz:ysz + csz] = uv[:, :, 0]
+        r[:, ysz + csz:] = uv[:, :, 1]
+        return r
+
+    if nv12:
+        frames = to_nv12(frames)
     out = torch.empty_like(frames)
 
     # ---- kernel-only: frames resident in HBM ------------------------------------------------
     def step():
-        dev.deblock_batch_device(frames, out, n, w, h, qp, vbs, hbs, stream=stream)
+        dev.deblock_batch_device_ex(frames, out, n, w, h, qp, vbs, hbs, flags=flags, stream=stream)
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -399,8 +419,9 @@ def run_ours(args, rank, world, local_rank):
         from oracle import oracle_py as orc
         idx = sorted(set([0, n // 3, (2 * n) // 3, n - 1] + ([3, 5, 6] if n > 6 else [])))
         sel = torch.tensor(idx, device="cuda")
-        got = out[sel].cpu().numpy()
-        src = frames[sel].cpu().numpy()
+        # NV12: the checkers take planar frames; the two layouts are byte permutations of each other
+        got = (to_yv12(out[sel]) if nv12 else out[sel]).cpu().numpy()
+        src = (to_yv12(frames[sel]) if nv12 else frames[sel]).cpu().numpy()
         q = qp[sel].cpu().numpy().astype(np.uint32)
         v = None if vbs is None else vbs[sel].cpu().numpy()
         hh = None if hbs is None else hbs[sel].cpu().numpy()
@@ -420,7 +441,7 @@ def run_ours(args, rank, world, local_rank):
     tm = hdb.Timing()
 
     def e2e_step():
-        dev.deblock_batch(h_in, w, h, h_qp, h_v, h_h, out=h_out, timing=tm, n_frames=n)
+        dev.deblock_batch_ex(h_in, w, h, h_qp, h_v, h_h, flags=flags, out=h_out, timing=tm, n_frames=n)
 
     for _ in range(max(1, min(args.warmup, 2))):
         e2e_step()
@@ -443,7 +464,7 @@ def run_ours(args, rank, world, local_rank):
         # checker (the unmodified reference on all host cores when oracle/_ref is there, else the port)
         from oracle import oracle_py as orc
         cores = os.cpu_count() or 1
-        np_in, np_out = h_in.numpy(), h_out.numpy()
+        np_in, np_out = (to_yv12(h_in).numpy(), to_yv12(h_out).numpy()) if nv12 else (h_in.numpy(), h_out.numpy())
         np_qp = h_qp.numpy().astype(np.uint32)
         np_v = None if h_v is None else h_v.numpy()
         np_h = None if h_h is None else h_h.numpy()
@@ -489,10 +510,10 @@ def run_ours(args, rank, world, local_rank):
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": ncu_traffic(args.workload, n),
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
-                         "kernel": "DeblockTiledKernel", "mean_launch_ms": round(mean_launch_ms, 4)},
+                         "kernel": "DeblockTiledKernel<0, 1>" if nv12 else "DeblockTiledKernel", "mean_launch_ms": round(mean_launch_ms, 4)},
             "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(e2e_s / args.steps * 1e3, 3), "launches_per_step": e2e_launches // max(args.steps, 1),
-                    "api": "hdb_deblock_batch (pinned host buffers, 3-stream pipeline)"},
+                    "api": "hdb_deblock_batch%s (pinned host buffers, 3-stream pipeline)" % ("_ex, HDB_FLAG_NV12" if nv12 else "")},
             "gpu_launches": kernel_launches,
             "clocks": clocks,
             "parity": parity,
@@ -501,7 +522,7 @@ def run_ours(args, rank, world, local_rank):
             cores = os.cpu_count() or 1
             ns = max(1, min(n, args.cpu_sample or 256))
             sel = torch.arange(ns, device="cuda")
-            src = frames[sel].cpu().numpy()
+            src = (to_yv12(frames[sel]) if nv12 else frames[sel]).cpu().numpy()
             q = qp[sel].cpu().numpy().astype(np.uint32)
             v = None if vbs is None else vbs[sel].cpu().numpy()
             hh = None if hbs is None else hbs[sel].cpu().numpy()

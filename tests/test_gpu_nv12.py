@@ -205,3 +205,31 @@ def test_sequence_file(dev, tmp_path, nv12):
     np.zeros(2 * 3 * 12 * 8 // 2, np.uint8).tofile(fin)
     with pytest.raises(hdb.DeblockError, match="multiplier of sample block size"):
         dev.execute_gpu_sequence(str(fin), str(fout), 12, 8, qp)
+
+
+def test_demo_driver(tmp_path):
+    """host/main.cpp (the reference's main.cu with arguments) over the C++ mirror: one frame goes through
+    b200::ReadYuvFrame + b200::ExecuteGpu, a longer file through b200::ExecuteGpuSequence."""
+    import os
+    import subprocess
+    demo = os.path.join(os.path.dirname(hdb.library_path()), "hevc_deblock_b200_demo")
+    if not os.path.exists(demo):
+        pytest.skip("demo driver not built")
+    case = [c for c in common.golden()["bundled"] if c["file"].startswith("mother") and c["qp"] == 35][0]
+    x = common.fixture(case["file"])
+    fin, fout = tmp_path / "one.yuv", tmp_path / "one_out.yuv"
+    x.tofile(fin)
+    r = subprocess.run([demo, str(fin), "352", "288", "35", str(fout)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    for line in ("Compute Capability: 10.", "Execution Time without copy on GPU:", "Execution Time with copy on GPU:",
+                 "Copy Operation Time with GPU buffers:"):                       # main.cu:92-107, gpu.cu:1292, 1302-1303
+        assert line in r.stdout, r.stdout
+    assert common.md5(np.fromfile(fout, np.uint8)) == case["md5"]
+    seq, sout = tmp_path / "seq.yuv", tmp_path / "seq_out.yuv"
+    np.tile(x, 5).tofile(seq)
+    r = subprocess.run([demo, str(seq), "352", "288", "35", str(sout)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "Frames: 5" in r.stdout, r.stdout + r.stderr
+    got = np.fromfile(sout, np.uint8).reshape(5, -1)
+    assert all(common.md5(g) == case["md5"] for g in got)
+    r = subprocess.run([demo, str(seq), "352", "280", "35", str(sout)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 1 and "Incorrect file size" in r.stderr               # cpu.h:43-45
