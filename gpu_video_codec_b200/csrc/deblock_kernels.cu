@@ -34,6 +34,12 @@
  * unbalanced); the runs shrink as the work runs out, and the last CTA to leave
  * resets the counter for the next launch.
  *
+ * Two template parameters widen the same kernel: kEdgeQp -- the luma strength
+ * arrays hold edge bytes (bs | qp << 2) and every luma segment takes beta / tc from its own entry -- and
+ * kNv12 -- two planes, Y and interleaved UV, a UV item holding 16 block columns of U and of V that lane
+ * pairs split, filter and re-interleave (UvBlockRow).  <false, false> is the kernel described above.
+ *
+ * DeriveEdgesKernel builds edge maps from per-8x8-block decoder data (H.265 8.7.2.4).
  * The generic kernels at the end cover frame sizes TMA cannot describe.
  */
 #include "deblock_kernels.cuh"
