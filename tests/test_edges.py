@@ -184,3 +184,23 @@ def test_all_intra_gives_reference_default_inside():
     b = orc.deblock_frame(frame, w, h, q, dv2.reshape(-1), dh2.reshape(-1))
     ysz = w * h
     assert np.array_equal(a[:ysz], b[:ysz])
+
+
+def test_bench_block_info_generator_packs_the_abi_layout():
+    """bench.device_block_info builds hdb_block_info records as three 32-bit words on the device; on the CPU the
+    same code must give records the oracle reads as sane block data and derives a mix of strengths from."""
+    import torch
+
+    import bench
+    n, w, h = 2, 352, 288
+    words = bench.device_block_info(torch, n, w, h, seed=1, device="cpu")
+    assert words.shape == (n, (h // 8) * (w // 8), 3) and words.dtype == torch.int32
+    info = words.numpy().view(np.uint8).reshape(n, h // 8, w // 8, 12).copy().view(orc.BLOCK_INFO).reshape(n, h // 8, w // 8)
+    assert info["qp"].min() >= 0 and info["qp"].max() <= 51
+    assert set(np.unique(info["ref"])) <= {-1, 0, 1, 2}
+    assert np.abs(info["mv"].astype(np.int64)).max() <= 40
+    intra = (info["flags"] & synth.BLK_INTRA) != 0
+    assert (info["ref"][intra] == -1).all()
+    v, hh = orc.derive_edges(info[0], w, h)
+    hist = np.bincount(np.concatenate([v, hh]) & 3, minlength=4)
+    assert hist[0] > 0 and hist[1] > 0 and hist[2] > 0 and hist[3] == 0
