@@ -130,6 +130,7 @@ def load_library():
     lib.hdb_derive_edges_device.argtypes = [vp, vp, C.c_uint, C.c_uint, C.c_uint, vp, vp, vp]
     lib.hdb_derive_edges.argtypes = [vp, vp, C.c_uint, C.c_uint, C.c_uint, vp, vp]
     lib.hdb_deblock_batch_ex.argtypes = [vp] + batch_args + [C.c_uint, C.POINTER(Timing)]
+    lib.hdb_deblock_batch_blocks.argtypes = [vp, vp, vp, C.c_uint, C.c_uint, C.c_uint, vp, vp, C.c_uint, C.POINTER(Timing)]
     lib.hdb_deblock_batch_device_ex.argtypes = [vp] + batch_args + [C.c_uint, vp]
     lib.hdb_deblock_nv12_surfaces_device.argtypes = [vp, C.POINTER(Nv12Surfaces), C.POINTER(Nv12Surfaces), C.c_uint, C.c_uint,
                                                      C.c_uint, vp, vp, vp, C.c_uint, vp]
@@ -336,6 +337,18 @@ class Deblocker:
         self._check(self._lib.hdb_deblock_batch_ex(self._ctx, _addr(frames), _addr(out), n, width, height,
                                                    _addr(qps), _addr(vert), _addr(hor), flags,
                                                    None if timing is None else C.byref(timing)))
+        return out
+
+    def deblock_batch_blocks(self, frames, width, height, qps, info, flags=0, out=None, timing=None, n_frames=None):
+        """Host frames + host block data (BLOCK_INFO[n, H/8, W/8]); the edge maps are derived on the device."""
+        n = n_frames if n_frames is not None else int(frames.shape[0])
+        if out is None:
+            out = np.empty_like(frames)
+        if isinstance(info, np.ndarray):
+            info = np.ascontiguousarray(info, BLOCK_INFO)
+        self._check(self._lib.hdb_deblock_batch_blocks(self._ctx, _addr(frames), _addr(out), n, width, height,
+                                                       _addr(qps), _addr(info), flags,
+                                                       None if timing is None else C.byref(timing)))
         return out
 
     def deblock_batch_device_ex(self, d_in, d_out, n_frames, width, height, d_qp, d_vert=None, d_hor=None, flags=0,

@@ -98,7 +98,7 @@ void DestroyContext(hdb_context *ctx)
 	DeviceGuard guard(ctx->device);
 	cudaDeviceSynchronize();
 	for (auto &s : ctx->sizes) { cudaFree(s.chroma_bs); cudaFree(s.def_vbs); cudaFree(s.def_hbs); }
-	for (auto &sl : ctx->slots) { cudaFree(sl.frames); cudaFree(sl.vbs); cudaFree(sl.hbs); }
+	for (auto &sl : ctx->slots) { cudaFree(sl.frames); cudaFree(sl.vbs); cudaFree(sl.hbs); cudaFree(sl.info); }
 	cudaFree(ctx->qp_dev);
 	cudaFree(ctx->derive_dev);
 	for (auto ev : ctx->event_pool) cudaEventDestroy(ev);
@@ -286,9 +286,15 @@ int ValidateFrameArgs(hdb_context *ctx, unsigned w, unsigned h, const unsigned c
 /* ------------------------------------------------------------------ */
 /* pinned multi-stream pipeline                                        */
 /* ------------------------------------------------------------------ */
-static int EnsureSlots(hdb_context *ctx, size_t frame_bytes, int chunk, unsigned nv, unsigned nh, bool with_bs)
+static int EnsureSlots(hdb_context *ctx, size_t frame_bytes, int chunk, unsigned nv, unsigned nh, bool with_bs,
+	size_t info_bytes_per_frame)
 {
 	for (auto &sl : ctx->slots) {
+		if (info_bytes_per_frame && sl.info_cap < info_bytes_per_frame * chunk) {
+			cudaFree(sl.info); sl.info = nullptr; sl.info_cap = 0;
+			HDB_CUDA(ctx, cudaMalloc(&sl.info, info_bytes_per_frame * chunk));
+			sl.info_cap = info_bytes_per_frame * chunk;
+		}
 		if (sl.frames_cap < frame_bytes * chunk) {
 			cudaFree(sl.frames); sl.frames = nullptr; sl.frames_cap = 0;
 			HDB_CUDA(ctx, cudaMalloc(&sl.frames, frame_bytes * chunk));
@@ -364,13 +370,16 @@ static int GetEvents(hdb_context *ctx, size_t n)
  * single slice runs on one stream.
  */
 int BatchHost(hdb_context *ctx, const unsigned char *in, unsigned char *out, unsigned n, unsigned w, unsigned h,
-	const unsigned *qp, const unsigned char *vbs, const unsigned char *hbs, hdb_timing *timing, unsigned flags)
+	const unsigned *qp, const unsigned char *vbs, const unsigned char *hbs, hdb_timing *timing, unsigned flags,
+	const hdb_block_info *info)
 {
 	if (!ctx) return HDB_ERR_INVALID_ARG;
-	const bool edge_qp = (flags & HDB_FLAG_EDGE_MAPS) != 0, nv12 = (flags & HDB_FLAG_NV12) != 0;
+	/* block data given: the edge maps of every slice are derived on the device, into the slot's own arrays */
+	const bool edge_qp = (flags & HDB_FLAG_EDGE_MAPS) != 0 || info != nullptr, nv12 = (flags & HDB_FLAG_NV12) != 0;
 	std::lock_guard<std::mutex> lock(ctx->mu);
 	if (!in || !out || !qp || n == 0) return Fail(ctx, HDB_ERR_INVALID_ARG, "NULL buffer or empty batch");
-	if (edge_qp && (!vbs || !hbs)) return Fail(ctx, HDB_ERR_INVALID_ARG, "edge maps are required: there is no default for them");
+	if (info && (vbs || hbs)) return Fail(ctx, HDB_ERR_INVALID_ARG, "give block data or edge maps, not both");
+	if (edge_qp && !info && (!vbs || !hbs)) return Fail(ctx, HDB_ERR_INVALID_ARG, "edge maps are required: there is no default for them");
 	int rc = ValidateFrameArgs(ctx, w, h, vbs, 0, hbs, 0, false);
 	if (rc) return rc;
 	DeviceGuard guard(ctx->device);
@@ -380,7 +389,9 @@ int BatchHost(hdb_context *ctx, const unsigned char *in, unsigned char *out, uns
 	const int chunk = (int)std::min<size_t>(n, std::max<size_t>(1, ((size_t)ctx->chunk_bytes) / fb));
 	const std::vector<int> slices = PlanSlices(n, chunk);
 	const int nchunks = (int)slices.size();
-	if ((rc = EnsureSlots(ctx, fb, chunk, nv, nh, vbs != nullptr))) return rc;
+	const size_t ib = info ? sizeof(hdb_block_info) * (size_t)(w / 8) * (h / 8) : 0;     /* block data per frame */
+	const bool with_bs = vbs != nullptr || info != nullptr;
+	if ((rc = EnsureSlots(ctx, fb, chunk, nv, nh, with_bs, ib))) return rc;
 	const bool uniform_qp = (n == 1);
 	if (!uniform_qp && ctx->qp_cap < n) {
 		cudaFree(ctx->qp_dev); ctx->qp_dev = nullptr; ctx->qp_cap = 0;
@@ -391,7 +402,8 @@ int BatchHost(hdb_context *ctx, const unsigned char *in, unsigned char *out, uns
 	if (nv12 && w % 32 != 0) return Fail(ctx, HDB_ERR_DIMENSIONS, "NV12 frames need a width that is a multiple of 32");
 
 	PinHostRange pin_in(in, fb * n), pin_out(out != in ? out : nullptr, fb * n);
-	PinHostRange pin_v(vbs, (size_t)nv * n), pin_h(hbs, (size_t)nh * n);
+	PinHostRange pin_v(vbs, (size_t)nv * n), pin_h(hbs, (size_t)nh * n), pin_i(info, ib * n);
+	const unsigned char *info_bytes = reinterpret_cast<const unsigned char *>(info);
 
 	const bool timed = timing != nullptr;
 	if (timed && (rc = GetEvents(ctx, (size_t)nchunks * 6))) return rc;
@@ -422,10 +434,15 @@ int BatchHost(hdb_context *ctx, const unsigned char *in, unsigned char *out, uns
 			HDB_CUDA(ctx, cudaMemcpyAsync(sl.vbs, vbs, (size_t)nv * n, cudaMemcpyHostToDevice, s_k));
 			HDB_CUDA(ctx, cudaMemcpyAsync(sl.hbs, hbs, (size_t)nh * n, cudaMemcpyHostToDevice, s_k));
 		}
+		if (info) {
+			HDB_CUDA(ctx, cudaMemcpyAsync(sl.info, info_bytes, ib * n, cudaMemcpyHostToDevice, s_k));
+			HDB_CUDA(ctx, LaunchDeriveEdges(sl.info, (int)w, (int)h, (int)n, sl.vbs, sl.hbs, s_k));
+			ctx->launches += 1;
+		}
 		cudaEvent_t *ev = timed ? &ctx->event_pool[0] : nullptr;
 		if (timed) HDB_CUDA(ctx, cudaEventRecord(ev[0], s_k));
 		rc = EnqueueFilter(ctx, view, z_in, z_out, (int)n, uniform_qp ? nullptr : ctx->qp_dev, qp[0],
-			vbs ? sl.vbs : nullptr, nv, vbs ? sl.hbs : nullptr, nh, s_k, &path, edge_qp);
+			with_bs ? sl.vbs : nullptr, nv, with_bs ? sl.hbs : nullptr, nh, s_k, &path, edge_qp);
 		if (rc) { cudaDeviceSynchronize(); return rc; }
 		if (timed) HDB_CUDA(ctx, cudaEventRecord(ev[1], s_k));
 		HDB_CUDA(ctx, cudaStreamSynchronize(s_k));
@@ -438,7 +455,7 @@ int BatchHost(hdb_context *ctx, const unsigned char *in, unsigned char *out, uns
 			timing->copy_ms = 0;
 			timing->total_ms = std::chrono::duration<double, std::milli>(t_done - t_begin).count();
 			timing->h2d_bytes = (unsigned long long)fb * n + (n == 1 ? 0 : sizeof(unsigned) * (unsigned long long)n)
-				+ (vbs ? (unsigned long long)(nv + nh) * n : 0);
+				+ (vbs ? (unsigned long long)(nv + nh) * n : 0) + (unsigned long long)ib * n;
 			timing->d2h_bytes = (unsigned long long)fb * n;
 			timing->kernel_launches = (int)(ctx->launches - launches0);
 			timing->path = path;
@@ -464,14 +481,19 @@ int BatchHost(hdb_context *ctx, const unsigned char *in, unsigned char *out, uns
 			HDB_CUDA(ctx, cudaMemcpyAsync(sl.vbs, vbs + (size_t)f0 * nv, (size_t)nv * nf, cudaMemcpyHostToDevice, s_h2d));
 			HDB_CUDA(ctx, cudaMemcpyAsync(sl.hbs, hbs + (size_t)f0 * nh, (size_t)nh * nf, cudaMemcpyHostToDevice, s_h2d));
 		}
+		if (info) HDB_CUDA(ctx, cudaMemcpyAsync(sl.info, info_bytes + (size_t)f0 * ib, ib * nf, cudaMemcpyHostToDevice, s_h2d));
 		if (timed) HDB_CUDA(ctx, cudaEventRecord(ev[1], s_h2d));
 		if (!single) {
 			HDB_CUDA(ctx, cudaEventRecord(sl.h2d_done, s_h2d));
 			HDB_CUDA(ctx, cudaStreamWaitEvent(s_k, sl.h2d_done, 0));
 		}
 		if (timed) HDB_CUDA(ctx, cudaEventRecord(ev[2], s_k));
+		if (info) {
+			HDB_CUDA(ctx, LaunchDeriveEdges(sl.info, (int)w, (int)h, nf, sl.vbs, sl.hbs, s_k));
+			ctx->launches += 1;
+		}
 		rc = EnqueueFilter(ctx, view, sl.frames, sl.frames, nf, uniform_qp ? nullptr : ctx->qp_dev + f0, qp[0],
-			vbs ? sl.vbs : nullptr, nv, vbs ? sl.hbs : nullptr, nh, s_k, &path, edge_qp);
+			with_bs ? sl.vbs : nullptr, nv, with_bs ? sl.hbs : nullptr, nh, s_k, &path, edge_qp);
 		if (rc) { cudaDeviceSynchronize(); return rc; }
 		if (timed) HDB_CUDA(ctx, cudaEventRecord(ev[3], s_k));
 		if (!single) {
@@ -499,7 +521,7 @@ int BatchHost(hdb_context *ctx, const unsigned char *in, unsigned char *out, uns
 		}
 		timing->total_ms = std::chrono::duration<double, std::milli>(t_end - t_begin).count();
 		timing->h2d_bytes = (unsigned long long)fb * n + (n == 1 ? 0 : sizeof(unsigned) * (unsigned long long)n)
-			+ (vbs ? (unsigned long long)(nv + nh) * n : 0);
+			+ (vbs ? (unsigned long long)(nv + nh) * n : 0) + (unsigned long long)ib * n;
 		timing->d2h_bytes = (unsigned long long)fb * n;
 		timing->kernel_launches = (int)(ctx->launches - launches0);
 		timing->path = path;
@@ -796,6 +818,16 @@ int hdb_deblock_batch_ex(hdb_context *ctx, const unsigned char *frames_in, unsig
 {
 	if (flags & ~(HDB_FLAG_EDGE_MAPS | HDB_FLAG_NV12)) return ctx ? Fail(ctx, HDB_ERR_INVALID_ARG, "unknown flag") : HDB_ERR_INVALID_ARG;
 	return BatchHost(ctx, frames_in, frames_out, n_frames, width, height, qp, vert, hor, timing, flags);
+}
+
+int hdb_deblock_batch_blocks(hdb_context *ctx, const unsigned char *frames_in, unsigned char *frames_out,
+	unsigned n_frames, unsigned width, unsigned height, const unsigned *qp,
+	const hdb_block_info *info, unsigned flags, hdb_timing *timing)
+{
+	if (!ctx) return HDB_ERR_INVALID_ARG;
+	if (flags & ~HDB_FLAG_NV12) return Fail(ctx, HDB_ERR_INVALID_ARG, "unknown flag");
+	if (!info) return Fail(ctx, HDB_ERR_INVALID_ARG, "block data is required");
+	return BatchHost(ctx, frames_in, frames_out, n_frames, width, height, qp, nullptr, nullptr, timing, flags, info);
 }
 
 int hdb_deblock_batch_device_ex(hdb_context *ctx, const void *d_frames_in, void *d_frames_out,

@@ -34,7 +34,8 @@ constexpr int kSchedSlots = 64;      /* scheduler-word sets handed to successive
 
 struct Slot {          /* one slice of a batch in flight */
 	unsigned char *frames = nullptr, *vbs = nullptr, *hbs = nullptr;
-	size_t frames_cap = 0, vbs_cap = 0, hbs_cap = 0;
+	unsigned char *info = nullptr;             /* block data of the slice (edge maps derived on the device) */
+	size_t frames_cap = 0, vbs_cap = 0, hbs_cap = 0, info_cap = 0;
 	cudaEvent_t h2d_done = nullptr, k_done = nullptr, d2h_done = nullptr;
 	bool ev_ready = false;
 };
@@ -113,7 +114,8 @@ int EnqueueFilter(hdb_context *ctx, const FrameView &view, const unsigned char *
 	int n, const unsigned *d_qp, unsigned qp_value, const unsigned char *d_vbs, long long vbs_stride,
 	const unsigned char *d_hbs, long long hbs_stride, cudaStream_t stream, int *path, bool edge_qp = false);
 int BatchHost(hdb_context *ctx, const unsigned char *in, unsigned char *out, unsigned n, unsigned w, unsigned h,
-	const unsigned *qp, const unsigned char *vbs, const unsigned char *hbs, hdb_timing *timing, unsigned flags = 0);
+	const unsigned *qp, const unsigned char *vbs, const unsigned char *hbs, hdb_timing *timing, unsigned flags = 0,
+	const hdb_block_info *info = nullptr);
 
 /* beta / tc on the host (cpu.h:1021-1033, 1064-1072); defined in deblock_kernels.cu next to the device tables */
 int HostBeta(unsigned qp);

@@ -245,6 +245,15 @@ int hdb_deblock_batch_device_ex(hdb_context *ctx, const void *d_frames_in, void 
 	unsigned n_frames, unsigned width, unsigned height, const unsigned *d_qp,
 	const unsigned char *d_vert, const unsigned char *d_hor, unsigned flags, void *stream);
 
+/*
+ * The decoder-loop form from host memory: frames and their block data in, deblocked frames out.  The block
+ * data of every slice travels with its frames (12 bytes per 8x8 block), the edge maps are derived on the
+ * device (hdb_derive_edges_device) and never leave it.  flags: HDB_FLAG_NV12 or 0.
+ */
+int hdb_deblock_batch_blocks(hdb_context *ctx, const unsigned char *frames_in, unsigned char *frames_out,
+	unsigned n_frames, unsigned width, unsigned height, const unsigned *qp,
+	const hdb_block_info *info, unsigned flags, hdb_timing *timing);
+
 /* pitched NV12 surfaces in device memory, as hdb_deblock_surfaces_device; flags: HDB_FLAG_EDGE_MAPS or 0 */
 typedef struct hdb_nv12_surfaces {
 	void *y, *uv;                            /* device pointers to frame 0 of each plane */

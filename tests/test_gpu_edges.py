@@ -178,3 +178,23 @@ def test_full_size_edge_batch_properties(dev):
     dev.deblock_batch_device(d_in, d_ref, n, w, h, d_qp, bs_v, bs_h, stream=st)
     torch.cuda.synchronize()
     assert bool((d_out == d_ref).all())
+
+
+@pytest.mark.parametrize("n,w,h,nv12", [(1, 352, 288, False), (7, 352, 288, True), (40, 1920, 1080, False), (5, 24, 40, False)])
+def test_batch_from_block_data(dev, n, w, h, nv12):
+    """hdb_deblock_batch_blocks: frames + block data from host memory, edge maps derived on the device slice by
+    slice (one slice, several slices, both kernel paths, NV12) == oracle derivation + oracle per-edge-QP filter."""
+    rng = np.random.default_rng(n * 31 + w)
+    frames = np.stack([synth.make_frame(rng, w, h, "blocky") for _ in range(n)])
+    info = np.stack([synth.make_block_info(rng, w, h, ("cu16", "random", "intra")[f % 3]) for f in range(n)])
+    qps = rng.integers(18, 52, n).astype(np.uint32)
+    stored = np.stack([orc.yv12_to_nv12(f, w, h) for f in frames]) if nv12 else frames
+    t = hdb.Timing()
+    got = dev.deblock_batch_blocks(stored, w, h, qps, info, flags=hdb.FLAG_NV12 if nv12 else 0, timing=t)
+    for f in range(n):
+        ov, oh = orc.derive_edges(info[f], w, h)
+        want = orc.deblock_frame_edges(frames[f], w, h, int(qps[f]), ov, oh)
+        assert np.array_equal(orc.nv12_to_yv12(got[f], w, h) if nv12 else got[f], want), f
+    assert t.h2d_bytes >= frames.nbytes + info.nbytes and t.d2h_bytes == frames.nbytes
+    with pytest.raises(hdb.DeblockError):
+        dev.deblock_batch_blocks(stored, w, h, qps, None)
