@@ -25,10 +25,10 @@ bs_kinds = [None, "uniform012", "wide", "twos", "zeros", "ones"]
 t0, n_cases, fails = time.time(), 0, 0
 st = torch.cuda.current_stream().cuda_stream
 while time.time() - t0 < budget:
-    mode = int(rng.integers(9))
+    mode = int(rng.integers(11))
     w = 8 * int(rng.integers(1, 200))
     h = 8 * int(rng.integers(1, 80))
-    if mode in (2, 3, 4, 6, 7) or rng.integers(2):
+    if mode in (2, 3, 4, 6, 7, 9) or rng.integers(2):
         w = 32 * max(1, w // 32)
     n = int(rng.integers(1, 7))
     kind = kinds[int(rng.integers(len(kinds)))]
@@ -95,6 +95,14 @@ while time.time() - t0 < budget:
             ov, oh = zip(*[orc.derive_edges(info[i], w, h) for i in range(n)])
             want = np.concatenate([np.stack(ov), np.stack(oh)], 1)
             got = np.concatenate([gv, gh], 1)
+        elif mode == 9:    # the strip split with edge maps (logical shards)
+            want = np.stack([orc.deblock_frame_edges(frames[i], w, h, int(qps[i]), ev[i], eh[i]) for i in range(n)])
+            got = np.stack([multi.deblock_frame_strips(frames[i], w, h, int(qps[i]), ev[i], eh[i], flags=hdb.FLAG_EDGE_MAPS) for i in range(n)])
+        elif mode == 10:   # host frames + host block data, maps derived on the device slice by slice
+            ik = ["intra", "random", "cu16", "extreme"][int(rng.integers(4))]
+            info = np.stack([synth.make_block_info(rng, w, h, ik) for _ in range(n)])
+            want = np.stack([orc.deblock_frame_edges(frames[i], w, h, int(qps[i]), *orc.derive_edges(info[i], w, h)) for i in range(n)])
+            got = dev.deblock_batch_blocks(frames, w, h, qps, info)
         if mode >= 5:
             pass
         elif mode == 0:
