@@ -64,6 +64,18 @@ public:
 			throw "Incorrect size of input boundary strenght array";                        /* cpu.h:122-123 */
 		_vert_bs.assign(vert_bs, vert_bs + num_vert_bs);
 		_hor_bs.assign(hor_bs, hor_bs + num_hor_bs);
+		_edge_maps = false;
+	}
+
+	/*
+	 * Beyond the reference: the same two arrays with an edge byte HDB_EDGE(bs, qp) in every entry, so that
+	 * every luma edge has its own QP (include/hevc_deblock_b200.h).  Same size rule and message as the
+	 * strengths-only setter.
+	 */
+	void SetEdgeMaps(unsigned char *vert_edges, unsigned int num_vert, unsigned char *hor_edges, unsigned int num_hor)
+	{
+		SetBoundaryStrenght(vert_edges, num_vert, hor_edges, num_hor);
+		_edge_maps = true;
 	}
 
 	/* cpu.h:134: filters luma then both chroma planes, in place */
@@ -71,11 +83,15 @@ public:
 	{
 		(void)num_threads;
 		const bool custom = !_vert_bs.empty();
-		int rc = hdb_deblock_frame(_ctx, _frame, _frame, _width, _height, _Qp,
-			custom ? (const unsigned char *)_vert_bs.data() : nullptr, _num_vert_bs,
-			custom ? (const unsigned char *)_hor_bs.data() : nullptr, _num_hor_bs, &_timing);
+		const unsigned char *v = custom ? (const unsigned char *)_vert_bs.data() : nullptr;
+		const unsigned char *h = custom ? (const unsigned char *)_hor_bs.data() : nullptr;
+		int rc = _edge_maps
+			? hdb_deblock_frame_edges(_ctx, _frame, _frame, _width, _height, _Qp, v, _num_vert_bs, h, _num_hor_bs, &_timing)
+			: hdb_deblock_frame(_ctx, _frame, _frame, _width, _height, _Qp, v, _num_vert_bs, h, _num_hor_bs, &_timing);
 		if (rc != HDB_OK) { _error = hdb_last_error(_ctx); throw _error.c_str(); }
 	}
+
+	const unsigned char *Frame() const { return _frame; }          /* tight YV12, 3 * width * height / 2 bytes */
 
 	/* cpu.h:995: writes the tight YV12 frame */
 	void Save(char const *output_file_name)
@@ -103,6 +119,7 @@ private:
 	std::basic_string<unsigned char> _vert_bs, _hor_bs;
 	hdb_timing _timing{};
 	std::string _error;
+	bool _edge_maps = false;
 };
 
 /* main.cu:92-107 */

@@ -233,3 +233,24 @@ def test_demo_driver(tmp_path):
     assert all(common.md5(g) == case["md5"] for g in got)
     r = subprocess.run([demo, str(seq), "352", "280", "35", str(sout)], capture_output=True, text=True, timeout=120)
     assert r.returncode == 1 and "Incorrect file size" in r.stderr               # cpu.h:43-45
+
+
+def test_cpp_mirror_selftest(tmp_path):
+    """host/selftest.cpp: b200::ReadYuvFrame (ctor / SetBoundaryStrenght / SetEdgeMaps / DeblockingFilter / Save and
+    the reference's thrown messages) against the C ABI in-process; its two output files against the oracle here."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(hdb.library_path()), "hevc_deblock_b200_selftest")
+    if not os.path.exists(exe):
+        pytest.skip("selftest not built")
+    w, h, qp = 352, 288, 35
+    x = common.fixture("mother-daughter_352x288_yv12.yuv")
+    fin, f_plain, f_edges = tmp_path / "in.yuv", tmp_path / "plain.yuv", tmp_path / "edges.yuv"
+    x.tofile(fin)
+    r = subprocess.run([exe, str(fin), str(w), str(h), str(qp), str(f_plain), str(f_edges)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "selftest ok" in r.stdout, r.stdout + r.stderr
+    nv, nh = hdb.num_vert_bs(w, h), hdb.num_hor_bs(w, h)
+    maps = np.fromfile(str(f_plain) + ".maps", np.uint8)
+    v, hh, ve, he = maps[:nv], maps[nv:nv + nh], maps[nv + nh:2 * nv + nh], maps[2 * nv + nh:]
+    assert np.array_equal(np.fromfile(f_plain, np.uint8), orc.deblock_frame(x, w, h, qp, v, hh))
+    assert np.array_equal(np.fromfile(f_edges, np.uint8), orc.deblock_frame_edges(x, w, h, qp, ve, he))
