@@ -70,3 +70,26 @@ def test_no_cpu_fallback_without_gpu(lib):
     assert b"CUDA" in lib.hdb_last_error(None) or b"device" in lib.hdb_last_error(None)
     with pytest.raises(hdb.DeblockError):
         hdb.Deblocker(0)
+
+
+def test_struct_layouts_and_constants_match_the_header(tmp_path):
+    """The ctypes mirrors in binding.py against the C compiler's view of include/hevc_deblock_b200.h."""
+    import subprocess
+    from gpu_video_codec_b200 import binding
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "hevc_deblock_b200.h"\n'
+                   'int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %u %u %u\\n", sizeof(hdb_timing), sizeof(hdb_surfaces),'
+                   ' sizeof(hdb_nv12_surfaces), sizeof(hdb_block_info), sizeof(hdb_device_info), offsetof(hdb_timing, kernel_launches),'
+                   ' offsetof(hdb_nv12_surfaces, frame_stride_uv), offsetof(hdb_block_info, flags), offsetof(hdb_device_info, total_global_mem),'
+                   ' HDB_FLAG_EDGE_MAPS, HDB_FLAG_NV12, (unsigned)HDB_EDGE(2, 37)); return 0; }\n')
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    want = [C.sizeof(binding.Timing), C.sizeof(binding.Surfaces), C.sizeof(binding.Nv12Surfaces), binding.BLOCK_INFO.itemsize,
+            C.sizeof(binding.DeviceInfo), binding.Timing.kernel_launches.offset, binding.Nv12Surfaces.frame_stride_uv.offset,
+            binding.BLOCK_INFO.fields["flags"][1], binding.DeviceInfo.total_global_mem.offset,
+            binding.FLAG_EDGE_MAPS, binding.FLAG_NV12, int(binding.edge_bytes(2, 37))]
+    assert got == want, (got, want)
+    assert (binding.BLK_INTRA, binding.BLK_CBF, binding.BLK_TU_LEFT, binding.BLK_TU_TOP, binding.BLK_PU_LEFT, binding.BLK_PU_TOP) \
+        == (1, 2, 4, 8, 16, 32)
