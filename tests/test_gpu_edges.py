@@ -198,3 +198,28 @@ def test_batch_from_block_data(dev, n, w, h, nv12):
     assert t.h2d_bytes >= frames.nbytes + info.nbytes and t.d2h_bytes == frames.nbytes
     with pytest.raises(hdb.DeblockError):
         dev.deblock_batch_blocks(stored, w, h, qps, None)
+
+
+@pytest.mark.parametrize("n,w,h", [(1, 352, 288), (4, 768, 576)])
+def test_batch_from_block_data_on_mapped_pinned_buffers(dev, n, w, h):
+    """The single-slice form of hdb_deblock_batch_blocks on page-locked mapped buffers (the kernel reads and writes
+    host memory itself; block data and derivation still go through the device) and with per-edge maps likewise."""
+    import torch
+    rng = np.random.default_rng(n + w)
+    frames = np.stack([synth.make_frame(rng, w, h, "blocky") for _ in range(n)])
+    info = np.stack([synth.make_block_info(rng, w, h, "cu16") for _ in range(n)])
+    qps = rng.integers(18, 52, n).astype(np.uint32)
+    t_in = torch.from_numpy(frames).pin_memory()
+    t_out = torch.zeros_like(t_in).pin_memory()
+    t_qp = torch.from_numpy(qps.astype(np.int32)).pin_memory()
+    tm = hdb.Timing()
+    dev.deblock_batch_blocks(t_in, w, h, t_qp, info, out=t_out, timing=tm, n_frames=n)
+    maps = [orc.derive_edges(info[f], w, h) for f in range(n)]
+    want = np.stack([orc.deblock_frame_edges(frames[f], w, h, int(qps[f]), *maps[f]) for f in range(n)])
+    assert np.array_equal(t_out.numpy(), want)
+    assert tm.copy_ms == 0.0 and tm.kernel_launches == 2          # derive + filter, no copy-engine leg for the frames
+    assert np.array_equal(t_in.numpy(), frames)
+    v, hh = np.stack([m[0] for m in maps]), np.stack([m[1] for m in maps])
+    t_out.zero_()
+    dev.deblock_batch_edges(t_in, w, h, t_qp, v, hh, out=t_out, n_frames=n)
+    assert np.array_equal(t_out.numpy(), want)
