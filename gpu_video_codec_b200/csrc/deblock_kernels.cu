@@ -59,9 +59,10 @@
 /*
  * One warp per CTA.  Warps share nothing -- each runs its own pipeline -- so the CTA is only the
  * unit of residency, and with a single warp in it the warp's shared-memory addresses are
- * compile-time constants: the kernel then fits 72 registers without spilling (96 with four warps
- * per CTA; 80 spills) and 28 warps are resident per SM instead of 20: 6.47 -> 6.04 ms for 1024 4K
- * frames (profiles/r01i_cta_shapes.txt).
+ * compile-time constants: with one block row per item the kernel then fitted 72 registers without
+ * spilling (96 with four warps per CTA; 80 spills) and 28 warps were resident per SM instead of 20:
+ * 6.47 -> 6.04 ms for 1024 4K frames (profiles/r01i_cta_shapes.txt).  With two block rows per item:
+ * 80 registers, no spills, 23 resident warps (shared memory is the limit).
  */
 #ifndef HDB_WARPS
 #define HDB_WARPS 1
