@@ -68,16 +68,21 @@ def measured_peak():
 
 
 def ncu_traffic(workload, frames_in_launch):
-    """DRAM bytes of one launch over `frames_in_launch` frames, from the committed ncu --set full capture
-    (dram__bytes_read.sum + dram__bytes_write.sum per frame of this workload), or None."""
+    """(DRAM bytes of one launch over `frames_in_launch` frames, where the figure comes from).  STATIC: ncu
+    cannot run inside the bench, so this is dram__bytes_read.sum + dram__bytes_write.sum per frame from the
+    committed ncu --set full capture of this workload's kernel (profiles/traffic.json names the capture),
+    scaled by the frames in the launch; (None, reason) without one."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         try:
-            per_frame = json.load(open(p)).get(workload + "_per_frame")
-            return None if per_frame is None else int(per_frame * frames_in_launch)
+            t = json.load(open(p))
+            per_frame = t.get(workload + "_per_frame")
+            if per_frame is None:
+                return None, "no ncu capture of this workload"
+            return int(per_frame * frames_in_launch), "static: %s, per frame x frames in the launch" % (t.get("source") or "profiles/traffic.json")
         except Exception:
-            return None
-    return None
+            return None, "profiles/traffic.json unreadable"
+    return None, "no profiles/traffic.json"
 
 
 class ClockSampler:
@@ -211,34 +216,66 @@ def shard(total, world, rank):
     return first, n
 
 
-def device_batch(torch, n, w, h, seed):
-    """Frames ('blocky' recipe of tests/synth.py, built on the device), QPs and luma BS maps for n frames."""
-    g = torch.Generator(device="cuda").manual_seed(seed)
+GEN_CHUNK = 16      # frames per generator chunk: chunk c of a workload is a function of (workload seed, c) alone
+
+
+def workload_frames(torch, first, n, w, h, seed, device="cuda"):
+    """Frames [first, first + n) of a workload ('blocky' recipe of tests/synth.py), with their QPs and luma BS
+    maps.  Content depends on the GLOBAL frame number only (chunks of GEN_CHUNK frames, each with its own
+    generator seed), so every rank of our arm and the reference arm draw the same frames whatever their
+    shard.  device "cuda" (Philox) and "cpu" (Mersenne) give different streams: both arms use "cuda" when a
+    GPU is visible, and the line says which was used."""
     fb = 3 * w * h // 2
-    frames = torch.empty((n, fb), dtype=torch.uint8, device="cuda")
-    step = 16
-    for f0 in range(0, n, step):
-        m = min(step, n - f0)
+    nv, nh = (w // 8 + 1) * h // 8, (h // 8 + 1) * w // 8
+    frames = torch.empty((n, fb), dtype=torch.uint8, device=device)
+    qp = torch.empty((n,), dtype=torch.int32, device=device)
+    vbs = torch.empty((n, nv), dtype=torch.uint8, device=device)
+    hbs = torch.empty((n, nh), dtype=torch.uint8, device=device)
+    c0, c1 = first // GEN_CHUNK, (first + n + GEN_CHUNK - 1) // GEN_CHUNK
+    for c in range(c0, c1):
+        g = torch.Generator(device=device).manual_seed(seed * 100003 + c)
+        m = GEN_CHUNK
+        chunk = torch.empty((m, fb), dtype=torch.uint8, device=device)
         off = 0
         for (pw, ph) in ((w, h), (w // 2, h // 2), (w // 2, h // 2)):
-            xx = torch.arange(pw, device="cuda", dtype=torch.float32)[None, None, :] / pw
-            yy = torch.arange(ph, device="cuda", dtype=torch.float32)[None, :, None] / ph
+            xx = torch.arange(pw, device=device, dtype=torch.float32)[None, None, :] / pw
+            yy = torch.arange(ph, device=device, dtype=torch.float32)[None, :, None] / ph
             ramp = 96.0 + 64.0 * xx + 32.0 * yy
             bh, bw = (ph + 7) // 8, (pw + 7) // 8
-            dc = torch.randint(-12, 13, (m, bh, bw), device="cuda", generator=g, dtype=torch.int16)
+            dc = torch.randint(-12, 13, (m, bh, bw), device=device, generator=g, dtype=torch.int16)
             dc = dc.repeat_interleave(8, 1).repeat_interleave(8, 2)[:, :ph, :pw]
-            noise = torch.randint(-2, 3, (m, ph, pw), device="cuda", generator=g, dtype=torch.int16)
-            frames[f0:f0 + m, off:off + pw * ph] = (ramp + dc + noise).clamp_(0, 255).to(torch.uint8).reshape(m, -1)
+            noise = torch.randint(-2, 3, (m, ph, pw), device=device, generator=g, dtype=torch.int16)
+            chunk[:, off:off + pw * ph] = (ramp + dc + noise).clamp_(0, 255).to(torch.uint8).reshape(m, -1)
             off += pw * ph
-    qp = torch.randint(18, 52, (n,), device="cuda", generator=g, dtype=torch.int32)
-    if n >= 8:  # a few frames on the no-op (QP <= 17) and clamp (QP > 51) ranges
-        qp[3::64] = 12
-        qp[5::64] = 17
-        qp[6::64] = 60
-    nv, nh = (w // 8 + 1) * h // 8, (h // 8 + 1) * w // 8
-    vbs = torch.randint(0, 3, (n, nv), device="cuda", generator=g, dtype=torch.uint8)
-    hbs = torch.randint(0, 3, (n, nh), device="cuda", generator=g, dtype=torch.uint8)
+        cq = torch.randint(18, 52, (m,), device=device, generator=g, dtype=torch.int32)
+        gidx = torch.arange(c * GEN_CHUNK, (c + 1) * GEN_CHUNK, device=device)
+        # a few frames on the no-op (QP <= 17) and clamp (QP > 51) ranges
+        cq = torch.where(gidx % 64 == 3, torch.full_like(cq, 12), cq)
+        cq = torch.where(gidx % 64 == 5, torch.full_like(cq, 17), cq)
+        cq = torch.where(gidx % 64 == 6, torch.full_like(cq, 60), cq)
+        cv = torch.randint(0, 3, (m, nv), device=device, generator=g, dtype=torch.uint8)
+        ch = torch.randint(0, 3, (m, nh), device=device, generator=g, dtype=torch.uint8)
+        lo, hi = max(first, c * GEN_CHUNK), min(first + n, (c + 1) * GEN_CHUNK)
+        a, b = lo - c * GEN_CHUNK, hi - c * GEN_CHUNK
+        frames[lo - first:hi - first] = chunk[a:b]
+        qp[lo - first:hi - first] = cq[a:b]
+        vbs[lo - first:hi - first] = cv[a:b]
+        hbs[lo - first:hi - first] = ch[a:b]
     return frames, qp, vbs, hbs
+
+
+WORKLOAD_SEED = {"4k_batch1024": 1000, "1080p_batch256": 2000, "4k_nv12_512": 3000, "4k_edges512": 4242, "8k_strips": 77}
+
+
+def workload_config(name, world, gen_device):
+    """The `config` object of a line: facts about the workload only, identical in both arms."""
+    w, h, total, desc = WORKLOADS[name]
+    fb = 3 * w * h // 2
+    per = (total + world - 1) // world
+    return {"workload": name, "description": desc, "width": w, "height": h, "frames": total,
+            "frames_per_gpu": per, "sharding": "contiguous frame ranges, no collective",
+            "l2": "inputs larger than L2 (%.1f GB in + %.1f GB out per GPU)" % (per * fb / 1e9, per * fb / 1e9),
+            "generator": "bench.workload_frames, seed %d, torch %s generator" % (WORKLOAD_SEED.get(name, 0), gen_device)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -273,30 +310,34 @@ def cpu_reference_run(frames, w, h, qps, vbs, hbs, cores):
 def run_reference_arm(args, rank):
     if rank != 0:
         return
-    from tests import synth
     w, h, total, desc = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
     n = max(1, min(total, args.cpu_sample or 256))
-    distinct = min(n, 8)   # a few distinct synthetic frames, tiled: numpy generation of 4K frames is slow
-    frames, qps, vbs, hbs = synth.make_batch(2024, distinct, w, h)
-    reps = (n + distinct - 1) // distinct
-    frames, qps = np.tile(frames, (reps, 1))[:n], np.tile(qps, reps)[:n]
-    vbs, hbs = np.tile(vbs, (reps, 1))[:n], np.tile(hbs, (reps, 1))[:n]
+    gen_device = "cpu"
     if args.workload == "image2_single":
         from tests import common
         frames = common.fixture("image2_768x576.yuv")[None, :]
         qps, vbs, hbs = np.array([30], np.uint32), None, None
+    else:
+        # the first n frames of the very workload our arm times (same generator, same seed)
+        import torch
+        gen_device = "cuda" if torch.cuda.is_available() else "cpu"
+        t_f, t_q, t_v, t_h = workload_frames(torch, 0, n, w, h, WORKLOAD_SEED.get(args.workload, 0), gen_device)
+        frames, qps = t_f.cpu().numpy(), t_q.cpu().numpy().astype(np.uint32)
+        vbs, hbs = t_v.cpu().numpy(), t_h.cpu().numpy()
+        del t_f, t_q, t_v, t_h
     vals, kind, used, detail = [], None, None, None
     for i in range(args.warmup + args.steps):
         v, kind, used, detail = cpu_reference_run(frames, w, h, qps, vbs, hbs, cores)
         if i >= args.warmup:
             vals.append(v)
     value = float(np.median(vals))
-    sample = "%d of %d frames per step (%s), best of OpenMP-in-frame and frame-parallel on %d threads" % (n, total, desc, used)
+    sample = "first %d of the %d frames of the workload per step, best of OpenMP-in-frame and frame-parallel on %d threads" % (n, total, used)
     line = {"impl": "reference", "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(n * w * h / 1e3 / value, 3),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": args.workload, "description": desc, "width": w, "height": h, "frames": total},
+            "config": workload_config(args.workload, max(args.gpus, 1), gen_device),
+            "timing": "wall clock around the reference's DeblockingFilter calls on the host cores",
             "cpu_baseline": {"value": round(value, 1), "unit": UNIT, "cores": used, "kind": kind, "sample": sample, "detail": detail},
             "e2e": {"value": round(value, 1), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -328,46 +369,66 @@ def emit(line):
         os.write(_REAL_STDOUT, data)
 
 
-def run_ours(args, rank, world, local_rank):
-    import torch
-    import gpu_video_codec_b200 as hdb
-    quiet_stdout()
+class Dist:
+    """torch.distributed plumbing of one rank: NCCL carries the barrier and the max-over-ranks of the timings
+    (nothing else -- the path has no data-path collective); a gloo group lets ranks idle on the CPU while rank 0
+    drives all devices for the strip-split sub-record."""
 
-    torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    def __init__(self, torch, world, local_rank):
+        self.torch, self.world, self.dist, self.cpu_group = torch, world, None, None
+        if world > 1:
+            import torch.distributed as dist
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            self.dist = dist
+            self.cpu_group = dist.new_group(backend="gloo")
 
-    def barrier():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    def max_over_ranks(x):
-        if dist is None:
+    def cpu_barrier(self):
+        if self.dist is not None:
+            self.dist.barrier(group=self.cpu_group)
+
+    def max(self, x):
+        if self.dist is None:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
-    w, h, total, desc = WORKLOADS[args.workload]
+    def sum_ints(self, xs):
+        if self.dist is None:
+            return [int(x) for x in xs]
+        t = self.torch.tensor(list(xs), dtype=self.torch.int64, device="cuda")
+        self.dist.all_reduce(t)
+        return [int(x) for x in t.tolist()]
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def measure_workload(args, torch, hdb, dev, dd, rank, world, workload, steps, warmup, sampler=None, full_parity=True):
+    """Kernel-only, e2e, link probe and parity of one workload on this rank's shard.  Returns the pieces of the
+    JSON line (rank 0) -- the caller assembles them."""
+    w, h, total, desc = WORKLOADS[workload]
     first, n = shard(total, world, rank)
     fb = 3 * w * h // 2
-    dev = hdb.Deblocker(local_rank)
     stream = torch.cuda.current_stream().cuda_stream
-
-    if args.workload == "image2_single":
+    if workload == "image2_single":
         from tests import common
         frames = torch.from_numpy(common.fixture("image2_768x576.yuv")[None, :].copy()).cuda()
         qp = torch.tensor([30], dtype=torch.int32, device="cuda")
         vbs = hbs = None
         n = 1
     else:
-        frames, qp, vbs, hbs = device_batch(torch, n, w, h, seed=1000 + first)
-    nv12 = "nv12" in args.workload
+        frames, qp, vbs, hbs = workload_frames(torch, first, n, w, h, WORKLOAD_SEED.get(workload, 0), "cuda")
+    nv12 = "nv12" in workload
     flags = hdb.FLAG_NV12 if nv12 else 0
     ysz, csz = w * h, (w // 2) * (h // 2)
 
@@ -391,26 +452,26 @@ def run_ours(args, rank, world, local_rank):
     def step():
         dev.deblock_batch_device_ex(frames, out, n, w, h, qp, vbs, hbs, flags=flags, stream=stream)
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         step()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    dd.barrier()
+    if sampler is not None:
+        sampler.resume(0.002)
     launches0 = dev.kernel_launch_count()
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    barrier()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    dd.barrier()
     evs[0].record()
-    for i in range(args.steps):
+    for i in range(steps):
         step()
         evs[i + 1].record()
-    barrier()
-    sampler.pause()             # resumed for the e2e timed region; both regions feed the clocks record
+    dd.barrier()
+    if sampler is not None:
+        sampler.pause()             # resumed for the e2e timed region; both regions feed the clocks record
     kernel_launches = dev.kernel_launch_count() - launches0
-    total_ms = max_over_ranks(evs[0].elapsed_time(evs[-1]))
-    launch_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
-    mean_launch_ms = max_over_ranks(float(np.mean(launch_ms)))
-    ms_per_step = total_ms / args.steps
+    total_ms = dd.max(evs[0].elapsed_time(evs[-1]))
+    launch_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(steps)]
+    mean_launch_ms = dd.max(float(np.mean(launch_ms)))
+    ms_per_step = total_ms / steps
     value = total * w * h / 1e6 / (ms_per_step / 1e3)
 
     # ---- parity of what was just timed: a strided sample of this rank's frames vs the oracle ---
@@ -443,23 +504,52 @@ def run_ours(args, rank, world, local_rank):
     def e2e_step():
         dev.deblock_batch_ex(h_in, w, h, h_qp, h_v, h_h, flags=flags, out=h_out, timing=tm, n_frames=n)
 
-    for _ in range(max(1, min(args.warmup, 2))):
+    for _ in range(max(1, min(warmup, 2))):
         e2e_step()
-    barrier()
+    dd.barrier()
     l0 = dev.kernel_launch_count()
-    sampler.resume(0.05)   # a sparse poll: NVML queries take driver locks the copy submissions also need
+    if sampler is not None:
+        sampler.resume(0.05)   # a sparse poll: NVML queries take driver locks the copy submissions also need
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         e2e_step()     # returns after the last D2H copy has completed
     torch.cuda.synchronize()
     e2e_wall = time.perf_counter() - t0
-    clocks = sampler.stop() if rank == 0 else None
-    e2e_s = max_over_ranks(e2e_wall)
+    if sampler is not None:
+        sampler.pause()
+    e2e_s = dd.max(e2e_wall)
     e2e_launches = dev.kernel_launch_count() - l0
-    e2e_value = total * w * h / 1e6 / (e2e_s / args.steps)
+    e2e_value = total * w * h / 1e6 / (e2e_s / steps)
     h2d = int(tm.h2d_bytes)
     d2h = int(tm.d2h_bytes)
-    if rank == 0:
+
+    # ---- link probe: what the host links of this box carry when every rank copies the SAME pinned buffers
+    #      both ways at once with plain cudaMemcpyAsync in 128 MB pieces and nothing else runs ----
+    link = None
+    if n * fb >= (64 << 20):
+        s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+        piece = max(1, (128 << 20) // fb)
+
+        def probe():
+            for f0 in range(0, n, piece):
+                f1 = min(n, f0 + piece)
+                with torch.cuda.stream(s_up):
+                    frames[f0:f1].copy_(h_in[f0:f1], non_blocking=True)      # the bytes already there: nothing is disturbed
+                with torch.cuda.stream(s_dn):
+                    h_out[f0:f1].copy_(out[f0:f1], non_blocking=True)        # likewise
+            s_up.synchronize(); s_dn.synchronize()
+
+        probe()
+        dd.barrier()
+        reps = max(1, min(steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            probe()
+        probe_s = dd.max((time.perf_counter() - t0) / reps)
+        link = {"ms_per_step": round(probe_s * 1e3, 3), "gb_s_per_direction_all_gpus": round(world * n * fb / probe_s / 1e9, 2),
+                "what": "all ranks at once: cudaMemcpyAsync H2D + D2H of the e2e leg's pinned buffers, 128 MB pieces, two streams, no kernel"}
+
+    if rank == 0 and full_parity:
         # every frame of this rank's shard, as delivered to the host by the e2e path, against the CPU
         # checker (the unmodified reference on all host cores when oracle/_ref is there, else the port)
         from oracle import oracle_py as orc
@@ -490,35 +580,27 @@ def run_ours(args, rank, world, local_rank):
         parity["bit_exact"] = parity["bit_exact"] and bad == 0
         if bad:
             raise SystemExit("PARITY FAILURE: %d of %d e2e frames differ from the CPU checker; no number is reported" % (bad, n))
-    if dist is not None:
-        t = torch.tensor([h2d, d2h, kernel_launches, e2e_launches], dtype=torch.int64, device="cuda")
-        dist.all_reduce(t)
-        h2d, d2h, kernel_launches, e2e_launches = [int(x) for x in t.tolist()]
+    h2d, d2h, kernel_launches, e2e_launches = dd.sum_ints([h2d, d2h, kernel_launches, e2e_launches])
 
+    res = None
     if rank == 0:
         peak, peak_src = measured_peak()
         alg = alg_bytes_per_frame(w, h) * n          # one launch processes this rank's n frames
         achieved = alg / (mean_launch_ms / 1e3) / 1e9
-        line = {
-            "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": args.workload, "description": desc, "width": w, "height": h, "frames": total,
-                       "frames_per_gpu": n, "sharding": "contiguous frame ranges, no collective",
-                       "l2": "inputs larger than L2 (%.1f GB in + %.1f GB out per GPU)" % (n * fb / 1e9, n * fb / 1e9),
-                       "timing": "CUDA events on the launching stream, max over ranks"},
-            "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4), "traffic": ncu_traffic(args.workload, n),
-                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
-                         "kernel": "DeblockTiledKernel<0, 1>" if nv12 else "DeblockTiledKernel", "mean_launch_ms": round(mean_launch_ms, 4)},
-            "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": round(e2e_s / args.steps * 1e3, 3), "launches_per_step": e2e_launches // max(args.steps, 1),
-                    "api": "hdb_deblock_batch%s (pinned host buffers, 3-stream pipeline)" % ("_ex, HDB_FLAG_NV12" if nv12 else "")},
-            "gpu_launches": kernel_launches,
-            "clocks": clocks,
-            "parity": parity,
-        }
-        if world == 1 and not args.no_cpu:
+        traffic, traffic_src = ncu_traffic(workload, n)
+        e2e = {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": round(e2e_s / steps * 1e3, 3), "launches_per_step": e2e_launches // max(steps, 1),
+               "api": "hdb_deblock_batch%s (pinned host buffers, 3-stream pipeline)" % ("_ex, HDB_FLAG_NV12" if nv12 else "")}
+        if link is not None:
+            e2e["frac_of_link"] = round(link["ms_per_step"] / e2e["ms_per_step"], 4)
+        res = {"value": round(value, 1), "ms_per_step": round(ms_per_step, 4),
+               "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                            "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
+                            "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
+                            "kernel": "DeblockTiledKernel<0, 1, 0>" if nv12 else "DeblockTiledKernel<0, 0, 0>",
+                            "mean_launch_ms": round(mean_launch_ms, 4)},
+               "e2e": e2e, "link_probe": link, "gpu_launches": kernel_launches, "parity": parity}
+        if world == 1 and not args.no_cpu and full_parity:
             cores = os.cpu_count() or 1
             ns = max(1, min(n, args.cpu_sample or 256))
             sel = torch.arange(ns, device="cuda")
@@ -527,78 +609,210 @@ def run_ours(args, rank, world, local_rank):
             v = None if vbs is None else vbs[sel].cpu().numpy()
             hh = None if hbs is None else hbs[sel].cpu().numpy()
             best, kind, used, detail = cpu_reference_run(src, w, h, q, v, hh, cores)
-            line["cpu_baseline"] = {"value": round(best, 1), "unit": UNIT, "cores": used, "kind": kind,
-                                    "sample": "first %d of the %d frames of the workload, best of OpenMP-in-frame and "
-                                              "frame-parallel on %d threads" % (ns, total, used), "detail": detail}
+            res["cpu_baseline"] = {"value": round(best, 1), "unit": UNIT, "cores": used, "kind": kind,
+                                   "sample": "first %d of the %d frames of the workload, best of OpenMP-in-frame and "
+                                             "frame-parallel on %d threads" % (ns, total, used), "detail": detail}
+    del frames, out, h_in, h_out
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import gpu_video_codec_b200 as hdb
+    quiet_stdout()
+    torch.cuda.set_device(local_rank)
+    dd = Dist(torch, world, local_rank)
+    dev = hdb.Deblocker(local_rank)
+    w, h, total, desc = WORKLOADS[args.workload]
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler is not None:
+        sampler.paused = True
+        sampler.start()
+    res = measure_workload(args, torch, hdb, dev, dd, rank, world, args.workload, args.steps, args.warmup, sampler)
+    clocks = sampler.stop() if sampler is not None else None
+    line = None
+    if rank == 0:
+        line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": workload_config(args.workload, world, "cuda"),
+                "timing": "CUDA events on the launching stream, max over ranks",
+                "roofline": res["roofline"], "e2e": res["e2e"], "link_probe": res["link_probe"],
+                "gpu_launches": res["gpu_launches"], "clocks": clocks, "parity": res["parity"]}
+        if "cpu_baseline" in res:
+            line["cpu_baseline"] = res["cpu_baseline"]
+    # ---- the other single-GPU configurations of BASELINE.json (configs[2], configs[1]) ride along at N = 1 ----
+    if world == 1 and args.workload == "4k_batch1024" and not args.no_sub:
+        sub = {}
+        for name, st in (("1080p_batch256", max(3, args.steps)), ("image2_single", 50)):
+            r = measure_workload(args, torch, hdb, dev, dd, rank, world, name, st, 3, None, full_parity=(name != "image2_single"))
+            r.pop("link_probe", None)
+            r.pop("cpu_baseline", None)
+            sub[name] = dict(r, config=workload_config(name, 1, "cuda"), steps=st)
+        line["other_configs"] = sub
+    # ---- BASELINE.json configs[4] rides along at N > 1: rank 0 alone drives all N devices, the others idle ----
+    if world > 1 and args.workload == "4k_batch1024" and not args.no_sub:
+        dev.close()
+        dev = None
+        torch.cuda.empty_cache()
+        dd.barrier()
+        if rank == 0:
+            try:
+                line["strips_8k"] = strips_record(args, torch, hdb, list(range(world)), steps=max(2, min(args.steps, 3)))
+            except SystemExit:
+                raise
+            except Exception as e:      # the main line stands on its own
+                line["strips_8k"] = {"error": "%s: %s" % (type(e).__name__, e)}
+        dd.cpu_barrier()
+    if rank == 0:
         emit(line)
-    dev.close()
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    if dev is not None:
+        dev.close()
+    dd.close()
+
+
+def nvlink_counters(devices):
+    """Sum of the NVLink data bytes (tx, rx) of the devices from NVML's field values, or None."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        tx = rx = 0
+        for d in devices:
+            hnd = nv.nvmlDeviceGetHandleByIndex(d)
+            vals = nv.nvmlDeviceGetFieldValues(hnd, [(nv.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, 0xffffffff),
+                                                     (nv.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX, 0xffffffff)])
+            if vals[0].nvmlReturn != 0 or vals[1].nvmlReturn != 0:
+                return None
+            tx += int(vals[0].value.ullVal) * 1024      # KiB
+            rx += int(vals[1].value.ullVal) * 1024
+        return tx, rx
+    except Exception:
+        return None
+
+
+def strips_record(args, torch, hdb, devices, steps):
+    """BASELINE configs[4]: a stream of 8K frames, each cut into CTU-row strips over `devices` (one process
+    drives them all).  Legs: the pipelined stream (hdb_multi_deblock_stream_strips), frame-at-a-time calls
+    (hdb_multi_deblock_frame_strips: the latency of one frame), the same stream through ONE GPU unsplit
+    (hdb_deblock_batch), and strips resident in each GPU's memory (kernel + NVLink only).  Parity: every
+    distinct frame of every leg against the unsplit CPU checker."""
+    from oracle import oracle_py as orc
+    from tests import synth
+    w, h, total, desc = WORKLOADS["8k_strips"]
+    fb = 3 * w * h // 2
+    m = hdb.MultiDeblocker(devices)
+    one = hdb.Deblocker(devices[0])
+    distinct = 4
+    frames, qps, v, hh = synth.make_batch(WORKLOAD_SEED["8k_strips"], distinct, w, h)
+    idx = [i % distinct for i in range(total)]
+    h_in = torch.from_numpy(frames[idx]).pin_memory()
+    h_out = torch.empty_like(h_in).pin_memory()
+    h_qp = torch.from_numpy(qps[idx].astype(np.int32)).pin_memory()
+    h_v, h_h = torch.from_numpy(v[idx]).pin_memory(), torch.from_numpy(hh[idx]).pin_memory()
+    cores = os.cpu_count() or 1
+    want, _ = orc.ref_deblock_batch(frames, w, h, qps, v, hh, min(cores, distinct), 1) if orc.have_ref() else (orc.deblock_batch(frames, w, h, qps, v, hh), 0)
+    tm = hdb.Timing()
+    np_in, np_out = h_in.numpy(), h_out.numpy()
+
+    def check(name):
+        for f in range(total):
+            if not np.array_equal(np_out[f], want[idx[f]]):
+                raise SystemExit("PARITY FAILURE (%s): frame %d differs from the CPU checker" % (name, f))
+        np_out[:] = 0
+
+    def leg_stream():
+        m.deblock_stream_strips(h_in, w, h, h_qp, h_v, h_h, out=h_out, timing=tm, n_frames=total)
+        return tm.kernel_ms
+
+    def leg_frames():
+        k = 0.0
+        for f in range(total):
+            m.deblock_frame_strips(np_in[f], w, h, int(qps[idx[f]]), v[idx[f]], hh[idx[f]], out=np_out[f], timing=tm)
+            k += tm.kernel_ms
+        return k
+
+    def leg_unsplit():
+        one.deblock_batch(h_in, w, h, h_qp, h_v, h_h, out=h_out, timing=tm, n_frames=total)
+        return tm.kernel_ms
+
+    res = {}
+    nvl0 = nvlink_counters(sorted(set(devices)))
+    for name, fn in (("stream", leg_stream), ("frame_at_a_time", leg_frames), ("unsplit_1gpu_stream", leg_unsplit)):
+        for _ in range(2):
+            fn()
+        check(name)
+        t0 = time.perf_counter()
+        kms = 0.0
+        for _ in range(steps):
+            kms += fn()
+        dt = time.perf_counter() - t0
+        check(name)
+        res[name] = {"mpixel_s": round(steps * total * w * h / 1e6 / dt, 1), "ms_per_frame": round(dt * 1e3 / (steps * total), 4),
+                     "kernel_ms_per_frame": round(kms / (steps * total), 4)}
+    nvl1 = nvlink_counters(sorted(set(devices)))
+    # strips resident in each GPU's memory: kernel + NVLink only
+    lay = m.strip_layout(h)
+    cw = w // 2
+    Y, U, V = (frames[0][:w * h].reshape(h, w), frames[0][w * h:w * h * 5 // 4].reshape(h // 2, cw),
+               frames[0][w * h * 5 // 4:].reshape(h // 2, cw))
+    ins, outs, dv, dh = [], [], [], []
+    for d, (y0, rows) in enumerate(lay):
+        where = "cuda:%d" % devices[d]
+        ins.append(tuple(torch.from_numpy(np.ascontiguousarray(p)).to(where) for p in (Y[y0:y0 + rows], U[y0 // 2:(y0 + rows) // 2], V[y0 // 2:(y0 + rows) // 2])))
+        outs.append(tuple(torch.zeros_like(p) for p in ins[-1]))
+        dv.append(torch.from_numpy(v[0]).to(where))
+        dh.append(torch.from_numpy(hh[0]).to(where))
+    for d in set(devices):
+        torch.cuda.synchronize(d)
+    ks = []
+    for i in range(3 + 20):
+        m.deblock_strips_device(ins, outs, w, h, int(qps[0]), dv, dh, timing=tm)
+        if i >= 3:
+            ks.append(tm.kernel_ms)
+    got = np.concatenate([np.concatenate([o[p].cpu().numpy().reshape(-1) for o in outs]) for p in range(3)])
+    if not np.array_equal(got, want[0]):
+        raise SystemExit("PARITY FAILURE (device-resident strips): differs from the CPU checker")
+    halo = m.strip_halo_bytes(w, h)
+    res["device_resident"] = {"kernel_ms_per_frame_slowest_gpu": round(float(np.median(ks)), 4),
+                              "mpixel_s": round(w * h / 1e6 / (float(np.median(ks)) / 1e3), 1),
+                              "nvlink_halo_bytes_per_frame": halo,
+                              "what": "strips already in each GPU's HBM; one kernel per GPU, halo rows read by peer loads inside it"}
+    if nvl0 is not None and nvl1 is not None:
+        frames_run = 3 * (2 + steps) * total
+        res["nvlink_counters"] = {"tx_bytes": nvl1[0] - nvl0[0], "rx_bytes": nvl1[1] - nvl0[1], "frames": frames_run,
+                                  "expected_halo_bytes": halo * (2 * (2 + steps) * total) if len(set(devices)) > 1 else 0,
+                                  "source": "NVML NVLINK_THROUGHPUT_DATA_TX/RX, all links, all devices, over the three host legs"}
+    res.update({"devices": devices, "strips": len(lay), "frames_in_stream": total, "width": w, "height": h,
+                "h2d_bytes_per_frame": fb + v.shape[1] + hh.shape[1], "d2h_bytes_per_frame": fb,
+                "parity": {"bit_exact": True, "frames_checked_per_leg": total, "checker": "reference (oracle/_ref)" if orc.have_ref() else "port"},
+                "speedup_stream_vs_unsplit": round(res["unsplit_1gpu_stream"]["ms_per_frame"] / res["stream"]["ms_per_frame"], 3)})
+    m.close()
+    one.close()
+    return res
 
 
 def run_strips(args):
-    """BASELINE configs[4]: a stream of 8K frames, each cut into CTU-row strips over --gpus devices of this
-    process (logical shards on device 0 when the box has fewer).  One step = the whole stream, frame by
-    frame, host buffers in and out (the strip path has no device-resident form: its point is latency of
-    one frame that arrives on the host).  Beside it: the same stream through one GPU unsplit."""
+    """`--workload 8k_strips`: the strip-split record as a line of its own (one process drives --gpus devices;
+    logical shards on device 0 when the box has fewer)."""
     import torch
     import gpu_video_codec_b200 as hdb
-    from oracle import oracle_py as orc
-    from tests import synth
     quiet_stdout()
     w, h, total, desc = WORKLOADS[args.workload]
     have = torch.cuda.device_count()
     devices = list(range(args.gpus)) if have >= args.gpus else [i % have for i in range(args.gpus)]
-    m = hdb.MultiDeblocker(devices)
-    one = hdb.Deblocker(0)
-    distinct = 4
-    frames, qps, v, hh = synth.make_batch(77, distinct, w, h)
-    h_in = torch.from_numpy(frames).pin_memory()
-    h_out = torch.empty_like(h_in).pin_memory()
-    np_in, np_out = h_in.numpy(), h_out.numpy()
-    want, _ = orc.ref_deblock_batch(frames, w, h, qps, v, hh, distinct, 1) if orc.have_ref() else (orc.deblock_batch(frames, w, h, qps, v, hh), 0)
-    tm = hdb.Timing()
-
-    def stream(fn):
-        k = 0.0
-        for f in range(total):
-            i = f % distinct
-            fn(np_in[i], w, h, int(qps[i]), v[i], hh[i], out=np_out[i], timing=tm)
-            k += tm.kernel_ms
-        return k
-
-    res = {}
-    for name, fn in (("strips", m.deblock_frame_strips), ("unsplit_1gpu", one.deblock_frame)):
-        for _ in range(max(args.warmup, 3)):
-            stream(fn)
-        ok = all(np.array_equal(np_out[i], want[i]) for i in range(distinct))
-        if not ok:
-            raise SystemExit("PARITY FAILURE (%s): output differs from the CPU checker" % name)
-        np_out[:] = 0
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        kms = 0.0
-        for _ in range(args.steps):
-            kms += stream(fn)
-        dt = time.perf_counter() - t0
-        res[name] = {"mpixel_s": round(args.steps * total * w * h / 1e6 / dt, 1), "ms_per_frame": round(dt * 1e3 / (args.steps * total), 4),
-                     "kernel_ms_per_frame": round(kms / (args.steps * total), 4)}
+    res = strips_record(args, torch, hdb, devices, steps=args.steps)
     fb = 3 * w * h // 2
-    line = {"metric": METRIC, "value": res["strips"]["mpixel_s"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": round(res["strips"]["ms_per_frame"] * total, 3),
+    line = {"metric": METRIC, "value": res["stream"]["mpixel_s"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": 2, "ms_per_step": round(res["stream"]["ms_per_frame"] * total, 3),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": args.workload, "description": desc, "width": w, "height": h, "frames": total,
-                       "devices": devices, "timing": "wall clock around the calls (host buffers in and out)"},
-            "e2e": {"value": res["strips"]["mpixel_s"], "unit": UNIT, "h2d_bytes_per_step": total * (fb + v.shape[1] + hh.shape[1]),
-                    "d2h_bytes_per_step": total * fb, "ms_per_step": round(res["strips"]["ms_per_frame"] * total, 3),
-                    "api": "hdb_multi_deblock_frame_strips"},
-            "strips": res["strips"], "unsplit_1gpu": res["unsplit_1gpu"],
-            "gpu_launches": args.steps * total * len(devices),
-            "parity": {"bit_exact": True, "frames_checked": distinct}}
+            "config": workload_config(args.workload, 1, "numpy (tests/synth.py)"),
+            "timing": "wall clock around the calls (host buffers in and out)",
+            "e2e": {"value": res["stream"]["mpixel_s"], "unit": UNIT, "h2d_bytes_per_step": total * res["h2d_bytes_per_frame"],
+                    "d2h_bytes_per_step": total * fb, "ms_per_step": round(res["stream"]["ms_per_frame"] * total, 3),
+                    "api": "hdb_multi_deblock_stream_strips"},
+            "strips_8k": res, "gpu_launches": args.steps * total * res["strips"], "parity": res["parity"]}
     emit(line)
-    m.close()
-    one.close()
 
 
 def device_block_info(torch, n, w, h, seed, device="cuda"):
@@ -646,7 +860,7 @@ def run_edges(args):
     fb = 3 * w * h // 2
     dev = hdb.Deblocker(0)
     stream = torch.cuda.current_stream().cuda_stream
-    frames, qp, vbs, hbs = device_batch(torch, n, w, h, seed=4242)
+    frames, qp, vbs, hbs = workload_frames(torch, 0, n, w, h, WORKLOAD_SEED[args.workload], "cuda")
     info = device_block_info(torch, n, w, h, seed=99)
     nv, nh = hdb.num_vert_bs(w, h), hdb.num_hor_bs(w, h)
     d_v = torch.empty((n, nv), dtype=torch.uint8, device="cuda")
@@ -759,6 +973,7 @@ def main():
     ap.add_argument("--workload", default="4k_batch1024", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-sample", type=int, default=0, help="frames in the CPU sample (default 256)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-sub", action="store_true", help="skip the sub-records (other_configs at N = 1, strips_8k at N > 1)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

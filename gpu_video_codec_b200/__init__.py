@@ -14,6 +14,7 @@ from .binding import (  # noqa: F401
     FLAG_NV12,
     MultiDeblocker,
     Nv12Surfaces,
+    StripPlanes,
     Surfaces,
     Timing,
     build_library,

@@ -50,6 +50,11 @@ class Nv12Surfaces(C.Structure):
                 ("frame_stride_y", C.c_size_t), ("frame_stride_uv", C.c_size_t)]
 
 
+class StripPlanes(C.Structure):
+    """hdb_strip_planes: the three planes of one strip in one GPU's memory."""
+    _fields_ = [("y", C.c_void_p), ("u", C.c_void_p), ("v", C.c_void_p)]
+
+
 FLAG_EDGE_MAPS, FLAG_NV12 = 1, 2
 
 
@@ -148,6 +153,12 @@ def load_library():
     lib.hdb_multi_deblock_batch_ex.argtypes = [vp] + batch_args + [C.c_uint, C.POINTER(Timing)]
     lib.hdb_multi_deblock_frame_strips.argtypes = [vp, vp, vp] + frame_args
     lib.hdb_multi_deblock_frame_strips_ex.argtypes = [vp, vp, vp] + frame_args[:-1] + [C.c_uint, C.POINTER(Timing)]
+    lib.hdb_multi_deblock_stream_strips.argtypes = [vp] + batch_args + [C.c_uint, C.POINTER(Timing)]
+    lib.hdb_multi_strip_layout.argtypes = [vp, C.c_uint, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.hdb_multi_deblock_strips_device.argtypes = [vp, C.POINTER(StripPlanes), C.POINTER(StripPlanes), C.c_uint, C.c_uint, C.c_uint,
+                                                    C.POINTER(vp), C.POINTER(vp), C.c_uint, C.POINTER(vp), C.POINTER(Timing)]
+    lib.hdb_multi_strip_halo_bytes.argtypes = [vp, C.c_uint, C.c_uint]
+    lib.hdb_multi_strip_halo_bytes.restype = C.c_ulonglong
     _lib = lib
     return lib
 
@@ -429,3 +440,34 @@ class MultiDeblocker:
                                                                 _addr(h), 0 if h is None else h.size, flags,
                                                                 None if timing is None else C.byref(timing)))
         return out
+
+    def deblock_stream_strips(self, frames, width, height, qps, vert=None, hor=None, flags=0, out=None, timing=None,
+                              n_frames=None):
+        """A stream of frames, each split into CTU-row strips over the devices; pipelined across frames."""
+        n = n_frames if n_frames is not None else int(frames.shape[0])
+        if out is None:
+            out = np.empty_like(frames)
+        self._check(self._lib.hdb_multi_deblock_stream_strips(self._m, _addr(frames), _addr(out), n, width, height,
+                                                              _addr(qps), _addr(vert), _addr(hor), flags,
+                                                              None if timing is None else C.byref(timing)))
+        return out
+
+    def strip_layout(self, height):
+        """[(first luma row, luma rows)] per device in use."""
+        n = self.device_count()
+        a, b = (C.c_int * n)(), (C.c_int * n)()
+        g = int(self._lib.hdb_multi_strip_layout(self._m, height, a, b))
+        return [(int(a[i]), int(b[i])) for i in range(g)]
+
+    def strip_halo_bytes(self, width, height):
+        return int(self._lib.hdb_multi_strip_halo_bytes(self._m, width, height))
+
+    def deblock_strips_device(self, strips_in, strips_out, width, height, qp, d_vert=None, d_hor=None, flags=0,
+                              streams=None, timing=None):
+        """strips_in / strips_out: per device (y, u, v) device tensors or addresses holding that device's rows."""
+        g = len(strips_in)
+        mk = lambda strips: (StripPlanes * g)(*[StripPlanes(_addr(y), _addr(u), _addr(v)) for (y, u, v) in strips])
+        arr = lambda xs: None if xs is None else (C.c_void_p * g)(*[_addr(x) for x in xs])
+        self._check(self._lib.hdb_multi_deblock_strips_device(self._m, mk(strips_in), mk(strips_out), width, height, qp,
+                                                              arr(d_vert), arr(d_hor), flags, arr(streams),
+                                                              None if timing is None else C.byref(timing)))

@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <sys/stat.h>
 
 namespace hdb {
 
@@ -38,6 +39,9 @@ int FailCuda(hdb_context *ctx, cudaError_t e, const char *what)
 /* ------------------------------------------------------------------ */
 /* context                                                             */
 /* ------------------------------------------------------------------ */
+/* cpu.h:86-87 evaluated as the reference does (unsigned, left to right); the operands are range-checked first */
+static unsigned NumBs32(unsigned w, unsigned h, bool vert) { return vert ? (w / 8 + 1) * h / 8 : (h / 8 + 1) * w / 8; }
+
 static int CreateContext(hdb_context **out, int device)
 {
 	if (!out) return Fail(nullptr, HDB_ERR_INVALID_ARG, "ctx is NULL");
@@ -72,6 +76,8 @@ static int CreateContext(hdb_context **out, int device)
 	ctx->encode = reinterpret_cast<EncodeTiledFn>(fn);
 	/* measurement knob: HDB_ZERO_COPY=0 sends single-slice calls through the copy engines too */
 	if (const char *z = getenv("HDB_ZERO_COPY")) ctx->zero_copy = atoi(z) != 0;
+	/* test / measurement knob: HDB_NO_LDGSTS sends widths off the 32 grid through the padded-scratch kernels */
+	if (getenv("HDB_NO_LDGSTS")) ctx->use_ldgsts = false;
 	/* tuning knob for measurements: slice size of the host pipeline in MB */
 	if (const char *mb = getenv("HDB_CHUNK_MB")) {
 		const long v = strtol(mb, nullptr, 10);
@@ -81,8 +87,11 @@ static int CreateContext(hdb_context **out, int device)
 		&& cudaStreamCreateWithFlags(&ctx->s_k, cudaStreamNonBlocking) == cudaSuccess
 		&& cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking) == cudaSuccess
 		&& PrepareTiled(ctx->tiled_ctas_per_sm) == cudaSuccess
+		&& cudaStreamCreateWithFlags(&ctx->s_setup, cudaStreamNonBlocking) == cudaSuccess
 		&& cudaMalloc(&ctx->sched, TiledSchedBytes() * kSchedSlots) == cudaSuccess
 		&& cudaMemset(ctx->sched, 0, TiledSchedBytes() * kSchedSlots) == cudaSuccess;
+	for (int i = 0; ok && i < kSchedSlots; i++)
+		ok = cudaEventCreateWithFlags(&ctx->sched_done[i], cudaEventDisableTiming) == cudaSuccess;
 	if (!ok) {
 		e = cudaGetLastError();
 		DestroyContext(ctx);
@@ -98,14 +107,16 @@ void DestroyContext(hdb_context *ctx)
 	DeviceGuard guard(ctx->device);
 	cudaDeviceSynchronize();
 	for (auto &s : ctx->sizes) { cudaFree(s.chroma_bs); cudaFree(s.def_vbs); cudaFree(s.def_hbs); }
-	for (auto &sl : ctx->slots) { cudaFree(sl.frames); cudaFree(sl.vbs); cudaFree(sl.hbs); cudaFree(sl.info); }
+	for (auto &sl : ctx->slots) {
+		cudaFree(sl.frames); cudaFree(sl.vbs); cudaFree(sl.hbs); cudaFree(sl.info);
+		if (sl.ev_ready) { cudaEventDestroy(sl.h2d_done); cudaEventDestroy(sl.k_done); cudaEventDestroy(sl.d2h_done); }
+	}
+	for (auto ev : ctx->sched_done) if (ev) cudaEventDestroy(ev);
+	if (ctx->s_setup) cudaStreamDestroy(ctx->s_setup);
 	cudaFree(ctx->qp_dev);
 	cudaFree(ctx->derive_dev);
 	for (auto ev : ctx->event_pool) cudaEventDestroy(ev);
-	cudaFree(ctx->generic_scratch);
 	cudaFree(ctx->sched);
-	if (ctx->stage_in) cudaFreeHost(ctx->stage_in);
-	if (ctx->stage_out) cudaFreeHost(ctx->stage_out);
 	if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
 	if (ctx->s_k) cudaStreamDestroy(ctx->s_k);
 	if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
@@ -119,14 +130,15 @@ int GetSizeState(hdb_context *ctx, int w, int h, SizeState **out)
 	SizeState s{};
 	s.w = w; s.h = h;
 	const size_t ncb = (size_t)((w / 2 + 8) / 8) * ((h / 2 + 8) / 8);
-	const unsigned nv = (unsigned)(w / 8 + 1) * h / 8, nh = (unsigned)(h / 8 + 1) * w / 8;
+	const unsigned nv = NumBs32((unsigned)w, (unsigned)h, true), nh = NumBs32((unsigned)w, (unsigned)h, false);
 	HDB_CUDA(ctx, cudaMalloc(&s.chroma_bs, std::max<size_t>(ncb, 1) * sizeof(uint32_t)));
 	HDB_CUDA(ctx, cudaMalloc(&s.def_vbs, std::max(nv, 1u)));
 	HDB_CUDA(ctx, cudaMalloc(&s.def_hbs, std::max(nh, 1u)));
-	/* built on the legacy default stream, then a full sync: visible to every stream afterwards */
-	HDB_CUDA(ctx, LaunchChromaBsTable(s.chroma_bs, w, h, 0));
-	HDB_CUDA(ctx, LaunchDefaultLumaBs(s.def_vbs, s.def_hbs, w, h, 0));
-	HDB_CUDA(ctx, cudaDeviceSynchronize());
+	/* built on a stream of the context's own and waited for here, once per frame size: visible to every stream
+	 * afterwards, and no other stream of the device is touched (the public header says so) */
+	HDB_CUDA(ctx, LaunchChromaBsTable(s.chroma_bs, w, h, ctx->s_setup));
+	HDB_CUDA(ctx, LaunchDefaultLumaBs(s.def_vbs, s.def_hbs, w, h, ctx->s_setup));
+	HDB_CUDA(ctx, cudaStreamSynchronize(ctx->s_setup));
 	ctx->sizes.push_back(s);
 	*out = &ctx->sizes.back();
 	return HDB_OK;
@@ -157,6 +169,14 @@ bool TiledPathUsable(int w, int h, const void *d_in, const void *d_out)
 	return w % 32 == 0 && ((uintptr_t)d_in % 16 == 0) && ((uintptr_t)d_out % 16 == 0);
 }
 
+/* the tiled kernel with its cp.async loader: any width the reference accepts (cpu.h:46-48) from 32 up;
+ * tight planes of such frames start on 4-byte boundaries when the frame does */
+bool LdgstsPathUsable(int w, int h, const void *d_in, const void *d_out)
+{
+	(void)h;
+	return w >= 32 && w <= 262136 && ((uintptr_t)d_in % 4 == 0) && ((uintptr_t)d_out % 4 == 0);
+}
+
 /*
  * Enqueue the filter for frames resident in device memory.  view describes which
  * rows the buffers hold (whole frames unless a strip).  No synchronisation.
@@ -173,41 +193,47 @@ int EnqueueFilter(hdb_context *ctx, const FrameView &view, const unsigned char *
 	if (!d_vbs || !d_hbs) { d_vbs = ss->def_vbs; d_hbs = ss->def_hbs; vbs_stride = hbs_stride = 0; }
 	const TiledConfig cfg = GetTiledConfig();
 
-	if (view.nv12 && !TiledPathUsable(w, h, d_in, d_out))
-		return Fail(ctx, HDB_ERR_DIMENSIONS, "NV12 frames need a width that is a multiple of 32 and 16-byte aligned buffers");
-	if (view.whole_frame && !TiledPathUsable(w, h, d_in, d_out)) {
+	const bool tma_ok = TiledPathUsable(w, h, d_in, d_out) && view.luma_pitch % 16 == 0 && view.chroma_pitch % 16 == 0
+		&& view.frame_stride % 16 == 0 && view.chroma_frame_stride % 16 == 0 && view.u_offset % 16 == 0 && view.v_offset % 16 == 0
+		&& view.u_offset_out % 16 == 0 && view.v_offset_out % 16 == 0;
+	const bool ldgsts_ok = !tma_ok && !view.strip_halo && ctx->use_ldgsts && LdgstsPathUsable(w, h, d_in, d_out);
+	if (view.nv12 && !tma_ok && !ldgsts_ok)
+		return Fail(ctx, HDB_ERR_DIMENSIONS, "NV12 frames need a width of at least 32 and 4-byte aligned buffers");
+	if (!tma_ok && !ldgsts_ok && !view.whole_frame)
+		return Fail(ctx, HDB_ERR_DIMENSIONS, "pitched or partial planes need a width of at least 32 and 4-byte aligned buffers");
+	if (!tma_ok && !ldgsts_ok) {
 		/* generic path: explicit padded planes in scratch memory */
 		if (path) *path = 2;
 		const size_t per = GenericScratchBytes(w, h);
 		const int max_n = (int)std::max<size_t>(1, ((size_t)256 << 20) / per);
 		const int chunk = std::min(n, max_n);
-		if (ctx->generic_scratch_bytes < per * chunk) {
-			HDB_CUDA(ctx, cudaStreamSynchronize(stream));
-			cudaFree(ctx->generic_scratch);
-			ctx->generic_scratch = nullptr; ctx->generic_scratch_bytes = 0;
-			HDB_CUDA(ctx, cudaMalloc(&ctx->generic_scratch, per * chunk));
-			ctx->generic_scratch_bytes = per * chunk;
-		}
-		/* a single uniform QP is materialised on the device for this path */
+		/* the padded planes live in scratch memory that belongs to this call alone, allocated and freed in
+		 * stream order: calls in flight on different streams never share it, and nothing synchronises */
+		unsigned char *scratch = nullptr;
+		HDB_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void **>(&scratch), per * chunk, stream));
 		const long long fs = (long long)w * h * 3 / 2;
 		for (int f0 = 0; f0 < n; f0 += chunk) {
 			GenericBatch g{};
 			g.n_frames = std::min(chunk, n - f0); g.width = w; g.height = h;
 			g.in = d_in + f0 * fs; g.out = d_out + f0 * fs; g.frame_stride = fs;
-			g.scratch = ctx->generic_scratch;
+			g.scratch = scratch;
 			g.qp = d_qp ? d_qp + f0 : nullptr; g.qp_value = qp_value;
 			g.vert_bs = d_vbs + f0 * vbs_stride; g.hor_bs = d_hbs + f0 * hbs_stride;
 			g.vert_bs_stride = vbs_stride; g.hor_bs_stride = hbs_stride;
 			g.edge_qp = edge_qp;
-			HDB_CUDA(ctx, LaunchGeneric(g, stream));
+			const cudaError_t e = LaunchGeneric(g, stream);
+			if (e != cudaSuccess) { cudaFreeAsync(scratch, stream); return FailCuda(ctx, e, "LaunchGeneric"); }
 			ctx->launches += 3;
 		}
+		HDB_CUDA(ctx, cudaFreeAsync(scratch, stream));
 		return HDB_OK;
 	}
 
-	if (path) *path = 1;
+	if (path) *path = tma_ok ? 1 : 3;
 	const int cw = w / 2, ch = h / 2;
 	TiledBatch b{};
+	b.load_mode = tma_ok ? (view.strip_halo ? 1 : 0) : 2;
+	for (int p = 0; p < 3; p++) { b.halo_top[p] = view.halo_top[p]; b.halo_bot[p] = view.halo_bot[p]; }
 	b.width = w; b.height = h;
 	b.luma_nbx = (w + 8) / 8; b.luma_nby = (h + 8) / 8;
 	b.chroma_nbx = (cw + 8) / 8; b.chroma_nby = (ch + 8) / 8;
@@ -242,14 +268,22 @@ int EnqueueFilter(hdb_context *ctx, const FrameView &view, const unsigned char *
 		memset(&maps, 0, sizeof maps);
 		for (int p = 0; p < (view.nv12 ? 2 : 3); p++) {
 			const long long pfs = p ? cfs : fs;
-			if ((rc = EncodePlaneMap(ctx, &maps.in[p], d_in + off_in[p] + f0 * pfs, pw[p], ph[p], nf,
+			if (tma_ok && (rc = EncodePlaneMap(ctx, &maps.in[p], d_in + off_in[p] + f0 * pfs, pw[p], ph[p], nf,
 					p ? view.chroma_pitch : view.luma_pitch, pfs, 8 * cfg.block_rows_per_item))) return rc;
+			b.in_plane[p] = d_in + off_in[p] + f0 * pfs;
 			b.out_plane[p] = d_out + off_out[p] + f0 * pfs;
 		}
 		/* launches take the scheduler words in turn: two launches that overlap on the device (different
 		 * streams) must not share a work counter, and each launch leaves its own words zeroed */
-		void *sched = static_cast<char *>(ctx->sched) + TiledSchedBytes() * (ctx->launches % kSchedSlots);
+		const int slot = (int)(ctx->sched_turn++ % kSchedSlots);
+		void *sched = static_cast<char *>(ctx->sched) + TiledSchedBytes() * slot;
+		/* the launch that had these words kSchedSlots launches ago may still be running on another stream: wait
+		 * for it there (the same stream orders itself) */
+		if (ctx->sched_used[slot] && ctx->sched_stream[slot] != stream)
+			HDB_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->sched_done[slot], 0));
 		HDB_CUDA(ctx, LaunchTiled(maps, b, sched, ctx->prop.multiProcessorCount, ctx->tiled_ctas_per_sm, stream, edge_qp));
+		HDB_CUDA(ctx, cudaEventRecord(ctx->sched_done[slot], stream));
+		ctx->sched_used[slot] = true; ctx->sched_stream[slot] = stream;
 		ctx->launches += 1;
 	}
 	return HDB_OK;
@@ -275,7 +309,11 @@ int ValidateFrameArgs(hdb_context *ctx, unsigned w, unsigned h, const unsigned c
 	const unsigned char *hbs, unsigned nh, bool sizes_given)
 {
 	if (w == 0 || h == 0 || w % 8 != 0 || h % 8 != 0) return Fail(ctx, HDB_ERR_DIMENSIONS, kMsgDims);
-	if (w > (1u << 20) || h > (1u << 20)) return Fail(ctx, HDB_ERR_INVALID_ARG, "frame too large");
+	/* the item descriptor of the tiled kernel numbers 32-block chunks in 10 bits and row groups in 20; the
+	 * reference's own unsigned array sizes (cpu.h:86-87) must not wrap either */
+	if (w > 262136u || h > (1u << 20) || (unsigned long long)(w / 8 + 1) * h >= (1ull << 32)
+		|| (unsigned long long)(h / 8 + 1) * w >= (1ull << 32) || (unsigned long long)w * h * 3 / 2 >= (1ull << 40))
+		return Fail(ctx, HDB_ERR_INVALID_ARG, "frame too large (width up to 262136, height up to 1048576, (width/8+1)*height below 2^32)");
 	if ((vbs != nullptr) != (hbs != nullptr))
 		return Fail(ctx, HDB_ERR_INVALID_ARG, "vert_bs and hor_bs must both be given or both be NULL");
 	if (vbs && sizes_given && (nv != (w / 8 + 1) * h / 8 || nh != (h / 8 + 1) * w / 8))
@@ -369,14 +407,35 @@ static int GetEvents(hdb_context *ctx, size_t n)
  * slice i-2's D2H copy run concurrently on three streams, chained by events.  A
  * single slice runs on one stream.
  */
+/* On any failure after work has been enqueued, nothing may still be in flight when the caller gets its
+ * buffers back (and before they are un-pinned): declared after the PinHostRange objects, destroyed before them. */
+struct DrainOnFailure {
+	hdb_context *ctx;
+	bool armed = true;
+	explicit DrainOnFailure(hdb_context *c) : ctx(c) {}
+	~DrainOnFailure()
+	{
+		if (!armed) return;
+		cudaStreamSynchronize(ctx->s_h2d); cudaStreamSynchronize(ctx->s_k); cudaStreamSynchronize(ctx->s_d2h);
+		cudaGetLastError();
+	}
+};
+
 int BatchHost(hdb_context *ctx, const unsigned char *in, unsigned char *out, unsigned n, unsigned w, unsigned h,
 	const unsigned *qp, const unsigned char *vbs, const unsigned char *hbs, hdb_timing *timing, unsigned flags,
 	const hdb_block_info *info)
 {
 	if (!ctx) return HDB_ERR_INVALID_ARG;
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	return BatchHostLocked(ctx, in, out, n, w, h, qp, vbs, hbs, timing, flags, info);
+}
+
+int BatchHostLocked(hdb_context *ctx, const unsigned char *in, unsigned char *out, unsigned n, unsigned w, unsigned h,
+	const unsigned *qp, const unsigned char *vbs, const unsigned char *hbs, hdb_timing *timing, unsigned flags,
+	const hdb_block_info *info)
+{
 	/* block data given: the edge maps of every slice are derived on the device, into the slot's own arrays */
 	const bool edge_qp = (flags & HDB_FLAG_EDGE_MAPS) != 0 || info != nullptr, nv12 = (flags & HDB_FLAG_NV12) != 0;
-	std::lock_guard<std::mutex> lock(ctx->mu);
 	if (!in || !out || !qp || n == 0) return Fail(ctx, HDB_ERR_INVALID_ARG, "NULL buffer or empty batch");
 	if (info && (vbs || hbs)) return Fail(ctx, HDB_ERR_INVALID_ARG, "give block data or edge maps, not both");
 	if (edge_qp && !info && (!vbs || !hbs)) return Fail(ctx, HDB_ERR_INVALID_ARG, "edge maps are required: there is no default for them");
@@ -399,11 +458,12 @@ int BatchHost(hdb_context *ctx, const unsigned char *in, unsigned char *out, uns
 		ctx->qp_cap = n;
 	}
 	const FrameView view = WholeFrameView((int)w, (int)h, nv12);
-	if (nv12 && w % 32 != 0) return Fail(ctx, HDB_ERR_DIMENSIONS, "NV12 frames need a width that is a multiple of 32");
+	if (nv12 && w < 32) return Fail(ctx, HDB_ERR_DIMENSIONS, "NV12 frames need a width of at least 32");
 
 	PinHostRange pin_in(in, fb * n), pin_out(out != in ? out : nullptr, fb * n);
 	PinHostRange pin_v(vbs, (size_t)nv * n), pin_h(hbs, (size_t)nh * n), pin_i(info, ib * n);
 	const unsigned char *info_bytes = reinterpret_cast<const unsigned char *>(info);
+	DrainOnFailure drain(ctx);
 
 	const bool timed = timing != nullptr;
 	if (timed && (rc = GetEvents(ctx, (size_t)nchunks * 6))) return rc;
@@ -460,6 +520,7 @@ int BatchHost(hdb_context *ctx, const unsigned char *in, unsigned char *out, uns
 			timing->kernel_launches = (int)(ctx->launches - launches0);
 			timing->path = path;
 		}
+		drain.armed = false;
 		return HDB_OK;
 	}
 	unsigned f0 = 0;
@@ -523,6 +584,61 @@ int BatchHost(hdb_context *ctx, const unsigned char *in, unsigned char *out, uns
 		timing->h2d_bytes = (unsigned long long)fb * n + (n == 1 ? 0 : sizeof(unsigned) * (unsigned long long)n)
 			+ (vbs ? (unsigned long long)(nv + nh) * n : 0) + (unsigned long long)ib * n;
 		timing->d2h_bytes = (unsigned long long)fb * n;
+		timing->kernel_launches = (int)(ctx->launches - launches0);
+		timing->path = path;
+	}
+	drain.armed = false;
+	return HDB_OK;
+}
+
+/*
+ * One frame given as three separate planes (the reference keeps ext_Y / ext_U / ext_V, cpu.h:1041-1048): the
+ * planes go straight into one device slot with three copies and come back with three, on one stream, under
+ * the context lock from the first copy to the last.
+ */
+int PlanesHost(hdb_context *ctx, const unsigned char *y_in, const unsigned char *u_in, const unsigned char *v_in,
+	unsigned char *y_out, unsigned char *u_out, unsigned char *v_out, unsigned w, unsigned h, unsigned qp,
+	const unsigned char *vbs, const unsigned char *hbs, hdb_timing *timing)
+{
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	DeviceGuard guard(ctx->device);
+	const auto t_begin = std::chrono::steady_clock::now();
+	const size_t ysz = (size_t)w * h, csz = (size_t)(w / 2) * (h / 2), fb = ysz + 2 * csz;
+	const unsigned nv = (w / 8 + 1) * h / 8, nh = (h / 8 + 1) * w / 8;
+	int rc = EnsureSlots(ctx, fb, 1, nv, nh, vbs != nullptr, 0);
+	if (rc) return rc;
+	if (timing && (rc = GetEvents(ctx, 2))) return rc;
+	Slot &sl = ctx->slots[0];
+	cudaStream_t st = ctx->s_k;
+	DrainOnFailure drain(ctx);
+	const unsigned long long launches0 = ctx->launches;
+	HDB_CUDA(ctx, cudaMemcpyAsync(sl.frames, y_in, ysz, cudaMemcpyHostToDevice, st));
+	HDB_CUDA(ctx, cudaMemcpyAsync(sl.frames + ysz, u_in, csz, cudaMemcpyHostToDevice, st));
+	HDB_CUDA(ctx, cudaMemcpyAsync(sl.frames + ysz + csz, v_in, csz, cudaMemcpyHostToDevice, st));
+	if (vbs) {
+		HDB_CUDA(ctx, cudaMemcpyAsync(sl.vbs, vbs, nv, cudaMemcpyHostToDevice, st));
+		HDB_CUDA(ctx, cudaMemcpyAsync(sl.hbs, hbs, nh, cudaMemcpyHostToDevice, st));
+	}
+	if (timing) HDB_CUDA(ctx, cudaEventRecord(ctx->event_pool[0], st));
+	int path = 0;
+	rc = EnqueueFilter(ctx, WholeFrameView((int)w, (int)h), sl.frames, sl.frames, 1, nullptr, qp,
+		vbs ? sl.vbs : nullptr, nv, vbs ? sl.hbs : nullptr, nh, st, &path, false);
+	if (rc) return rc;
+	if (timing) HDB_CUDA(ctx, cudaEventRecord(ctx->event_pool[1], st));
+	HDB_CUDA(ctx, cudaMemcpyAsync(y_out, sl.frames, ysz, cudaMemcpyDeviceToHost, st));
+	HDB_CUDA(ctx, cudaMemcpyAsync(u_out, sl.frames + ysz, csz, cudaMemcpyDeviceToHost, st));
+	HDB_CUDA(ctx, cudaMemcpyAsync(v_out, sl.frames + ysz + csz, csz, cudaMemcpyDeviceToHost, st));
+	HDB_CUDA(ctx, cudaStreamSynchronize(st));
+	drain.armed = false;
+	if (timing) {
+		memset(timing, 0, sizeof *timing);
+		float k = 0;
+		cudaEventElapsedTime(&k, ctx->event_pool[0], ctx->event_pool[1]);
+		timing->kernel_ms = k;
+		timing->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+		timing->copy_ms = std::max(0.0, timing->total_ms - timing->kernel_ms);
+		timing->h2d_bytes = fb + (vbs ? nv + nh : 0);
+		timing->d2h_bytes = fb;
 		timing->kernel_launches = (int)(ctx->launches - launches0);
 		timing->path = path;
 	}
@@ -613,23 +729,7 @@ int hdb_deblock_planes(hdb_context *ctx, const unsigned char *y_in, const unsign
 	if (!y_in || !u_in || !v_in || !y_out || !u_out || !v_out) return Fail(ctx, HDB_ERR_INVALID_ARG, "NULL plane");
 	int rc = ValidateFrameArgs(ctx, width, height, vert_bs, num_vert_bs, hor_bs, num_hor_bs, true);
 	if (rc) return rc;
-	/* gather into one pinned YV12 frame, run, scatter */
-	const size_t ysz = (size_t)width * height, csz = (size_t)(width / 2) * (height / 2), fb = ysz + 2 * csz;
-	{
-		std::lock_guard<std::mutex> lock(ctx->mu);
-		if (ctx->stage_cap < fb) {
-			if (ctx->stage_in) cudaFreeHost(ctx->stage_in);
-			ctx->stage_in = nullptr; ctx->stage_cap = 0;
-			if (cudaMallocHost(&ctx->stage_in, fb) != cudaSuccess) return FailCuda(ctx, cudaGetLastError(), "cudaMallocHost");
-			ctx->stage_cap = fb;
-		}
-	}
-	unsigned char *st = static_cast<unsigned char *>(ctx->stage_in);
-	memcpy(st, y_in, ysz); memcpy(st + ysz, u_in, csz); memcpy(st + ysz + csz, v_in, csz);
-	rc = BatchHost(ctx, st, st, 1, width, height, &qp, vert_bs, hor_bs, timing);
-	if (rc) return rc;
-	memcpy(y_out, st, ysz); memcpy(u_out, st + ysz, csz); memcpy(v_out, st + ysz + csz, csz);
-	return HDB_OK;
+	return PlanesHost(ctx, y_in, u_in, v_in, y_out, u_out, v_out, width, height, qp, vert_bs, hor_bs, timing);
 }
 
 int hdb_execute_gpu(hdb_context *ctx, const char *input_file_name, const char *output_file_name,
@@ -910,6 +1010,13 @@ int hdb_execute_gpu_sequence(hdb_context *ctx, const char *input_file_name, cons
 	const unsigned chunk = (unsigned)std::min<unsigned long long>(total, std::max<size_t>(1, ((size_t)512 << 20) / fb));
 	unsigned char *buf = static_cast<unsigned char *>(hdb_host_alloc(fb * chunk));
 	if (!buf) { fclose(f); return Fail(ctx, HDB_ERR_NO_MEMORY, "cudaMallocHost failed"); }
+	/* the output is written while the input is still being read: the two must be different files */
+	struct stat st_in, st_out;
+	if (stat(input_file_name, &st_in) == 0 && stat(output_file_name, &st_out) == 0
+		&& st_in.st_dev == st_out.st_dev && st_in.st_ino == st_out.st_ino) {
+		fclose(f); hdb_host_free(buf);
+		return Fail(ctx, HDB_ERR_INVALID_ARG, "input and output name the same file");
+	}
 	FILE *o = fopen(output_file_name, "wb");
 	int rc = o ? HDB_OK : Fail(ctx, HDB_ERR_IO, std::string("cannot write ") + output_file_name);
 	std::vector<unsigned> qps(chunk, qp);

@@ -71,6 +71,10 @@ struct FrameView {
 	int luma_pitch, chroma_pitch;  /* bytes between rows */
 	long long frame_stride, chroma_frame_stride;   /* bytes between frames, luma plane / chroma planes */
 	bool nv12;                     /* two planes: Y and interleaved UV at u_offset (v_offset unused) */
+	/* a strip of a frame split across GPUs whose buffers hold its own rows only: per plane, the 4 rows above /
+	 * below them in the neighbouring strips' buffers (peer pointers, same pitch); all NULL otherwise */
+	const unsigned char *halo_top[3], *halo_bot[3];
+	bool strip_halo;
 };
 
 } // namespace hdb
@@ -80,20 +84,24 @@ struct hdb_context {
 	cudaDeviceProp prop{};
 	hdb::EncodeTiledFn encode = nullptr;
 	cudaStream_t s_h2d = nullptr, s_k = nullptr, s_d2h = nullptr;
+	cudaStream_t s_setup = nullptr;          /* per-size tables are built here */
 	void *sched = nullptr;
-	int tiled_ctas_per_sm[4] = { 1, 1, 1, 1 };   /* resident CTAs per SM of the tiled kernel's variants on this device */
+	/* scheduler-word sets are handed to successive launches in turn; each remembers the stream that used it
+	 * last and an event recorded behind that launch, which a launch on another stream waits for */
+	unsigned long long sched_turn = 0;
+	cudaEvent_t sched_done[hdb::kSchedSlots] = {};
+	cudaStream_t sched_stream[hdb::kSchedSlots] = {};
+	bool sched_used[hdb::kSchedSlots] = {};
+	int tiled_ctas_per_sm[hdb::kTiledVariants] = {};   /* resident CTAs per SM of the tiled kernel's variants on this device */
 	std::vector<hdb::SizeState> sizes;
 	hdb::Slot slots[hdb::kSlots];
 	std::vector<cudaEvent_t> event_pool;
-	unsigned char *generic_scratch = nullptr;
-	size_t generic_scratch_bytes = 0;
-	void *stage_in = nullptr, *stage_out = nullptr;
-	size_t stage_cap = 0;
 	void *derive_dev = nullptr;              /* block data and edge maps of a host-side hdb_derive_edges call */
 	size_t derive_cap = 0;
 	unsigned *qp_dev = nullptr;              /* the QPs of the batch in flight */
 	size_t qp_cap = 0;
 	size_t chunk_bytes = (size_t)128 << 20;  /* full slice size of the host pipeline (HDB_CHUNK_MB) */
+	bool use_ldgsts = true;                  /* widths off the 32 grid take the tiled kernel's cp.async loader */
 	bool zero_copy = true;                   /* single-slice calls on mapped pinned buffers skip the copy engines */
 	unsigned long long launches = 0;
 	std::string err;
@@ -108,12 +116,18 @@ void DestroyContext(hdb_context *ctx);
 int GetSizeState(hdb_context *ctx, int w, int h, SizeState **out);
 FrameView WholeFrameView(int w, int h, bool nv12 = false);
 bool TiledPathUsable(int w, int h, const void *d_in, const void *d_out);
+bool LdgstsPathUsable(int w, int h, const void *d_in, const void *d_out);
 int ValidateFrameArgs(hdb_context *ctx, unsigned w, unsigned h, const unsigned char *vbs, unsigned nv,
 	const unsigned char *hbs, unsigned nh, bool sizes_given);
 int EnqueueFilter(hdb_context *ctx, const FrameView &view, const unsigned char *d_in, unsigned char *d_out,
 	int n, const unsigned *d_qp, unsigned qp_value, const unsigned char *d_vbs, long long vbs_stride,
 	const unsigned char *d_hbs, long long hbs_stride, cudaStream_t stream, int *path, bool edge_qp = false);
 int BatchHost(hdb_context *ctx, const unsigned char *in, unsigned char *out, unsigned n, unsigned w, unsigned h,
+	const unsigned *qp, const unsigned char *vbs, const unsigned char *hbs, hdb_timing *timing, unsigned flags = 0,
+	const hdb_block_info *info = nullptr);
+
+/* the same with ctx->mu already held by the caller */
+int BatchHostLocked(hdb_context *ctx, const unsigned char *in, unsigned char *out, unsigned n, unsigned w, unsigned h,
 	const unsigned *qp, const unsigned char *vbs, const unsigned char *hbs, hdb_timing *timing, unsigned flags = 0,
 	const hdb_block_info *info = nullptr);
 

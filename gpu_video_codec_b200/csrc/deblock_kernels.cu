@@ -73,6 +73,12 @@
 #ifndef HDB_NV12_MIN_CTAS
 #define HDB_NV12_MIN_CTAS HDB_MIN_CTAS          /* the two-plane variants (measurement knob) */
 #endif
+#ifndef HDB_LDGSTS_MIN_CTAS
+#define HDB_LDGSTS_MIN_CTAS 16                  /* the cp.async loader variants: up to 128 registers */
+#endif
+#ifndef HDB_SMEM_ALIGN
+#define HDB_SMEM_ALIGN 128                      /* a TMA destination without swizzle needs 128 bytes */
+#endif
 #ifndef HDB_TRACE
 #define HDB_TRACE 0     /* 1: development build that records per-warp timestamps (tools/trace_tail.py) */
 #endif
@@ -89,6 +95,20 @@ constexpr int kTileH = 8 * kRB;
 constexpr int kTileBytes = kTileW * kTileH;     /* 2176 * kRB: a multiple of 128 */
 constexpr int kSmemBytes = kWarps * kStages * (kTileBytes + 8 + 8);
 constexpr uint32_t kNoItem = 0xffffffffu;
+/*
+ * How a tile gets into shared memory (third template parameter of the kernel):
+ *   kLoadTma      one TMA box per item (UTMALDG.3D), issued by lane 0 -- the kernel described above;
+ *   kLoadTmaHalo  the same for one CTU-row strip of a frame that is split across GPUs (deblock_multi.cu):
+ *                 the buffer holds the strip's own rows only, and the 4 input rows on the far side of a
+ *                 cut are read by the warp straight from the neighbouring GPU's buffer (peer loads over
+ *                 NVLink) into the tile rows TMA has zero-filled -- the halo exchange is fused into the
+ *                 filter kernel, there is no copy step;
+ *   kLoadLdgsts   planes a tensor map cannot describe (row pitch not a multiple of 16 bytes: every width
+ *                 that is a multiple of 8 but not of 32, cpu.h:46-48): all lanes fetch the box with 4-byte
+ *                 cp.async (LDGSTS, zero fill outside the plane) one item ahead, and rows are stored as
+ *                 32-bit words because their global addresses are only 4-byte aligned.
+ */
+enum { kLoadTma = 0, kLoadTmaHalo = 1, kLoadLdgsts = 2 };
 static_assert(kStages >= 2, "the stage after the current one holds the next item (boundary-strength prefetch)");
 
 #if HDB_TRACE
@@ -254,12 +274,12 @@ __device__ __forceinline__ void UvBlockRow(u32 *base, u32 s4, const FilterParams
 /* kEdgeQp: the luma boundary-strength arrays hold edge bytes (bs | qp << 2, deblock_core.cuh) and every
  * luma segment takes beta / tc from its own entry; chroma is untouched by it (frame QP, cpu.h:110-117) */
 /* kNv12: two planes, Y and interleaved UV (lanes 0-15 filter the U blocks of a UV item, lanes 16-31 the V blocks) */
-template <bool kEdgeQp, bool kNv12>
-__global__ void __launch_bounds__(kWarps * 32, kNv12 ? HDB_NV12_MIN_CTAS : HDB_MIN_CTAS)
+template <bool kEdgeQp, bool kNv12, int kLoad>
+__global__ void __launch_bounds__(kWarps * 32, kLoad == kLoadLdgsts ? HDB_LDGSTS_MIN_CTAS : (kNv12 ? HDB_NV12_MIN_CTAS : HDB_MIN_CTAS))
 DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_constant__ TiledBatch b,
 	SchedWords *sched, const uint32_t run_len)
 {
-	extern __shared__ __align__(1024) unsigned char smem[];
+	extern __shared__ __align__(HDB_SMEM_ALIGN) unsigned char smem[];
 	const int warp = threadIdx.x >> 5;
 	const int lane = threadIdx.x & 31;
 	unsigned char *tiles = smem + warp * (kStages * kTileBytes);
@@ -302,11 +322,50 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_consta
 		if (run_next >= total) { held[s] = make_uint2(0u, kNoItem); return; }
 		run_next++;
 		held[s] = make_uint2(cur.frame, cur.Desc());
+		if (kLoad == kLoadLdgsts) return;      /* every lane fetches its share of the box: fetch_tile */
 		const uint32_t bar = bars_s + 8u * s;
 		MbarArriveExpectTx(bar, kTileBytes);
 		/* x in 32-bit elements: (8*bx0 - 4 - kLead) / 4, a multiple of 4 elements = 16 bytes */
 		TmaLoad3D(tiles_s + s * kTileBytes, &maps.in[cur.plane], 64 * (int)cur.chunk - 4,
 			8 * kRB * (int)cur.grp + (cur.plane ? b.chroma_y_org : b.luma_y_org), (int)cur.frame, bar);
+	};
+	/*
+	 * kLoadLdgsts: the box of the item lane 0 has just put into held[s], fetched by all lanes with 4-byte
+	 * cp.async -- word w of tile row t comes from plane byte 4 * (64 * chunk - 4 + w) of buffer row
+	 * 8 * kRB * grp + y_org + t, or is zero where that lies outside the plane (src-size 0: the zero fill is
+	 * the reference's padding, as TMA's out-of-bounds fill is in the other variants).  One commit group per
+	 * item, empty for "no item", so that wait_group counts items.
+	 */
+	auto fetch_tile = [&](int s) {          /* all lanes, after a __syncwarp() that follows issue_load */
+		const uint2 it = held[s];
+		if (it.y != kNoItem) {
+			int plane, bx0, lby0;
+			ItemCoords<kNv12>(it.y, plane, bx0, lby0);
+			const bool c = plane != 0;
+			const int pw = (c && !kNv12) ? (b.width >> 1) : b.width;
+			const int pitch = c ? b.chroma_pitch : b.luma_pitch;
+			const int rows = c ? b.chroma_buf_rows : b.luma_buf_rows;
+			const int y0 = 8 * lby0 + (c ? b.chroma_y_org : b.luma_y_org);
+			const int xw0 = (int)((it.y >> 2) & 0x3ffu) * 64 - 4;          /* plane word of tile word 0 */
+			const unsigned char *src = b.in_plane[plane] + (long long)it.x * (c ? b.chroma_frame_stride : b.frame_stride);
+			const uint32_t dst = tiles_s + s * kTileBytes;
+#pragma unroll
+			for (int k = 0; k < 3; k++) {
+				const int w = lane + 32 * k;
+				const int xb = 4 * (xw0 + w);
+				const bool col_ok = w < kTileWords && xb >= 0 && xb < pw;
+				if (w < kTileWords) {
+#pragma unroll 4
+					for (int t = 0; t < kTileH; t++) {
+						const int y = y0 + t;
+						const bool ok = col_ok && y >= 0 && y < rows;
+						const unsigned char *g = ok ? src + (long long)y * pitch + xb : src;
+						CpAsync4(dst + 4u * (uint32_t)(t * kTileWords + w), g, ok ? 4u : 0u);
+					}
+				}
+			}
+		}
+		CpAsyncCommit();
 	};
 
 #if HDB_TRACE
@@ -321,6 +380,9 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_consta
 		for (int s = 0; s < kStages; s++) issue_load(s);
 	}
 	__syncwarp();
+	if (kLoad == kLoadLdgsts) {
+		for (int s = 0; s < kStages; s++) fetch_tile(s);
+	}
 
 	int s = 0;
 	uint32_t parity = 0;
@@ -364,12 +426,46 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_consta
 			for (int rb = 0; rb < kRB; rb++) bs_raw[rb] = ItemBsRaw<kNv12>(b, it_next.x, it_next.y, lane, rb);
 		}
 
-		MbarWait(bars_s + 8u * s, parity);
+		if (kLoad == kLoadLdgsts) {
+			/* this item's group is the older of the kStages in flight; the copies of the other lanes become
+			 * visible through the warp barrier */
+			CpAsyncWait<kStages - 1>();
+			__syncwarp();
+		} else {
+			MbarWait(bars_s + 8u * s, parity);
+		}
 #if HDB_TRACE
 		if (n_done++ == 0) t_first = GlobalTimerNs();
 #endif
 		u32 *tile = reinterpret_cast<u32 *>(tiles + s * kTileBytes);
 		unsigned char *dst = pl.out + (long long)frame * pl.frame_stride;
+		if (kLoad == kLoadTmaHalo) {
+			/*
+			 * A strip of a frame that is split across GPUs: the buffer holds the strip's own rows, so the tile
+			 * rows above its first and below its last row came out of TMA as zeros.  Where a neighbouring strip
+			 * exists they are its last / first 4 input rows: fetch them from the neighbour's buffer (a peer
+			 * pointer: NVLink) into the tile.  Rare: the first and the last row group of a plane only.
+			 */
+			const int y_first = 8 * lby0 + pl.y_org;
+			const unsigned char *top = b.halo_top[plane], *bot = b.halo_bot[plane];
+			const bool need_top = y_first < 0 && top != nullptr;
+			const bool need_bot = y_first + kTileH > pl.buf_rows && bot != nullptr;
+			if (need_top || need_bot) {
+				const int xw0 = (int)((desc >> 2) & 0x3ffu) * 64 - 4;       /* plane word of tile word 0 */
+				for (int t = 0; t < kTileH; t++) {
+					const int y = y_first + t;
+					const unsigned char *row = nullptr;
+					if (need_top && y < 0 && y >= -4) row = top + (long long)(y + 4) * pl.pitch;
+					if (need_bot && y >= pl.buf_rows && y < pl.buf_rows + 4) row = bot + (long long)(y - pl.buf_rows) * pl.pitch;
+					if (row == nullptr) continue;
+					for (int w = lane; w < kTileWords; w += 32) {
+						const int xb = 4 * (xw0 + w);
+						tile[t * kTileWords + w] = (xb >= 0 && xb < pl.pw) ? LdPeer32(row + xb) : 0u;
+					}
+				}
+				__syncwarp();
+			}
+		}
 		/* not unrolled: one copy of the block code, or the kernel outgrows the instruction cache
 		 * (unrolled, two block rows per item run 25 % slower than one) */
 #pragma unroll 1
@@ -418,7 +514,23 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_consta
 			const int fword = uv ? (k < 2 ? 2 + k : 62 + k) : (k == 0 ? 3 : 63 + k);
 			const int fcol = x_img + 4 * (fword - 3);
 			const bool f_lane = fcol >= 0 && fcol < pl.pw;
-			if (y0 >= 0 && y0 + kTileH <= pl.buf_rows) {
+			if (kLoad == kLoadLdgsts) {
+				/* rows start on 4-byte boundaries only: the item's 256 plane bytes per row (tile words 3 .. 66, for
+				 * a UV item 2 .. 65) go out as two 128-byte runs of 32-bit words */
+				const int word0 = uv ? 2 : 3;
+#pragma unroll 4
+				for (int rr = 0; rr < kTileH; rr++) {
+					const int y = y0 + rr;
+					if (y < 0 || y >= pl.buf_rows) continue;
+#pragma unroll
+					for (int k = 0; k < 2; k++) {
+						const int wi = lane + 32 * k;
+						const int col = x_img + 4 * wi;
+						if (col >= 0 && col < pl.pw)
+							*reinterpret_cast<u32 *>(dst + (long long)y * pl.pitch + col) = tile[rr * kTileWords + word0 + wi];
+					}
+				}
+			} else if (y0 >= 0 && y0 + kTileH <= pl.buf_rows) {
 				/* every row of the tile is inside the plane */
 #pragma unroll
 				for (int rr = 0; rr < kTileH; rr += 2) {
@@ -444,10 +556,11 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_consta
 			}
 		}
 		/* the stage is free again: refill it with the item kStages ahead */
-		FenceProxyAsyncShared();
+		if (kLoad != kLoadLdgsts) FenceProxyAsyncShared();
 		__syncwarp();
 		if (lane == 0) issue_load(s);
 		__syncwarp();
+		if (kLoad == kLoadLdgsts) fetch_tile(s);
 		if (++s == kStages) { s = 0; parity ^= 1u; }
 	}
 	if (lane == 0) {
@@ -505,16 +618,35 @@ void FinalizeTiledBatch(TiledBatch &b)
 
 typedef void (*TiledKernelFn)(const TensorMaps3, const TiledBatch, SchedWords *, const uint32_t);
 
-static TiledKernelFn TiledKernelOf(bool edge_qp, bool nv12)
+/* variant index = (edge maps ? 1 : 0) | (NV12 ? 2 : 0) | load mode << 2; strips are planar only */
+static TiledKernelFn TiledKernelOf(int v)
 {
-	if (nv12) return edge_qp ? DeblockTiledKernel<true, true> : DeblockTiledKernel<false, true>;
-	return edge_qp ? DeblockTiledKernel<true, false> : DeblockTiledKernel<false, false>;
+	switch (v) {
+	case 0: return DeblockTiledKernel<false, false, kLoadTma>;
+	case 1: return DeblockTiledKernel<true, false, kLoadTma>;
+	case 2: return DeblockTiledKernel<false, true, kLoadTma>;
+	case 3: return DeblockTiledKernel<true, true, kLoadTma>;
+	case 4: return DeblockTiledKernel<false, false, kLoadTmaHalo>;
+	case 5: return DeblockTiledKernel<true, false, kLoadTmaHalo>;
+	case 8: return DeblockTiledKernel<false, false, kLoadLdgsts>;
+	case 9: return DeblockTiledKernel<true, false, kLoadLdgsts>;
+	case 10: return DeblockTiledKernel<false, true, kLoadLdgsts>;
+	case 11: return DeblockTiledKernel<true, true, kLoadLdgsts>;
+	}
+	return nullptr;
 }
 
-cudaError_t PrepareTiled(int ctas_per_sm[4])
+static int VariantOf(const TiledBatch &b, bool edge_qp)
 {
-	for (int v = 0; v < 4; v++) {
-		const TiledKernelFn fn = TiledKernelOf(v & 1, v & 2);
+	return (edge_qp ? 1 : 0) | (b.nv12 ? 2 : 0) | (b.load_mode << 2);
+}
+
+cudaError_t PrepareTiled(int ctas_per_sm[kTiledVariants])
+{
+	for (int v = 0; v < kTiledVariants; v++) {
+		ctas_per_sm[v] = 1;
+		const TiledKernelFn fn = TiledKernelOf(v);
+		if (!fn) continue;
 		cudaError_t err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
 		if (err != cudaSuccess) return err;
 		int n = 0;
@@ -525,13 +657,16 @@ cudaError_t PrepareTiled(int ctas_per_sm[4])
 	return cudaSuccess;
 }
 
-cudaError_t LaunchTiled(const TensorMaps3 &maps, const TiledBatch &b, void *sched, int sm_count, const int ctas_per_sm[4],
+cudaError_t LaunchTiled(const TensorMaps3 &maps, const TiledBatch &b, void *sched, int sm_count, const int ctas_per_sm[kTiledVariants],
 	cudaStream_t stream, bool edge_qp)
 {
 	if (b.total_items <= 0) return cudaSuccess;
 	if (b.total_items >= (1ll << 31)) return cudaErrorInvalidValue;
+	const int variant = VariantOf(b, edge_qp);
+	const TiledKernelFn fn = TiledKernelOf(variant);
+	if (!fn) return cudaErrorInvalidValue;
 	const long long warps_wanted = b.total_items;
-	const int resident = std::max(ctas_per_sm[(edge_qp ? 1 : 0) | (b.nv12 ? 2 : 0)], 1);
+	const int resident = std::max(ctas_per_sm[variant], 1);
 	long long ctas = std::min<long long>((long long)sm_count * resident, (warps_wanted + kWarps - 1) / kWarps);
 	ctas = std::max<long long>(ctas, 1);
 	/* consecutive items per scheduler request: an upper bound, the kernel shortens the runs as the work runs
@@ -540,8 +675,7 @@ cudaError_t LaunchTiled(const TensorMaps3 &maps, const TiledBatch &b, void *sche
 	uint32_t run_len = b.total_items / (ctas * kWarps) >= 512 ? 8 : 4;
 	static const int run_len_env = getenv("HDB_RUN_LEN") ? atoi(getenv("HDB_RUN_LEN")) : 0;   /* measurement knob */
 	if (run_len_env > 0) run_len = (uint32_t)run_len_env;
-	TiledKernelOf(edge_qp, b.nv12 != 0)<<<(unsigned)ctas, kWarps * 32, kSmemBytes, stream>>>(maps, b,
-		reinterpret_cast<SchedWords *>(sched), run_len);
+	fn<<<(unsigned)ctas, kWarps * 32, kSmemBytes, stream>>>(maps, b, reinterpret_cast<SchedWords *>(sched), run_len);
 	return cudaGetLastError();
 }
 

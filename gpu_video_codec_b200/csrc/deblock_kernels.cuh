@@ -59,6 +59,12 @@ struct TiledBatch {
 	const unsigned char *hor_bs;
 	long long vert_bs_stride, hor_bs_stride; /* bytes between frames; 0 = one array for all */
 	const uint32_t *chroma_bs;      /* [chroma_nby][chroma_nbx] resolved, packed 4 x u8 */
+	/* how the tiles are fetched (deblock_kernels.cu): 0 tensor maps, 1 tensor maps + peer halo rows, 2 cp.async */
+	int load_mode;
+	const unsigned char *in_plane[3];       /* input plane base pointers of frame 0 (load mode 2 reads through them) */
+	/* load mode 1, a strip of a frame split across GPUs: the 4 rows above the buffer's first row / below its
+	 * last row in the neighbouring strips' buffers (peer pointers, same pitch), NULL at the frame's own top / bottom */
+	const unsigned char *halo_top[3], *halo_bot[3];
 	/* output: plane base pointers of frame 0 (may equal the input's), rows present, frame pitch */
 	unsigned char *out_plane[3];
 	int luma_buf_rows, chroma_buf_rows;
@@ -76,10 +82,11 @@ TiledConfig GetTiledConfig();
 void FinalizeTiledBatch(TiledBatch &b);
 
 /* Once per device (the current one): function attributes; returns the resident CTAs per SM the grid is sized
- * with, per kernel variant: index = (edge maps ? 1 : 0) | (NV12 ? 2 : 0). */
-cudaError_t PrepareTiled(int ctas_per_sm[4]);
+ * with, per kernel variant: index = (edge maps ? 1 : 0) | (NV12 ? 2 : 0) | load mode << 2. */
+constexpr int kTiledVariants = 12;
+cudaError_t PrepareTiled(int ctas_per_sm[kTiledVariants]);
 /* Persistent tiled kernel: one launch filters Y, U and V of every frame of the batch. */
-cudaError_t LaunchTiled(const TensorMaps3 &maps, const TiledBatch &b, void *sched, int sm_count, const int ctas_per_sm[4],
+cudaError_t LaunchTiled(const TensorMaps3 &maps, const TiledBatch &b, void *sched, int sm_count, const int ctas_per_sm[kTiledVariants],
 	cudaStream_t stream, bool edge_qp = false);
 /* bytes of zero-initialised device memory the scheduler needs (one per context) */
 size_t TiledSchedBytes();

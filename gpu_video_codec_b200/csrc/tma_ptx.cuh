@@ -69,5 +69,33 @@ __device__ __forceinline__ void TmaStoreWaitRead()
 	asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(kPending) : "memory");
 }
 
+/* ------------------------------------------------------------------ */
+/* cp.async (SASS: LDGSTS) and peer loads                              */
+/* ------------------------------------------------------------------ */
+/* 4 bytes global -> shared, asynchronously; src_bytes = 0 writes zeros instead (the address is not read) */
+__device__ __forceinline__ void CpAsync4(uint32_t dst, const void *src, uint32_t src_bytes)
+{
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+
+__device__ __forceinline__ void CpAsyncCommit()
+{
+	asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+template <int kPending>
+__device__ __forceinline__ void CpAsyncWait()
+{
+	asm volatile("cp.async.wait_group %0;" :: "n"(kPending) : "memory");
+}
+
+/* one word from another GPU's memory (a peer mapping: the load travels over NVLink); L2 only -- the line
+ * belongs to a buffer the neighbour refills between launches */
+__device__ __forceinline__ uint32_t LdPeer32(const void *p)
+{
+	uint32_t v;
+	asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
 
 } // namespace hdb

@@ -67,7 +67,8 @@ typedef struct hdb_timing {
 	double total_ms;           /* "Execution Time with copy on GPU": wall time of the whole call */
 	unsigned long long h2d_bytes, d2h_bytes;
 	int kernel_launches;       /* filter-kernel launches made by the call */
-	int path;                  /* 1 = TMA tiled kernel, 2 = generic kernel */
+	int path;                  /* 1 = tiled kernel, TMA loads; 3 = tiled kernel, cp.async loads (width not a multiple of 32);
+	                              2 = padded-scratch kernels (width below 32 or unaligned buffers) */
 } hdb_timing;
 
 typedef struct hdb_device_info {  /* what GetGpuDeviceInfo prints, main.cu:92-107 */
@@ -309,6 +310,44 @@ int hdb_multi_deblock_frame_strips_ex(hdb_multi *m, const unsigned char *yuv_in,
 	unsigned width, unsigned height, unsigned qp,
 	const unsigned char *vert, unsigned num_vert,
 	const unsigned char *hor, unsigned num_hor, unsigned flags, hdb_timing *timing);
+
+/*
+ * A STREAM of such frames (n_frames frames back to back in host memory, qp[n_frames], strengths per frame or
+ * NULL), every frame split into the same strips.  The stream is pipelined: on every GPU the upload of frame
+ * f + 1, the kernel of frame f and the download of frame f - 1 overlap (three streams and three buffers per
+ * GPU, one host thread per GPU), and the halo rows are not copied at all -- each GPU's kernel reads the 4
+ * input rows beyond a cut straight from the neighbouring GPU's buffer over NVLink.  hdb_multi_deblock_frame_strips
+ * is this call with n_frames = 1.  Blocking; results are identical to the unsplit filter.
+ */
+int hdb_multi_deblock_stream_strips(hdb_multi *m, const unsigned char *frames_in, unsigned char *frames_out,
+	unsigned n_frames, unsigned width, unsigned height, const unsigned *qp,
+	const unsigned char *vert, const unsigned char *hor, unsigned flags, hdb_timing *timing);
+
+/*
+ * The split itself: fills first_row[d] / n_rows[d] (luma rows; either may be NULL) for the devices in use and
+ * returns their number -- CTU rows (64 luma lines) dealt out evenly, earlier devices first; fewer strips than
+ * devices when the frame has fewer CTU rows.  0 on invalid arguments.
+ */
+int hdb_multi_strip_layout(const hdb_multi *m, unsigned height, int *first_row, int *n_rows);
+
+/*
+ * Strips that already sit in each GPU's memory (a decoder per GPU, an earlier stage): nothing crosses the
+ * host link.  in[d] / out[d] are the three planes of strip d on device d, tight rows (pitch = width for Y,
+ * width / 2 for U and V), holding exactly the rows hdb_multi_strip_layout assigns to d; 16-byte aligned;
+ * out of place (a strip's input rows are read by its neighbours' kernels too).  d_vert[d] / d_hor[d]: frame-sized
+ * strength (or edge-map) arrays on device d, or both NULL for the defaults.  streams[d]: the cudaStream_t of
+ * device d to enqueue on (NULL array: the library's own); a strip's kernel starts after the work already
+ * enqueued on its own and on both neighbours' streams.  With timing the call waits for completion and reports
+ * kernel_ms = the slowest device's kernel (halo traffic included: it happens inside the kernel); without, it
+ * returns once everything is enqueued.  width must be a multiple of 32.
+ */
+typedef struct hdb_strip_planes { void *y, *u, *v; } hdb_strip_planes;
+int hdb_multi_deblock_strips_device(hdb_multi *m, const hdb_strip_planes *in, const hdb_strip_planes *out,
+	unsigned width, unsigned height, unsigned qp,
+	const unsigned char *const *d_vert, const unsigned char *const *d_hor,
+	unsigned flags, void *const *streams, hdb_timing *timing);
+/* bytes that cross NVLink per frame of that size: 4 rows of each plane per cut and direction */
+unsigned long long hdb_multi_strip_halo_bytes(const hdb_multi *m, unsigned width, unsigned height);
 
 #ifdef __cplusplus
 }

@@ -39,3 +39,9 @@ def synth_case(seed, w, h, kind, bs_kind):
     frame = synth.make_frame(rng, w, h, kind)
     v, hh = (None, None) if bs_kind is None else synth.make_bs(rng, w, h, bs_kind)
     return frame, v, hh
+
+
+def expected_path(w):
+    """hdb_timing.path for a frame of width w: 1 tiled kernel with TMA loads, 3 tiled kernel with cp.async
+    loads (width off the 32 grid), 2 padded-scratch kernels (width below 32)."""
+    return 1 if w % 32 == 0 else (3 if w >= 32 else 2)

@@ -34,7 +34,7 @@ def test_golden_edges(dev, case):
     t = hdb.Timing()
     y = dev.deblock_frame_edges(frame, case["w"], case["h"], case["qp"], v, hh, timing=t)
     assert common.md5(y) == case["md5"] and common.sha256(y) == case["sha256"]
-    assert t.path == (1 if case["w"] % 32 == 0 else 2)
+    assert t.path == common.expected_path(case["w"])
 
 
 SIZES = [(32, 8), (64, 48), (256, 64), (352, 288), (768, 576), (8192, 16), (1920, 1080),        # tiled kernel

@@ -96,3 +96,68 @@ def test_strip_split_with_edge_maps(devices, size):
     with pytest.raises(hdb.DeblockError):
         m.deblock_frame_strips(frame, w, h, 37, flags=hdb.FLAG_EDGE_MAPS)       # maps are required
     m.close()
+
+
+@pytest.mark.parametrize("devices", _device_sets()[1:], ids=lambda d: "dev" + "".join(map(str, d)))
+@pytest.mark.parametrize("size,n", [((1920, 1080), 7), ((7680, 4320), 4), ((256, 136), 11)], ids=lambda s: str(s).replace(" ", ""))
+def test_strip_stream_equals_unsplit(devices, size, n):
+    """A stream of frames, each cut into strips, pipelined over three slots per device (more frames than slots):
+    every frame == the unsplit oracle; per-frame QP and strengths; a second call continues the slot ring."""
+    w, h = size
+    m = hdb.MultiDeblocker(devices)
+    frames, qps, v, hh = synth.make_batch(w + n, min(n, 4), w, h)
+    want = orc.deblock_batch(frames, w, h, qps, v, hh)
+    idx = [i % frames.shape[0] for i in range(n)]
+    t = hdb.Timing()
+    got = m.deblock_stream_strips(frames[idx], w, h, qps[idx], v[idx], hh[idx], timing=t)
+    for f in range(n):
+        assert np.array_equal(got[f], want[idx[f]]), (f, int((got[f] != want[idx[f]]).sum()))
+    assert t.kernel_launches == n * len(m.strip_layout(h)) and t.kernel_ms > 0
+    # defaults, in place, continuing the ring at an odd position
+    buf = frames[idx][:5].copy()
+    m.deblock_stream_strips(buf, w, h, qps[idx][:5], out=buf)
+    assert np.array_equal(buf, orc.deblock_batch(frames[idx][:5], w, h, qps[idx][:5]))
+    m.close()
+
+
+def test_strip_layout_and_halo_bytes():
+    m = hdb.MultiDeblocker([0] * 8)
+    lay = m.strip_layout(4320)
+    assert [r for _, r in lay] == [576, 576, 576, 576, 512, 512, 512, 480]      # 68 CTU rows: 9,9,9,9,8,8,8,8 (the last one partial)
+    assert [y for y, _ in lay] == [0, 576, 1152, 1728, 2304, 2816, 3328, 3840]
+    assert m.strip_halo_bytes(7680, 4320) == 7 * 2 * (4 * 7680 + 2 * 4 * 3840)
+    assert len(m.strip_layout(64)) == 1
+    m.close()
+
+
+@pytest.mark.parametrize("devices", _device_sets()[1:], ids=lambda d: "dev" + "".join(map(str, d)))
+@pytest.mark.parametrize("edges", [False, True])
+def test_strips_resident_in_device_memory(devices, edges):
+    """Strips that already sit in each GPU's memory: one kernel per GPU, halo rows by peer loads inside it."""
+    import torch
+    w, h = 3840, 2160
+    m = hdb.MultiDeblocker(devices)
+    rng = np.random.default_rng(12 + edges)
+    frame = synth.make_frame(rng, w, h, "blocky")
+    v, hh = synth.make_edge_maps(rng, w, h, "random", picture_edges=True) if edges else synth.make_bs(rng, w, h, "uniform012")
+    want = orc.deblock_frame_edges(frame, w, h, 36, v, hh) if edges else orc.deblock_frame(frame, w, h, 36, v, hh)
+    cw = w // 2
+    Y, U, V = frame[:w * h].reshape(h, w), frame[w * h:w * h * 5 // 4].reshape(h // 2, cw), frame[w * h * 5 // 4:].reshape(h // 2, cw)
+    lay = m.strip_layout(h)
+    ins, outs, dv, dh = [], [], [], []
+    for d, (y0, rows) in enumerate(lay):
+        dev = "cuda:%d" % devices[d]
+        ins.append(tuple(torch.from_numpy(np.ascontiguousarray(p)).to(dev) for p in (Y[y0:y0 + rows], U[y0 // 2:(y0 + rows) // 2], V[y0 // 2:(y0 + rows) // 2])))
+        outs.append(tuple(torch.zeros_like(p) for p in ins[-1]))
+        dv.append(torch.from_numpy(v).to(dev))
+        dh.append(torch.from_numpy(hh).to(dev))
+    for d in set(devices):
+        torch.cuda.synchronize(d)
+    t = hdb.Timing()
+    m.deblock_strips_device(ins, outs, w, h, 36, dv, dh, flags=hdb.FLAG_EDGE_MAPS if edges else 0, timing=t)
+    got = np.concatenate([np.concatenate([o[p].cpu().numpy().reshape(-1) for o in outs]) for p in range(3)])
+    assert np.array_equal(got, want), int((got != want).sum())
+    assert t.kernel_launches == len(lay) and t.kernel_ms > 0
+    with pytest.raises(hdb.DeblockError, match="out of place"):
+        m.deblock_strips_device(ins, ins, w, h, 36, dv, dh, flags=hdb.FLAG_EDGE_MAPS if edges else 0)
+    m.close()

@@ -63,10 +63,24 @@ def test_nv12_sizes_vs_oracle(dev, size):
     assert np.array_equal(got, _oracle(frames, w, h, qps, None, None))
 
 
-def test_nv12_rejects_widths_off_the_tile_grid(dev):
-    w, h = 72, 40
+@pytest.mark.parametrize("size", [(40, 24), (72, 40), (200, 120), (360, 288), (1080, 1920)], ids=lambda s: "%dx%d" % s)
+def test_nv12_widths_off_the_tile_grid(dev, size):
+    """Widths that are a multiple of 8 but not of 32 (cpu.h:46-48 accepts them): the cp.async loader of the tiled kernel."""
+    w, h = size
+    for edges in (False, True):
+        frames, qps, v, hh = _nv12_batch(w * 13 + h + edges, 2, w, h, edges)
+        t = hdb.Timing()
+        got = dev.deblock_batch_ex(frames, w, h, qps, v, hh, flags=hdb.FLAG_NV12 | (hdb.FLAG_EDGE_MAPS if edges else 0), timing=t)
+        want = _oracle(frames, w, h, qps, v, hh, edges)
+        assert t.path == 3
+        for f in range(2):
+            assert np.array_equal(got[f], want[f]), (size, edges, f, int((got[f] != want[f]).sum()))
+
+
+def test_nv12_rejects_what_no_kernel_takes(dev):
+    w, h = 24, 40
     frames = np.zeros((1, 3 * w * h // 2), np.uint8)
-    with pytest.raises(hdb.DeblockError, match="multiple of 32"):
+    with pytest.raises(hdb.DeblockError, match="at least 32"):
         dev.deblock_batch_ex(frames, w, h, np.array([30], np.uint32), flags=hdb.FLAG_NV12)
     with pytest.raises(hdb.DeblockError):
         dev.deblock_batch_ex(frames, w, h, np.array([30], np.uint32), flags=64)

@@ -47,10 +47,12 @@ def test_golden_synthetic(dev, case):
 # ---- sizes x content x QP x BS against the oracle -----------------------------------------
 TILED_SIZES = [(32, 8), (32, 32), (64, 48), (256, 64), (288, 72), (352, 288), (768, 576), (1024, 8), (8192, 16),
                (1920, 1080), (2048, 1096)]
-GENERIC_SIZES = [(8, 8), (16, 16), (24, 40), (40, 24), (72, 40), (200, 120), (1912, 1080)]
+GENERIC_SIZES = [(8, 8), (16, 16), (24, 40)]                                         # padded-scratch kernels
+# widths off the 32 grid (cpu.h:46-48 accepts every multiple of 8): the tiled kernel's cp.async loader
+LDGSTS_SIZES = [(40, 24), (72, 40), (200, 120), (360, 288), (1000, 64), (1080, 1920), (1912, 1080), (2056, 40)]
 
 
-@pytest.mark.parametrize("size", TILED_SIZES + GENERIC_SIZES, ids=lambda s: "%dx%d" % s)
+@pytest.mark.parametrize("size", TILED_SIZES + GENERIC_SIZES + LDGSTS_SIZES, ids=lambda s: "%dx%d" % s)
 def test_sizes_vs_oracle(dev, size):
     w, h = size
     rng = np.random.default_rng(w * 131 + h)
@@ -61,7 +63,7 @@ def test_sizes_vs_oracle(dev, size):
         t = hdb.Timing()
         got = dev.deblock_frame(frame, w, h, qp, v, hh, timing=t)
         want = orc.deblock_frame(frame, w, h, qp, v, hh)
-        assert t.path == (1 if w % 32 == 0 else 2)
+        assert t.path == common.expected_path(w)
         assert np.array_equal(got, want), (size, kind, bs_kind, qp, int((got != want).sum()))
 
 
@@ -369,3 +371,95 @@ def test_8k_frame(dev):
     frame, v, hh = common.synth_case(case["seed"], 7680, 4320, case["kind"], case["bs_kind"])
     y = dev.deblock_frame(frame, 7680, 4320, case["qp"], v, hh)
     assert common.md5(y) == case["md5"]
+
+
+def test_padded_scratch_kernels_still_match(monkeypatch):
+    """The padded-scratch kernels serve widths below 32 only; a context created with HDB_NO_LDGSTS set sends
+    every width off the 32 grid through them, so that they stay covered at real sizes."""
+    monkeypatch.setenv("HDB_NO_LDGSTS", "1")
+    d = hdb.Deblocker(0)
+    monkeypatch.delenv("HDB_NO_LDGSTS")
+    rng = np.random.default_rng(77)
+    for (w, h) in [(72, 40), (200, 120), (1912, 1080)]:
+        frame = synth.make_frame(rng, w, h, "blocky")
+        v, hh = synth.make_bs(rng, w, h, "uniform012")
+        t = hdb.Timing()
+        got = d.deblock_frame(frame, w, h, 37, v, hh, timing=t)
+        assert t.path == 2
+        assert np.array_equal(got, orc.deblock_frame(frame, w, h, 37, v, hh))
+    d.close()
+
+
+def test_ldgsts_batch_device_resident_with_guards(dev):
+    """A batch of 1080x1920 (portrait: width off the 32 grid) frames resident in HBM between guard bands,
+    out of place and in place."""
+    import torch
+    n, w, h = 6, 1080, 1920
+    frames, qps, v, hh = synth.make_batch(5, n, w, h)
+    want = orc.deblock_batch(frames, w, h, qps, v, hh)
+    fb, guard = frames.shape[1], 1 << 16
+    buf = torch.full((guard + n * fb + guard,), 0xA5, dtype=torch.uint8, device="cuda")
+    d_in = torch.from_numpy(frames).cuda()
+    d_qp = torch.from_numpy(qps.astype(np.int32)).cuda()
+    d_v, d_h = torch.from_numpy(v).cuda(), torch.from_numpy(hh).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    out = buf[guard:guard + n * fb].view(n, fb)
+    dev.deblock_batch_device(d_in, out, n, w, h, d_qp, d_v, d_h, stream=st)
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), want)
+    assert bool((buf[:guard] == 0xA5).all()) and bool((buf[guard + n * fb:] == 0xA5).all())
+    out.copy_(d_in)
+    dev.deblock_batch_device(out, out, n, w, h, d_qp, d_v, d_h, stream=st)     # in place
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), want)
+    assert bool((buf[:guard] == 0xA5).all()) and bool((buf[guard + n * fb:] == 0xA5).all())
+
+
+def test_small_frames_in_flight_on_two_streams(dev):
+    """Two calls of the padded-scratch path in flight on different streams: each has scratch memory of its own."""
+    import torch
+    n, w, h = 64, 24, 40
+    a, qa, va, ha = synth.make_batch(1, n, w, h)
+    b, qb, vb, hb = synth.make_batch(2, n, w, h)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    da, db = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    oa, ob = torch.empty_like(da), torch.empty_like(db)
+    dqa, dqb = torch.from_numpy(qa.astype(np.int32)).cuda(), torch.from_numpy(qb.astype(np.int32)).cuda()
+    dva, dha, dvb, dhb = (torch.from_numpy(x).cuda() for x in (va, ha, vb, hb))
+    torch.cuda.synchronize()
+    for _ in range(20):
+        dev.deblock_batch_device(da, oa, n, w, h, dqa, dva, dha, stream=s1.cuda_stream)
+        dev.deblock_batch_device(db, ob, n, w, h, dqb, dvb, dhb, stream=s2.cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(oa.cpu().numpy(), orc.deblock_batch(a, w, h, qa, va, ha))
+    assert np.array_equal(ob.cpu().numpy(), orc.deblock_batch(b, w, h, qb, vb, hb))
+
+
+def test_planes_entry_point_from_two_threads(dev):
+    """hdb_deblock_planes holds the context lock from its first copy to its last: two threads on one context."""
+    import threading
+    rng = np.random.default_rng(9)
+    cases = []
+    for (w, h) in [(352, 288), (768, 576)]:
+        frame = synth.make_frame(rng, w, h, "blocky")
+        cases.append((w, h, frame, orc.deblock_frame(frame, w, h, 35)))
+    bad = []
+
+    def work(case):
+        w, h, frame, want = case
+        y, u, v = frame[:w * h], frame[w * h:w * h * 5 // 4], frame[w * h * 5 // 4:]
+        for _ in range(25):
+            yo, uo, vo = dev.deblock_planes(y, u, v, w, h, 35)
+            if not np.array_equal(np.concatenate([yo, uo, vo]), want):
+                bad.append((w, h))
+    ths = [threading.Thread(target=work, args=(c,)) for c in cases]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    assert not bad
+
+
+def test_frame_too_wide_is_refused(dev):
+    with pytest.raises(hdb.DeblockError, match="too large"):
+        dev.deblock_batch_device(1 << 20, 1 << 21, 1, 262144, 8, 1 << 22)
