@@ -87,6 +87,7 @@ static int CreateContext(hdb_context **out, int device)
 		&& cudaStreamCreateWithFlags(&ctx->s_k, cudaStreamNonBlocking) == cudaSuccess
 		&& cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking) == cudaSuccess
 		&& PrepareTiled(ctx->tiled_ctas_per_sm) == cudaSuccess
+		&& PrepareTiled16(ctx->tiled16_ctas_per_sm) == cudaSuccess
 		&& cudaStreamCreateWithFlags(&ctx->s_setup, cudaStreamNonBlocking) == cudaSuccess
 		&& cudaMalloc(&ctx->sched, TiledSchedBytes() * kSchedSlots) == cudaSuccess
 		&& cudaMemset(ctx->sched, 0, TiledSchedBytes() * kSchedSlots) == cudaSuccess;
@@ -145,12 +146,13 @@ int GetSizeState(hdb_context *ctx, int w, int h, SizeState **out)
 }
 
 static int EncodePlaneMap(hdb_context *ctx, CUtensorMap *map, const void *base, int pw, int ph, int n,
-	long long pitch, long long frame_stride, int box_rows)
+	long long pitch, long long frame_stride, int box_rows, unsigned box_elems = 68u)
 {
-	/* 32-bit elements: a box may then be 272 bytes wide (a box dimension is limited to 256 elements) */
+	/* pw: bytes per row.  32-bit elements: a box may then be 272 (8-bit samples) or 528 bytes (16-bit) wide (a box
+	 * dimension is limited to 256 elements) */
 	cuuint64_t dims[3] = { (cuuint64_t)pw / 4, (cuuint64_t)ph, (cuuint64_t)n };
 	cuuint64_t strides[2] = { (cuuint64_t)pitch, (cuuint64_t)frame_stride };
-	cuuint32_t box[3] = { 68u, (cuuint32_t)box_rows, 1u };
+	cuuint32_t box[3] = { box_elems, (cuuint32_t)box_rows, 1u };
 	cuuint32_t estr[3] = { 1u, 1u, 1u };
 	CUresult r = ctx->encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<void *>(base), dims, strides, box, estr,
 		CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -174,7 +176,83 @@ bool TiledPathUsable(int w, int h, const void *d_in, const void *d_out)
 bool LdgstsPathUsable(int w, int h, const void *d_in, const void *d_out)
 {
 	(void)h;
-	return w >= 32 && w <= 262136 && ((uintptr_t)d_in % 4 == 0) && ((uintptr_t)d_out % 4 == 0);
+	return w >= 32 && w <= 262136 && ((uintptr_t)d_in % 8 == 0) && ((uintptr_t)d_out % 8 == 0);
+}
+
+/* the scheduler words of the next launch on `stream` (EnqueueFilter explains the rotation); *slot for SchedLaunched */
+static int SchedAcquire(hdb_context *ctx, cudaStream_t stream, void **sched, int *slot)
+{
+	*slot = (int)(ctx->sched_turn++ % kSchedSlots);
+	*sched = static_cast<char *>(ctx->sched) + TiledSchedBytes() * *slot;
+	if (ctx->sched_used[*slot] && ctx->sched_stream[*slot] != stream)
+		HDB_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->sched_done[*slot], 0));
+	return HDB_OK;
+}
+
+static int SchedLaunched(hdb_context *ctx, cudaStream_t stream, int slot)
+{
+	HDB_CUDA(ctx, cudaEventRecord(ctx->sched_done[slot], stream));
+	ctx->sched_used[slot] = true; ctx->sched_stream[slot] = stream;
+	ctx->launches += 1;
+	return HDB_OK;
+}
+
+/* 16-bit samples (view.bit_depth 8 .. 10): planar frames through DeblockTiled16Kernel; TMA only */
+static int EnqueueFilter16(hdb_context *ctx, const FrameView &view, SizeState *ss, const unsigned char *d_in, unsigned char *d_out,
+	int n, const unsigned *d_qp, unsigned qp_value, const unsigned char *d_vbs, long long vbs_stride,
+	const unsigned char *d_hbs, long long hbs_stride, cudaStream_t stream, int *path, bool edge_qp)
+{
+	const int w = view.width, h = view.height, cw = w / 2, ch = h / 2;
+	if (view.bit_depth < 8 || view.bit_depth > 10)
+		return Fail(ctx, HDB_ERR_INVALID_ARG, "bit depth must be 8, 9 or 10 (16-bit containers)");
+	if (view.nv12 || view.strip_halo)
+		return Fail(ctx, HDB_ERR_INVALID_ARG, "16-bit samples are planar and unsplit");
+	if (w % 16 != 0 || w < 32 || ((uintptr_t)d_in | (uintptr_t)d_out) % 16 != 0 || view.luma_pitch % 16 != 0 || view.chroma_pitch % 16 != 0
+		|| view.frame_stride % 16 != 0 || view.chroma_frame_stride % 16 != 0 || (view.u_offset | view.v_offset | view.u_offset_out | view.v_offset_out) % 16 != 0)
+		return Fail(ctx, HDB_ERR_DIMENSIONS, "16-bit frames need a width that is a multiple of 16, at least 32, and 16-byte aligned buffers");
+	if (path) *path = 1;
+	const TiledConfig cfg = GetTiledConfig();
+	TiledBatch b{};
+	b.width = w; b.height = h;
+	b.luma_nbx = (w + 8) / 8; b.luma_nby = (h + 8) / 8;
+	b.chroma_nbx = (cw + 8) / 8; b.chroma_nby = (ch + 8) / 8;
+	b.luma_row0 = view.luma_row0; b.luma_rows = view.luma_rows;
+	b.chroma_row0 = view.chroma_row0; b.chroma_rows = view.chroma_rows;
+	b.luma_y_org = view.luma_y_org; b.chroma_y_org = view.chroma_y_org;
+	b.vert_bs_stride = vbs_stride; b.hor_bs_stride = hbs_stride;
+	b.chroma_bs = ss->chroma_bs;
+	b.qp_value = qp_value;
+	b.n_frames = 1;
+	FinalizeTiledBatch(b);
+	const long long max_frames = std::max<long long>(1, ((1ll << 31) - (1 << 20)) / std::max(b.items_per_frame, 1));
+	for (long long f0 = 0; f0 < n; f0 += max_frames) {
+		const int nf = (int)std::min<long long>(max_frames, n - f0);
+		b.n_frames = nf;
+		FinalizeTiledBatch(b);
+		b.qp = d_qp ? d_qp + f0 : nullptr;
+		b.vert_bs = d_vbs + f0 * vbs_stride;
+		b.hor_bs = d_hbs + f0 * hbs_stride;
+		b.frame_stride = view.frame_stride; b.chroma_frame_stride = view.chroma_frame_stride;
+		b.luma_pitch = view.luma_pitch; b.chroma_pitch = view.chroma_pitch;
+		b.luma_buf_rows = view.luma_buf_rows; b.chroma_buf_rows = view.chroma_buf_rows;
+		const long long off_in[3] = { 0, view.u_offset, view.v_offset }, off_out[3] = { 0, view.u_offset_out, view.v_offset_out };
+		TensorMaps3 maps;
+		memset(&maps, 0, sizeof maps);
+		for (int p = 0; p < 3; p++) {
+			const long long pfs = p ? view.chroma_frame_stride : view.frame_stride;
+			int rc = EncodePlaneMap(ctx, &maps.in[p], d_in + off_in[p] + f0 * pfs, 2 * (p ? cw : w), p ? view.chroma_buf_rows : view.luma_buf_rows, nf,
+				p ? view.chroma_pitch : view.luma_pitch, pfs, 8 * cfg.block_rows_per_item, 132u);
+			if (rc) return rc;
+			b.in_plane[p] = d_in + off_in[p] + f0 * pfs;
+			b.out_plane[p] = d_out + off_out[p] + f0 * pfs;
+		}
+		void *sched; int slot;
+		int rc = SchedAcquire(ctx, stream, &sched, &slot);
+		if (rc) return rc;
+		HDB_CUDA(ctx, LaunchTiled16(maps, b, sched, ctx->prop.multiProcessorCount, ctx->tiled16_ctas_per_sm, stream, view.bit_depth, edge_qp));
+		if ((rc = SchedLaunched(ctx, stream, slot))) return rc;
+	}
+	return HDB_OK;
 }
 
 /*
@@ -193,12 +271,15 @@ int EnqueueFilter(hdb_context *ctx, const FrameView &view, const unsigned char *
 	if (!d_vbs || !d_hbs) { d_vbs = ss->def_vbs; d_hbs = ss->def_hbs; vbs_stride = hbs_stride = 0; }
 	const TiledConfig cfg = GetTiledConfig();
 
+	if (view.bit_depth) return EnqueueFilter16(ctx, view, ss, d_in, d_out, n, d_qp, qp_value, d_vbs, vbs_stride, d_hbs, hbs_stride, stream, path, edge_qp);
 	const bool tma_ok = TiledPathUsable(w, h, d_in, d_out) && view.luma_pitch % 16 == 0 && view.chroma_pitch % 16 == 0
 		&& view.frame_stride % 16 == 0 && view.chroma_frame_stride % 16 == 0 && view.u_offset % 16 == 0 && view.v_offset % 16 == 0
 		&& view.u_offset_out % 16 == 0 && view.v_offset_out % 16 == 0;
 	const bool ldgsts_ok = !tma_ok && !view.strip_halo && ctx->use_ldgsts && LdgstsPathUsable(w, h, d_in, d_out);
-	if (view.nv12 && !tma_ok && !ldgsts_ok)
-		return Fail(ctx, HDB_ERR_DIMENSIONS, "NV12 frames need a width of at least 32 and 4-byte aligned buffers");
+	/* NV12 with a chroma width of 4 mod 8: the reference's skewed chroma blocks (deblock_kernels.cu: SkewToImage)
+	 * straddle the interleaving; no kernel takes that */
+	if (view.nv12 && (w % 16 != 0 || (!tma_ok && !ldgsts_ok)))
+		return Fail(ctx, HDB_ERR_DIMENSIONS, "NV12 frames need a width that is a multiple of 16, at least 32, and 8-byte aligned buffers");
 	if (!tma_ok && !ldgsts_ok && !view.whole_frame)
 		return Fail(ctx, HDB_ERR_DIMENSIONS, "pitched or partial planes need a width of at least 32 and 4-byte aligned buffers");
 	if (!tma_ok && !ldgsts_ok) {
@@ -275,24 +356,21 @@ int EnqueueFilter(hdb_context *ctx, const FrameView &view, const unsigned char *
 		}
 		/* launches take the scheduler words in turn: two launches that overlap on the device (different
 		 * streams) must not share a work counter, and each launch leaves its own words zeroed */
-		const int slot = (int)(ctx->sched_turn++ % kSchedSlots);
-		void *sched = static_cast<char *>(ctx->sched) + TiledSchedBytes() * slot;
-		/* the launch that had these words kSchedSlots launches ago may still be running on another stream: wait
-		 * for it there (the same stream orders itself) */
-		if (ctx->sched_used[slot] && ctx->sched_stream[slot] != stream)
-			HDB_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->sched_done[slot], 0));
+		/* the launch that had these words kSchedSlots launches ago may still be running on another stream: the new
+		 * one waits for it there (the same stream orders itself) */
+		void *sched; int slot;
+		if ((rc = SchedAcquire(ctx, stream, &sched, &slot))) return rc;
 		HDB_CUDA(ctx, LaunchTiled(maps, b, sched, ctx->prop.multiProcessorCount, ctx->tiled_ctas_per_sm, stream, edge_qp));
-		HDB_CUDA(ctx, cudaEventRecord(ctx->sched_done[slot], stream));
-		ctx->sched_used[slot] = true; ctx->sched_stream[slot] = stream;
-		ctx->launches += 1;
+		if ((rc = SchedLaunched(ctx, stream, slot))) return rc;
 	}
 	return HDB_OK;
 }
 
-FrameView WholeFrameView(int w, int h, bool nv12)
+FrameView WholeFrameView(int w, int h, bool nv12, int bit_depth)
 {
 	FrameView v{};
 	v.nv12 = nv12;
+	v.bit_depth = bit_depth;
 	v.width = w; v.height = h; v.whole_frame = true;
 	v.luma_row0 = 0; v.luma_rows = (h + 8) / 8;
 	v.chroma_row0 = 0; v.chroma_rows = (h / 2 + 8) / 8;
@@ -302,6 +380,10 @@ FrameView WholeFrameView(int w, int h, bool nv12)
 	v.u_offset_out = v.u_offset; v.v_offset_out = v.v_offset;
 	v.luma_pitch = w; v.chroma_pitch = nv12 ? w : w / 2;
 	v.frame_stride = v.chroma_frame_stride = (long long)w * h * 3 / 2;
+	if (bit_depth) {      /* two bytes a sample: every byte quantity doubles */
+		v.u_offset *= 2; v.v_offset *= 2; v.u_offset_out *= 2; v.v_offset_out *= 2;
+		v.luma_pitch *= 2; v.chroma_pitch *= 2; v.frame_stride *= 2; v.chroma_frame_stride *= 2;
+	}
 	return v;
 }
 
@@ -436,6 +518,9 @@ int BatchHostLocked(hdb_context *ctx, const unsigned char *in, unsigned char *ou
 {
 	/* block data given: the edge maps of every slice are derived on the device, into the slot's own arrays */
 	const bool edge_qp = (flags & HDB_FLAG_EDGE_MAPS) != 0 || info != nullptr, nv12 = (flags & HDB_FLAG_NV12) != 0;
+	const int depth = DepthOfFlags(flags);
+	if ((flags & HDB_FLAG_SAMPLES16) && (depth < 8 || depth > 10)) return Fail(ctx, HDB_ERR_INVALID_ARG, "bit depth must be 8, 9 or 10 (HDB_FLAG_DEPTH)");
+	if (depth && nv12) return Fail(ctx, HDB_ERR_INVALID_ARG, "16-bit samples are planar: HDB_FLAG_NV12 does not combine with HDB_FLAG_DEPTH");
 	if (!in || !out || !qp || n == 0) return Fail(ctx, HDB_ERR_INVALID_ARG, "NULL buffer or empty batch");
 	if (info && (vbs || hbs)) return Fail(ctx, HDB_ERR_INVALID_ARG, "give block data or edge maps, not both");
 	if (edge_qp && !info && (!vbs || !hbs)) return Fail(ctx, HDB_ERR_INVALID_ARG, "edge maps are required: there is no default for them");
@@ -443,7 +528,7 @@ int BatchHostLocked(hdb_context *ctx, const unsigned char *in, unsigned char *ou
 	if (rc) return rc;
 	DeviceGuard guard(ctx->device);
 	const auto t_begin = std::chrono::steady_clock::now();
-	const size_t fb = (size_t)w * h * 3 / 2;
+	const size_t fb = (size_t)w * h * 3 / 2 * (depth ? 2 : 1);
 	const unsigned nv = (w / 8 + 1) * h / 8, nh = (h / 8 + 1) * w / 8;
 	const int chunk = (int)std::min<size_t>(n, std::max<size_t>(1, ((size_t)ctx->chunk_bytes) / fb));
 	const std::vector<int> slices = PlanSlices(n, chunk);
@@ -457,8 +542,9 @@ int BatchHostLocked(hdb_context *ctx, const unsigned char *in, unsigned char *ou
 		HDB_CUDA(ctx, cudaMalloc(&ctx->qp_dev, sizeof(unsigned) * n));
 		ctx->qp_cap = n;
 	}
-	const FrameView view = WholeFrameView((int)w, (int)h, nv12);
-	if (nv12 && w < 32) return Fail(ctx, HDB_ERR_DIMENSIONS, "NV12 frames need a width of at least 32");
+	const FrameView view = WholeFrameView((int)w, (int)h, nv12, depth);
+	if (depth && (w % 16 != 0 || w < 32)) return Fail(ctx, HDB_ERR_DIMENSIONS, "16-bit frames need a width that is a multiple of 16 and at least 32");
+	if (nv12 && (w < 32 || w % 16 != 0)) return Fail(ctx, HDB_ERR_DIMENSIONS, "NV12 frames need a width that is a multiple of 16 and at least 32");
 
 	PinHostRange pin_in(in, fb * n), pin_out(out != in ? out : nullptr, fb * n);
 	PinHostRange pin_v(vbs, (size_t)nv * n), pin_h(hbs, (size_t)nh * n), pin_i(info, ib * n);
@@ -916,7 +1002,7 @@ int hdb_deblock_batch_ex(hdb_context *ctx, const unsigned char *frames_in, unsig
 	unsigned n_frames, unsigned width, unsigned height, const unsigned *qp,
 	const unsigned char *vert, const unsigned char *hor, unsigned flags, hdb_timing *timing)
 {
-	if (flags & ~(HDB_FLAG_EDGE_MAPS | HDB_FLAG_NV12)) return ctx ? Fail(ctx, HDB_ERR_INVALID_ARG, "unknown flag") : HDB_ERR_INVALID_ARG;
+	if (flags & ~(HDB_FLAG_EDGE_MAPS | HDB_FLAG_NV12 | HDB_FLAG_SAMPLES16 | 0xff00u)) return ctx ? Fail(ctx, HDB_ERR_INVALID_ARG, "unknown flag") : HDB_ERR_INVALID_ARG;
 	return BatchHost(ctx, frames_in, frames_out, n_frames, width, height, qp, vert, hor, timing, flags);
 }
 
@@ -936,12 +1022,14 @@ int hdb_deblock_batch_device_ex(hdb_context *ctx, const void *d_frames_in, void 
 {
 	if (!ctx) return HDB_ERR_INVALID_ARG;
 	std::lock_guard<std::mutex> lock(ctx->mu);
-	if (flags & ~(HDB_FLAG_EDGE_MAPS | HDB_FLAG_NV12)) return Fail(ctx, HDB_ERR_INVALID_ARG, "unknown flag");
+	if (flags & ~(HDB_FLAG_EDGE_MAPS | HDB_FLAG_NV12 | HDB_FLAG_SAMPLES16 | 0xff00u)) return Fail(ctx, HDB_ERR_INVALID_ARG, "unknown flag");
 	if (!d_frames_in || !d_frames_out || !d_qp || n_frames == 0) return Fail(ctx, HDB_ERR_INVALID_ARG, "NULL buffer or empty batch");
 	int rc = ValidateFrameArgs(ctx, width, height, d_vert, 0, d_hor, 0, false);
 	if (rc) return rc;
+	const int depth = DepthOfFlags(flags);
+	if ((flags & HDB_FLAG_SAMPLES16) && (depth < 8 || depth > 10)) return Fail(ctx, HDB_ERR_INVALID_ARG, "bit depth must be 8, 9 or 10 (HDB_FLAG_DEPTH)");
 	DeviceGuard guard(ctx->device);
-	const FrameView view = WholeFrameView((int)width, (int)height, (flags & HDB_FLAG_NV12) != 0);
+	const FrameView view = WholeFrameView((int)width, (int)height, (flags & HDB_FLAG_NV12) != 0, depth);
 	return EnqueueFilter(ctx, view, static_cast<const unsigned char *>(d_frames_in),
 		static_cast<unsigned char *>(d_frames_out), (int)n_frames, d_qp, 0,
 		d_vert, hdb_num_vert_bs(width, height), d_hor, hdb_num_hor_bs(width, height),

@@ -75,6 +75,7 @@ struct FrameView {
 	 * below them in the neighbouring strips' buffers (peer pointers, same pitch); all NULL otherwise */
 	const unsigned char *halo_top[3], *halo_bot[3];
 	bool strip_halo;
+	int bit_depth;                 /* 0: 8-bit samples, one byte each; 8 .. 10: that many bits in 16-bit containers (planar) */
 };
 
 } // namespace hdb
@@ -93,6 +94,7 @@ struct hdb_context {
 	cudaStream_t sched_stream[hdb::kSchedSlots] = {};
 	bool sched_used[hdb::kSchedSlots] = {};
 	int tiled_ctas_per_sm[hdb::kTiledVariants] = {};   /* resident CTAs per SM of the tiled kernel's variants on this device */
+	int tiled16_ctas_per_sm[hdb::kTiled16Variants] = {};
 	std::vector<hdb::SizeState> sizes;
 	hdb::Slot slots[hdb::kSlots];
 	std::vector<cudaEvent_t> event_pool;
@@ -114,7 +116,9 @@ int Fail(hdb_context *ctx, int status, const std::string &msg);
 int FailCuda(hdb_context *ctx, cudaError_t e, const char *what);
 void DestroyContext(hdb_context *ctx);
 int GetSizeState(hdb_context *ctx, int w, int h, SizeState **out);
-FrameView WholeFrameView(int w, int h, bool nv12 = false);
+FrameView WholeFrameView(int w, int h, bool nv12 = false, int bit_depth = 0);
+/* bit depth carried in the flags of the _ex entry points (0 = 8-bit samples) */
+inline int DepthOfFlags(unsigned flags) { return (flags & HDB_FLAG_SAMPLES16) ? (int)((flags >> 8) & 0xffu) : 0; }
 bool TiledPathUsable(int w, int h, const void *d_in, const void *d_out);
 bool LdgstsPathUsable(int w, int h, const void *d_in, const void *d_out);
 int ValidateFrameArgs(hdb_context *ctx, unsigned w, unsigned h, const unsigned char *vbs, unsigned nv,

@@ -44,6 +44,7 @@
  */
 #include "deblock_kernels.cuh"
 #include "deblock_core.cuh"
+#include "deblock_core16.cuh"
 #include "tma_ptx.cuh"
 
 #include <algorithm>
@@ -74,7 +75,7 @@
 #define HDB_NV12_MIN_CTAS HDB_MIN_CTAS          /* the two-plane variants (measurement knob) */
 #endif
 #ifndef HDB_LDGSTS_MIN_CTAS
-#define HDB_LDGSTS_MIN_CTAS 16                  /* the cp.async loader variants: up to 128 registers */
+#define HDB_LDGSTS_MIN_CTAS HDB_MIN_CTAS         /* the cp.async loader variants: 80 registers as well, no spills */
 #endif
 #ifndef HDB_SMEM_ALIGN
 #define HDB_SMEM_ALIGN 128                      /* a TMA destination without swizzle needs 128 bytes */
@@ -271,6 +272,21 @@ __device__ __forceinline__ void UvBlockRow(u32 *base, u32 s4, const FilterParams
 	}
 }
 
+/*
+ * Skewed chroma plane (see fetch_tile in the kernel): byte (vr, vc) of the virtual padded plane -- pitch
+ * b.chroma_vpitch = 8 * chroma_nbx -- is byte vr * vpitch + vc of the reference's padded buffer, whose real pitch
+ * is b.chroma_rpitch = cw + 8 with the image at (4, 4).  Returns whether that is an image sample, and which.
+ */
+__device__ __forceinline__ bool SkewToImage(const TiledBatch &b, int vr, int vc, int &ix, int &iy)
+{
+	if (vc < 0 || vc >= b.chroma_vpitch) return false;
+	const uint32_t o = (uint32_t)vr * (uint32_t)b.chroma_vpitch + (uint32_t)vc;
+	const uint32_t r = b.div_chroma_rpitch.Div(o);
+	ix = (int)(o - r * (uint32_t)b.chroma_rpitch) - 4;
+	iy = (int)r - 4;
+	return ix >= 0 && ix < (b.width >> 1) && iy >= 0 && iy < b.chroma_buf_rows;
+}
+
 /* kEdgeQp: the luma boundary-strength arrays hold edge bytes (bs | qp << 2, deblock_core.cuh) and every
  * luma segment takes beta / tc from its own entry; chroma is untouched by it (frame QP, cpu.h:110-117) */
 /* kNv12: two planes, Y and interleaved UV (lanes 0-15 filter the U blocks of a UV item, lanes 16-31 the V blocks) */
@@ -330,11 +346,18 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_consta
 			8 * kRB * (int)cur.grp + (cur.plane ? b.chroma_y_org : b.luma_y_org), (int)cur.frame, bar);
 	};
 	/*
-	 * kLoadLdgsts: the box of the item lane 0 has just put into held[s], fetched by all lanes with 4-byte
-	 * cp.async -- word w of tile row t comes from plane byte 4 * (64 * chunk - 4 + w) of buffer row
-	 * 8 * kRB * grp + y_org + t, or is zero where that lies outside the plane (src-size 0: the zero fill is
-	 * the reference's padding, as TMA's out-of-bounds fill is in the other variants).  One commit group per
-	 * item, empty for "no item", so that wait_group counts items.
+	 * kLoadLdgsts: the box of the item lane 0 has just put into held[s], fetched by all lanes with cp.async;
+	 * where the box leaves the plane the copy writes zeros instead (src-size 0: the zero fill is the reference's
+	 * padding, as TMA's out-of-bounds fill is in the other variants).  One commit group per item, empty for "no
+	 * item", so that wait_group counts items.
+	 *   Straight planes (luma always; chroma when its width is a multiple of 8): 8-byte copies -- rows of such
+	 * planes start on 8-byte boundaries.  34 units per tile row: lane l takes unit l of every row, and the two
+	 * left-over units of row l / 2.
+	 *   Skewed chroma planes (chroma width = 4 mod 8, i.e. frame width = 8 mod 16): the reference pads such a
+	 * plane to cw + 8 columns but addresses it with a pitch of 8 * (number of blocks) = cw + 4 (cpu.h:450-451,
+	 * 469-471), so its blocks tile a VIRTUAL plane -- the same linear memory read with the shorter pitch.
+	 * SkewToImage maps a word of the virtual plane to the image sample it really is (or to padding); 4-byte
+	 * copies, one division per word.  The generic kernels reproduce the same thing with an explicit padded copy.
 	 */
 	auto fetch_tile = [&](int s) {          /* all lanes, after a __syncwarp() that follows issue_load */
 		const uint2 it = held[s];
@@ -342,26 +365,50 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_consta
 			int plane, bx0, lby0;
 			ItemCoords<kNv12>(it.y, plane, bx0, lby0);
 			const bool c = plane != 0;
-			const int pw = (c && !kNv12) ? (b.width >> 1) : b.width;
 			const int pitch = c ? b.chroma_pitch : b.luma_pitch;
-			const int rows = c ? b.chroma_buf_rows : b.luma_buf_rows;
-			const int y0 = 8 * lby0 + (c ? b.chroma_y_org : b.luma_y_org);
-			const int xw0 = (int)((it.y >> 2) & 0x3ffu) * 64 - 4;          /* plane word of tile word 0 */
 			const unsigned char *src = b.in_plane[plane] + (long long)it.x * (c ? b.chroma_frame_stride : b.frame_stride);
 			const uint32_t dst = tiles_s + s * kTileBytes;
+			const int xb0 = 256 * (int)((it.y >> 2) & 0x3ffu) - 16;        /* plane byte of tile byte 0 */
+			if (!kNv12 && c && b.chroma_skew) {
+				const int vr0 = 8 * lby0, vc0 = xb0 + 4;                   /* virtual padded row / column of tile word 0 */
+				for (int t = 0; t < kTileH; t++) {
 #pragma unroll
-			for (int k = 0; k < 3; k++) {
-				const int w = lane + 32 * k;
-				const int xb = 4 * (xw0 + w);
-				const bool col_ok = w < kTileWords && xb >= 0 && xb < pw;
-				if (w < kTileWords) {
+					for (int k = 0; k < 2; k++) {
+						const int w = lane + 32 * k;
+						int ix, iy;
+						const bool ok = SkewToImage(b, vr0 + t, vc0 + 4 * w, ix, iy);
+						CpAsync4(dst + 4u * (uint32_t)(t * kTileWords + w), ok ? src + (long long)iy * pitch + ix : src, ok ? 4u : 0u);
+					}
+				}
+#pragma unroll
+				for (int k = 0; k < 2; k++) {          /* words 64 .. 67 of the kTileH rows: 4 * kTileH = 2 * 32 words */
+					const int t = (lane + 32 * k) >> 2, w = 64 + (lane & 3);
+					if (t < kTileH) {
+						int ix, iy;
+						const bool ok = SkewToImage(b, vr0 + t, vc0 + 4 * w, ix, iy);
+						CpAsync4(dst + 4u * (uint32_t)(t * kTileWords + w), ok ? src + (long long)iy * pitch + ix : src, ok ? 4u : 0u);
+					}
+				}
+			} else {
+				const int pw = (c && !kNv12) ? (b.width >> 1) : b.width;
+				const int rows = c ? b.chroma_buf_rows : b.luma_buf_rows;
+				const int y0 = 8 * lby0 + (c ? b.chroma_y_org : b.luma_y_org);
+				{
+					const int xb = xb0 + 8 * lane;
+					const bool col_ok = xb >= 0 && xb < pw;
+					const unsigned char *g = src + (long long)y0 * pitch + xb;
 #pragma unroll 4
 					for (int t = 0; t < kTileH; t++) {
-						const int y = y0 + t;
-						const bool ok = col_ok && y >= 0 && y < rows;
-						const unsigned char *g = ok ? src + (long long)y * pitch + xb : src;
-						CpAsync4(dst + 4u * (uint32_t)(t * kTileWords + w), g, ok ? 4u : 0u);
+						const bool ok = col_ok && y0 + t >= 0 && y0 + t < rows;
+						CpAsync8(dst + (uint32_t)(t * kTileW + 8 * lane), ok ? g : src, ok ? 8u : 0u);
+						g += pitch;
 					}
+				}
+				{
+					const int t = lane >> 1, u = 32 + (lane & 1);
+					const int xb = xb0 + 8 * u, y = y0 + t;
+					const bool ok = t < kTileH && xb >= 0 && xb < pw && y >= 0 && y < rows;
+					if (t < kTileH) CpAsync8(dst + (uint32_t)(t * kTileW + 8 * u), ok ? src + (long long)y * pitch + xb : src, ok ? 8u : 0u);
 				}
 			}
 		}
@@ -514,20 +561,40 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_consta
 			const int fword = uv ? (k < 2 ? 2 + k : 62 + k) : (k == 0 ? 3 : 63 + k);
 			const int fcol = x_img + 4 * (fword - 3);
 			const bool f_lane = fcol >= 0 && fcol < pl.pw;
-			if (kLoad == kLoadLdgsts) {
-				/* rows start on 4-byte boundaries only: the item's 256 plane bytes per row (tile words 3 .. 66, for
-				 * a UV item 2 .. 65) go out as two 128-byte runs of 32-bit words */
-				const int word0 = uv ? 2 : 3;
-#pragma unroll 4
+			if (kLoad == kLoadLdgsts && !kNv12 && chroma && b.chroma_skew) {
+				/* the item's 256 bytes per row of the VIRTUAL plane, word by word to the image samples they are */
+				const int vr0 = 8 * lby0, vc0 = 8 * bx0;                  /* virtual padded row / column of tile word 3 */
 				for (int rr = 0; rr < kTileH; rr++) {
-					const int y = y0 + rr;
-					if (y < 0 || y >= pl.buf_rows) continue;
 #pragma unroll
 					for (int k = 0; k < 2; k++) {
 						const int wi = lane + 32 * k;
-						const int col = x_img + 4 * wi;
-						if (col >= 0 && col < pl.pw)
-							*reinterpret_cast<u32 *>(dst + (long long)y * pl.pitch + col) = tile[rr * kTileWords + word0 + wi];
+						int ix, iy;
+						if (SkewToImage(b, vr0 + rr, vc0 + 4 * wi, ix, iy))
+							*reinterpret_cast<u32 *>(dst + (long long)iy * pl.pitch + ix) = tile[rr * kTileWords + 3 + wi];
+					}
+				}
+			} else if (kLoad == kLoadLdgsts) {
+				/* rows start on 8-byte boundaries: 64-bit stores.  The item's columns begin 4 bytes before such a
+				 * boundary (at one, for a UV item): 31 aligned units per row (tile byte 16 + 8 l <-> plane byte
+				 * 256 chunk + 8 l) and one word at each end, or 32 units (tile byte 8 + 8 l) */
+				const int xb0 = 256 * (int)((desc >> 2) & 0x3ffu);             /* plane byte of tile byte 16 */
+				const int col = uv ? xb0 - 8 + 8 * lane : xb0 + 8 * lane;
+				const bool col_ok = (uv || lane < 31) && col >= 0 && col < pl.pw;
+				const unsigned char *sp = tile8 + (uv ? 8 : 16) + 8 * lane;
+#pragma unroll 4
+				for (int rr = 0; rr < kTileH; rr++) {
+					const int y = y0 + rr;
+					if (col_ok && y >= 0 && y < pl.buf_rows)
+						*reinterpret_cast<uint2 *>(dst + (long long)y * pl.pitch + col) = *reinterpret_cast<const uint2 *>(sp + rr * kTileW);
+				}
+				if (!uv) {
+#pragma unroll
+					for (int r0 = 0; r0 < kTileH; r0 += 16) {
+						const int rr = r0 + (lane >> 1), y = y0 + rr;
+						const int fw = (lane & 1) ? 66 : 3;                      /* tile word (byte 264 or 12); plane byte xb0 + 248 or xb0 - 4 */
+						const int fc = (lane & 1) ? xb0 + 248 : xb0 - 4;
+						if (rr < kTileH && fc >= 0 && fc < pl.pw && y >= 0 && y < pl.buf_rows)
+							*reinterpret_cast<u32 *>(dst + (long long)y * pl.pitch + fc) = tile[rr * kTileWords + fw];
 					}
 				}
 			} else if (y0 >= 0 && y0 + kTileH <= pl.buf_rows) {
@@ -589,6 +656,232 @@ extern "C" int hdb_debug_read_trace(unsigned long long *dst, int n_warps)
 }
 #endif
 
+/* ------------------------------------------------------------------ */
+/* the same kernel for 16-bit samples   */
+/* ------------------------------------------------------------------ */
+/*
+ * Planar frames of 16-bit containers holding kDepth-bit samples (deblock_core16.cuh; depth 8 .. 10).  Items,
+ * scheduling, boundary-strength prefetch and the per-warp two-stage TMA pipeline are those of DeblockTiledKernel;
+ * what differs is the geometry -- a block row is 16 bytes per block, so an item's box is 528 x 16 bytes (8 bytes
+ * of lead-in to the 16-byte boundary, 32 blocks of 16 bytes, 8 of tail: 132 32-bit elements) at byte
+ * 512 * chunk - 16 of the row -- and the arithmetic.  Per pixel it moves twice the bytes for the same number of
+ * instructions, which puts it nearer the HBM roofline than the 8-bit kernel.  TMA loads only: the chroma pitch
+ * (width bytes) must be a multiple of 16, i.e. the width a multiple of 16.
+ */
+constexpr int kTileW16 = 528;
+constexpr int kTileWords16 = kTileW16 / 4;        /* 132 */
+constexpr int kTileBytes16 = kTileW16 * kTileH;   /* 8448: a multiple of 128 */
+constexpr int kSmemBytes16 = kWarps * kStages * (kTileBytes16 + 8 + 8);
+#ifndef HDB_MIN_CTAS16
+#define HDB_MIN_CTAS16 12
+#endif
+
+template <int kDepth, bool kEdgeQp>
+__global__ void __launch_bounds__(kWarps * 32, HDB_MIN_CTAS16)
+DeblockTiled16Kernel(const __grid_constant__ TensorMaps3 maps, const __grid_constant__ TiledBatch b,
+	SchedWords *sched, const uint32_t run_len)
+{
+	extern __shared__ __align__(HDB_SMEM_ALIGN) unsigned char smem[];
+	const int warp = threadIdx.x >> 5;
+	const int lane = threadIdx.x & 31;
+	unsigned char *tiles = smem + warp * (kStages * kTileBytes16);
+	uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kWarps * kStages * kTileBytes16) + warp * kStages;
+	uint2 *held = reinterpret_cast<uint2 *>(smem + kWarps * kStages * (kTileBytes16 + 8)) + warp * kStages;
+	const uint32_t tiles_s = SmemAddr(tiles);
+	const uint32_t bars_s = SmemAddr(bars);
+	const uint32_t total = (uint32_t)b.total_items;
+
+	uint32_t run_next = 0, run_end = 0, run_pending = 0, pending_len = 0;
+	const uint32_t two_grid_warps = 2u * gridDim.x * kWarps;
+	auto next_len = [&](uint32_t seen) -> uint32_t {
+		const uint32_t left = total > seen ? total - seen : 0u;
+		return min(max(left / two_grid_warps, 1u), run_len);
+	};
+	ItemCursor cur;
+	cur.frame = cur.plane = cur.grp = cur.chunk = 0; cur.chunks = cur.groups = 1;
+	auto issue_load = [&](int s) {         /* lane 0 only */
+		if (run_next == run_end) {
+			run_next = run_pending;
+			run_end = run_pending + pending_len;
+			if (run_next < total) {
+				pending_len = next_len(run_end);
+				run_pending = atomicAdd(&sched->next, pending_len);
+				cur.Seek(b, run_next);
+			}
+		} else {
+			cur.template Next<false>(b);
+		}
+		if (run_next >= total) { held[s] = make_uint2(0u, kNoItem); return; }
+		run_next++;
+		held[s] = make_uint2(cur.frame, cur.Desc());
+		const uint32_t bar = bars_s + 8u * s;
+		MbarArriveExpectTx(bar, kTileBytes16);
+		/* x in 32-bit elements: (512 * chunk - 16) / 4 */
+		TmaLoad3D(tiles_s + s * kTileBytes16, &maps.in[cur.plane], 128 * (int)cur.chunk - 4,
+			8 * kRB * (int)cur.grp + (cur.plane ? b.chroma_y_org : b.luma_y_org), (int)cur.frame, bar);
+	};
+	if (lane == 0) {
+		for (int s = 0; s < kStages; s++) MbarInit(bars_s + 8u * s, 1);
+		FenceMbarInit();
+		pending_len = next_len(0u);
+		run_pending = atomicAdd(&sched->next, pending_len);
+		for (int s = 0; s < kStages; s++) issue_load(s);
+	}
+	__syncwarp();
+
+	int s = 0;
+	uint32_t parity = 0;
+	uint32_t cur_frame = 0xffffffffu;
+	int cur_plane = -1;
+	FilterParams16 fp;
+	PlaneInfo pl;
+	MakeFilterParams16<kDepth>(fp, 0, 0);
+	pl = MakePlaneInfo<false>(b, 0);
+	BsRaw bs_raw[kRB];
+	{
+		const uint2 it0 = held[0];
+#pragma unroll
+		for (int rb = 0; rb < kRB; rb++) bs_raw[rb] = ItemBsRaw<false>(b, it0.x, it0.y, lane, rb);
+	}
+	for (;;) {
+		const uint2 it = held[s];
+		const uint32_t frame = it.x, desc = it.y;
+		if (desc == kNoItem) break;
+		int plane, bx0, lby0;
+		ItemCoords<false>(desc, plane, bx0, lby0);
+		const bool chroma = plane != 0;
+		if (frame != cur_frame) {
+			cur_frame = frame;
+			const unsigned qp = b.qp ? __ldg(b.qp + frame) : b.qp_value;
+			MakeFilterParams16<kDepth>(fp, BetaOf(qp), TcOf(qp));      /* cpu.h:136-137, scaled to the depth */
+		}
+		if (plane != cur_plane) { cur_plane = plane; pl = MakePlaneInfo<false>(b, plane); }
+		const int bx = bx0 + lane;
+		u32 bs[kRB];
+		{
+			const uint2 it_next = held[s + 1 == kStages ? 0 : s + 1];
+#pragma unroll
+			for (int rb = 0; rb < kRB; rb++) bs[rb] = PackBs(bs_raw[rb], chroma);
+#pragma unroll
+			for (int rb = 0; rb < kRB; rb++) bs_raw[rb] = ItemBsRaw<false>(b, it_next.x, it_next.y, lane, rb);
+		}
+		MbarWait(bars_s + 8u * s, parity);
+		u32 *tile = reinterpret_cast<u32 *>(tiles + s * kTileBytes16);
+		unsigned char *dst = pl.out + (long long)frame * pl.frame_stride;
+#pragma unroll 1
+		for (int rb = 0; rb < kRB; rb++) {
+			if (bx < pl.nbx && lby0 + rb < pl.rows) {
+				/* lane l owns bytes 8 + 16 l .. 23 + 16 l of each of the block row's 8 tile rows */
+				u32 *base = tile + rb * 8 * kTileWords16 + 2 + 4 * lane;
+				u32 w[8][4];
+#pragma unroll
+				for (int r = 0; r < 8; r++) {
+					const uint2 a = *reinterpret_cast<const uint2 *>(base + r * kTileWords16);
+					const uint2 c = *reinterpret_cast<const uint2 *>(base + r * kTileWords16 + 2);
+					w[r][0] = a.x; w[r][1] = a.y; w[r][2] = c.x; w[r][3] = c.y;
+				}
+				u32 s4 = bs[0];
+#pragma unroll
+				for (int k = 1; k < kRB; k++) if (rb == k) s4 = bs[k];
+				if (chroma) ChromaBlock16<kDepth>(w, s4 & 0xff, (s4 >> 8) & 0xff, (s4 >> 16) & 0xff, s4 >> 24, fp);
+				else LumaBlock16<kDepth, kEdgeQp>(w, s4 & 0xff, (s4 >> 8) & 0xff, (s4 >> 16) & 0xff, s4 >> 24, fp);
+#pragma unroll
+				for (int r = 0; r < 8; r++) {
+					*reinterpret_cast<uint2 *>(base + r * kTileWords16) = make_uint2(w[r][0], w[r][1]);
+					*reinterpret_cast<uint2 *>(base + r * kTileWords16 + 2) = make_uint2(w[r][2], w[r][3]);
+				}
+			}
+		}
+		__syncwarp();
+		/* the item's own bytes of every row: tile bytes 8 .. 519 <-> plane bytes 512 chunk - 8 .. + 503: thirty-one
+		 * 16-byte vectors (tile byte 16 + 16 j <-> plane byte 512 chunk + 16 j) and two words at each end */
+		{
+			const int y0 = 8 * lby0 + pl.y_org;
+			const int pwb = 2 * pl.pw;                                  /* plane width in bytes */
+			const int xb0 = 512 * (int)((desc >> 2) & 0x3ffu);
+			const unsigned char *tile8 = reinterpret_cast<const unsigned char *>(tile);
+			const int vcol = xb0 + 16 * lane;
+			const bool vec_lane = lane < 31 && vcol < pwb;
+			const unsigned char *vsrc = tile8 + 16 + 16 * lane;
+			unsigned char *vdst = dst + (long long)y0 * pl.pitch + vcol;
+			const int k = lane & 3, ftr = lane >> 2;
+			const int fword = k < 2 ? 2 + k : 126 + k;                  /* tile words 2, 3 and 128, 129 */
+			const int fcol = k < 2 ? xb0 - 8 + 4 * k : xb0 + 496 + 4 * (k - 2);
+			const bool f_lane = fcol >= 0 && fcol < pwb;
+#pragma unroll
+			for (int rr = 0; rr < kTileH; rr++) {
+				const int y = y0 + rr;
+				if (vec_lane && y >= 0 && y < pl.buf_rows) *reinterpret_cast<uint4 *>(vdst) = *reinterpret_cast<const uint4 *>(vsrc + rr * kTileW16);
+				vdst += pl.pitch;
+			}
+#pragma unroll
+			for (int rr = 0; rr < kTileH; rr += 8) {
+				const int y = y0 + rr + ftr;
+				if (f_lane && y >= 0 && y < pl.buf_rows) *reinterpret_cast<u32 *>(dst + (long long)y * pl.pitch + fcol) = tile[(rr + ftr) * kTileWords16 + fword];
+			}
+		}
+		FenceProxyAsyncShared();
+		__syncwarp();
+		if (lane == 0) issue_load(s);
+		__syncwarp();
+		if (++s == kStages) { s = 0; parity ^= 1u; }
+	}
+	if (lane == 0) asm volatile("" :: "r"(run_pending) : "memory");
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		__threadfence();
+		if (atomicAdd(&sched->done, 1u) == gridDim.x - 1) {
+			sched->next = 0u;
+			sched->done = 0u;
+			__threadfence();
+		}
+	}
+}
+
+typedef void (*TiledKernelFn16)(const TensorMaps3, const TiledBatch, SchedWords *, const uint32_t);
+
+/* variant index = (edge maps ? 1 : 0) | (depth - 8) << 1 */
+static TiledKernelFn16 TiledKernel16Of(int v)
+{
+	switch (v) {
+	case 0: return DeblockTiled16Kernel<8, false>;
+	case 1: return DeblockTiled16Kernel<8, true>;
+	case 2: return DeblockTiled16Kernel<9, false>;
+	case 3: return DeblockTiled16Kernel<9, true>;
+	case 4: return DeblockTiled16Kernel<10, false>;
+	case 5: return DeblockTiled16Kernel<10, true>;
+	}
+	return nullptr;
+}
+
+cudaError_t PrepareTiled16(int ctas_per_sm[kTiled16Variants])
+{
+	for (int v = 0; v < kTiled16Variants; v++) {
+		const TiledKernelFn16 fn = TiledKernel16Of(v);
+		cudaError_t err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes16);
+		if (err != cudaSuccess) return err;
+		int n = 0;
+		err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, kWarps * 32, kSmemBytes16);
+		if (err != cudaSuccess) return err;
+		ctas_per_sm[v] = std::max(n, 1);
+	}
+	return cudaSuccess;
+}
+
+cudaError_t LaunchTiled16(const TensorMaps3 &maps, const TiledBatch &b, void *sched, int sm_count,
+	const int ctas_per_sm[kTiled16Variants], cudaStream_t stream, int bit_depth, bool edge_qp)
+{
+	if (b.total_items <= 0) return cudaSuccess;
+	if (b.total_items >= (1ll << 31) || bit_depth < 8 || bit_depth > 10) return cudaErrorInvalidValue;
+	const int variant = (edge_qp ? 1 : 0) | ((bit_depth - 8) << 1);
+	const int resident = std::max(ctas_per_sm[variant], 1);
+	long long ctas = std::min<long long>((long long)sm_count * resident, (b.total_items + kWarps - 1) / kWarps);
+	ctas = std::max<long long>(ctas, 1);
+	const uint32_t run_len = b.total_items / (ctas * kWarps) >= 512 ? 8 : 4;
+	TiledKernel16Of(variant)<<<(unsigned)ctas, kWarps * 32, kSmemBytes16, stream>>>(maps, b, reinterpret_cast<SchedWords *>(sched), run_len);
+	return cudaGetLastError();
+}
+
 int HostBeta(unsigned qp) { return BetaOf(qp); }
 int HostTc(unsigned qp) { return TcOf(qp); }
 
@@ -614,6 +907,13 @@ void FinalizeTiledBatch(TiledBatch &b)
 	b.div_luma_chunks.Init((uint32_t)b.luma_chunks);
 	b.div_chroma_chunks.Init((uint32_t)b.chroma_chunks);
 	b.div_items_chroma.Init((uint32_t)std::max(b.items_chroma, 1));
+	/* the reference addresses a padded chroma plane with a pitch of 8 * (number of blocks) (cpu.h:469-471), which
+	 * is 4 short of its real pitch when the chroma width is 4 mod 8 */
+	const int cw = b.width / 2;
+	b.chroma_skew = (!b.nv12 && cw % 8 != 0) ? 1 : 0;
+	b.chroma_vpitch = 8 * b.chroma_nbx;
+	b.chroma_rpitch = cw + 8;
+	b.div_chroma_rpitch.Init((uint32_t)b.chroma_rpitch);
 }
 
 typedef void (*TiledKernelFn)(const TensorMaps3, const TiledBatch, SchedWords *, const uint32_t);

@@ -52,6 +52,10 @@ struct TiledBatch {
 	int items_luma, items_chroma, items_per_frame;
 	long long total_items;
 	FastDiv div_items_per_frame, div_luma_chunks, div_chroma_chunks, div_items_chroma;
+	/* chroma width = 4 mod 8: the reference's blocks tile a virtual plane of pitch chroma_vpitch laid over its
+	 * padded buffer of pitch chroma_rpitch (deblock_kernels.cu: SkewToImage); cp.async load mode only */
+	int chroma_skew, chroma_vpitch, chroma_rpitch;
+	FastDiv div_chroma_rpitch;
 	/* per-frame inputs */
 	const unsigned *qp;             /* [n_frames], or NULL: every frame uses qp_value */
 	unsigned qp_value;
@@ -88,6 +92,13 @@ cudaError_t PrepareTiled(int ctas_per_sm[kTiledVariants]);
 /* Persistent tiled kernel: one launch filters Y, U and V of every frame of the batch. */
 cudaError_t LaunchTiled(const TensorMaps3 &maps, const TiledBatch &b, void *sched, int sm_count, const int ctas_per_sm[kTiledVariants],
 	cudaStream_t stream, bool edge_qp = false);
+/* 16-bit samples (planar; bit depth 8 .. 10 in 16-bit containers): the tensor maps describe rows of 2 * width
+ * bytes with a 132-element box; pitches in TiledBatch are bytes as always.  Variant index = (edge maps ? 1 : 0)
+ * | (depth - 8) << 1. */
+constexpr int kTiled16Variants = 6;
+cudaError_t PrepareTiled16(int ctas_per_sm[kTiled16Variants]);
+cudaError_t LaunchTiled16(const TensorMaps3 &maps, const TiledBatch &b, void *sched, int sm_count,
+	const int ctas_per_sm[kTiled16Variants], cudaStream_t stream, int bit_depth, bool edge_qp);
 /* bytes of zero-initialised device memory the scheduler needs (one per context) */
 size_t TiledSchedBytes();
 

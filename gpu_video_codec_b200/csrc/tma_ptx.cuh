@@ -78,6 +78,11 @@ __device__ __forceinline__ void CpAsync4(uint32_t dst, const void *src, uint32_t
 	asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 
+__device__ __forceinline__ void CpAsync8(uint32_t dst, const void *src, uint32_t src_bytes)
+{
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+
 __device__ __forceinline__ void CpAsyncCommit()
 {
 	asm volatile("cp.async.commit_group;" ::: "memory");

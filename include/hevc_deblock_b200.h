@@ -238,6 +238,20 @@ int hdb_derive_edges(hdb_context *ctx, const hdb_block_info *info, unsigned n_fr
 #define HDB_FLAG_EDGE_MAPS 1u   /* vert / hor hold edge bytes (HDB_EDGE) and are required */
 #define HDB_FLAG_NV12      2u   /* frames are NV12 instead of YV12 */
 
+/*
+ * Samples deeper than 8 bits (the third of the caller-side data formats): planar frames like the 8-bit ones -- Y,
+ * then the two chroma planes, tight rows -- of 16-bit little-endian containers holding `depth`-bit samples in their
+ * low bits (what software decoders call yuv420p10le), 3 * width * height bytes a frame.  The reference is 8-bit
+ * only: unsigned char planes (cpu.h:1041-1048) and the sample maximum 255 in its clips (cpu.h:1202, 1228, 1474).
+ * Deeper samples follow the one rule the published standard adds (H.265 8.7.2.5.3): beta and tc from the
+ * reference's tables times 1 << (depth - 8), and (1 << depth) - 1 in place of 255; geometry, order, decisions and
+ * formulas are the reference's.  HDB_FLAG_DEPTH(8) -- 8-bit samples in 16-bit containers -- gives the reference's
+ * results exactly; 9 and 10 have nothing in the reference to be compared with.  Width a multiple of 16, at least
+ * 32; combines with HDB_FLAG_EDGE_MAPS, not with HDB_FLAG_NV12.
+ */
+#define HDB_FLAG_SAMPLES16 4u
+#define HDB_FLAG_DEPTH(d)  (HDB_FLAG_SAMPLES16 | ((unsigned)(d) << 8))   /* d = 8, 9 or 10 */
+
 /* hdb_deblock_batch / hdb_deblock_batch_device with flags (0 = exactly those two) */
 int hdb_deblock_batch_ex(hdb_context *ctx, const unsigned char *frames_in, unsigned char *frames_out,
 	unsigned n_frames, unsigned width, unsigned height, const unsigned *qp,

@@ -54,18 +54,28 @@ void hdbo_default_hor_bs(unsigned width, unsigned height, uint8_t *dst)
 	for (i = 0; i < n; i++) dst[i] = (i % (height / S + 1) == 0) ? 0 : 2;
 }
 
+/*
+ * Samples are held as 16-bit values whatever their depth: an 8-bit frame is widened on the way in and narrowed on
+ * the way out (the reference's own storage is unsigned char, cpu.h:1041-1048, its arithmetic int: no value changes).
+ * The one constant of the reference that depends on the depth is the sample maximum, 255 (cpu.h:1202, 1228, 1474);
+ * g_maxv carries it.  Not thread-safe on purpose: set per call, test infrastructure.
+ */
+typedef uint16_t px_t;
+static int g_maxv = 255;
+static int g_depth_shift = 0;      /* bit depth - 8: beta and tc scale with it (see deblock_oracle.h) */
+
 static int iabs(int v) { return v < 0 ? -v : v; }
 /* cpu.h:1117-1120 Clip1: [-c, c] */
 static int clip_sym(int d, int c) { int lo = -c; if (d < lo) d = lo; if (d > c) d = c; return d; }
-/* cpu.h:1123-1126 Clip2 with c = 255 */
-static uint8_t clip_px(int v) { if (v < 0) v = 0; if (v > 255) v = 255; return (uint8_t)v; }
+/* cpu.h:1123-1126 Clip2 with c = 255 (the sample maximum of the depth) */
+static px_t clip_px(int v) { if (v < 0) v = 0; if (v > g_maxv) v = g_maxv; return (px_t)v; }
 
 /*
  * One 4-line edge segment.  Line L (0..3), tap k (0..3):
  *   p_k = pb[L*ls - k*ts]      q_k = qb[L*ls + k*ts]
  * pb points at p0 of line 0, qb at q0 of line 0.
  */
-typedef struct { uint8_t *pb, *qb; ptrdiff_t ts, ls; } seg_t;
+typedef struct { px_t *pb, *qb; ptrdiff_t ts, ls; } seg_t;
 
 #define P(L, k) ((int)sg->pb[(L) * sg->ls - (k) * sg->ts])
 #define Q(L, k) ((int)sg->qb[(L) * sg->ls + (k) * sg->ts])
@@ -159,14 +169,14 @@ static unsigned bs_at(const uint8_t *bs, unsigned n, unsigned idx)
  * "not last block" tests -- the LUMA counts for both plane kinds (cpu.h:515,
  * 645, 786, 916).
  */
-static void filter_plane(uint8_t *pl, int nbx, int nby, ptrdiff_t pitch, unsigned bw,
+static void filter_plane(px_t *pl, int nbx, int nby, ptrdiff_t pitch, unsigned bw,
 	int lim_x, int lim_y, const uint8_t *vbs, unsigned nv, const uint8_t *hbs, unsigned nh,
 	int beta, int tc, int chroma, int edges)
 {
 	int bx, by;
 	for (bx = 0; bx < nbx; bx++) {
 		for (by = 0; by < nby; by++) {
-			uint8_t *b = pl + (ptrdiff_t)by * S * pitch + (ptrdiff_t)bx * S;
+			px_t *b = pl + (ptrdiff_t)by * S * pitch + (ptrdiff_t)bx * S;
 			unsigned bs[4];
 			seg_t sg[4];
 			int e;
@@ -186,7 +196,7 @@ static void filter_plane(uint8_t *pl, int nbx, int nby, ptrdiff_t pitch, unsigne
 				if (chroma) { if (bs[e] == 2) chroma_segment(&sg[e], tc); } /* cpu.h:463 */
 				else if (edges) {
 					/* edge byte = bs | qp << 2: the segment's own beta / tc (deblock_oracle.h) */
-					if ((bs[e] & 3u) > 0) luma_segment(&sg[e], hdbo_beta(bs[e] >> 2), hdbo_tc(bs[e] >> 2));
+					if ((bs[e] & 3u) > 0) luma_segment(&sg[e], hdbo_beta(bs[e] >> 2) << g_depth_shift, hdbo_tc(bs[e] >> 2) << g_depth_shift);
 				}
 				else { if (bs[e] > 0) luma_segment(&sg[e], beta, tc); }     /* cpu.h:164 */
 			}
@@ -194,9 +204,29 @@ static void filter_plane(uint8_t *pl, int nbx, int nby, ptrdiff_t pitch, unsigne
 	}
 }
 
-static int deblock_frame(const uint8_t *in, uint8_t *out, unsigned width, unsigned height,
+/* one row of samples between the caller's storage (1 or 2 bytes per sample) and the 16-bit working planes */
+static void row_in(px_t *dst, const void *src, size_t first, unsigned n, int bytes)
+{
+	unsigned i;
+	if (bytes == 1) for (i = 0; i < n; i++) dst[i] = ((const uint8_t *)src)[first + i];
+	else memcpy(dst, (const uint16_t *)src + first, (size_t)n * 2);
+}
+
+static void row_out(void *dst, size_t first, const px_t *src, unsigned n, int bytes)
+{
+	unsigned i;
+	if (bytes == 1) for (i = 0; i < n; i++) ((uint8_t *)dst)[first + i] = (uint8_t)src[i];
+	else memcpy((uint16_t *)dst + first, src, (size_t)n * 2);
+}
+
+/*
+ * bytes = 1: the reference's own 8-bit frames (depth 8).  bytes = 2: 16-bit containers holding `depth`-bit samples
+ * in their low bits (deblock_oracle.h: hdbo_deblock_frame16); depth 8 in such containers is the reference's
+ * arithmetic unchanged.
+ */
+static int deblock_frame(const void *in, void *out, unsigned width, unsigned height,
 	unsigned qp, const uint8_t *vert_bs, unsigned num_vert_bs,
-	const uint8_t *hor_bs, unsigned num_hor_bs, int edges)
+	const uint8_t *hor_bs, unsigned num_hor_bs, int edges, int bytes, unsigned depth)
 {
 	unsigned cw = width / 2, ch = height / 2;                    /* cpu.h:59-60 */
 	unsigned nw = width + S, nh = height + S;                    /* cpu.h:55-56 */
@@ -205,8 +235,9 @@ static int deblock_frame(const uint8_t *in, uint8_t *out, unsigned width, unsign
 	unsigned ncV = hdbo_num_vert_bs(cw, ch), ncH = hdbo_num_hor_bs(cw, ch);
 	int nbx = (int)(nw / S), nby = (int)(nh / S);                /* cpu.h:141-142 */
 	int cnbx = (int)(ncw / S), cnby = (int)(nch / S);            /* cpu.h:450-451 */
-	int beta = hdbo_beta(qp), tc = hdbo_tc(qp);                  /* cpu.h:136-137 */
-	uint8_t *Y, *C, *vbs, *hbs, *cvbs, *chbs;
+	int beta = hdbo_beta(qp) << (depth - 8), tc = hdbo_tc(qp) << (depth - 8);   /* cpu.h:136-137; scaled for depth > 8 */
+	px_t *Y, *C;
+	uint8_t *vbs, *hbs, *cvbs, *chbs;
 	unsigned r, pl;
 
 	if (width % S != 0 || height % S != 0) return HDBO_ERR_SIZE; /* cpu.h:46-48 */
@@ -214,10 +245,12 @@ static int deblock_frame(const uint8_t *in, uint8_t *out, unsigned width, unsign
 		if (!vert_bs || !hor_bs) return HDBO_ERR_BS_SIZE;
 		if (num_vert_bs != nV || num_hor_bs != nH) return HDBO_ERR_BS_SIZE; /* cpu.h:122-123 */
 	}
+	g_maxv = (1 << depth) - 1;
+	g_depth_shift = (int)depth - 8;
 
 	/* zero padding: the reference leaves it uninitialised (cpu.h:57, 63-64) */
-	Y = (uint8_t *)calloc((size_t)nw * nh, 1);
-	C = (uint8_t *)calloc((size_t)ncw * nch, 1);
+	Y = (px_t *)calloc((size_t)nw * nh, sizeof(px_t));
+	C = (px_t *)calloc((size_t)ncw * nch, sizeof(px_t));
 	vbs = (uint8_t *)malloc(nV + 1); hbs = (uint8_t *)malloc(nH + 1);
 	cvbs = (uint8_t *)malloc(ncV + 1); chbs = (uint8_t *)malloc(ncH + 1);
 	if (vert_bs) { memcpy(vbs, vert_bs, nV); memcpy(hbs, hor_bs, nH); } /* cpu.h:125-130 */
@@ -227,27 +260,27 @@ static int deblock_frame(const uint8_t *in, uint8_t *out, unsigned width, unsign
 
 	/* luma: image at (4,4) of the padded plane  cpu.h:68-71 */
 	for (r = 0; r < height; r++)
-		memcpy(Y + (size_t)(r + S / 2) * nw + S / 2, in + (size_t)r * width, width);
+		row_in(Y + (size_t)(r + S / 2) * nw + S / 2, in, (size_t)r * width, width, bytes);
 	filter_plane(Y, nbx, nby, (ptrdiff_t)nbx * S, width / S, nbx, nby,
 		vbs, nV, hbs, nH, beta, tc, 0, edges);
 	for (r = 0; r < height; r++)                                 /* cpu.h:1000-1004 */
-		memcpy(out + (size_t)r * width, Y + (size_t)(r + S / 2) * nw + S / 2, width);
+		row_out(out, (size_t)r * width, Y + (size_t)(r + S / 2) * nw + S / 2, width, bytes);
 
 	/* the two chroma planes, identical treatment  cpu.h:73-82, 453-992, 1007-1016 */
 	for (pl = 0; pl < 2; pl++) {
-		const uint8_t *src = in + (size_t)width * height + (size_t)pl * cw * ch;
-		uint8_t *dst = out + (size_t)width * height + (size_t)pl * cw * ch;
-		memset(C, 0, (size_t)ncw * nch);
+		const size_t first = (size_t)width * height + (size_t)pl * cw * ch;
+		memset(C, 0, (size_t)ncw * nch * sizeof(px_t));
 		for (r = 0; r < ch; r++)
-			memcpy(C + (size_t)(r + S / 2) * ncw + S / 2, src + (size_t)r * cw, cw);
+			row_in(C + (size_t)(r + S / 2) * ncw + S / 2, in, first + (size_t)r * cw, cw, bytes);
 		/* addressing pitch is cnbx*8 (cpu.h:469-471), "last block" limits are the
 		 * luma counts (cpu.h:515, 645) */
 		filter_plane(C, cnbx, cnby, (ptrdiff_t)cnbx * S, cw / S, nbx, nby,
 			cvbs, ncV, chbs, ncH, beta, tc, 1, 0);
 		for (r = 0; r < ch; r++)
-			memcpy(dst + (size_t)r * cw, C + (size_t)(r + S / 2) * ncw + S / 2, cw);
+			row_out(out, first + (size_t)r * cw, C + (size_t)(r + S / 2) * ncw + S / 2, cw, bytes);
 	}
 	free(Y); free(C); free(vbs); free(hbs); free(cvbs); free(chbs);
+	g_maxv = 255; g_depth_shift = 0;
 	return HDBO_OK;
 }
 
@@ -255,7 +288,7 @@ int hdbo_deblock_frame(const uint8_t *in, uint8_t *out, unsigned width, unsigned
 	unsigned qp, const uint8_t *vert_bs, unsigned num_vert_bs,
 	const uint8_t *hor_bs, unsigned num_hor_bs)
 {
-	return deblock_frame(in, out, width, height, qp, vert_bs, num_vert_bs, hor_bs, num_hor_bs, 0);
+	return deblock_frame(in, out, width, height, qp, vert_bs, num_vert_bs, hor_bs, num_hor_bs, 0, 1, 8);
 }
 
 /* cpu.h unchanged except that a luma segment takes beta / tc from its own edge byte */
@@ -263,7 +296,17 @@ int hdbo_deblock_frame_edges(const uint8_t *in, uint8_t *out, unsigned width, un
 	unsigned qp, const uint8_t *vert_edges, unsigned num_vert, const uint8_t *hor_edges, unsigned num_hor)
 {
 	if (!vert_edges || !hor_edges) return HDBO_ERR_BS_SIZE;
-	return deblock_frame(in, out, width, height, qp, vert_edges, num_vert, hor_edges, num_hor, 1);
+	return deblock_frame(in, out, width, height, qp, vert_edges, num_vert, hor_edges, num_hor, 1, 1, 8);
+}
+
+/* 16-bit containers, bit_depth 8 .. 12 (deblock_oracle.h) */
+int hdbo_deblock_frame16(const uint16_t *in, uint16_t *out, unsigned width, unsigned height,
+	unsigned qp, const uint8_t *vert, unsigned num_vert, const uint8_t *hor, unsigned num_hor,
+	unsigned bit_depth, int edges)
+{
+	if (bit_depth < 8 || bit_depth > 12) return HDBO_ERR_SIZE;
+	if (edges && (!vert || !hor)) return HDBO_ERR_BS_SIZE;
+	return deblock_frame(in, out, width, height, qp, vert, num_vert, hor, num_hor, edges ? 1 : 0, 2, bit_depth);
 }
 
 /* ------------------------------------------------------------------ */

@@ -99,6 +99,27 @@ int hdbo_deblock_batch(const uint8_t *in, uint8_t *out, unsigned n, unsigned wid
 int hdbo_deblock_frame_edges(const uint8_t *in, uint8_t *out, unsigned width, unsigned height,
 	unsigned qp, const uint8_t *vert_edges, unsigned num_vert, const uint8_t *hor_edges, unsigned num_hor);
 
+/* ---------------------------------------------------------------------------
+ * Samples deeper than 8 bits: SURVEY.md section 8(f) rank 2.  The reference is 8-bit only -- unsigned char planes
+ * (cpu.h:1041-1048) and the sample maximum 255 written into its three clips (cpu.h:1202, 1228, 1474) -- so this
+ * entry point DEFINES the deeper filter, by the one rule the published standard adds for it (H.265 8.7.2.5.3:
+ * beta = beta' * (1 << (BitDepth - 8)), tc = tc' * (1 << (BitDepth - 8))) and the sample maximum
+ * (1 << bit_depth) - 1 in place of 255; geometry, order, decisions and filter formulas are cpu.h unchanged.
+ *
+ * in / out: a planar frame like the 8-bit one (Y, then the two chroma planes, tight rows) of 16-bit little-endian
+ * containers holding bit_depth-bit samples in their low bits; 3*w*h/2 samples.  edges != 0: vert / hor hold
+ * edge bytes (bs | qp << 2) as in hdbo_deblock_frame_edges.
+ *
+ * Parity status: bit_depth == 8 is PINNED -- it must equal hdbo_deblock_frame (hence the unmodified reference)
+ * on the same samples widened to 16 bits (tests/test_depth.py).  bit_depth > 8 is UNPINNED against the
+ * reference: it has nothing there to be compared with.  Anchors: the depth-8 identity above; scale covariance --
+ * a frame whose samples are all multiples of 4 filtered at depth 10 is NOT 4x the depth-8 result in general
+ * (rounding), but flat regions, QP <= 17 and all-zero strengths are identities at every depth.
+ */
+int hdbo_deblock_frame16(const uint16_t *in, uint16_t *out, unsigned width, unsigned height,
+	unsigned qp, const uint8_t *vert, unsigned num_vert, const uint8_t *hor, unsigned num_hor,
+	unsigned bit_depth, int edges);
+
 /* what a decoder knows about one 8x8 luma block (12 bytes) */
 typedef struct hdbo_block_info {
 	int16_t mv[2][2];   /* [list][x, y] in quarter samples */

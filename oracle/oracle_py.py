@@ -53,6 +53,8 @@ def _load_port():
                                              _u8p, C.c_uint, _u8p, C.c_uint]
     lib.hdbo_derive_edges.argtypes = [C.c_void_p, C.c_uint, C.c_uint, _u8p, _u8p]
     lib.hdbo_derive_edges.restype = None
+    lib.hdbo_deblock_frame16.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_uint,
+                                         _u8p, C.c_uint, _u8p, C.c_uint, C.c_uint, C.c_int]
     return lib
 
 
@@ -197,6 +199,24 @@ def deblock_frame_edges(frame, w, h, qp, vert_edges, hor_edges):
     v = np.ascontiguousarray(vert_edges, np.uint8)
     hh = np.ascontiguousarray(hor_edges, np.uint8)
     rc = port().hdbo_deblock_frame_edges(_ptr(frame), _ptr(out), w, h, qp, _ptr(v), v.size, _ptr(hh), hh.size)
+    if rc:
+        raise OracleError({1: "Width and height of image must be multiplier of sample block size",
+                           2: "Incorrect size of input boundary strenght array"}[rc])
+    return out
+
+
+def deblock_frame16(frame, w, h, qp, vert=None, hor=None, bit_depth=10, edges=False):
+    """16-bit containers holding bit_depth-bit samples (deblock_oracle.h: hdbo_deblock_frame16).  Depth 8 is the
+    reference's filter; deeper is the H.265 scaling rule on top of it (unpinned against the reference)."""
+    frame = np.ascontiguousarray(frame, np.uint16).reshape(-1)
+    if frame.size != 3 * w * h // 2:
+        raise OracleError("Incorrect file size")
+    out = np.empty_like(frame)
+    v = None if vert is None else np.ascontiguousarray(vert, np.uint8)
+    hh = None if hor is None else np.ascontiguousarray(hor, np.uint8)
+    rc = port().hdbo_deblock_frame16(frame.ctypes.data, out.ctypes.data, w, h, qp,
+                                     None if v is None else _ptr(v), 0 if v is None else v.size,
+                                     None if hh is None else _ptr(hh), 0 if hh is None else hh.size, bit_depth, int(edges))
     if rc:
         raise OracleError({1: "Width and height of image must be multiplier of sample block size",
                            2: "Incorrect size of input boundary strenght array"}[rc])

@@ -147,3 +147,68 @@ extern "C" int emu_deblock_uv_plane(const uint8_t *uv_in, uint8_t *uv_out, unsig
 	for (unsigned r = 0; r < ch; r++) memcpy(uv_out + (size_t)r * w, &P[(size_t)(r + 4) * pitch + 8], w);
 	return 0;
 }
+
+/* ---- samples deeper than 8 bits: deblock_core16.cuh driven the same way over 16-bit planes ---- */
+#include "../../gpu_video_codec_b200/csrc/deblock_core16.cuh"
+
+template <int kDepth>
+static void FilterPlane16(uint16_t *pl, int nbx, int nby, size_t pitch, bool chroma, unsigned w, unsigned h,
+	int luma_nbx, int luma_nby, const uint8_t *vbs, const uint8_t *hbs, const FilterParams16 &fp, bool edges)
+{
+	for (int by = 0; by < nby; by++)
+		for (int bx = 0; bx < nbx; bx++) {
+			uint16_t *b = pl + (size_t)by * 8 * pitch + (size_t)bx * 8;
+			u32 wd[8][4];
+			for (int r = 0; r < 8; r++) memcpy(wd[r], b + r * pitch, 16);
+			u32 bs = chroma ? ChromaBsOfBlock(bx, by, w, h, luma_nbx, luma_nby)
+				: LumaBsOfBlock(bx, by, (int)(w / 8), nbx, nby, vbs, hbs);
+			if (chroma) ChromaBlock16<kDepth>(wd, bs & 0xff, (bs >> 8) & 0xff, (bs >> 16) & 0xff, bs >> 24, fp);
+			else if (edges) LumaBlock16<kDepth, true>(wd, bs & 0xff, (bs >> 8) & 0xff, (bs >> 16) & 0xff, bs >> 24, fp);
+			else LumaBlock16<kDepth, false>(wd, bs & 0xff, (bs >> 8) & 0xff, (bs >> 16) & 0xff, bs >> 24, fp);
+			for (int r = 0; r < 8; r++) memcpy(b + r * pitch, wd[r], 16);
+		}
+}
+
+template <int kDepth>
+static int DeblockFrame16(const uint16_t *in, uint16_t *out, unsigned w, unsigned h, unsigned qp,
+	const uint8_t *vbs, const uint8_t *hbs, bool edges)
+{
+	if (w % 8 || h % 8) return 1;
+	unsigned cw = w / 2, ch = h / 2;
+	unsigned nw = w + 8, nh = h + 8, ncw = cw + 8, nch = ch + 8;
+	int nbx = nw / 8, nby = nh / 8, cnbx = ncw / 8, cnby = nch / 8;
+	FilterParams16 fp;
+	MakeFilterParams16<kDepth>(fp, BetaOf(qp), TcOf(qp));
+	std::vector<uint8_t> dv, dh;
+	if (!vbs) {
+		dv.resize(NumVertBs(w, h)); dh.resize(NumHorBs(w, h));
+		for (size_t i = 0; i < dv.size(); i++) dv[i] = (i % (w / 8 + 1) == 0) ? 0 : 2;
+		for (size_t i = 0; i < dh.size(); i++) dh[i] = (i % (h / 8 + 1) == 0) ? 0 : 2;
+		vbs = dv.data(); hbs = dh.data();
+	}
+	std::vector<uint16_t> Y((size_t)nw * nh, 0), C((size_t)ncw * nch);
+	for (unsigned r = 0; r < h; r++) memcpy(&Y[(size_t)(r + 4) * nw + 4], in + (size_t)r * w, 2 * w);
+	FilterPlane16<kDepth>(Y.data(), nbx, nby, (size_t)nbx * 8, false, w, h, nbx, nby, vbs, hbs, fp, edges);
+	for (unsigned r = 0; r < h; r++) memcpy(out + (size_t)r * w, &Y[(size_t)(r + 4) * nw + 4], 2 * w);
+	for (int p = 0; p < 2; p++) {
+		const uint16_t *src = in + (size_t)w * h + (size_t)p * cw * ch;
+		uint16_t *dst = out + (size_t)w * h + (size_t)p * cw * ch;
+		std::fill(C.begin(), C.end(), 0);
+		for (unsigned r = 0; r < ch; r++) memcpy(&C[(size_t)(r + 4) * ncw + 4], src + (size_t)r * cw, 2 * cw);
+		FilterPlane16<kDepth>(C.data(), cnbx, cnby, (size_t)cnbx * 8, true, cw, ch, nbx, nby, nullptr, nullptr, fp, false);
+		for (unsigned r = 0; r < ch; r++) memcpy(dst + (size_t)r * cw, &C[(size_t)(r + 4) * ncw + 4], 2 * cw);
+	}
+	return 0;
+}
+
+extern "C" int emu_deblock_frame16(const uint16_t *in, uint16_t *out, unsigned w, unsigned h, unsigned qp,
+	const uint8_t *vbs, const uint8_t *hbs, unsigned depth, int edges)
+{
+	if (edges && (!vbs || !hbs)) return 2;
+	switch (depth) {
+	case 8: return DeblockFrame16<8>(in, out, w, h, qp, vbs, hbs, edges != 0);
+	case 9: return DeblockFrame16<9>(in, out, w, h, qp, vbs, hbs, edges != 0);
+	case 10: return DeblockFrame16<10>(in, out, w, h, qp, vbs, hbs, edges != 0);
+	}
+	return 3;
+}

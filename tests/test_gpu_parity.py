@@ -49,7 +49,10 @@ TILED_SIZES = [(32, 8), (32, 32), (64, 48), (256, 64), (288, 72), (352, 288), (7
                (1920, 1080), (2048, 1096)]
 GENERIC_SIZES = [(8, 8), (16, 16), (24, 40)]                                         # padded-scratch kernels
 # widths off the 32 grid (cpu.h:46-48 accepts every multiple of 8): the tiled kernel's cp.async loader
-LDGSTS_SIZES = [(40, 24), (72, 40), (200, 120), (360, 288), (1000, 64), (1080, 1920), (1912, 1080), (2056, 40)]
+# (8 mod 16: the chroma planes are "skewed" -- the reference addresses them with a pitch 4 short of their padded
+# width, cpu.h:450-451 with 469-471; 16 mod 32: straight)
+LDGSTS_SIZES = [(40, 24), (72, 40), (200, 120), (360, 288), (1000, 64), (1080, 1920), (1912, 1080), (2056, 40),
+                (48, 24), (80, 40), (1008, 64), (2000, 1048)]
 
 
 @pytest.mark.parametrize("size", TILED_SIZES + GENERIC_SIZES + LDGSTS_SIZES, ids=lambda s: "%dx%d" % s)
