@@ -42,6 +42,8 @@ WORKLOADS = {
     "8k_strips": (7680, 4320, 16, "stream of single 7680x4320 frames, each split into CTU-row strips across the GPUs, P2P halos"),
     # the same kind of batch stored as NV12 (Y + interleaved UV), one GPU
     "4k_nv12_512": (3840, 2160, 512, "synthetic 3840x2160 NV12 batch of 512 frames, random QP/BS maps"),
+    # 10-bit samples in 16-bit containers, planar (yuv420p10le); one GPU
+    "4k_yuv420p10_512": (3840, 2160, 512, "synthetic 3840x2160 planar 10-bit (16-bit containers) batch of 512 frames, random QP/BS maps"),
     # block data -> edge maps (bs | qp << 2) -> per-edge-QP filter; one GPU
     "4k_edges512": (3840, 2160, 512, "synthetic 3840x2160 YV12 batch of 512 frames, per-8x8-block decoder data -> derived edge maps -> per-edge-QP filter"),
 }
@@ -49,12 +51,12 @@ METRIC = "deblocked Mpixel/s"
 UNIT = "Mpixel/s"
 
 
-def alg_bytes_per_frame(w, h):
+def alg_bytes_per_frame(w, h, sample_bytes=1):
     """every sample read once and written once + every BS byte read once."""
     cw, ch = w // 2, h // 2
     nv, nh = (w // 8 + 1) * h // 8, (h // 8 + 1) * w // 8
     ncv, nch = (cw // 8 + 1) * ch // 8, (ch // 8 + 1) * cw // 8
-    return 3 * w * h + nv + nh + ncv + nch
+    return 3 * w * h * sample_bytes + nv + nh + ncv + nch
 
 
 def measured_peak():
@@ -264,13 +266,13 @@ def workload_frames(torch, first, n, w, h, seed, device="cuda"):
     return frames, qp, vbs, hbs
 
 
-WORKLOAD_SEED = {"4k_batch1024": 1000, "1080p_batch256": 2000, "4k_nv12_512": 3000, "4k_edges512": 4242, "8k_strips": 77}
+WORKLOAD_SEED = {"4k_yuv420p10_512": 5000, "4k_batch1024": 1000, "1080p_batch256": 2000, "4k_nv12_512": 3000, "4k_edges512": 4242, "8k_strips": 77}
 
 
 def workload_config(name, world, gen_device):
     """The `config` object of a line: facts about the workload only, identical in both arms."""
     w, h, total, desc = WORKLOADS[name]
-    fb = 3 * w * h // 2
+    fb = 3 * w * h // 2 * (2 if "p10" in name else 1)
     per = (total + world - 1) // world
     return {"workload": name, "description": desc, "width": w, "height": h, "frames": total,
             "frames_per_gpu": per, "sharding": "contiguous frame ranges, no collective",
@@ -429,8 +431,14 @@ def measure_workload(args, torch, hdb, dev, dd, rank, world, workload, steps, wa
     else:
         frames, qp, vbs, hbs = workload_frames(torch, first, n, w, h, WORKLOAD_SEED.get(workload, 0), "cuda")
     nv12 = "nv12" in workload
-    flags = hdb.FLAG_NV12 if nv12 else 0
+    depth = 10 if "p10" in workload else 0
+    flags = hdb.FLAG_NV12 if nv12 else (hdb.flag_depth(depth) if depth else 0)
     ysz, csz = w * h, (w // 2) * (h // 2)
+    if depth:
+        # the same frames scaled to the depth, the low bits filled at random: int16 tensors (torch has no uint16 arithmetic)
+        g16 = torch.Generator(device="cuda").manual_seed(WORKLOAD_SEED[workload] + 7 * first)
+        frames = (frames.to(torch.int16) << (depth - 8)) | torch.randint(0, 1 << (depth - 8), frames.shape, device="cuda", generator=g16, dtype=torch.int16)
+        fb *= 2
 
     def to_nv12(t):      # [k, 3wh/2] planar -> NV12, on whatever device t lives
         r = t.clone()
@@ -486,15 +494,19 @@ def measure_workload(args, torch, hdb, dev, dd, rank, world, workload, steps, wa
         q = qp[sel].cpu().numpy().astype(np.uint32)
         v = None if vbs is None else vbs[sel].cpu().numpy()
         hh = None if hbs is None else hbs[sel].cpu().numpy()
-        want = orc.deblock_batch(src, w, h, q, v, hh)
+        if depth:
+            got, src = got.view(np.uint16), src.view(np.uint16)
+            want = np.stack([orc.deblock_frame16(src[i], w, h, int(q[i]), v[i], hh[i], bit_depth=depth) for i in range(len(idx))])
+        else:
+            want = orc.deblock_batch(src, w, h, q, v, hh)
         ok = bool(np.array_equal(got, want))
         parity = {"bit_exact": ok, "frames_checked": len(idx), "changed_fraction": round(float((got != src).mean()), 4)}
         if not ok:
             raise SystemExit("PARITY FAILURE: GPU output differs from the oracle; no number is reported")
 
     # ---- end to end: pinned host buffers through hdb_deblock_batch -----------------------------
-    h_in = torch.empty((n, fb), dtype=torch.uint8).pin_memory()
-    h_out = torch.empty((n, fb), dtype=torch.uint8).pin_memory()
+    h_in = torch.empty(frames.shape, dtype=frames.dtype).pin_memory()
+    h_out = torch.empty(frames.shape, dtype=frames.dtype).pin_memory()
     h_in.copy_(frames)
     h_qp = qp.cpu().pin_memory()
     h_v = None if vbs is None else vbs.cpu().pin_memory()
@@ -559,7 +571,17 @@ def measure_workload(args, torch, hdb, dev, dd, rank, world, workload, steps, wa
         np_v = None if h_v is None else h_v.numpy()
         np_h = None if h_h is None else h_h.numpy()
         bad, t_chk = 0, time.perf_counter()
-        for f0 in range(0, n, 64):
+        e2e_checked = n
+        if depth:
+            # the 16-bit checker is the single-threaded port: a strided 32 frames of the e2e output, the rest through
+            # the device-resident output, which is compared with the e2e output frame for frame below
+            chk = list(range(0, n, max(1, n // 32)))
+            e2e_checked = len(chk)
+            a_in, a_out = h_in.numpy().view(np.uint16), h_out.numpy().view(np.uint16)
+            for f in chk:
+                wnt = orc.deblock_frame16(a_in[f], w, h, int(np_qp[f]), np_v[f], np_h[f], bit_depth=depth)
+                bad += 0 if np.array_equal(a_out[f], wnt) else 1
+        for f0 in range(0, 0 if depth else n, 64):
             f1 = min(n, f0 + 64)
             vv = None if np_v is None else np_v[f0:f1]
             hv = None if np_h is None else np_h[f0:f1]
@@ -573,9 +595,10 @@ def measure_workload(args, torch, hdb, dev, dd, rank, world, workload, steps, wa
             f1 = min(n, f0 + 64)
             if not torch.equal(out[f0:f1], h_out[f0:f1].cuda(non_blocking=False)):
                 raise SystemExit("PARITY FAILURE: device-resident output differs from the e2e output in frames %d..%d" % (f0, f1))
-        parity["e2e_frames_checked"] = n
+        parity["e2e_frames_checked"] = e2e_checked
         parity["e2e_frames_differing"] = bad
-        parity["checker"] = "reference (oracle/_ref)" if orc.have_ref() else "port (oracle/deblock_oracle.c)"
+        parity["checker"] = "port at depth %d (oracle/deblock_oracle.c: hdbo_deblock_frame16; unpinned against the reference above depth 8)" % depth if depth \
+            else ("reference (oracle/_ref)" if orc.have_ref() else "port (oracle/deblock_oracle.c)")
         parity["check_seconds"] = round(time.perf_counter() - t_chk, 1)
         parity["bit_exact"] = parity["bit_exact"] and bad == 0
         if bad:
@@ -585,19 +608,19 @@ def measure_workload(args, torch, hdb, dev, dd, rank, world, workload, steps, wa
     res = None
     if rank == 0:
         peak, peak_src = measured_peak()
-        alg = alg_bytes_per_frame(w, h) * n          # one launch processes this rank's n frames
+        alg = alg_bytes_per_frame(w, h, 2 if depth else 1) * n          # one launch processes this rank's n frames
         achieved = alg / (mean_launch_ms / 1e3) / 1e9
         traffic, traffic_src = ncu_traffic(workload, n)
         e2e = {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": round(e2e_s / steps * 1e3, 3), "launches_per_step": e2e_launches // max(steps, 1),
-               "api": "hdb_deblock_batch%s (pinned host buffers, 3-stream pipeline)" % ("_ex, HDB_FLAG_NV12" if nv12 else "")}
+               "api": "hdb_deblock_batch%s (pinned host buffers, 3-stream pipeline)" % ("_ex, HDB_FLAG_NV12" if nv12 else ("_ex, HDB_FLAG_DEPTH(%d)" % depth if depth else ""))}
         if link is not None:
             e2e["frac_of_link"] = round(link["ms_per_step"] / e2e["ms_per_step"], 4)
         res = {"value": round(value, 1), "ms_per_step": round(ms_per_step, 4),
                "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                             "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
                             "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
-                            "kernel": "DeblockTiledKernel<0, 1, 0>" if nv12 else "DeblockTiledKernel<0, 0, 0>",
+                            "kernel": "DeblockTiled16Kernel<%d, 0>" % depth if depth else ("DeblockTiledKernel<0, 1, 0>" if nv12 else "DeblockTiledKernel<0, 0, 0>"),
                             "mean_launch_ms": round(mean_launch_ms, 4)},
                "e2e": e2e, "link_probe": link, "gpu_launches": kernel_launches, "parity": parity}
         if world == 1 and not args.no_cpu and full_parity:
@@ -608,7 +631,16 @@ def measure_workload(args, torch, hdb, dev, dd, rank, world, workload, steps, wa
             q = qp[sel].cpu().numpy().astype(np.uint32)
             v = None if vbs is None else vbs[sel].cpu().numpy()
             hh = None if hbs is None else hbs[sel].cpu().numpy()
-            best, kind, used, detail = cpu_reference_run(src, w, h, q, v, hh, cores)
+            if depth:
+                src16 = src.view(np.uint16)[:8]
+                t0 = time.perf_counter()
+                for i in range(src16.shape[0]):
+                    orc.deblock_frame16(src16[i], w, h, int(q[i]), v[i], hh[i], bit_depth=depth)
+                dt = time.perf_counter() - t0
+                best, kind, used, detail = src16.shape[0] * w * h / 1e6 / dt, "port", 1, {"frames": int(src16.shape[0])}
+                ns = int(src16.shape[0])
+            else:
+                best, kind, used, detail = cpu_reference_run(src, w, h, q, v, hh, cores)
             res["cpu_baseline"] = {"value": round(best, 1), "unit": UNIT, "cores": used, "kind": kind,
                                    "sample": "first %d of the %d frames of the workload, best of OpenMP-in-frame and "
                                              "frame-parallel on %d threads" % (ns, total, used), "detail": detail}
@@ -635,7 +667,7 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": res["ms_per_step"], "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "scaling": "strong", "vs_baseline": None, "dtype": "u16" if "p10" in args.workload else "u8", "data": "synthetic",
                 "config": workload_config(args.workload, world, "cuda"),
                 "timing": "CUDA events on the launching stream, max over ranks",
                 "roofline": res["roofline"], "e2e": res["e2e"], "link_probe": res["link_probe"],

@@ -12,6 +12,7 @@ from .binding import (  # noqa: F401
     DeblockError,
     FLAG_EDGE_MAPS,
     FLAG_NV12,
+    FLAG_SAMPLES16,
     MultiDeblocker,
     Nv12Surfaces,
     StripPlanes,
@@ -20,6 +21,7 @@ from .binding import (  # noqa: F401
     build_library,
     default_boundary_strength,
     exported_symbols,
+    flag_depth,
     header_symbols,
     library_path,
     load_library,

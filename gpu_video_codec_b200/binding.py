@@ -55,7 +55,12 @@ class StripPlanes(C.Structure):
     _fields_ = [("y", C.c_void_p), ("u", C.c_void_p), ("v", C.c_void_p)]
 
 
-FLAG_EDGE_MAPS, FLAG_NV12 = 1, 2
+FLAG_EDGE_MAPS, FLAG_NV12, FLAG_SAMPLES16 = 1, 2, 4
+
+
+def flag_depth(bits):
+    """HDB_FLAG_DEPTH(bits): planar frames of 16-bit containers holding `bits`-bit samples (8, 9 or 10)."""
+    return FLAG_SAMPLES16 | (int(bits) << 8)
 
 
 class DeviceInfo(C.Structure):

@@ -274,17 +274,83 @@ __device__ __forceinline__ void UvBlockRow(u32 *base, u32 s4, const FilterParams
 
 /*
  * Skewed chroma plane (see fetch_tile in the kernel): byte (vr, vc) of the virtual padded plane -- pitch
- * b.chroma_vpitch = 8 * chroma_nbx -- is byte vr * vpitch + vc of the reference's padded buffer, whose real pitch
- * is b.chroma_rpitch = cw + 8 with the image at (4, 4).  Returns whether that is an image sample, and which.
+ * b.chroma_vpitch = 8 * chroma_nbx -- is byte o = vr * vpitch + vc of the reference's padded buffer, whose real
+ * pitch is b.chroma_rpitch = cw + 8 with the image at (4, 4): buffer row r = o / rpitch, column c = o - r * rpitch.
+ * A SkewWalk follows one virtual column down the rows of an item: one division where it starts, then
+ * c += vpitch with at most one wrap per row (vpitch = rpitch - 4).
  */
-__device__ __forceinline__ bool SkewToImage(const TiledBatch &b, int vr, int vc, int &ix, int &iy)
+struct SkewWalk {
+	int r, c;          /* row / column in the padded buffer */
+	bool col_ok;       /* the virtual column exists (0 <= vc < vpitch) */
+
+	__device__ __forceinline__ void Start(const TiledBatch &b, int vr, int vc)
+	{
+		col_ok = vc >= 0 && vc < b.chroma_vpitch;
+		const uint32_t o = (uint32_t)vr * (uint32_t)b.chroma_vpitch + (uint32_t)(col_ok ? vc : 0);
+		const uint32_t q = b.div_chroma_rpitch.Div(o);
+		r = (int)q; c = (int)(o - q * (uint32_t)b.chroma_rpitch);
+	}
+	__device__ __forceinline__ void NextRow(const TiledBatch &b)
+	{
+		c += b.chroma_vpitch;
+		if (c >= b.chroma_rpitch) { c -= b.chroma_rpitch; r++; }
+	}
+	/* offset of the image sample this is, or -1 for padding */
+	__device__ __forceinline__ long long ImageOffset(const TiledBatch &b, int pitch) const
+	{
+		const int ix = c - 4, iy = r - 4;
+		return (col_ok && ix >= 0 && ix < (b.width >> 1) && iy >= 0 && iy < b.chroma_buf_rows) ? (long long)iy * pitch + ix : -1ll;
+	}
+};
+
+template <bool kNv12>
+__device__ __noinline__ void FetchTileLdgsts(const TiledBatch &b, const uint2 it, const uint32_t dst, const int lane)
 {
-	if (vc < 0 || vc >= b.chroma_vpitch) return false;
-	const uint32_t o = (uint32_t)vr * (uint32_t)b.chroma_vpitch + (uint32_t)vc;
-	const uint32_t r = b.div_chroma_rpitch.Div(o);
-	ix = (int)(o - r * (uint32_t)b.chroma_rpitch) - 4;
-	iy = (int)r - 4;
-	return ix >= 0 && ix < (b.width >> 1) && iy >= 0 && iy < b.chroma_buf_rows;
+	if (it.y != kNoItem) {
+		int plane, bx0, lby0;
+		ItemCoords<kNv12>(it.y, plane, bx0, lby0);
+		const bool c = plane != 0;
+		const int pitch = c ? b.chroma_pitch : b.luma_pitch;
+		const unsigned char *src = b.in_plane[plane] + (long long)it.x * (c ? b.chroma_frame_stride : b.frame_stride);
+		const int xb0 = 256 * (int)((it.y >> 2) & 0x3ffu) - 16;        /* plane byte of tile byte 0 */
+		/* loops kept rolled: the cp.async variants must not outgrow the instruction cache (ncu: "no instruction"
+		 * was their first stall reason when these were unrolled) */
+		if (!kNv12 && c && b.chroma_skew) {
+			/* words lane, lane + 32 and (lanes 0 .. 3) lane + 64 of every tile row */
+			SkewWalk wk[3];
+#pragma unroll
+			for (int k = 0; k < 3; k++) wk[k].Start(b, 8 * lby0, xb0 + 4 + 4 * (lane + 32 * k));
+			wk[2].col_ok = wk[2].col_ok && lane < 4;
+			uint32_t d = dst + 4u * (uint32_t)lane;
+#pragma unroll 1
+			for (int t = 0; t < kTileH; t++) {
+#pragma unroll
+				for (int k = 0; k < 3; k++) {
+					const long long off = wk[k].ImageOffset(b, pitch);
+					if (k < 2 || lane < 4) CpAsync4(d + 128u * k, off >= 0 ? src + off : src, off >= 0 ? 4u : 0u);
+					wk[k].NextRow(b);
+				}
+				d += kTileW;
+			}
+		} else {
+			const int pw = (c && !kNv12) ? (b.width >> 1) : b.width;
+			const int rows = c ? b.chroma_buf_rows : b.luma_buf_rows;
+			const int y0 = 8 * lby0 + (c ? b.chroma_y_org : b.luma_y_org);
+			/* 34 units of 8 bytes per row: lane l takes unit l, lanes 0 and 1 units 32 and 33 as well */
+			const int xb = xb0 + 8 * lane;
+			const bool col_ok = xb >= 0 && xb < pw, col2_ok = lane < 2 && xb + 256 < pw;
+			const unsigned char *g = src + (long long)y0 * pitch + xb;
+			uint32_t d = dst + 8u * (uint32_t)lane;
+#pragma unroll 1
+			for (int t = 0; t < kTileH; t++) {
+				const bool row_ok = y0 + t >= 0 && y0 + t < rows;
+				CpAsync8(d, (row_ok && col_ok) ? g : src, (row_ok && col_ok) ? 8u : 0u);
+				if (lane < 2) CpAsync8(d + 256u, (row_ok && col2_ok) ? g + 256 : src, (row_ok && col2_ok) ? 8u : 0u);
+				g += pitch; d += kTileW;
+			}
+		}
+	}
+CpAsyncCommit();
 }
 
 /* kEdgeQp: the luma boundary-strength arrays hold edge bytes (bs | qp << 2, deblock_core.cuh) and every
@@ -359,61 +425,9 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_consta
 	 * SkewToImage maps a word of the virtual plane to the image sample it really is (or to padding); 4-byte
 	 * copies, one division per word.  The generic kernels reproduce the same thing with an explicit padded copy.
 	 */
-	auto fetch_tile = [&](int s) {          /* all lanes, after a __syncwarp() that follows issue_load */
-		const uint2 it = held[s];
-		if (it.y != kNoItem) {
-			int plane, bx0, lby0;
-			ItemCoords<kNv12>(it.y, plane, bx0, lby0);
-			const bool c = plane != 0;
-			const int pitch = c ? b.chroma_pitch : b.luma_pitch;
-			const unsigned char *src = b.in_plane[plane] + (long long)it.x * (c ? b.chroma_frame_stride : b.frame_stride);
-			const uint32_t dst = tiles_s + s * kTileBytes;
-			const int xb0 = 256 * (int)((it.y >> 2) & 0x3ffu) - 16;        /* plane byte of tile byte 0 */
-			if (!kNv12 && c && b.chroma_skew) {
-				const int vr0 = 8 * lby0, vc0 = xb0 + 4;                   /* virtual padded row / column of tile word 0 */
-				for (int t = 0; t < kTileH; t++) {
-#pragma unroll
-					for (int k = 0; k < 2; k++) {
-						const int w = lane + 32 * k;
-						int ix, iy;
-						const bool ok = SkewToImage(b, vr0 + t, vc0 + 4 * w, ix, iy);
-						CpAsync4(dst + 4u * (uint32_t)(t * kTileWords + w), ok ? src + (long long)iy * pitch + ix : src, ok ? 4u : 0u);
-					}
-				}
-#pragma unroll
-				for (int k = 0; k < 2; k++) {          /* words 64 .. 67 of the kTileH rows: 4 * kTileH = 2 * 32 words */
-					const int t = (lane + 32 * k) >> 2, w = 64 + (lane & 3);
-					if (t < kTileH) {
-						int ix, iy;
-						const bool ok = SkewToImage(b, vr0 + t, vc0 + 4 * w, ix, iy);
-						CpAsync4(dst + 4u * (uint32_t)(t * kTileWords + w), ok ? src + (long long)iy * pitch + ix : src, ok ? 4u : 0u);
-					}
-				}
-			} else {
-				const int pw = (c && !kNv12) ? (b.width >> 1) : b.width;
-				const int rows = c ? b.chroma_buf_rows : b.luma_buf_rows;
-				const int y0 = 8 * lby0 + (c ? b.chroma_y_org : b.luma_y_org);
-				{
-					const int xb = xb0 + 8 * lane;
-					const bool col_ok = xb >= 0 && xb < pw;
-					const unsigned char *g = src + (long long)y0 * pitch + xb;
-#pragma unroll 4
-					for (int t = 0; t < kTileH; t++) {
-						const bool ok = col_ok && y0 + t >= 0 && y0 + t < rows;
-						CpAsync8(dst + (uint32_t)(t * kTileW + 8 * lane), ok ? g : src, ok ? 8u : 0u);
-						g += pitch;
-					}
-				}
-				{
-					const int t = lane >> 1, u = 32 + (lane & 1);
-					const int xb = xb0 + 8 * u, y = y0 + t;
-					const bool ok = t < kTileH && xb >= 0 && xb < pw && y >= 0 && y < rows;
-					if (t < kTileH) CpAsync8(dst + (uint32_t)(t * kTileW + 8 * u), ok ? src + (long long)y * pitch + xb : src, ok ? 8u : 0u);
-				}
-			}
-		}
-		CpAsyncCommit();
-	};
+	/* kLoadLdgsts: the box of stage s, fetched by all lanes after a __syncwarp() that follows issue_load; out of
+	 * line, so that its two call sites share one copy of the code (instruction cache) */
+	auto fetch_tile = [&](int s) { FetchTileLdgsts<kNv12>(b, held[s], tiles_s + s * kTileBytes, lane); };
 
 #if HDB_TRACE
 	const unsigned long long t_entry = GlobalTimerNs();
@@ -562,16 +576,21 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_consta
 			const int fcol = x_img + 4 * (fword - 3);
 			const bool f_lane = fcol >= 0 && fcol < pl.pw;
 			if (kLoad == kLoadLdgsts && !kNv12 && chroma && b.chroma_skew) {
-				/* the item's 256 bytes per row of the VIRTUAL plane, word by word to the image samples they are */
-				const int vr0 = 8 * lby0, vc0 = 8 * bx0;                  /* virtual padded row / column of tile word 3 */
+				/* the item's 256 bytes per row of the VIRTUAL plane (tile words 3 .. 66), word by word to the image
+				 * samples they are */
+				SkewWalk wk[2];
+#pragma unroll
+				for (int k = 0; k < 2; k++) wk[k].Start(b, 8 * lby0, 8 * bx0 + 4 * (lane + 32 * k));
+				const u32 *sp = tile + 3 + lane;
+#pragma unroll 1
 				for (int rr = 0; rr < kTileH; rr++) {
 #pragma unroll
 					for (int k = 0; k < 2; k++) {
-						const int wi = lane + 32 * k;
-						int ix, iy;
-						if (SkewToImage(b, vr0 + rr, vc0 + 4 * wi, ix, iy))
-							*reinterpret_cast<u32 *>(dst + (long long)iy * pl.pitch + ix) = tile[rr * kTileWords + 3 + wi];
+						const long long off = wk[k].ImageOffset(b, pl.pitch);
+						if (off >= 0) *reinterpret_cast<u32 *>(dst + off) = sp[32 * k];
+						wk[k].NextRow(b);
 					}
+					sp += kTileWords;
 				}
 			} else if (kLoad == kLoadLdgsts) {
 				/* rows start on 8-byte boundaries: 64-bit stores.  The item's columns begin 4 bytes before such a
@@ -581,14 +600,15 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_consta
 				const int col = uv ? xb0 - 8 + 8 * lane : xb0 + 8 * lane;
 				const bool col_ok = (uv || lane < 31) && col >= 0 && col < pl.pw;
 				const unsigned char *sp = tile8 + (uv ? 8 : 16) + 8 * lane;
-#pragma unroll 4
+				unsigned char *gp = dst + (long long)y0 * pl.pitch + col;
+#pragma unroll 1
 				for (int rr = 0; rr < kTileH; rr++) {
 					const int y = y0 + rr;
-					if (col_ok && y >= 0 && y < pl.buf_rows)
-						*reinterpret_cast<uint2 *>(dst + (long long)y * pl.pitch + col) = *reinterpret_cast<const uint2 *>(sp + rr * kTileW);
+					if (col_ok && y >= 0 && y < pl.buf_rows) *reinterpret_cast<uint2 *>(gp) = *reinterpret_cast<const uint2 *>(sp);
+					sp += kTileW; gp += pl.pitch;
 				}
 				if (!uv) {
-#pragma unroll
+#pragma unroll 1
 					for (int r0 = 0; r0 < kTileH; r0 += 16) {
 						const int rr = r0 + (lane >> 1), y = y0 + rr;
 						const int fw = (lane & 1) ? 66 : 3;                      /* tile word (byte 264 or 12); plane byte xb0 + 248 or xb0 - 4 */

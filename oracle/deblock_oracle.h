@@ -138,6 +138,32 @@ typedef struct hdbo_block_info {
 void hdbo_derive_edges(const hdbo_block_info *info, unsigned width, unsigned height,
 	uint8_t *vert_edges, uint8_t *hor_edges);
 
+/* ---------------------------------------------------------------------------
+ * Sample adaptive offset: SURVEY.md section 8(f) rank 3, the in-loop stage that follows deblocking in HEVC.
+ * ABSENT FROM THE REFERENCE (its in-loop chain ends with the deblocking filter, cpu.h:134-993), so this is a
+ * restatement of the published process (H.265 8.7.3) and PARITY IS UNPINNED BY NATURE.  What bounds the risk of a
+ * transcription error: oracle/sao_spec.py, a second statement written independently in numpy terms, must agree
+ * with this one on random and exhaustive-small inputs (tests/test_sao.py).
+ *
+ * Per coding tree block (ctb_size x ctb_size luma samples, ctb_size/2 square for each chroma plane of a 4:2:0
+ * frame) and colour component: type 0 off; 1 band offset -- band = sample >> (bit depth - 5), the four
+ * consecutive bands starting at band_position (wrapping at 32) get offset[0..3]; 2 edge offset -- the sample is
+ * compared with its two neighbours along the class's direction (0 horizontal, 1 vertical, 2 the 135-degree
+ * diagonal (up-left, down-right), 3 the 45-degree one (up-right, down-left)), edgeIdx = 2 + sign(c - a) +
+ * sign(c - b), categories 0 / 1 / 3 / 4 get offset[0..3] (a local minimum, a concave corner, a convex corner, a
+ * local maximum), category 2 nothing; a sample with a neighbour outside the picture is left alone.  Neighbours
+ * are always the INPUT (deblocked) samples.  Results are clipped to the sample range.  8-bit samples.
+ * params[3][ctb_rows][ctb_cols], ctb_rows = ceil(height / ctb_size), ctb_cols = ceil(width / ctb_size).
+ */
+typedef struct hdbo_sao_params {
+	uint8_t type;        /* 0 off, 1 band offset, 2 edge offset */
+	uint8_t position;    /* band offset: first band, 0..31; edge offset: class, 0..3 */
+	int8_t offset[4];
+} hdbo_sao_params;      /* 6 bytes */
+
+int hdbo_sao_frame(const uint8_t *in, uint8_t *out, unsigned width, unsigned height,
+	const hdbo_sao_params *params, unsigned ctb_size);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,6 +53,7 @@ def _load_port():
                                              _u8p, C.c_uint, _u8p, C.c_uint]
     lib.hdbo_derive_edges.argtypes = [C.c_void_p, C.c_uint, C.c_uint, _u8p, _u8p]
     lib.hdbo_derive_edges.restype = None
+    lib.hdbo_sao_frame.argtypes = [_u8p, _u8p, C.c_uint, C.c_uint, C.c_void_p, C.c_uint]
     lib.hdbo_deblock_frame16.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_uint,
                                          _u8p, C.c_uint, _u8p, C.c_uint, C.c_uint, C.c_int]
     return lib
@@ -220,6 +221,22 @@ def deblock_frame16(frame, w, h, qp, vert=None, hor=None, bit_depth=10, edges=Fa
     if rc:
         raise OracleError({1: "Width and height of image must be multiplier of sample block size",
                            2: "Incorrect size of input boundary strenght array"}[rc])
+    return out
+
+
+SAO_PARAMS = np.dtype([("type", np.uint8), ("position", np.uint8), ("offset", np.int8, (4,))])
+
+
+def sao_frame(frame, w, h, params, ctb_size=64):
+    """Sample adaptive offset of one 8-bit YV12 frame (deblock_oracle.h: hdbo_sao_frame; H.265 8.7.3, unpinned: the
+    reference has no SAO).  params: SAO_PARAMS[3, ceil(h / ctb), ceil(w / ctb)]."""
+    frame = _check_frame(frame, w, h)
+    params = np.ascontiguousarray(params, SAO_PARAMS)
+    assert params.shape == (3, (h + ctb_size - 1) // ctb_size, (w + ctb_size - 1) // ctb_size), params.shape
+    out = np.empty_like(frame)
+    rc = port().hdbo_sao_frame(_ptr(frame), _ptr(out), w, h, params.ctypes.data, ctb_size)
+    if rc:
+        raise OracleError("sao: bad size or ctb size")
     return out
 
 
