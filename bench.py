@@ -44,6 +44,8 @@ WORKLOADS = {
     "4k_nv12_512": (3840, 2160, 512, "synthetic 3840x2160 NV12 batch of 512 frames, random QP/BS maps"),
     # 10-bit samples in 16-bit containers, planar (yuv420p10le); one GPU
     "4k_yuv420p10_512": (3840, 2160, 512, "synthetic 3840x2160 planar 10-bit (16-bit containers) batch of 512 frames, random QP/BS maps"),
+    # the in-loop pair, deblocking then sample adaptive offset; one GPU
+    "4k_sao256": (3840, 2160, 256, "synthetic 3840x2160 YV12 batch of 256 frames: deblocking filter, then sample adaptive offset with random per-CTB parameters (a third off, a third band, a third edge)"),
     # block data -> edge maps (bs | qp << 2) -> per-edge-QP filter; one GPU
     "4k_edges512": (3840, 2160, 512, "synthetic 3840x2160 YV12 batch of 512 frames, per-8x8-block decoder data -> derived edge maps -> per-edge-QP filter"),
 }
@@ -266,7 +268,7 @@ def workload_frames(torch, first, n, w, h, seed, device="cuda"):
     return frames, qp, vbs, hbs
 
 
-WORKLOAD_SEED = {"4k_yuv420p10_512": 5000, "4k_batch1024": 1000, "1080p_batch256": 2000, "4k_nv12_512": 3000, "4k_edges512": 4242, "8k_strips": 77}
+WORKLOAD_SEED = {"4k_sao256": 6000, "4k_yuv420p10_512": 5000, "4k_batch1024": 1000, "1080p_batch256": 2000, "4k_nv12_512": 3000, "4k_edges512": 4242, "8k_strips": 77}
 
 
 def workload_config(name, world, gen_device):
@@ -343,6 +345,75 @@ def run_reference_arm(args, rank):
             "cpu_baseline": {"value": round(value, 1), "unit": UNIT, "cores": used, "kind": kind, "sample": sample, "detail": detail},
             "e2e": {"value": round(value, 1), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def exact_block_shape(nbx, nby, limit=1024):
+    """A thread-block shape (dx, dy) with dx | nbx and dy | nby: the reference's kernels have no bounds guard
+    (gpu.cu:540-541), so its rounded-up grid (gpu.cu:1268) must not round.  The most threads under `limit`,
+    wider first."""
+    best = (1, 1)
+    for dx in range(1, min(nbx, limit) + 1):
+        if nbx % dx:
+            continue
+        for dy in range(1, min(nby, limit // dx) + 1):
+            if nby % dy == 0 and (dx * dy, dx) > (best[0] * best[1], best[0]):
+                best = (dx, dy)
+    return best
+
+
+def run_reference_gpu_arm(args, rank):
+    """Courtesy datapoint: the reference's OWN CUDA kernels (hevc_deblocking_filter_gpu.cu,
+    unmodified, compiled for sm_100a by oracle/Makefile into oracle/_ref/ref_gpu_demo) on one frame of the workload,
+    timed by the reference's own protocol (gpu.cu:1246-1303: wall clock around synchronous copies and three launches).
+    Not an oracle and not bit-exact: its kernels differ from its CPU filter."""
+    if rank != 0:
+        return
+    import re
+    import tempfile
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_gpu_demo")
+    w, h, total, desc = WORKLOADS[args.workload]
+    if not os.path.exists(exe):
+        print(json.dumps({"impl": "reference_gpu", "unavailable": "oracle/_ref/ref_gpu_demo has not been built (needs /root/reference and nvcc)"}), flush=True)
+        return
+    import torch
+    from oracle import oracle_py as orc
+    gen_device = "cuda" if torch.cuda.is_available() else "cpu"
+    if args.workload == "image2_single":
+        from tests import common
+        frame, qp = common.fixture("image2_768x576.yuv"), 30
+    else:
+        t_f, t_q, _, _ = workload_frames(torch, 0, 1, w, h, WORKLOAD_SEED.get(args.workload, 0), gen_device)
+        frame, qp = t_f[0].cpu().numpy(), int(t_q[0])
+    d1 = exact_block_shape((w + 8) // 8, (h + 8) // 8)
+    d2 = exact_block_shape((w // 2 + 8) // 8, (h // 2 + 8) // 8)
+    reps = 1 + args.warmup + args.steps
+    with tempfile.TemporaryDirectory() as tmp:
+        fin, fout = os.path.join(tmp, "in.yuv"), os.path.join(tmp, "out.yuv")
+        frame.tofile(fin)
+        p = subprocess.run([exe, fin, fout, str(w), str(h), str(qp), str(d1[0]), str(d1[1]), str(d2[0]), str(d2[1]), str(reps)],
+                           capture_output=True, text=True, timeout=300)
+        if p.returncode != 0 or not os.path.exists(fout):
+            print(json.dumps({"impl": "reference_gpu", "unavailable": "ref_gpu_demo failed: %s" % (p.stderr.strip() or p.stdout.strip())[-200:]}), flush=True)
+            return
+        got = np.fromfile(fout, np.uint8)
+    k = [float(x) for x in re.findall(r"Execution Time without copy on GPU: ([0-9.eE+-]+)s", p.stdout)][1 + args.warmup:]
+    c = [float(x) for x in re.findall(r"Execution Time with copy on GPU: ([0-9.eE+-]+)s", p.stdout)][1 + args.warmup:]
+    want = orc.deblock_frame(frame, w, h, qp)
+    diff = int((got != want).sum()) if got.size == want.size else -1
+    mpix = w * h / 1e6
+    value, e2e = mpix / float(np.median(k)), mpix / float(np.median(c))
+    line = {"impl": "reference_gpu", "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(float(np.median(k)) * 1e3, 4), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(args.workload, 1, gen_device),
+            "timing": "the reference's own protocol (gpu.cu:1246-1303): host wall clock around three launches + cudaDeviceSynchronize, one frame per call",
+            "label": "courtesy datapoint: the reference's own CUDA kernels recompiled for sm_100a; NOT an oracle and NOT bit-exact",
+            "sample": "frame 0 of the workload, default boundary strengths (ExecuteGpu has no setter), one frame per ExecuteGpu call",
+            "block_shapes": {"luma": list(d1), "chroma": list(d2), "why": "exact divisors of the block counts: the reference's kernels have no bounds guard"},
+            "bytes_differing_from_the_reference_cpu_filter": diff, "frame_bytes": int(want.size),
+            "e2e": {"value": round(e2e, 1), "unit": UNIT, "h2d_bytes_per_step": int(want.size), "d2h_bytes_per_step": int(want.size),
+                    "what": "the reference's 'Execution Time with copy on GPU' (padded planes + 4 BS arrays in, padded planes out, synchronous cudaMemcpy)"},
+            "gpu_launches": 3 * args.steps}
     print(json.dumps(line), flush=True)
 
 
@@ -996,12 +1067,90 @@ def run_edges(args):
     dev.close()
 
 
+def run_sao(args):
+    """SURVEY.md section 8(f) rank 3 on one GPU: SaoKernel alone, DeblockTiledKernel alone and the chained pair
+    (hdb_deblock_sao_batch_device) on frames resident in HBM; parity of a strided sample against the oracles."""
+    import torch
+    import gpu_video_codec_b200 as hdb
+    from oracle import oracle_py as orc
+    quiet_stdout()
+    torch.cuda.set_device(0)
+    w, h, n, desc = WORKLOADS[args.workload]
+    fb, ctb = 3 * w * h // 2, 64
+    dev = hdb.Deblocker(0)
+    stream = torch.cuda.current_stream().cuda_stream
+    frames, qp, vbs, hbs = workload_frames(torch, 0, n, w, h, WORKLOAD_SEED[args.workload], "cuda")
+    rows, cols = (h + ctb - 1) // ctb, (w + ctb - 1) // ctb
+    g = torch.Generator(device="cuda").manual_seed(17)
+    R = lambda lo, hi, shape: torch.randint(lo, hi, shape, device="cuda", generator=g, dtype=torch.int32)
+    typ = R(0, 3, (n, 3, rows, cols))
+    pos = torch.where(typ == 1, R(0, 32, typ.shape), R(0, 4, typ.shape))
+    mag = R(0, 8, typ.shape + (4,))
+    sign = torch.where((typ == 2)[..., None], torch.tensor([1, 1, -1, -1], device="cuda", dtype=torch.int32).expand(mag.shape),
+                       2 * R(0, 2, mag.shape) - 1)
+    params = torch.cat([typ[..., None], pos[..., None], (mag * sign) & 0xff], dim=-1).to(torch.uint8).contiguous()   # [n, 3, rows, cols, 6]
+    deb = torch.empty_like(frames)
+    out = torch.empty_like(frames)
+    out_pair = torch.empty_like(frames)
+
+    def timed(fn, reps):
+        for _ in range(max(args.warmup, 3)):
+            fn()
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+        ev[0].record()
+        for i in range(reps):
+            fn()
+            ev[i + 1].record()
+        torch.cuda.synchronize()
+        return ev[0].elapsed_time(ev[-1]) / reps
+
+    sampler = ClockSampler(0)
+    sampler.start()
+    l0 = dev.kernel_launch_count()
+    ms_deb = timed(lambda: dev.deblock_batch_device(frames, deb, n, w, h, qp, vbs, hbs, stream=stream), args.steps)
+    ms_sao = timed(lambda: dev.sao_batch_device(deb, out, n, w, h, params, ctb, stream=stream), args.steps)
+    ms_pair = timed(lambda: dev.deblock_sao_batch_device(frames, out_pair, n, w, h, qp, vbs, hbs, params, ctb, stream=stream), args.steps)
+    launches = dev.kernel_launch_count() - l0
+    clocks = sampler.stop()
+    if not torch.equal(out, out_pair):
+        raise SystemExit("PARITY FAILURE: the chained pair differs from the two stages run one after the other")
+    idx = [0, n // 3, (2 * n) // 3, n - 1]
+    np_par = params[idx].cpu().numpy().reshape(len(idx), 3, rows, cols, 6).copy().view(orc.SAO_PARAMS).reshape(len(idx), 3, rows, cols)
+    for k, f in enumerate(idx):
+        d = orc.deblock_frame(frames[f].cpu().numpy(), w, h, int(qp[f]), vbs[f].cpu().numpy(), hbs[f].cpu().numpy())
+        if not np.array_equal(deb[f].cpu().numpy(), d):
+            raise SystemExit("PARITY FAILURE: deblocked frame %d differs from the oracle" % f)
+        if not np.array_equal(out[f].cpu().numpy(), orc.sao_frame(d, w, h, np_par[k], ctb)):
+            raise SystemExit("PARITY FAILURE: sample adaptive offset of frame %d differs from the oracle" % f)
+    peak, peak_src = measured_peak()
+    mpix = n * w * h / 1e6
+    alg_sao = (2 * fb + 6 * 3 * rows * cols) * n                # every sample read once and written once + the parameters
+    alg_deb = alg_bytes_per_frame(w, h) * n
+    line = {"metric": METRIC, "value": round(mpix / (ms_pair / 1e3), 1), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_pair, 4), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(args.workload, 1, "cuda"),
+            "timing": "CUDA events on the launching stream",
+            "roofline": {"bound": "hbm", "achieved": round(alg_sao / (ms_sao / 1e3) / 1e9, 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(alg_sao / (ms_sao / 1e3) / 1e9 / peak, 4), "traffic": None, "traffic_source": "no ncu capture of this workload",
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_sao, "kernel": "SaoKernel", "mean_launch_ms": round(ms_sao, 4)},
+            "deblock_alone": {"ms": round(ms_deb, 4), "mpixel_s": round(mpix / (ms_deb / 1e3), 1), "achieved_gbs": round(alg_deb / (ms_deb / 1e3) / 1e9, 1)},
+            "sao_alone": {"ms": round(ms_sao, 4), "mpixel_s": round(mpix / (ms_sao / 1e3), 1)},
+            "deblock_plus_sao": {"ms": round(ms_pair, 4), "mpixel_s": round(mpix / (ms_pair / 1e3), 1), "ratio_to_deblock_alone": round(ms_pair / ms_deb, 3),
+                                 "api": "hdb_deblock_sao_batch_device (two kernels on one stream, scratch of the call's own between them)"},
+            "gpu_launches": launches, "clocks": clocks,
+            "parity": {"bit_exact": True, "frames_checked": len(idx), "changed_fraction_by_sao": round(float((out[idx] != deb[idx]).float().mean()), 4),
+                       "checker": "port (oracle/deblock_oracle.c: hdbo_deblock_frame pinned to the reference; hdbo_sao_frame H.265 8.7.3 restated, unpinned: the reference has no SAO)"}}
+    emit(line)
+    dev.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference_gpu"])
     ap.add_argument("--workload", default="4k_batch1024", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-sample", type=int, default=0, help="frames in the CPU sample (default 256)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -1013,6 +1162,9 @@ def main():
     if args.impl == "reference":
         run_reference_arm(args, rank)
         return
+    if args.impl == "reference_gpu":
+        run_reference_gpu_arm(args, rank)
+        return
     if args.workload == "8k_strips":
         if rank == 0:
             run_strips(args)
@@ -1020,6 +1172,10 @@ def main():
     if args.workload == "4k_edges512":
         if rank == 0:
             run_edges(args)
+        return
+    if args.workload == "4k_sao256":
+        if rank == 0:
+            run_sao(args)
         return
     if world != args.gpus and world == 1 and args.gpus > 1:
         raise SystemExit("--gpus %d needs torchrun: python -m torch.distributed.run --nnodes=1 --nproc-per-node %d "

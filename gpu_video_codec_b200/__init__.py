@@ -15,6 +15,7 @@ from .binding import (  # noqa: F401
     FLAG_SAMPLES16,
     MultiDeblocker,
     Nv12Surfaces,
+    SAO_PARAMS,
     StripPlanes,
     Surfaces,
     Timing,

@@ -146,6 +146,9 @@ def load_library():
                                                      C.c_uint, vp, vp, vp, C.c_uint, vp]
     lib.hdb_execute_gpu_sequence.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_uint, C.c_uint, C.c_uint, C.c_uint,
                                              C.POINTER(C.c_uint), C.POINTER(Timing)]
+    lib.hdb_sao_batch_device.argtypes = [vp, vp, vp, C.c_uint, C.c_uint, C.c_uint, vp, C.c_uint, vp]
+    lib.hdb_sao_batch.argtypes = [vp, vp, vp, C.c_uint, C.c_uint, C.c_uint, vp, C.c_uint]
+    lib.hdb_deblock_sao_batch_device.argtypes = [vp, vp, vp, C.c_uint, C.c_uint, C.c_uint, vp, vp, vp, C.c_uint, vp, C.c_uint, vp]
     lib.hdb_kernel_launch_count.argtypes = [vp]
     lib.hdb_kernel_launch_count.restype = C.c_ulonglong
     lib.hdb_multi_create.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), C.c_int]
@@ -186,6 +189,9 @@ def default_boundary_strength(width, height):
         raise DeblockError(rc, lib.hdb_status_string(rc).decode())
     return v, h
 
+
+# hdb_sao_params: sample adaptive offset of one coding tree block and colour component (6 bytes)
+SAO_PARAMS = np.dtype([("type", np.uint8), ("position", np.uint8), ("offset", np.int8, (4,))])
 
 # hdb_block_info: what a decoder knows about one 8x8 luma block (12 bytes)
 BLOCK_INFO = np.dtype([("mv", np.int16, (2, 2)), ("ref", np.int8, (2,)), ("flags", np.uint8), ("qp", np.uint8)])
@@ -377,6 +383,26 @@ class Deblocker:
         self._check(self._lib.hdb_deblock_nv12_surfaces_device(self._ctx, C.byref(src), C.byref(dst), n_frames, width,
                                                                height, _addr(d_qp), _addr(d_vert), _addr(d_hor), flags,
                                                                stream))
+
+    # --- sample adaptive offset (H.265 8.7.3; absent from the reference) ---
+    def sao_batch(self, frames, width, height, params, ctb_size=64, out=None):
+        """Host frames uint8[n, 3wh/2] and SAO_PARAMS[n, 3, ceil(h / ctb), ceil(w / ctb)] -> offset frames."""
+        n = int(frames.shape[0])
+        params = np.ascontiguousarray(params, SAO_PARAMS)
+        if out is None:
+            out = np.empty_like(frames)
+        self._check(self._lib.hdb_sao_batch(self._ctx, _addr(frames), _addr(out), n, width, height, _addr(params), ctb_size))
+        return out
+
+    def sao_batch_device(self, d_in, d_out, n_frames, width, height, d_params, ctb_size=64, stream=None):
+        self._check(self._lib.hdb_sao_batch_device(self._ctx, _addr(d_in), _addr(d_out), n_frames, width, height,
+                                                   _addr(d_params), ctb_size, stream))
+
+    def deblock_sao_batch_device(self, d_in, d_out, n_frames, width, height, d_qp, d_vert, d_hor, d_params, ctb_size=64,
+                                 flags=0, stream=None):
+        self._check(self._lib.hdb_deblock_sao_batch_device(self._ctx, _addr(d_in), _addr(d_out), n_frames, width, height,
+                                                           _addr(d_qp), _addr(d_vert), _addr(d_hor), flags, _addr(d_params),
+                                                           ctb_size, stream))
 
     def deblock_surfaces_device(self, src, dst, n_frames, width, height, d_qp, d_vert_bs=None, d_hor_bs=None,
                                 stream=None):

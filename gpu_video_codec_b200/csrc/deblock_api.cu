@@ -1128,6 +1128,98 @@ int hdb_execute_gpu_sequence(hdb_context *ctx, const char *input_file_name, cons
 	return rc;
 }
 
+/* ---- sample adaptive offset ---- */
+
+static int ValidateSao(hdb_context *ctx, unsigned width, unsigned height, unsigned ctb_size)
+{
+	int rc = ValidateFrameArgs(ctx, width, height, nullptr, 0, nullptr, 0, false);
+	if (rc) return rc;
+	if (ctb_size != 16 && ctb_size != 32 && ctb_size != 64) return Fail(ctx, HDB_ERR_INVALID_ARG, "coding tree block size must be 16, 32 or 64");
+	return HDB_OK;
+}
+
+int hdb_sao_batch_device(hdb_context *ctx, const void *d_frames_in, void *d_frames_out, unsigned n_frames,
+	unsigned width, unsigned height, const hdb_sao_params *d_params, unsigned ctb_size, void *stream)
+{
+	if (!ctx) return HDB_ERR_INVALID_ARG;
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	if (!d_frames_in || !d_frames_out || !d_params || n_frames == 0) return Fail(ctx, HDB_ERR_INVALID_ARG, "NULL buffer or empty batch");
+	if (d_frames_in == d_frames_out) return Fail(ctx, HDB_ERR_INVALID_ARG, "sample adaptive offset runs out of place: a sample's neighbours are input samples");
+	if (((uintptr_t)d_frames_in | (uintptr_t)d_frames_out) % 4 != 0) return Fail(ctx, HDB_ERR_INVALID_ARG, "frames must be 4-byte aligned");
+	int rc = ValidateSao(ctx, width, height, ctb_size);
+	if (rc) return rc;
+	DeviceGuard guard(ctx->device);
+	HDB_CUDA(ctx, LaunchSao(static_cast<const unsigned char *>(d_frames_in), static_cast<unsigned char *>(d_frames_out), (int)n_frames,
+		(int)width, (int)height, d_params, (int)ctb_size, ctx->prop.multiProcessorCount, static_cast<cudaStream_t>(stream)));
+	ctx->launches += 1;
+	return HDB_OK;
+}
+
+int hdb_sao_batch(hdb_context *ctx, const unsigned char *frames_in, unsigned char *frames_out, unsigned n_frames,
+	unsigned width, unsigned height, const hdb_sao_params *params, unsigned ctb_size)
+{
+	if (!ctx) return HDB_ERR_INVALID_ARG;
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	if (!frames_in || !frames_out || !params || n_frames == 0) return Fail(ctx, HDB_ERR_INVALID_ARG, "NULL buffer or empty batch");
+	int rc = ValidateSao(ctx, width, height, ctb_size);
+	if (rc) return rc;
+	DeviceGuard guard(ctx->device);
+	const size_t fb = (size_t)width * height * 3 / 2;
+	const size_t pb = sizeof(hdb_sao_params) * 3 * ((height + ctb_size - 1) / ctb_size) * ((width + ctb_size - 1) / ctb_size);
+	/* a bounded number of frames at a time, buffers of the call's own in stream order */
+	const unsigned chunk = (unsigned)std::min<size_t>(n_frames, std::max<size_t>(1, ((size_t)256 << 20) / fb));
+	cudaStream_t st = ctx->s_k;
+	unsigned char *d_in = nullptr, *d_out = nullptr, *d_par = nullptr;
+	HDB_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void **>(&d_in), fb * chunk, st));
+	HDB_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void **>(&d_out), fb * chunk, st));
+	HDB_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void **>(&d_par), pb * chunk, st));
+	cudaError_t e = cudaSuccess;
+	for (unsigned f0 = 0; f0 < n_frames && e == cudaSuccess; f0 += chunk) {
+		const unsigned nf = std::min(chunk, n_frames - f0);
+		e = cudaMemcpyAsync(d_in, frames_in + (size_t)f0 * fb, fb * nf, cudaMemcpyHostToDevice, st);
+		if (e == cudaSuccess) e = cudaMemcpyAsync(d_par, reinterpret_cast<const unsigned char *>(params) + (size_t)f0 * pb, pb * nf, cudaMemcpyHostToDevice, st);
+		if (e == cudaSuccess) e = LaunchSao(d_in, d_out, (int)nf, (int)width, (int)height, d_par, (int)ctb_size, ctx->prop.multiProcessorCount, st);
+		if (e == cudaSuccess) e = cudaMemcpyAsync(frames_out + (size_t)f0 * fb, d_out, fb * nf, cudaMemcpyDeviceToHost, st);
+		ctx->launches += 1;
+	}
+	cudaFreeAsync(d_in, st); cudaFreeAsync(d_out, st); cudaFreeAsync(d_par, st);
+	const cudaError_t e2 = cudaStreamSynchronize(st);
+	if (e != cudaSuccess) return FailCuda(ctx, e, "sample adaptive offset");
+	if (e2 != cudaSuccess) return FailCuda(ctx, e2, "cudaStreamSynchronize");
+	return HDB_OK;
+}
+
+int hdb_deblock_sao_batch_device(hdb_context *ctx, const void *d_frames_in, void *d_frames_out, unsigned n_frames,
+	unsigned width, unsigned height, const unsigned *d_qp, const unsigned char *d_vert, const unsigned char *d_hor,
+	unsigned flags, const hdb_sao_params *d_params, unsigned ctb_size, void *stream)
+{
+	if (!ctx) return HDB_ERR_INVALID_ARG;
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	if (flags & ~HDB_FLAG_EDGE_MAPS) return Fail(ctx, HDB_ERR_INVALID_ARG, "unknown flag");
+	if (!d_frames_in || !d_frames_out || !d_qp || !d_params || n_frames == 0) return Fail(ctx, HDB_ERR_INVALID_ARG, "NULL buffer or empty batch");
+	int rc = ValidateFrameArgs(ctx, width, height, d_vert, 0, d_hor, 0, false);
+	if (!rc) rc = ValidateSao(ctx, width, height, ctb_size);
+	if (rc) return rc;
+	DeviceGuard guard(ctx->device);
+	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	const size_t fb = (size_t)width * height * 3 / 2;
+	unsigned char *scratch = nullptr;
+	HDB_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void **>(&scratch), fb * n_frames, st));
+	const FrameView view = WholeFrameView((int)width, (int)height);
+	rc = EnqueueFilter(ctx, view, static_cast<const unsigned char *>(d_frames_in), scratch, (int)n_frames, d_qp, 0,
+		d_vert, hdb_num_vert_bs(width, height), d_hor, hdb_num_hor_bs(width, height), st, nullptr, (flags & HDB_FLAG_EDGE_MAPS) != 0);
+	cudaError_t e = cudaSuccess;
+	if (!rc) {
+		e = LaunchSao(scratch, static_cast<unsigned char *>(d_frames_out), (int)n_frames, (int)width, (int)height, d_params,
+			(int)ctb_size, ctx->prop.multiProcessorCount, st);
+		ctx->launches += 1;
+	}
+	cudaFreeAsync(scratch, st);
+	if (rc) return rc;
+	if (e != cudaSuccess) return FailCuda(ctx, e, "LaunchSao");
+	return HDB_OK;
+}
+
 unsigned long long hdb_kernel_launch_count(const hdb_context *ctx) { return ctx ? ctx->launches : 0; }
 
 } // extern "C"

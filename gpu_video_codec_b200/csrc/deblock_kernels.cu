@@ -529,8 +529,12 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_consta
 		}
 		/* not unrolled: one copy of the block code, or the kernel outgrows the instruction cache
 		 * (unrolled, two block rows per item run 25 % slower than one) */
+		/* tc = 0 (QP <= 17, cpu.h:1028-1033): every correction is clipped to +-0 (cpu.h:1192-1211, 1254-1276,
+		 * 1464-1476) -- the frame passes through unchanged, so its items are only moved.  Chroma always takes the
+		 * frame's QP; luma does unless the strengths are edge bytes. */
+		const bool pass_through = fp.tc == 0 && (chroma || !kEdgeQp);
 #pragma unroll 1
-		for (int rb = 0; rb < kRB; rb++) {
+		for (int rb = 0; rb < (pass_through ? 0 : kRB); rb++) {
 			if (kNv12 && chroma) {
 				u32 s4 = bs[0];
 #pragma unroll

@@ -135,4 +135,11 @@ cudaError_t LaunchGeneric(const GenericBatch &b, cudaStream_t stream);
 cudaError_t LaunchDeriveEdges(const void *info, int width, int height, int n_frames,
 	unsigned char *vert_edges, unsigned char *hor_edges, cudaStream_t stream);
 
+/*
+ * Sample adaptive offset (sao_kernels.cu; H.265 8.7.3, absent from the reference): tight 8-bit YV12 frames in
+ * device memory, out of place, d_params = hdb_sao_params[n_frames][3][ceil(H / ctb)][ceil(W / ctb)].
+ */
+cudaError_t LaunchSao(const unsigned char *d_in, unsigned char *d_out, int n_frames, int width, int height,
+	const void *d_params, int ctb, int sm_count, cudaStream_t stream);
+
 } // namespace hdb

@@ -1,0 +1,177 @@
+/*
+ * sao_kernels.cu -- sample adaptive offset, the in-loop stage that follows deblocking in HEVC (SURVEY.md section
+ * 8(f) rank 3).  The reference stops after the deblocking filter (hevc_deblocking_filter_cpu.h:134-993 is the end
+ * of its in-loop chain), so this stage restates the published process (H.265 8.7.3) and is checked against
+ * oracle/deblock_oracle.c::hdbo_sao_frame, which in turn agrees with an independent second statement
+ * (oracle/sao_spec.py).  Parity is unpinned by nature.
+ *
+ * A separate pass, out of place: an edge offset needs the DEBLOCKED values of a sample's neighbours, and the
+ * blocks of the deblocking kernel are independent only up to their own 64 samples -- a tile would have to be
+ * deblocked with a one-block apron to offset its rim, which costs more than the second pass moves.
+ *
+ * One warp walks one column strip of 128 bytes (lane l: the four samples of word 32 * strip + l) down the rows of
+ * one coding-tree-block row of one plane, so the parameters a lane needs are constant for the walk.  A lane keeps
+ * the words of rows y - 1, y, y + 1 and their left / right neighbours (from the adjacent lanes by shuffle; the
+ * strip's first and last lane load theirs) in registers.  Four samples at a time as two 16x2 pairs, with the
+ * packed-halfword instructions the deblocking core uses:
+ *   edge offset  256 + sign(c - a) per half = max(min(256 + c - a, 257), 255); category 2 + sign + sign in 0..4
+ *   band offset  min(((c >> 3) - band_position) & 31, 4) in 0..4
+ *   either way the index picks the offset out of an 8-byte pool with one byte permute (selector nibble | 8 for the
+ *   sign-replicating upper byte), and VIADDMNMX.RELU adds it and clips to 0..255.
+ * Samples with a neighbour outside the picture are left alone through a per-byte keep mask.
+ */
+#include "deblock_kernels.cuh"
+#include "deblock_core.cuh"
+
+#include <algorithm>
+
+namespace hdb {
+
+constexpr int kSaoWarps = 4;
+
+struct SaoBatch {
+	const unsigned char *in; unsigned char *out;    /* tight YV12 frames, frame_stride apart */
+	long long frame_stride;
+	int n_frames, width, height;
+	int ctb;                                         /* luma CTB size: 16, 32 or 64 */
+	int ctb_cols, ctb_rows;
+	const unsigned char *params;                     /* hdb_sao_params[n][3][ctb_rows][ctb_cols], 6 bytes each */
+	/* task space: frame-major, then plane, CTB row, strip */
+	int strips_luma, strips_chroma, tasks_luma, tasks_chroma, tasks_per_frame;
+	long long total_tasks;
+	FastDiv div_tasks_per_frame, div_strips_luma, div_strips_chroma;
+};
+
+/* bytes (b0, b1) / (b2, b3) of a word as a 16x2 pair */
+__device__ __forceinline__ u32 PairA(u32 w) { return Prmt(w, 0u, 0x4140); }
+__device__ __forceinline__ u32 PairB(u32 w) { return Prmt(w, 0u, 0x4342); }
+
+/* 256 + sign(c - n) per half */
+__device__ __forceinline__ u32 SignBiased(u32 c, u32 n) { return Max2(Min2(c + 0x01000100u - n, 0x01010101u), 0x00ff00ffu); }
+
+/* offsets picked by the index halves (0..4) out of the pool, as signed halves */
+__device__ __forceinline__ u32 PickOffsets(u32 idx, u32 pool_lo, u32 pool_hi)
+{
+	const u32 t = idx * 0x11u;                                   /* nibble | nibble << 4 in bytes 0 and 2 */
+	const u32 sel = Prmt(t, 0u, 0x4420) | 0x8080u;               /* nibbles: i0, i0 | 8, i1, i1 | 8 */
+	return Prmt(pool_lo, pool_hi, sel);
+}
+
+__global__ void __launch_bounds__(kSaoWarps * 32)
+SaoKernel(const __grid_constant__ SaoBatch b)
+{
+	const int lane = threadIdx.x & 31;
+	const long long warp0 = (long long)blockIdx.x * kSaoWarps + (threadIdx.x >> 5);
+	const long long n_warps = (long long)gridDim.x * kSaoWarps;
+	for (long long task = warp0; task < b.total_tasks; task += n_warps) {
+		const uint32_t frame = b.div_tasks_per_frame.Div((uint32_t)task);
+		uint32_t r = (uint32_t)task - frame * (uint32_t)b.tasks_per_frame;
+		int plane = 0;
+		if (r >= (uint32_t)b.tasks_luma) { r -= (uint32_t)b.tasks_luma; plane = 1; if (r >= (uint32_t)b.tasks_chroma) { r -= (uint32_t)b.tasks_chroma; plane = 2; } }
+		const int strips = plane ? b.strips_chroma : b.strips_luma;
+		const uint32_t crow = plane ? b.div_strips_chroma.Div(r) : b.div_strips_luma.Div(r);
+		const int strip = (int)(r - crow * (uint32_t)strips);
+		const int pw = plane ? b.width >> 1 : b.width, ph = plane ? b.height >> 1 : b.height;
+		const int ctb = plane ? b.ctb >> 1 : b.ctb;
+		const long long plane_off = plane == 0 ? 0 : (long long)b.width * b.height + (plane == 2 ? (long long)(b.width >> 1) * (b.height >> 1) : 0);
+		const unsigned char *src = b.in + (long long)frame * b.frame_stride + plane_off;
+		unsigned char *dst = b.out + (long long)frame * b.frame_stride + plane_off;
+		const int pww = pw >> 2;                                 /* words per row */
+		const int x = 32 * strip + lane;                         /* this lane's word */
+		const bool live = x < pww;
+		const int y0 = (int)crow * ctb, y1 = min(y0 + ctb, ph);
+		/* parameters of the CTB this lane's samples lie in (a word never straddles CTBs: their width is a multiple of 4) */
+		u32 type = 0, pos = 0, pool_lo = 0, pool_hi = 0;
+		if (live) {
+			const unsigned char *p = b.params + 6ll * ((((long long)frame * 3 + plane) * b.ctb_rows + crow) * b.ctb_cols + (4 * x) / ctb);
+			type = __ldg(p); pos = __ldg(p + 1);
+			const u32 o0 = __ldg(p + 2), o1 = __ldg(p + 3), o2 = __ldg(p + 4), o3 = __ldg(p + 5);
+			if (type == 2) { pool_lo = o0 | (o1 << 8) | (o2 << 24); pool_hi = o3; pos &= 3u; }     /* categories 0, 1, (2: none), 3, 4 */
+			else { pool_lo = o0 | (o1 << 8) | (o2 << 16) | (o3 << 24); pool_hi = 0u; }            /* bands k = 0..3, (4: none) */
+		}
+		/* bytes that keep their value whatever the row: no edge offset at all, or the picture's first / last column
+		 * for every class but the vertical one */
+		u32 keep_cols = 0u;
+		if (type == 0u) keep_cols = 0xffffffffu;
+		else if (type == 2u && pos != 1u) keep_cols = (x == 0 ? 0x000000ffu : 0u) | (x == pww - 1 ? 0xff000000u : 0u);
+		const u32 band_add = (32u - pos) * 0x10001u;
+
+		u32 *orow = reinterpret_cast<u32 *>(dst) + (long long)y0 * pww + x;
+		/* words of a row for this lane: left neighbour, own, right neighbour (0 outside the picture: those samples are kept) */
+		auto load_row = [&](int y, u32 &L, u32 &C, u32 &R) {
+			L = C = R = 0u;
+			if (y < 0 || y >= ph) return;
+			const u32 *p = reinterpret_cast<const u32 *>(src) + (long long)y * pww + x;
+			if (live) C = __ldg(p);
+			L = __shfl_up_sync(0xffffffffu, C, 1);
+			R = __shfl_down_sync(0xffffffffu, C, 1);
+			if (lane == 0) L = (live && x > 0) ? __ldg(p - 1) : 0u;
+			if (lane == 31) R = (live && x + 1 < pww) ? __ldg(p + 1) : 0u;
+		};
+		u32 L0, C0, R0, L1, C1, R1, L2, C2, R2;
+		load_row(y0 - 1, L0, C0, R0);
+		load_row(y0, L1, C1, R1);
+		for (int y = y0; y < y1; y++) {
+			load_row(y + 1, L2, C2, R2);
+			u32 res = C1;
+			if (type == 2u) {
+				/* the two neighbours along the class's direction, as words aligned with C1 (8.7.3.2: hPos / vPos) */
+				const u32 l0 = __funnelshift_l(L0, C0, 8), r0 = __funnelshift_r(C0, R0, 8);
+				const u32 l1 = __funnelshift_l(L1, C1, 8), r1 = __funnelshift_r(C1, R1, 8);
+				const u32 l2 = __funnelshift_l(L2, C2, 8), r2 = __funnelshift_r(C2, R2, 8);
+				const u32 a = pos == 0u ? l1 : (pos == 1u ? C0 : (pos == 2u ? l0 : r0));
+				const u32 n = pos == 0u ? r1 : (pos == 1u ? C2 : (pos == 2u ? r2 : l2));
+				const u32 cA = PairA(C1), cB = PairB(C1);
+				const u32 iA = SignBiased(cA, PairA(a)) + SignBiased(cA, PairA(n)) - 0x01fe01feu;
+				const u32 iB = SignBiased(cB, PairB(a)) + SignBiased(cB, PairB(n)) - 0x01fe01feu;
+				const u32 rA = AddMinRelu2(cA, PickOffsets(iA, pool_lo, pool_hi), 0x00ff00ffu);
+				const u32 rB = AddMinRelu2(cB, PickOffsets(iB, pool_lo, pool_hi), 0x00ff00ffu);
+				res = Prmt(rA, rB, 0x6420);
+			} else if (type == 1u) {
+				const u32 cA = PairA(C1), cB = PairB(C1);
+				const u32 iA = MinU2((((cA >> 3) & 0x001f001fu) + band_add) & 0x001f001fu, 0x00040004u);
+				const u32 iB = MinU2((((cB >> 3) & 0x001f001fu) + band_add) & 0x001f001fu, 0x00040004u);
+				const u32 rA = AddMinRelu2(cA, PickOffsets(iA, pool_lo, pool_hi), 0x00ff00ffu);
+				const u32 rB = AddMinRelu2(cB, PickOffsets(iB, pool_lo, pool_hi), 0x00ff00ffu);
+				res = Prmt(rA, rB, 0x6420);
+			}
+			/* the picture's first / last row for every class but the horizontal one */
+			const u32 keep = (type == 2u && pos != 0u && (y == 0 || y == ph - 1)) ? 0xffffffffu : keep_cols;
+			if (live) *orow = (C1 & keep) | (res & ~keep);
+			L0 = L1; C0 = C1; R0 = R1; L1 = L2; C1 = C2; R1 = R2;
+			orow += pww;
+		}
+	}
+}
+
+cudaError_t LaunchSao(const unsigned char *d_in, unsigned char *d_out, int n_frames, int width, int height,
+	const void *d_params, int ctb, int sm_count, cudaStream_t stream)
+{
+	if (n_frames <= 0) return cudaSuccess;
+	SaoBatch b{};
+	b.in = d_in; b.out = d_out;
+	b.frame_stride = (long long)width * height * 3 / 2;
+	b.width = width; b.height = height; b.ctb = ctb;
+	b.ctb_cols = (width + ctb - 1) / ctb; b.ctb_rows = (height + ctb - 1) / ctb;
+	b.params = static_cast<const unsigned char *>(d_params);
+	b.strips_luma = (width / 4 + 31) / 32; b.strips_chroma = (width / 8 + 31) / 32;
+	/* the chroma planes have as many CTB rows as luma (a chroma CTB is half as high as the plane's share of rows) */
+	b.tasks_luma = b.strips_luma * b.ctb_rows; b.tasks_chroma = b.strips_chroma * b.ctb_rows;
+	b.tasks_per_frame = b.tasks_luma + 2 * b.tasks_chroma;
+	b.div_tasks_per_frame.Init((uint32_t)b.tasks_per_frame);
+	b.div_strips_luma.Init((uint32_t)b.strips_luma); b.div_strips_chroma.Init((uint32_t)b.strips_chroma);
+	/* frames per launch bounded by the 31-bit task index */
+	const long long max_frames = std::max<long long>(1, ((1ll << 31) - 1) / b.tasks_per_frame);
+	for (long long f0 = 0; f0 < n_frames; f0 += max_frames) {
+		SaoBatch part = b;
+		part.n_frames = (int)std::min<long long>(max_frames, n_frames - f0);
+		part.in = d_in + f0 * b.frame_stride; part.out = d_out + f0 * b.frame_stride;
+		part.params = b.params + 6ll * 3 * b.ctb_rows * b.ctb_cols * f0;
+		part.total_tasks = (long long)part.n_frames * b.tasks_per_frame;
+		const long long ctas = std::min<long long>((part.total_tasks + kSaoWarps - 1) / kSaoWarps, (long long)sm_count * 16);
+		SaoKernel<<<(unsigned)ctas, kSaoWarps * 32, 0, stream>>>(part);
+	}
+	return cudaGetLastError();
+}
+
+} // namespace hdb

@@ -290,6 +290,42 @@ int hdb_deblock_nv12_surfaces_device(hdb_context *ctx, const hdb_nv12_surfaces *
 int hdb_execute_gpu_sequence(hdb_context *ctx, const char *input_file_name, const char *output_file_name,
 	unsigned width, unsigned height, unsigned qp, unsigned flags, unsigned *n_frames, hdb_timing *timing);
 
+/* ---- sample adaptive offset: the in-loop stage after deblocking --------------------------------- */
+/*
+ * The third of the components next to the path: absent from the reference, whose in-loop
+ * chain ends with the deblocking filter (cpu.h:134-993), so this follows the published process (H.265 8.7.3) and
+ * has nothing in the reference to be compared with.  Per coding tree block (ctb_size x ctb_size luma samples,
+ * half that in each direction for the chroma planes; ctb_size 16, 32 or 64) and colour component:
+ *   type 0  off
+ *   type 1  band offset: band = sample >> 3; the four bands from `position` on (wrapping at 32) get offset[0..3]
+ *   type 2  edge offset: class `position` -- 0 horizontal, 1 vertical, 2 diagonal (up-left / down-right),
+ *           3 diagonal (up-right / down-left); a sample below both neighbours gets offset[0], below one and equal
+ *           to the other offset[1], above one and equal to the other offset[2], above both offset[3]; a sample
+ *           with a neighbour outside the picture is left alone
+ * results clipped to 0..255; neighbours are always input samples, so the stage runs out of place.
+ * params[n_frames][3][ceil(height / ctb_size)][ceil(width / ctb_size)], component order Y, U, V.  8-bit YV12.
+ */
+typedef struct hdb_sao_params {
+	unsigned char type;        /* 0, 1, 2 */
+	unsigned char position;    /* band position 0..31, or edge class 0..3 */
+	signed char offset[4];
+} hdb_sao_params;             /* 6 bytes */
+
+/* device pointers (d_out != d_in); asynchronous on `stream` */
+int hdb_sao_batch_device(hdb_context *ctx, const void *d_frames_in, void *d_frames_out, unsigned n_frames,
+	unsigned width, unsigned height, const hdb_sao_params *d_params, unsigned ctb_size, void *stream);
+/* host pointers (runs on the GPU: copy in, kernel, copy out) */
+int hdb_sao_batch(hdb_context *ctx, const unsigned char *frames_in, unsigned char *frames_out, unsigned n_frames,
+	unsigned width, unsigned height, const hdb_sao_params *params, unsigned ctb_size);
+/*
+ * The in-loop pair on device-resident frames: the deblocking filter (arguments as hdb_deblock_batch_device_ex,
+ * flags HDB_FLAG_EDGE_MAPS or 0) into scratch memory of the call's own, then sample adaptive offset into
+ * d_frames_out; both on `stream`, asynchronous.  d_frames_out may equal d_frames_in.
+ */
+int hdb_deblock_sao_batch_device(hdb_context *ctx, const void *d_frames_in, void *d_frames_out, unsigned n_frames,
+	unsigned width, unsigned height, const unsigned *d_qp, const unsigned char *d_vert, const unsigned char *d_hor,
+	unsigned flags, const hdb_sao_params *d_params, unsigned ctb_size, void *stream);
+
 /* number of filter-kernel launches made through ctx since creation */
 unsigned long long hdb_kernel_launch_count(const hdb_context *ctx);
 

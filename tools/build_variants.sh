@@ -11,7 +11,7 @@ for v in "$@"; do
 	d=../../build_variants/obj_$tag
 	mkdir -p $d
 	(
-	for f in deblock_kernels deblock_api deblock_multi; do
+	for f in deblock_kernels sao_kernels deblock_api deblock_multi; do
 		nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v \
 			"$@" -c $f.cu -o $d/$f.o > $d/$f.log 2>&1 &
 	done

@@ -1,0 +1,12 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_sao.py -q -x > gpurun_out/r02e_pytest_sao.log 2>&1; echo "pytest sao exit $?" >> gpurun_out/r02e_pytest_sao.log
+tail -8 gpurun_out/r02e_pytest_sao.log
+timeout 600 python bench.py --workload 4k_sao256 > gpurun_out/r02e_bench_sao.json 2> gpurun_out/r02e_bench_sao.err; echo "bench sao exit $?"; tail -3 gpurun_out/r02e_bench_sao.err
+cat gpurun_out/r02e_bench_sao.json | head -c 2500
+timeout 120 python tools/quick_time.py --w 1080 --h 1920 --n 256 > gpurun_out/plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:DeblockTiled -s 3 -c 1 -o gpurun_out/prof_r02e_ldgsts python tools/quick_time.py --w 1080 --h 1920 --n 256 --iters 2 > gpurun_out/r02e_ncu.log 2>&1
+tail -2 gpurun_out/r02e_ncu.log
+timeout 300 python bench.py --impl reference_gpu --steps 5 --warmup 2 > gpurun_out/r02e_bench_refgpu.json 2> gpurun_out/r02e_bench_refgpu.err; echo "refgpu exit $?"; cat gpurun_out/r02e_bench_refgpu.json | head -c 1800
+timeout 300 python bench.py --impl reference_gpu --workload image2_single --steps 5 --warmup 2 > gpurun_out/r02e_bench_refgpu_image2.json 2>> gpurun_out/r02e_bench_refgpu.err; head -c 600 gpurun_out/r02e_bench_refgpu_image2.json
+timeout 300 python tools/quick_time.py --n 1024 --iters 10 2>&1 | tail -1
+ls /usr/lib/x86_64-linux-gnu 2>/dev/null | grep -i -E "nvcuvid|nvidia-encode|nvjpeg" | head
