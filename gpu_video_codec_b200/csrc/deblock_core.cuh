@@ -606,47 +606,52 @@ HDB_FN void ChromaBlock(u32 (&lo)[8], u32 (&hi)[8], u32 bs_ver1, u32 bs_ver2, u3
 struct BlockWords { u32 mv0, mv1, meta; };
 enum { kBlkIntra = 1, kBlkCbf = 2, kBlkTuLeft = 4, kBlkTuTop = 8, kBlkPuLeft = 16, kBlkPuTop = 32 };
 
-/* non-zero iff the two vectors (x | y << 16, signed halves) differ by 4 or more in a component: flip the
- * sign bits (signed order -> unsigned order), |a - b| per half as max - min (no borrow between the
- * halves, exact up to 65535), then any bit above bit 1 */
-HDB_FN u32 MvFarBits(u32 a, u32 b)
+/*
+ * A record is normalised once, by the thread that fetches it, and then used by the three edges it borders:
+ *   - the sign bits of the vectors' halves are flipped (signed order -> unsigned order), so that |a - b| per
+ *     half is max - min with no borrow between the halves, exact over the whole 16-bit range;
+ *   - the vector of an unused list (reference < 0) becomes one fixed value: wherever the two sides' lists pair up
+ *     (see DeriveBs) unused lists then compare as "no difference" by themselves;
+ *   - both reference bytes with every negative value turned into 0xff ("list unused").
+ */
+HDB_FN BlockWords NormalizeBlock(const BlockWords &raw)
 {
-	a ^= 0x80008000u; b ^= 0x80008000u;
-	return (MaxU2(a, b) - MinU2(a, b)) & 0xfffcfffcu;
+	BlockWords n;
+	const u32 r = raw.meta & 0xffffu;
+	const u32 refs = r | (((r >> 7) & 0x0101u) * 0xffu);
+	n.mv0 = (refs & 0x80u) ? 0u : (raw.mv0 ^ 0x80008000u);
+	n.mv1 = (refs & 0x8000u) ? 0u : (raw.mv1 ^ 0x80008000u);
+	n.meta = (raw.meta & 0xffff0000u) | refs;
+	return n;
 }
 
-/* both reference bytes of a block with every negative value turned into 0xff ("list unused") */
-HDB_FN u32 RefPair(u32 meta)
-{
-	const u32 r = meta & 0xffffu;
-	return r | (((r >> 7) & 0x0101u) * 0xffu);
-}
+/* non-zero iff the two (normalised) vectors differ by 4 or more in a component: any bit above bit 1 of |a - b| */
+HDB_FN u32 MvFarBits(u32 a, u32 b) { return (MaxU2(a, b) - MinU2(a, b)) & 0xfffcfffcu; }
 
 /*
- * Straight-line form of the rule (the kernel evaluates two edges per thread with lane-varying data:
- * branches would diverge on every one of them).  With pr / qr the two reference bytes of each side,
- * "same pictures, same vector count" is exactly  pr == qr  (lists pair up straight) or  pr == swap(qr)
- * (lists pair up crossed); both hold when all used references are one picture, and then -- as in the
- * standard -- the motion differs only if it differs under both pairings.  A pairing skips the lists
- * that are unused (reference 0xff on both sides of it).
+ * Straight-line form of the rule on normalised records (the kernel evaluates two edges per thread with
+ * lane-varying data: branches would diverge on every one of them).  With pr / qr the two reference bytes of each
+ * side, "same pictures, same vector count" is exactly  pr == qr  (lists pair up straight) or  pr == swap(qr)
+ * (lists pair up crossed); both hold when all used references are one picture, and then -- as in the standard --
+ * the motion differs only if it differs under both pairings.  Hence
+ *     motion differs  =  (far under the straight pairing  or  lists do not pair up straight)
+ *                    and (far under the crossed pairing   or  lists do not pair up crossed).
  */
 HDB_FN u32 DeriveBs(const BlockWords &p, const BlockWords &q, bool tu_edge, bool pu_edge)
 {
 	const u32 flags = (p.meta | q.meta) >> 16;
-	const u32 pr = RefPair(p.meta), qr = RefPair(q.meta);
+	const u32 pr = p.meta & 0xffffu, qr = q.meta & 0xffffu;
 	const u32 qr_swapped = Prmt(qr, 0u, 0x4401);
-	const bool straight = pr == qr, crossed = pr == qr_swapped;
-	const u32 use0 = (pr & 0x80u) ? 0u : 0xffffffffu, use1 = (pr & 0x8000u) ? 0u : 0xffffffffu;
-	const bool far_straight = ((MvFarBits(p.mv0, q.mv0) & use0) | (MvFarBits(p.mv1, q.mv1) & use1)) != 0u;
-	const bool far_crossed = ((MvFarBits(p.mv0, q.mv1) & use0) | (MvFarBits(p.mv1, q.mv0) & use1)) != 0u;
-	const u32 motion = straight ? (u32)(crossed ? (far_straight && far_crossed) : far_straight)
-		: (crossed ? (u32)far_crossed : 1u);
+	const bool far_straight = (MvFarBits(p.mv0, q.mv0) | MvFarBits(p.mv1, q.mv1)) != 0u || pr != qr;
+	const bool far_crossed = (MvFarBits(p.mv0, q.mv1) | MvFarBits(p.mv1, q.mv0)) != 0u || pr != qr_swapped;
+	const u32 motion = (far_straight && far_crossed) ? 1u : 0u;
 	const u32 inter = (tu_edge && (flags & kBlkCbf)) ? 1u : motion;
 	const u32 bs = (flags & kBlkIntra) ? 2u : inter;
 	return (tu_edge || pu_edge) ? bs : 0u;
 }
 
-/* edge byte between block p (left / above) and block q: strength by the rule above, QP = (QpP + QpQ + 1) >> 1 */
+/* edge byte between block p (left / above) and block q, both normalised: strength by the rule above,
+ * QP = (QpP + QpQ + 1) >> 1 */
 HDB_FN u32 DeriveEdge(const BlockWords &p, const BlockWords &q, bool tu_edge, bool pu_edge)
 {
 	return EdgeByte(DeriveBs(p, q, tu_edge, pu_edge), ((p.meta >> 24) + (q.meta >> 24) + 1u) >> 1);

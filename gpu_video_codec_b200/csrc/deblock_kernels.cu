@@ -1046,85 +1046,54 @@ cudaError_t LaunchDefaultLumaBs(unsigned char *vert_bs, unsigned char *hor_bs, i
  * Edge maps from block data (deblock_core.cuh: DeriveEdge).  Point (r, x) of the (H/8 + 1) x (W/8 + 1)
  * grid of block corners owns the vertical entry [r][x] -- the edge between blocks (r, x-1) and (r, x) --
  * and the horizontal entry [r][x] -- between (r-1, x) and (r, x).  Entries on the picture's four sides
- * are 0 (H.265 does not filter them).  A CTA takes kDeriveCols x kDeriveRows points of one frame: the
- * block data of those rows plus the row above and the column to the left go to shared memory first, as
- * consecutive 32-bit words (a 12-byte record read by its owner would cost three cache lines per warp
- * instruction, and every record is needed by three points), then one thread per column walks down the
- * rows.  Per 8x8 block 12 bytes are read (+ 1/kDeriveRows for the row above) and 2 written, against the
- * 192 the filter moves.
+ * are 0 (H.265 does not filter them).  One thread walks one column of corners down kDeriveRows rows: it
+ * fetches and normalises its own block's record once per row (three 32-bit loads; the 12-byte records of
+ * neighbouring lanes share their sectors), keeps it for the next row, where it is the block above, and gets the
+ * block to the left from the neighbouring lane by shuffle (lane 0 fetches it).  No shared memory and no barrier:
+ * the first version staged raw records of 128 x 8 corners in shared memory and normalised them in every edge that
+ * used them -- 200 instructions per corner and a barrier stall on top (profiles/r01o_ncu_variants_summary.json).
+ * Per 8x8 block 12 bytes are read (+ 1/kDeriveRows for the row above) and 2 written, against the 192 the filter
+ * moves.
  */
-constexpr int kDeriveCols = 128, kDeriveRows = 8;
-constexpr int kDeriveTileWords = 3 * kDeriveCols + 4;     /* 388: the 128 records, the one to their left, one word of slack in front */
+constexpr int kDeriveCols = 128, kDeriveRows = 32;
 
 __global__ void __launch_bounds__(kDeriveCols)
 DeriveEdgesKernel(const uint32_t *info, int w8, int h8, int n_frames, unsigned char *vert_edges, unsigned char *hor_edges)
 {
-	/* tile[rr][i]: word 3 * x0 - 4 + i of block row r0 - 1 + rr, so that record x0 - 1 + c starts at word 3c + 1
-	 * and the tile starts on a 16-byte boundary of the row (x0 is a multiple of 128) */
-	__shared__ __align__(16) uint32_t tile[kDeriveRows + 1][kDeriveTileWords];
-	const int t = threadIdx.x;
-	const int x0 = blockIdx.x * kDeriveCols, r0 = blockIdx.y * kDeriveRows;
-	const int x = x0 + t;
-	const int row_words = 3 * w8;
+	const int lane = threadIdx.x & 31;
+	const int x = blockIdx.x * kDeriveCols + threadIdx.x;          /* corner column, 0 .. w8 (beyond: idle, but kept for the shuffles) */
+	const int r0 = blockIdx.y * kDeriveRows, r1 = min(r0 + kDeriveRows, h8 + 1);
 	const long long nv = (long long)(w8 + 1) * h8, nh = (long long)(h8 + 1) * w8;
-	/* rows and frames start on 16-byte boundaries when W/8 is a multiple of 4 (every size the tiled filter takes) */
-	const bool vec = (w8 & 3) == 0 && (reinterpret_cast<uintptr_t>(info) & 15) == 0;
-	const int rr_first = r0 == 0 ? 1 : 0;
-	const int rr_last = min(kDeriveRows, h8 - r0);          /* last tile row that exists in the frame */
 	for (int f = blockIdx.z; f < n_frames; f += gridDim.z) {
 		const uint32_t *fi = info + 3ll * f * w8 * h8;
-		const int w_first = 3 * x0 - 4;
-		if (vec) {
-			if (t < kDeriveTileWords / 4) {
-				const int wi = w_first + 4 * t;
-				if (wi >= 0 && wi + 4 <= row_words) {
-					const uint4 *src = reinterpret_cast<const uint4 *>(fi + (long long)(r0 - 1 + rr_first) * row_words + wi);
-#pragma unroll
-					for (int rr = 0; rr <= kDeriveRows; rr++)
-						if (rr >= rr_first && rr <= rr_last)
-							*reinterpret_cast<uint4 *>(&tile[rr][4 * t]) = __ldg(src + (long long)(rr - rr_first) * (row_words / 4));
-				}
-			}
-		} else {
-#pragma unroll 1
-			for (int rr = rr_first; rr <= rr_last; rr++) {
-				const uint32_t *row = fi + (long long)(r0 - 1 + rr) * row_words;
-				for (int i = t; i < kDeriveTileWords; i += kDeriveCols) {
-					const int wi = w_first + i;
-					if (wi >= 0 && wi < row_words) tile[rr][i] = __ldg(row + wi);
-				}
-			}
-		}
-		__syncthreads();
-		if (x <= w8) {
-			unsigned char *vf = vert_edges + f * nv + (long long)r0 * (w8 + 1) + x;
-			unsigned char *hf = hor_edges + f * nh + (long long)r0 * w8 + x;
-			const bool has_q = x < w8, has_left = x > 0;
+		auto fetch = [&](int r, int c) -> BlockWords {
+			BlockWords raw = { 0u, 0u, 0u };
+			if (r < 0 || r >= h8 || c < 0 || c >= w8) return raw;
+			const uint32_t *p = fi + 3ll * ((long long)r * w8 + c);
+			raw.mv0 = __ldg(p); raw.mv1 = __ldg(p + 1); raw.meta = __ldg(p + 2);
+			return NormalizeBlock(raw);
+		};
+		BlockWords above = fetch(r0 - 1, x);
+		unsigned char *vf = vert_edges + f * nv + (long long)r0 * (w8 + 1) + x;
+		unsigned char *hf = hor_edges + f * nh + (long long)r0 * w8 + x;
 #pragma unroll 2
-			for (int rr = 1; rr <= kDeriveRows; rr++) {
-				const int r = r0 - 1 + rr;
-				if (r > h8) break;
-				u32 ev = 0, eh = 0;
-				if (r < h8 && has_q) {
-					const uint32_t *qw = &tile[rr][3 * t + 4];
-					const BlockWords q = { qw[0], qw[1], qw[2] };
-					const u32 fl = q.meta >> 16;
-					if (has_left) {
-						const BlockWords p = { qw[-3], qw[-2], qw[-1] };
-						ev = DeriveEdge(p, q, fl & kBlkTuLeft, fl & kBlkPuLeft);
-					}
-					if (r > 0) {
-						const uint32_t *pw = &tile[rr - 1][3 * t + 4];
-						const BlockWords p = { pw[0], pw[1], pw[2] };
-						eh = DeriveEdge(p, q, fl & kBlkTuTop, fl & kBlkPuTop);
-					}
-				}
-				if (r < h8) *vf = (unsigned char)ev;
-				if (has_q) *hf = (unsigned char)eh;
-				vf += w8 + 1; hf += w8;
-			}
+		for (int r = r0; r < r1; r++) {
+			const BlockWords q = fetch(r, x);
+			BlockWords left;
+			left.mv0 = __shfl_up_sync(0xffffffffu, q.mv0, 1);
+			left.mv1 = __shfl_up_sync(0xffffffffu, q.mv1, 1);
+			left.meta = __shfl_up_sync(0xffffffffu, q.meta, 1);
+			if (lane == 0) left = fetch(r, x - 1);
+			const u32 fl = q.meta >> 16;
+			const bool has_q = r < h8 && x < w8;
+			u32 ev = 0, eh = 0;
+			if (has_q && x > 0) ev = DeriveEdge(left, q, fl & kBlkTuLeft, fl & kBlkPuLeft);
+			if (has_q && r > 0) eh = DeriveEdge(above, q, fl & kBlkTuTop, fl & kBlkPuTop);
+			if (r < h8 && x <= w8) *vf = (unsigned char)ev;
+			if (x < w8) *hf = (unsigned char)eh;
+			vf += w8 + 1; hf += w8;
+			above = q;
 		}
-		__syncthreads();
 	}
 }
 

@@ -92,7 +92,11 @@ int hdbo_deblock_batch(const uint8_t *in, uint8_t *out, unsigned n, unsigned wid
  * pictures / motion-vector count, or a motion-vector difference of >= 4
  * quarter samples -> 1; else 0; QP of an edge = (QpP + QpQ + 1) >> 1) and is
  * anchored only on the cases the reference does define: all-intra input gives
- * the reference's "every inner edge 2" at one QP.
+ * the reference's "every inner edge 2" at one QP.  The risk of a transcription
+ * error is bounded by a second, independently written statement of the clause
+ * (oracle/derive_spec.py: set-based, sentence by sentence) that must agree with
+ * this one -- and with the product's branch-free form -- on an exhaustive
+ * reduced domain of 683 k cases (tests/test_derive_spec.py).
  */
 #define HDBO_EDGE(bs, qp) ((uint8_t)(((bs) & 3u) | ((qp) << 2)))
 

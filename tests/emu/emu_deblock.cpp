@@ -93,7 +93,7 @@ extern "C" int emu_deblock_frame_edges(const uint8_t *in, uint8_t *out, unsigned
 extern "C" void emu_derive_edges(const uint32_t *info, unsigned w, unsigned h, uint8_t *vert, uint8_t *hor)
 {
 	const unsigned w8 = w / 8, h8 = h / 8;
-	auto blk = [&](unsigned r, unsigned x) { const uint32_t *p = info + 3 * ((size_t)r * w8 + x); return BlockWords{ p[0], p[1], p[2] }; };
+	auto blk = [&](unsigned r, unsigned x) { const uint32_t *p = info + 3 * ((size_t)r * w8 + x); return NormalizeBlock(BlockWords{ p[0], p[1], p[2] }); };
 	for (unsigned r = 0; r <= h8; r++)
 		for (unsigned x = 0; x <= w8; x++) {
 			if (r < h8) {
