@@ -393,8 +393,11 @@ def run_reference_gpu_arm(args, rank):
         frame.tofile(fin)
         p = subprocess.run([exe, fin, fout, str(w), str(h), str(qp), str(d1[0]), str(d1[1]), str(d2[0]), str(d2[1]), str(reps)],
                            capture_output=True, text=True, timeout=300)
+        if os.environ.get("HDB_REFGPU_LOG"):
+            open(os.environ["HDB_REFGPU_LOG"], "w").write("rc=%s\n--- stdout\n%s\n--- stderr\n%s\n" % (p.returncode, p.stdout, p.stderr))
         if p.returncode != 0 or not os.path.exists(fout):
-            print(json.dumps({"impl": "reference_gpu", "unavailable": "ref_gpu_demo failed: %s" % (p.stderr.strip() or p.stdout.strip())[-200:]}), flush=True)
+            print(json.dumps({"impl": "reference_gpu", "unavailable": "ref_gpu_demo exited with %s after %d of %d repetitions: %s" % (
+                p.returncode, p.stdout.count("without copy"), reps, (p.stderr.strip() or p.stdout.strip())[-200:])}), flush=True)
             return
         got = np.fromfile(fout, np.uint8)
     k = [float(x) for x in re.findall(r"Execution Time without copy on GPU: ([0-9.eE+-]+)s", p.stdout)][1 + args.warmup:]

@@ -280,26 +280,35 @@ __device__ __forceinline__ void UvBlockRow(u32 *base, u32 s4, const FilterParams
  * c += vpitch with at most one wrap per row (vpitch = rpitch - 4).
  */
 struct SkewWalk {
-	int r, c;          /* row / column in the padded buffer */
-	bool col_ok;       /* the virtual column exists (0 <= vc < vpitch) */
+	int r, c;          /* row / column in the padded buffer of the unit's first byte */
+	int img;           /* byte offset in the image plane that position would have: (r - 4) * cw + (c - 4) */
+	bool lo_col, hi_col;   /* the unit's first / second four virtual columns exist (0 <= column < vpitch) */
 
 	__device__ __forceinline__ void Start(const TiledBatch &b, int vr, int vc)
 	{
-		col_ok = vc >= 0 && vc < b.chroma_vpitch;
-		const uint32_t o = (uint32_t)vr * (uint32_t)b.chroma_vpitch + (uint32_t)(col_ok ? vc : 0);
+		lo_col = (unsigned)vc < (unsigned)b.chroma_vpitch;
+		hi_col = (unsigned)(vc + 4) < (unsigned)b.chroma_vpitch;
+		/* vc can be a little negative (the box's lead-in): count from 8 buffer rows further up to stay positive */
+		const uint32_t o = (uint32_t)(vr * b.chroma_vpitch + vc + 8 * b.chroma_rpitch);
 		const uint32_t q = b.div_chroma_rpitch.Div(o);
-		r = (int)q; c = (int)(o - q * (uint32_t)b.chroma_rpitch);
+		r = (int)q - 8; c = (int)(o - q * (uint32_t)b.chroma_rpitch);
+		img = (r - 4) * (b.width >> 1) + c - 4;
 	}
+	/* one virtual row down: the same column is vpitch bytes further on in the buffer, i.e. vpitch further in the
+	 * image too unless the buffer row wraps, which takes the 8 bytes of padding out */
 	__device__ __forceinline__ void NextRow(const TiledBatch &b)
 	{
-		c += b.chroma_vpitch;
-		if (c >= b.chroma_rpitch) { c -= b.chroma_rpitch; r++; }
+		c += b.chroma_vpitch; img += b.chroma_vpitch;
+		if (c >= b.chroma_rpitch) { c -= b.chroma_rpitch; r++; img -= 8; }
 	}
-	/* offset of the image sample this is, or -1 for padding */
-	__device__ __forceinline__ long long ImageOffset(const TiledBatch &b, int pitch) const
+	/* which halves of the 8-byte unit at this position are image samples (a unit can straddle the 4-sample
+	 * padding at either end of a buffer row, or an end of the virtual row) */
+	__device__ __forceinline__ void Halves(const TiledBatch &b, bool &lo, bool &hi) const
 	{
-		const int ix = c - 4, iy = r - 4;
-		return (col_ok && ix >= 0 && ix < (b.width >> 1) && iy >= 0 && iy < b.chroma_buf_rows) ? (long long)iy * pitch + ix : -1ll;
+		const int cw = b.width >> 1;
+		const bool row_ok = (unsigned)(r - 4) < (unsigned)b.chroma_buf_rows;
+		lo = lo_col && row_ok && (unsigned)(c - 4) <= (unsigned)(cw - 4);      /* 4 <= c <= cw */
+		hi = hi_col && row_ok && (unsigned)c <= (unsigned)(cw - 4);            /* 0 <= c <= cw - 4 */
 	}
 };
 
@@ -316,18 +325,25 @@ __device__ __noinline__ void FetchTileLdgsts(const TiledBatch &b, const uint2 it
 		/* loops kept rolled: the cp.async variants must not outgrow the instruction cache (ncu: "no instruction"
 		 * was their first stall reason when these were unrolled) */
 		if (!kNv12 && c && b.chroma_skew) {
-			/* words lane, lane + 32 and (lanes 0 .. 3) lane + 64 of every tile row */
-			SkewWalk wk[3];
-#pragma unroll
-			for (int k = 0; k < 3; k++) wk[k].Start(b, 8 * lby0, xb0 + 4 + 4 * (lane + 32 * k));
-			wk[2].col_ok = wk[2].col_ok && lane < 4;
-			uint32_t d = dst + 4u * (uint32_t)lane;
+			/* 8-byte units like the straight planes: tile byte 0 is virtual column 4 mod 8, which is where the image's
+			 * 8-byte boundaries fall (SkewWalk); lane l takes unit l of every row, lanes 0 and 1 units 32 and 33 too.
+			 * A unit half in the padding goes as two 4-byte copies. */
+			SkewWalk wk[2];
+			wk[0].Start(b, 8 * lby0, xb0 + 4 + 8 * lane);
+			wk[1].Start(b, 8 * lby0, xb0 + 4 + 8 * (lane + 32));
+			if (lane >= 2) wk[1].lo_col = wk[1].hi_col = false;
+			uint32_t d = dst + 8u * (uint32_t)lane;
 #pragma unroll 1
 			for (int t = 0; t < kTileH; t++) {
 #pragma unroll
-				for (int k = 0; k < 3; k++) {
-					const long long off = wk[k].ImageOffset(b, pitch);
-					if (k < 2 || lane < 4) CpAsync4(d + 128u * k, off >= 0 ? src + off : src, off >= 0 ? 4u : 0u);
+				for (int k = 0; k < 2; k++) {
+					if (k == 0 || lane < 2) {
+						bool lo, hi;
+						wk[k].Halves(b, lo, hi);
+						const unsigned char *g = src + wk[k].img;
+						if (lo == hi) CpAsync8(d + 256u * k, lo ? g : src, lo ? 8u : 0u);
+						else { CpAsync4(d + 256u * k, lo ? g : src, lo ? 4u : 0u); CpAsync4(d + 256u * k + 4u, hi ? g + 4 : src, hi ? 4u : 0u); }
+					}
 					wk[k].NextRow(b);
 				}
 				d += kTileW;
@@ -580,21 +596,31 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_consta
 			const int fcol = x_img + 4 * (fword - 3);
 			const bool f_lane = fcol >= 0 && fcol < pl.pw;
 			if (kLoad == kLoadLdgsts && !kNv12 && chroma && b.chroma_skew) {
-				/* the item's 256 bytes per row of the VIRTUAL plane (tile words 3 .. 66), word by word to the image
-				 * samples they are */
-				SkewWalk wk[2];
-#pragma unroll
-				for (int k = 0; k < 2; k++) wk[k].Start(b, 8 * lby0, 8 * bx0 + 4 * (lane + 32 * k));
-				const u32 *sp = tile + 3 + lane;
+				/* the item's 256 bytes per row of the VIRTUAL plane (tile bytes 12 .. 267) to the image samples they are:
+				 * 31 units of 8 bytes from tile byte 16 on (image-aligned, see fetch) and one word at each end */
+				SkewWalk wk;
+				wk.Start(b, 8 * lby0, 8 * bx0 + 4 + 8 * lane);
+				if (lane == 31) wk.lo_col = wk.hi_col = false;
+				SkewWalk fr;                                               /* lanes 0 / 1: the word at virtual column 8 bx0 / 8 bx0 + 252 */
+				fr.Start(b, 8 * lby0, 8 * bx0 + (lane & 1 ? 252 : 0));
+				if (lane >= 2) fr.lo_col = false;
+				const unsigned char *sp = tile8 + 16 + 8 * lane;
+				const u32 *fp32 = tile + ((lane & 1) ? 66 : 3);
+				const int cw = b.width >> 1;
 #pragma unroll 1
 				for (int rr = 0; rr < kTileH; rr++) {
-#pragma unroll
-					for (int k = 0; k < 2; k++) {
-						const long long off = wk[k].ImageOffset(b, pl.pitch);
-						if (off >= 0) *reinterpret_cast<u32 *>(dst + off) = sp[32 * k];
-						wk[k].NextRow(b);
+					bool lo, hi;
+					wk.Halves(b, lo, hi);
+					const uint2 v = *reinterpret_cast<const uint2 *>(sp);
+					if (lo && hi) *reinterpret_cast<uint2 *>(dst + wk.img) = v;
+					else {
+						if (lo) *reinterpret_cast<u32 *>(dst + wk.img) = v.x;
+						if (hi) *reinterpret_cast<u32 *>(dst + wk.img + 4) = v.y;
 					}
-					sp += kTileWords;
+					if (fr.lo_col && (unsigned)(fr.r - 4) < (unsigned)b.chroma_buf_rows && (unsigned)(fr.c - 4) < (unsigned)cw)
+						*reinterpret_cast<u32 *>(dst + fr.img) = *fp32;
+					wk.NextRow(b); fr.NextRow(b);
+					sp += kTileW; fp32 += kTileWords;
 				}
 			} else if (kLoad == kLoadLdgsts) {
 				/* rows start on 8-byte boundaries: 64-bit stores.  The item's columns begin 4 bytes before such a
@@ -1049,48 +1075,52 @@ cudaError_t LaunchDefaultLumaBs(unsigned char *vert_bs, unsigned char *hor_bs, i
  * are 0 (H.265 does not filter them).  One thread walks one column of corners down kDeriveRows rows: it
  * fetches and normalises its own block's record once per row (three 32-bit loads; the 12-byte records of
  * neighbouring lanes share their sectors), keeps it for the next row, where it is the block above, and gets the
- * block to the left from the neighbouring lane by shuffle (lane 0 fetches it).  No shared memory and no barrier:
+ * block to the left from the neighbouring lane by shuffle (a warp covers 31 columns; its lane 0 repeats the column
+ * before them and writes nothing).  No shared memory and no barrier:
  * the first version staged raw records of 128 x 8 corners in shared memory and normalised them in every edge that
  * used them -- 200 instructions per corner and a barrier stall on top (profiles/r01o_ncu_variants_summary.json).
  * Per 8x8 block 12 bytes are read (+ 1/kDeriveRows for the row above) and 2 written, against the 192 the filter
  * moves.
  */
-constexpr int kDeriveCols = 128, kDeriveRows = 32;
+constexpr int kDeriveWarps = 4, kDeriveRows = 32;
+constexpr int kDeriveCols = 31 * kDeriveWarps;     /* corner columns per CTA: lane 0 of every warp only provides the block to the left of lane 1 */
 
-__global__ void __launch_bounds__(kDeriveCols)
+__global__ void __launch_bounds__(32 * kDeriveWarps)
 DeriveEdgesKernel(const uint32_t *info, int w8, int h8, int n_frames, unsigned char *vert_edges, unsigned char *hor_edges)
 {
 	const int lane = threadIdx.x & 31;
-	const int x = blockIdx.x * kDeriveCols + threadIdx.x;          /* corner column, 0 .. w8 (beyond: idle, but kept for the shuffles) */
+	/* corner column of this lane: a warp covers 31 of them, and its lane 0 repeats the last column of the warp
+	 * before it (column -1 for the first: no block there) so that every lane finds its left neighbour one lane down */
+	const int x = blockIdx.x * kDeriveCols + 31 * (int)(threadIdx.x >> 5) + lane - 1;
 	const int r0 = blockIdx.y * kDeriveRows, r1 = min(r0 + kDeriveRows, h8 + 1);
 	const long long nv = (long long)(w8 + 1) * h8, nh = (long long)(h8 + 1) * w8;
+	const bool col_has_block = x >= 0 && x < w8;
+	const bool writes = lane > 0;
 	for (int f = blockIdx.z; f < n_frames; f += gridDim.z) {
-		const uint32_t *fi = info + 3ll * f * w8 * h8;
-		auto fetch = [&](int r, int c) -> BlockWords {
+		const uint32_t *rec = info + 3ll * ((long long)f * w8 * h8 + (long long)(r0 - 1) * w8 + x);     /* record (r0 - 1, x) */
+		auto fetch = [&](int r) -> BlockWords {
 			BlockWords raw = { 0u, 0u, 0u };
-			if (r < 0 || r >= h8 || c < 0 || c >= w8) return raw;
-			const uint32_t *p = fi + 3ll * ((long long)r * w8 + c);
-			raw.mv0 = __ldg(p); raw.mv1 = __ldg(p + 1); raw.meta = __ldg(p + 2);
-			return NormalizeBlock(raw);
+			if (col_has_block && r >= 0 && r < h8) { raw.mv0 = __ldg(rec); raw.mv1 = __ldg(rec + 1); raw.meta = __ldg(rec + 2); raw = NormalizeBlock(raw); }
+			rec += 3 * w8;
+			return raw;
 		};
-		BlockWords above = fetch(r0 - 1, x);
+		BlockWords above = fetch(r0 - 1);
 		unsigned char *vf = vert_edges + f * nv + (long long)r0 * (w8 + 1) + x;
 		unsigned char *hf = hor_edges + f * nh + (long long)r0 * w8 + x;
 #pragma unroll 2
 		for (int r = r0; r < r1; r++) {
-			const BlockWords q = fetch(r, x);
+			const BlockWords q = fetch(r);
 			BlockWords left;
 			left.mv0 = __shfl_up_sync(0xffffffffu, q.mv0, 1);
 			left.mv1 = __shfl_up_sync(0xffffffffu, q.mv1, 1);
 			left.meta = __shfl_up_sync(0xffffffffu, q.meta, 1);
-			if (lane == 0) left = fetch(r, x - 1);
 			const u32 fl = q.meta >> 16;
-			const bool has_q = r < h8 && x < w8;
+			const bool has_q = r < h8 && col_has_block;
 			u32 ev = 0, eh = 0;
 			if (has_q && x > 0) ev = DeriveEdge(left, q, fl & kBlkTuLeft, fl & kBlkPuLeft);
 			if (has_q && r > 0) eh = DeriveEdge(above, q, fl & kBlkTuTop, fl & kBlkPuTop);
-			if (r < h8 && x <= w8) *vf = (unsigned char)ev;
-			if (x < w8) *hf = (unsigned char)eh;
+			if (writes && r < h8 && x <= w8) *vf = (unsigned char)ev;
+			if (writes && x < w8) *hf = (unsigned char)eh;
 			vf += w8 + 1; hf += w8;
 			above = q;
 		}
@@ -1103,7 +1133,7 @@ cudaError_t LaunchDeriveEdges(const void *info, int width, int height, int n_fra
 	const int w8 = width / 8, h8 = height / 8;
 	if (n_frames <= 0 || w8 <= 0 || h8 <= 0) return cudaSuccess;
 	const dim3 grid((w8 + kDeriveCols) / kDeriveCols, (h8 + kDeriveRows) / kDeriveRows, (unsigned)std::min(n_frames, 32768));
-	DeriveEdgesKernel<<<grid, kDeriveCols, 0, stream>>>(static_cast<const uint32_t *>(info), w8, h8, n_frames, vert_edges, hor_edges);
+	DeriveEdgesKernel<<<grid, 32 * kDeriveWarps, 0, stream>>>(static_cast<const uint32_t *>(info), w8, h8, n_frames, vert_edges, hor_edges);
 	return cudaGetLastError();
 }
 

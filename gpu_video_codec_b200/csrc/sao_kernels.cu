@@ -54,7 +54,11 @@ __device__ __forceinline__ u32 PickOffsets(u32 idx, u32 pool_lo, u32 pool_hi)
 {
 	const u32 t = idx * 0x11u;                                   /* nibble | nibble << 4 in bytes 0 and 2 */
 	const u32 sel = Prmt(t, 0u, 0x4420) | 0x8080u;               /* nibbles: i0, i0 | 8, i1, i1 | 8 */
-	return Prmt(pool_lo, pool_hi, sel);
+	/* prmt.b32 itself: bit 3 of a selector nibble replicates the sign of the selected byte (__byte_perm documents
+	 * the low three bits of each nibble only) */
+	u32 d;
+	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(pool_lo), "r"(pool_hi), "r"(sel));
+	return d;
 }
 
 __global__ void __launch_bounds__(kSaoWarps * 32)

@@ -12,3 +12,4 @@ timeout 300 python bench.py --impl reference_gpu --steps 5 --warmup 2 > gpurun_o
 timeout 300 python bench.py --impl reference_gpu --workload image2_single --steps 5 --warmup 2 > gpurun_out/r02e_bench_refgpu_image2.json 2>> gpurun_out/r02e_bench_refgpu.err; head -c 600 gpurun_out/r02e_bench_refgpu_image2.json
 timeout 300 python tools/quick_time.py --n 1024 --iters 10 2>&1 | tail -1
 ls /usr/lib/x86_64-linux-gnu 2>/dev/null | grep -i -E "nvcuvid|nvidia-encode|nvjpeg" | head
+tools/run_variants.sh 1024 > gpurun_out/r02e_variants.log 2>&1; cat gpurun_out/r02e_variants.log
