@@ -387,21 +387,26 @@ def run_reference_gpu_arm(args, rank):
         frame, qp = t_f[0].cpu().numpy(), int(t_q[0])
     d1 = exact_block_shape((w + 8) // 8, (h + 8) // 8)
     d2 = exact_block_shape((w // 2 + 8) // 8, (h // 2 + 8) // 8)
-    reps = 1 + args.warmup + args.steps
+    # One ExecuteGpu call per process, as main.cu makes it (main.cu:138): repeated calls inside one process corrupt the
+    # reference's state at 4K (the second call took 77 ms, the third died with SIGSEGV; profiles/r02*_refgpu*).
+    k, c, got, log = [], [], None, []
     with tempfile.TemporaryDirectory() as tmp:
         fin, fout = os.path.join(tmp, "in.yuv"), os.path.join(tmp, "out.yuv")
         frame.tofile(fin)
-        p = subprocess.run([exe, fin, fout, str(w), str(h), str(qp), str(d1[0]), str(d1[1]), str(d2[0]), str(d2[1]), str(reps)],
-                           capture_output=True, text=True, timeout=300)
-        if os.environ.get("HDB_REFGPU_LOG"):
-            open(os.environ["HDB_REFGPU_LOG"], "w").write("rc=%s\n--- stdout\n%s\n--- stderr\n%s\n" % (p.returncode, p.stdout, p.stderr))
-        if p.returncode != 0 or not os.path.exists(fout):
-            print(json.dumps({"impl": "reference_gpu", "unavailable": "ref_gpu_demo exited with %s after %d of %d repetitions: %s" % (
-                p.returncode, p.stdout.count("without copy"), reps, (p.stderr.strip() or p.stdout.strip())[-200:])}), flush=True)
-            return
-        got = np.fromfile(fout, np.uint8)
-    k = [float(x) for x in re.findall(r"Execution Time without copy on GPU: ([0-9.eE+-]+)s", p.stdout)][1 + args.warmup:]
-    c = [float(x) for x in re.findall(r"Execution Time with copy on GPU: ([0-9.eE+-]+)s", p.stdout)][1 + args.warmup:]
+        for i in range(args.warmup + args.steps):
+            p = subprocess.run([exe, fin, fout, str(w), str(h), str(qp), str(d1[0]), str(d1[1]), str(d2[0]), str(d2[1]), "1"],
+                               capture_output=True, text=True, timeout=300)
+            log.append("rc=%s\n%s%s" % (p.returncode, p.stdout, p.stderr))
+            if p.returncode != 0 or not os.path.exists(fout):
+                print(json.dumps({"impl": "reference_gpu", "unavailable": "ref_gpu_demo exited with %s: %s" % (
+                    p.returncode, (p.stderr.strip() or p.stdout.strip())[-200:])}), flush=True)
+                return
+            if i >= args.warmup:
+                k += [float(x) for x in re.findall(r"Execution Time without copy on GPU: ([0-9.eE+-]+)s", p.stdout)]
+                c += [float(x) for x in re.findall(r"Execution Time with copy on GPU: ([0-9.eE+-]+)s", p.stdout)]
+            got = np.fromfile(fout, np.uint8)
+    if os.environ.get("HDB_REFGPU_LOG"):
+        open(os.environ["HDB_REFGPU_LOG"], "w").write("\n".join(log))
     want = orc.deblock_frame(frame, w, h, qp)
     diff = int((got != want).sum()) if got.size == want.size else -1
     mpix = w * h / 1e6
@@ -411,7 +416,7 @@ def run_reference_gpu_arm(args, rank):
             "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(args.workload, 1, gen_device),
             "timing": "the reference's own protocol (gpu.cu:1246-1303): host wall clock around three launches + cudaDeviceSynchronize, one frame per call",
             "label": "courtesy datapoint: the reference's own CUDA kernels recompiled for sm_100a; NOT an oracle and NOT bit-exact",
-            "sample": "frame 0 of the workload, default boundary strengths (ExecuteGpu has no setter), one frame per ExecuteGpu call",
+            "sample": "frame 0 of the workload, default boundary strengths (ExecuteGpu has no setter), one frame per ExecuteGpu call, one call per process (as main.cu:138)",
             "block_shapes": {"luma": list(d1), "chroma": list(d2), "why": "exact divisors of the block counts: the reference's kernels have no bounds guard"},
             "bytes_differing_from_the_reference_cpu_filter": diff, "frame_bytes": int(want.size),
             "e2e": {"value": round(e2e, 1), "unit": UNIT, "h2d_bytes_per_step": int(want.size), "d2h_bytes_per_step": int(want.size),

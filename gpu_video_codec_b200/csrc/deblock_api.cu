@@ -91,6 +91,16 @@ static int CreateContext(hdb_context **out, int device)
 		&& cudaStreamCreateWithFlags(&ctx->s_setup, cudaStreamNonBlocking) == cudaSuccess
 		&& cudaMalloc(&ctx->sched, TiledSchedBytes() * kSchedSlots) == cudaSuccess
 		&& cudaMemset(ctx->sched, 0, TiledSchedBytes() * kSchedSlots) == cudaSuccess;
+	if (ok) {
+		cudaMemPoolProps props{};
+		props.allocType = cudaMemAllocationTypePinned;
+		props.handleTypes = cudaMemHandleTypeNone;
+		props.location.type = cudaMemLocationTypeDevice;
+		props.location.id = device;
+		unsigned long long keep = ~0ull;
+		ok = cudaMemPoolCreate(&ctx->pool, &props) == cudaSuccess
+			&& cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep) == cudaSuccess;
+	}
 	for (int i = 0; ok && i < kSchedSlots; i++)
 		ok = cudaEventCreateWithFlags(&ctx->sched_done[i], cudaEventDisableTiming) == cudaSuccess;
 	if (!ok) {
@@ -114,6 +124,7 @@ void DestroyContext(hdb_context *ctx)
 	}
 	for (auto ev : ctx->sched_done) if (ev) cudaEventDestroy(ev);
 	if (ctx->s_setup) cudaStreamDestroy(ctx->s_setup);
+	if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
 	cudaFree(ctx->qp_dev);
 	cudaFree(ctx->derive_dev);
 	for (auto ev : ctx->event_pool) cudaEventDestroy(ev);
@@ -291,7 +302,7 @@ int EnqueueFilter(hdb_context *ctx, const FrameView &view, const unsigned char *
 		/* the padded planes live in scratch memory that belongs to this call alone, allocated and freed in
 		 * stream order: calls in flight on different streams never share it, and nothing synchronises */
 		unsigned char *scratch = nullptr;
-		HDB_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void **>(&scratch), per * chunk, stream));
+		HDB_CUDA(ctx, cudaMallocFromPoolAsync(reinterpret_cast<void **>(&scratch), per * chunk, ctx->pool, stream));
 		const long long fs = (long long)w * h * 3 / 2;
 		for (int f0 = 0; f0 < n; f0 += chunk) {
 			GenericBatch g{};
@@ -1170,9 +1181,9 @@ int hdb_sao_batch(hdb_context *ctx, const unsigned char *frames_in, unsigned cha
 	const unsigned chunk = (unsigned)std::min<size_t>(n_frames, std::max<size_t>(1, ((size_t)256 << 20) / fb));
 	cudaStream_t st = ctx->s_k;
 	unsigned char *d_in = nullptr, *d_out = nullptr, *d_par = nullptr;
-	HDB_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void **>(&d_in), fb * chunk, st));
-	HDB_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void **>(&d_out), fb * chunk, st));
-	HDB_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void **>(&d_par), pb * chunk, st));
+	HDB_CUDA(ctx, cudaMallocFromPoolAsync(reinterpret_cast<void **>(&d_in), fb * chunk, ctx->pool, st));
+	HDB_CUDA(ctx, cudaMallocFromPoolAsync(reinterpret_cast<void **>(&d_out), fb * chunk, ctx->pool, st));
+	HDB_CUDA(ctx, cudaMallocFromPoolAsync(reinterpret_cast<void **>(&d_par), pb * chunk, ctx->pool, st));
 	cudaError_t e = cudaSuccess;
 	for (unsigned f0 = 0; f0 < n_frames && e == cudaSuccess; f0 += chunk) {
 		const unsigned nf = std::min(chunk, n_frames - f0);
@@ -1204,7 +1215,7 @@ int hdb_deblock_sao_batch_device(hdb_context *ctx, const void *d_frames_in, void
 	cudaStream_t st = static_cast<cudaStream_t>(stream);
 	const size_t fb = (size_t)width * height * 3 / 2;
 	unsigned char *scratch = nullptr;
-	HDB_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void **>(&scratch), fb * n_frames, st));
+	HDB_CUDA(ctx, cudaMallocFromPoolAsync(reinterpret_cast<void **>(&scratch), fb * n_frames, ctx->pool, st));
 	const FrameView view = WholeFrameView((int)width, (int)height);
 	rc = EnqueueFilter(ctx, view, static_cast<const unsigned char *>(d_frames_in), scratch, (int)n_frames, d_qp, 0,
 		d_vert, hdb_num_vert_bs(width, height), d_hor, hdb_num_hor_bs(width, height), st, nullptr, (flags & HDB_FLAG_EDGE_MAPS) != 0);

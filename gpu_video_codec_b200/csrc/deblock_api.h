@@ -86,6 +86,7 @@ struct hdb_context {
 	hdb::EncodeTiledFn encode = nullptr;
 	cudaStream_t s_h2d = nullptr, s_k = nullptr, s_d2h = nullptr;
 	cudaStream_t s_setup = nullptr;          /* per-size tables are built here */
+	cudaMemPool_t pool = nullptr;            /* stream-ordered scratch of calls (padded planes, the frames between deblocking and SAO): kept, not returned to the OS at every synchronisation */
 	void *sched = nullptr;
 	/* scheduler-word sets are handed to successive launches in turn; each remembers the stream that used it
 	 * last and an event recorded behind that launch, which a launch on another stream waits for */
