@@ -799,6 +799,20 @@ def nvlink_counters(devices):
             rx += int(vals[1].value.ullVal) * 1024
         return tx, rx
     except Exception:
+        pass
+    try:        # the same counters through nvidia-smi: "Link n: Data Tx: x KiB" / "Data Rx: y KiB" per link
+        import re
+        tx = rx = 0
+        for d in devices:
+            out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(d)], capture_output=True, text=True, timeout=20).stdout
+            t = [int(x) for x in re.findall(r"Data Tx:\s*(\d+)\s*KiB", out)]
+            r = [int(x) for x in re.findall(r"Data Rx:\s*(\d+)\s*KiB", out)]
+            if not t or not r:
+                return None
+            tx += sum(t) * 1024
+            rx += sum(r) * 1024
+        return tx, rx
+    except Exception:
         return None
 
 

@@ -9,11 +9,14 @@
  * blocks of the deblocking kernel are independent only up to their own 64 samples -- a tile would have to be
  * deblocked with a one-block apron to offset its rim, which costs more than the second pass moves.
  *
- * One warp walks one column strip of 128 bytes (lane l: the four samples of word 32 * strip + l) down the rows of
- * one coding-tree-block row of one plane, so the parameters a lane needs are constant for the walk.  A lane keeps
- * the words of rows y - 1, y, y + 1 and their left / right neighbours (from the adjacent lanes by shuffle; the
- * strip's first and last lane load theirs) in registers.  Four samples at a time as two 16x2 pairs, with the
- * packed-halfword instructions the deblocking core uses:
+ * One warp walks one column strip of 256 bytes (lane l: the eight samples of words 64 * strip + 2 l and + 1) down the
+ * rows of one coding-tree-block row of one plane, so the parameters a lane needs are constant for the walk.  A lane
+ * keeps the words of rows y - 1, y, y + 1 and their left / right neighbours (from the adjacent lanes by shuffle;
+ * the strip's first and last lane load theirs) in registers.  Neighbouring CTBs of a strip differ in type and
+ * class, so the row loop is branch-free: which rows and which side the two neighbours come from is a per-lane
+ * selection followed by one funnel shift, and the edge category and the band index are both computed and one is
+ * selected.  Four samples at a time as two 16x2 pairs, with the packed-halfword instructions the deblocking core
+ * uses:
  *   edge offset  256 + sign(c - a) per half = max(min(256 + c - a, 257), 255); category 2 + sign + sign in 0..4
  *   band offset  min(((c >> 3) - band_position) & 31, 4) in 0..4
  *   either way the index picks the offset out of an 8-byte pool with one byte permute (selector nibble | 8 for the
@@ -61,6 +64,19 @@ __device__ __forceinline__ u32 PickOffsets(u32 idx, u32 pool_lo, u32 pool_hi)
 	return d;
 }
 
+/* the word of a row's (L, w0, w1, R) window that lies `shift` samples to the left (shift = -1), at (0) or to the
+ * right (+1) of w0 / w1, as one funnel shift of a selected register pair */
+struct RowWin { u32 L, w0, w1, R; };
+
+__device__ __forceinline__ void Shifted(const RowWin &r, bool left, u32 amount, u32 &o0, u32 &o1)
+{
+	/* left: (w0 << 8 | L >> 24, w1 << 8 | w0 >> 24) = funnel-right by 24 of (L, w0), (w0, w1);
+	 * at / right: funnel-right by 0 / 8 of (w0, w1), (w1, R) */
+	const u32 a0 = left ? r.L : r.w0, a1 = left ? r.w0 : r.w1, a2 = left ? r.w1 : r.R;
+	o0 = __funnelshift_r(a0, a1, amount);
+	o1 = __funnelshift_r(a1, a2, amount);
+}
+
 __global__ void __launch_bounds__(kSaoWarps * 32)
 SaoKernel(const __grid_constant__ SaoBatch b)
 {
@@ -78,71 +94,73 @@ SaoKernel(const __grid_constant__ SaoBatch b)
 		const int pw = plane ? b.width >> 1 : b.width, ph = plane ? b.height >> 1 : b.height;
 		const int ctb = plane ? b.ctb >> 1 : b.ctb;
 		const long long plane_off = plane == 0 ? 0 : (long long)b.width * b.height + (plane == 2 ? (long long)(b.width >> 1) * (b.height >> 1) : 0);
-		const unsigned char *src = b.in + (long long)frame * b.frame_stride + plane_off;
-		unsigned char *dst = b.out + (long long)frame * b.frame_stride + plane_off;
+		const u32 *src = reinterpret_cast<const u32 *>(b.in + (long long)frame * b.frame_stride + plane_off);
+		u32 *dst = reinterpret_cast<u32 *>(b.out + (long long)frame * b.frame_stride + plane_off);
 		const int pww = pw >> 2;                                 /* words per row */
-		const int x = 32 * strip + lane;                         /* this lane's word */
-		const bool live = x < pww;
+		const int x = 2 * (32 * strip + lane);                   /* this lane's first word: eight samples, words x and x + 1 */
+		const bool live0 = x < pww, live1 = x + 1 < pww;
 		const int y0 = (int)crow * ctb, y1 = min(y0 + ctb, ph);
-		/* parameters of the CTB this lane's samples lie in (a word never straddles CTBs: their width is a multiple of 4) */
+		/* parameters of the CTB this lane's samples lie in (eight samples never straddle CTBs: their width is a
+		 * multiple of 8 and so is the lane's first sample) */
 		u32 type = 0, pos = 0, pool_lo = 0, pool_hi = 0;
-		if (live) {
+		if (live0) {
 			const unsigned char *p = b.params + 6ll * ((((long long)frame * 3 + plane) * b.ctb_rows + crow) * b.ctb_cols + (4 * x) / ctb);
 			type = __ldg(p); pos = __ldg(p + 1);
 			const u32 o0 = __ldg(p + 2), o1 = __ldg(p + 3), o2 = __ldg(p + 4), o3 = __ldg(p + 5);
 			if (type == 2) { pool_lo = o0 | (o1 << 8) | (o2 << 24); pool_hi = o3; pos &= 3u; }     /* categories 0, 1, (2: none), 3, 4 */
 			else { pool_lo = o0 | (o1 << 8) | (o2 << 16) | (o3 << 24); pool_hi = 0u; }            /* bands k = 0..3, (4: none) */
 		}
-		/* bytes that keep their value whatever the row: no edge offset at all, or the picture's first / last column
-		 * for every class but the vertical one */
-		u32 keep_cols = 0u;
-		if (type == 0u) keep_cols = 0xffffffffu;
-		else if (type == 2u && pos != 1u) keep_cols = (x == 0 ? 0x000000ffu : 0u) | (x == pww - 1 ? 0xff000000u : 0u);
+		const bool edge = type == 2u;
+		/* which rows and which side the two neighbours of the class come from (8.7.3.2: hPos / vPos):
+		 * class 0: left / right of row y; 1: rows y - 1 / y + 1; 2: left of y - 1 / right of y + 1; 3: right of y - 1 / left of y + 1 */
+		const bool a_same_row = pos == 0u, a_left = pos == 0u || pos == 2u, b_left = pos == 3u;
+		const u32 a_amount = pos == 1u ? 0u : (a_left ? 24u : 8u), b_amount = pos == 1u ? 0u : (b_left ? 24u : 8u);
+		/* bytes that keep their value whatever the row: nothing to do, or the picture's first / last column for every
+		 * class but the vertical one */
+		u32 keep0 = 0u, keep1 = 0u;
+		if (type == 0u) keep0 = keep1 = 0xffffffffu;
+		else if (edge && pos != 1u) { keep0 = x == 0 ? 0x000000ffu : 0u; keep0 |= x == pww - 1 ? 0xff000000u : 0u; keep1 = x + 1 == pww - 1 ? 0xff000000u : 0u; }
 		const u32 band_add = (32u - pos) * 0x10001u;
 
-		u32 *orow = reinterpret_cast<u32 *>(dst) + (long long)y0 * pww + x;
-		/* words of a row for this lane: left neighbour, own, right neighbour (0 outside the picture: those samples are kept) */
-		auto load_row = [&](int y, u32 &L, u32 &C, u32 &R) {
-			L = C = R = 0u;
-			if (y < 0 || y >= ph) return;
-			const u32 *p = reinterpret_cast<const u32 *>(src) + (long long)y * pww + x;
-			if (live) C = __ldg(p);
-			L = __shfl_up_sync(0xffffffffu, C, 1);
-			R = __shfl_down_sync(0xffffffffu, C, 1);
-			if (lane == 0) L = (live && x > 0) ? __ldg(p - 1) : 0u;
-			if (lane == 31) R = (live && x + 1 < pww) ? __ldg(p + 1) : 0u;
+		/* (L, w0, w1, R) of a row for this lane; 0 outside the picture (those samples are kept) */
+		auto load_row = [&](int y) -> RowWin {
+			RowWin w = { 0u, 0u, 0u, 0u };
+			if (y < 0 || y >= ph) return w;
+			const u32 *p = src + (long long)y * pww + x;
+			if (live0) w.w0 = __ldg(p);
+			if (live1) w.w1 = __ldg(p + 1);
+			w.L = __shfl_up_sync(0xffffffffu, w.w1, 1);
+			w.R = __shfl_down_sync(0xffffffffu, w.w0, 1);
+			if (lane == 0) w.L = (live0 && x > 0) ? __ldg(p - 1) : 0u;
+			if (lane == 31) w.R = (x + 2 < pww) ? __ldg(p + 2) : 0u;
+			return w;
 		};
-		u32 L0, C0, R0, L1, C1, R1, L2, C2, R2;
-		load_row(y0 - 1, L0, C0, R0);
-		load_row(y0, L1, C1, R1);
+		auto offset4 = [&](u32 c, u32 a, u32 n) -> u32 {          /* four samples of word c against neighbour words a, n */
+			const u32 cA = PairA(c), cB = PairB(c);
+			const u32 eA = SignBiased(cA, PairA(a)) + SignBiased(cA, PairA(n)) - 0x01fe01feu;
+			const u32 eB = SignBiased(cB, PairB(a)) + SignBiased(cB, PairB(n)) - 0x01fe01feu;
+			const u32 kA = MinU2((((cA >> 3) & 0x001f001fu) + band_add) & 0x001f001fu, 0x00040004u);
+			const u32 kB = MinU2((((cB >> 3) & 0x001f001fu) + band_add) & 0x001f001fu, 0x00040004u);
+			const u32 rA = AddMinRelu2(cA, PickOffsets(edge ? eA : kA, pool_lo, pool_hi), 0x00ff00ffu);
+			const u32 rB = AddMinRelu2(cB, PickOffsets(edge ? eB : kB, pool_lo, pool_hi), 0x00ff00ffu);
+			return Prmt(rA, rB, 0x6420);
+		};
+		RowWin r0 = load_row(y0 - 1), r1 = load_row(y0);
+		u32 *orow = dst + (long long)y0 * pww + x;
+#pragma unroll 1
 		for (int y = y0; y < y1; y++) {
-			load_row(y + 1, L2, C2, R2);
-			u32 res = C1;
-			if (type == 2u) {
-				/* the two neighbours along the class's direction, as words aligned with C1 (8.7.3.2: hPos / vPos) */
-				const u32 l0 = __funnelshift_l(L0, C0, 8), r0 = __funnelshift_r(C0, R0, 8);
-				const u32 l1 = __funnelshift_l(L1, C1, 8), r1 = __funnelshift_r(C1, R1, 8);
-				const u32 l2 = __funnelshift_l(L2, C2, 8), r2 = __funnelshift_r(C2, R2, 8);
-				const u32 a = pos == 0u ? l1 : (pos == 1u ? C0 : (pos == 2u ? l0 : r0));
-				const u32 n = pos == 0u ? r1 : (pos == 1u ? C2 : (pos == 2u ? r2 : l2));
-				const u32 cA = PairA(C1), cB = PairB(C1);
-				const u32 iA = SignBiased(cA, PairA(a)) + SignBiased(cA, PairA(n)) - 0x01fe01feu;
-				const u32 iB = SignBiased(cB, PairB(a)) + SignBiased(cB, PairB(n)) - 0x01fe01feu;
-				const u32 rA = AddMinRelu2(cA, PickOffsets(iA, pool_lo, pool_hi), 0x00ff00ffu);
-				const u32 rB = AddMinRelu2(cB, PickOffsets(iB, pool_lo, pool_hi), 0x00ff00ffu);
-				res = Prmt(rA, rB, 0x6420);
-			} else if (type == 1u) {
-				const u32 cA = PairA(C1), cB = PairB(C1);
-				const u32 iA = MinU2((((cA >> 3) & 0x001f001fu) + band_add) & 0x001f001fu, 0x00040004u);
-				const u32 iB = MinU2((((cB >> 3) & 0x001f001fu) + band_add) & 0x001f001fu, 0x00040004u);
-				const u32 rA = AddMinRelu2(cA, PickOffsets(iA, pool_lo, pool_hi), 0x00ff00ffu);
-				const u32 rB = AddMinRelu2(cB, PickOffsets(iB, pool_lo, pool_hi), 0x00ff00ffu);
-				res = Prmt(rA, rB, 0x6420);
-			}
+			const RowWin r2 = load_row(y + 1);
+			const RowWin ra = a_same_row ? r1 : r0, rb = a_same_row ? r1 : r2;
+			u32 a0, a1, n0, n1;
+			Shifted(ra, a_left, a_amount, a0, a1);
+			Shifted(rb, b_left, b_amount, n0, n1);
+			const u32 res0 = offset4(r1.w0, a0, n0), res1 = offset4(r1.w1, a1, n1);
 			/* the picture's first / last row for every class but the horizontal one */
-			const u32 keep = (type == 2u && pos != 0u && (y == 0 || y == ph - 1)) ? 0xffffffffu : keep_cols;
-			if (live) *orow = (C1 & keep) | (res & ~keep);
-			L0 = L1; C0 = C1; R0 = R1; L1 = L2; C1 = C2; R1 = R2;
+			const bool keep_row = edge && pos != 0u && (y == 0 || y == ph - 1);
+			const u32 k0 = keep_row ? 0xffffffffu : keep0, k1 = keep_row ? 0xffffffffu : keep1;
+			if (live0) orow[0] = (r1.w0 & k0) | (res0 & ~k0);
+			if (live1) orow[1] = (r1.w1 & k1) | (res1 & ~k1);
+			r0 = r1; r1 = r2;
 			orow += pww;
 		}
 	}
@@ -158,7 +176,7 @@ cudaError_t LaunchSao(const unsigned char *d_in, unsigned char *d_out, int n_fra
 	b.width = width; b.height = height; b.ctb = ctb;
 	b.ctb_cols = (width + ctb - 1) / ctb; b.ctb_rows = (height + ctb - 1) / ctb;
 	b.params = static_cast<const unsigned char *>(d_params);
-	b.strips_luma = (width / 4 + 31) / 32; b.strips_chroma = (width / 8 + 31) / 32;
+	b.strips_luma = (width / 4 + 63) / 64; b.strips_chroma = (width / 8 + 63) / 64;     /* 64 words = 256 bytes a strip */
 	/* the chroma planes have as many CTB rows as luma (a chroma CTB is half as high as the plane's share of rows) */
 	b.tasks_luma = b.strips_luma * b.ctb_rows; b.tasks_chroma = b.strips_chroma * b.ctb_rows;
 	b.tasks_per_frame = b.tasks_luma + 2 * b.tasks_chroma;

@@ -25,3 +25,4 @@ PY
 timeout 600 python bench.py --workload 8k_strips --gpus $N --steps 3 > gpurun_out/r02m_strips_n$N.json 2> gpurun_out/r02m_strips_n$N.err; echo "strips exit $?"; tail -2 gpurun_out/r02m_strips_n$N.err
 python -c "
 import json; d=json.load(open('gpurun_out/r02m_strips_n$N.json')); print(json.dumps(d['strips_8k'], indent=0)[:2500])"
+nvidia-smi nvlink -gt d -i 0 2>&1 | head -8 > gpurun_out/r02m_nvlink_sample_n$N.txt

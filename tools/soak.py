@@ -25,11 +25,13 @@ bs_kinds = [None, "uniform012", "wide", "twos", "zeros", "ones"]
 t0, n_cases, fails = time.time(), 0, 0
 st = torch.cuda.current_stream().cuda_stream
 while time.time() - t0 < budget:
-    mode = int(rng.integers(11))
+    mode = int(rng.integers(14))
     w = 8 * int(rng.integers(1, 200))
     h = 8 * int(rng.integers(1, 80))
-    if mode in (2, 3, 4, 6, 7, 9) or rng.integers(2):
+    if mode in (3, 4, 6, 7, 9, 11) or rng.integers(2):
         w = 32 * max(1, w // 32)
+    if mode == 12:
+        w = max(32, 16 * (w // 16))
     n = int(rng.integers(1, 7))
     kind = kinds[int(rng.integers(len(kinds)))]
     bs_kind = bs_kinds[int(rng.integers(len(bs_kinds)))]
@@ -40,7 +42,7 @@ while time.time() - t0 < budget:
     else:
         vs, hs = zip(*[synth.make_bs(rng, w, h, bs_kind) for _ in range(n)])
         v, hh = np.stack(vs), np.stack(hs)
-    if mode >= 5:
+    if 5 <= mode <= 10:
         # edge maps (bs | qp << 2) for modes 5, 6 (odd cases of 6), 7; derivation for mode 8
         edge_kind = ["random", "wide", "smooth", "uniform"][int(rng.integers(4))]
         maps = [synth.make_edge_maps(rng, w, h, edge_kind, picture_edges=bool(rng.integers(2))) for _ in range(n)]
@@ -103,6 +105,30 @@ while time.time() - t0 < budget:
             info = np.stack([synth.make_block_info(rng, w, h, ik) for _ in range(n)])
             want = np.stack([orc.deblock_frame_edges(frames[i], w, h, int(qps[i]), *orc.derive_edges(info[i], w, h)) for i in range(n)])
             got = dev.deblock_batch_blocks(frames, w, h, qps, info)
+        elif mode == 11:   # a stream of frames, each cut into strips (logical shards), pipelined over three slots
+            want = orc.deblock_batch(frames, w, h, qps, v, hh)
+            got = multi.deblock_stream_strips(frames, w, h, qps, v, hh)
+        elif mode == 12:   # 16-bit containers, depth 8 .. 10, host or device batch
+            depth = int(rng.integers(8, 11))
+            f16 = (frames.astype(np.uint16) << (depth - 8)) | rng.integers(0, 1 << (depth - 8), frames.shape).astype(np.uint16)
+            want = np.stack([orc.deblock_frame16(f16[i], w, h, int(qps[i]), None if v is None else v[i], None if hh is None else hh[i], bit_depth=depth) for i in range(n)])
+            if rng.integers(2):
+                got = dev.deblock_batch_ex(f16, w, h, qps, v, hh, flags=hdb.flag_depth(depth))
+            else:
+                d = torch.from_numpy(f16.view(np.int16)).cuda()
+                o = d if rng.integers(2) else torch.empty_like(d)
+                dev.deblock_batch_device_ex(d, o, n, w, h, torch.from_numpy(qps.astype(np.int32)).cuda(),
+                                            None if v is None else torch.from_numpy(v).cuda(), None if hh is None else torch.from_numpy(hh).cuda(),
+                                            flags=hdb.flag_depth(depth), stream=st)
+                torch.cuda.synchronize()
+                got = o.cpu().numpy().view(np.uint16)
+        elif mode == 13:   # sample adaptive offset, random parameters per coding tree block
+            from tests.test_sao import make_sao_params
+            ctb = int(rng.choice([16, 32, 64]))
+            pk = ["mixed", "edge", "band", "extreme"][int(rng.integers(4))]
+            params = np.stack([make_sao_params(rng, w, h, ctb, pk) for _ in range(n)])
+            want = np.stack([orc.sao_frame(frames[i], w, h, params[i], ctb) for i in range(n)])
+            got = dev.sao_batch(frames, w, h, params, ctb)
         if mode >= 5:
             pass
         elif mode == 0:
