@@ -44,6 +44,8 @@ WORKLOADS = {
     "4k_nv12_512": (3840, 2160, 512, "synthetic 3840x2160 NV12 batch of 512 frames, random QP/BS maps"),
     # 10-bit samples in 16-bit containers, planar (yuv420p10le); one GPU
     "4k_yuv420p10_512": (3840, 2160, 512, "synthetic 3840x2160 planar 10-bit (16-bit containers) batch of 512 frames, random QP/BS maps"),
+    # the same in the layout a hardware decoder writes: P010 (Y + interleaved UV, samples in the high 10 bits); one GPU
+    "4k_p010_512": (3840, 2160, 512, "synthetic 3840x2160 P010 (semi-planar 10-bit, high-aligned) batch of 512 frames, random QP/BS maps"),
     # the in-loop pair, deblocking then sample adaptive offset; one GPU
     "4k_sao256": (3840, 2160, 256, "synthetic 3840x2160 YV12 batch of 256 frames: deblocking filter, then sample adaptive offset with random per-CTB parameters (a third off, a third band, a third edge)"),
     # block data -> edge maps (bs | qp << 2) -> per-edge-QP filter; one GPU
@@ -268,13 +270,13 @@ def workload_frames(torch, first, n, w, h, seed, device="cuda"):
     return frames, qp, vbs, hbs
 
 
-WORKLOAD_SEED = {"4k_sao256": 6000, "4k_yuv420p10_512": 5000, "4k_batch1024": 1000, "1080p_batch256": 2000, "4k_nv12_512": 3000, "4k_edges512": 4242, "8k_strips": 77}
+WORKLOAD_SEED = {"4k_p010_512": 5000, "4k_sao256": 6000, "4k_yuv420p10_512": 5000, "4k_batch1024": 1000, "1080p_batch256": 2000, "4k_nv12_512": 3000, "4k_edges512": 4242, "8k_strips": 77}
 
 
 def workload_config(name, world, gen_device):
     """The `config` object of a line: facts about the workload only, identical in both arms."""
     w, h, total, desc = WORKLOADS[name]
-    fb = 3 * w * h // 2 * (2 if "p10" in name else 1)
+    fb = 3 * w * h // 2 * (2 if ("p10" in name or "p010" in name) else 1)
     per = (total + world - 1) // world
     return {"workload": name, "description": desc, "width": w, "height": h, "frames": total,
             "frames_per_gpu": per, "sharding": "contiguous frame ranges, no collective",
@@ -510,14 +512,18 @@ def measure_workload(args, torch, hdb, dev, dd, rank, world, workload, steps, wa
     else:
         frames, qp, vbs, hbs = workload_frames(torch, first, n, w, h, WORKLOAD_SEED.get(workload, 0), "cuda")
     nv12 = "nv12" in workload
-    depth = 10 if "p10" in workload else 0
-    flags = hdb.FLAG_NV12 if nv12 else (hdb.flag_depth(depth) if depth else 0)
+    depth = 10 if ("p10" in workload or "p010" in workload) else 0
+    p010 = "p010" in workload
+    flags = hdb.FLAG_NV12 if nv12 else (hdb.flag_depth(depth) | (hdb.FLAG_NV12 if p010 else 0) if depth else 0)
     ysz, csz = w * h, (w // 2) * (h // 2)
     if depth:
         # the same frames scaled to the depth, the low bits filled at random: int16 tensors (torch has no uint16 arithmetic)
         g16 = torch.Generator(device="cuda").manual_seed(WORKLOAD_SEED[workload] + 7 * first)
         frames = (frames.to(torch.int16) << (depth - 8)) | torch.randint(0, 1 << (depth - 8), frames.shape, device="cuda", generator=g16, dtype=torch.int16)
         fb *= 2
+        if p010:      # interleave the chroma planes and move the samples to the high bits
+            uv = torch.stack([frames[:, ysz:ysz + csz], frames[:, ysz + csz:]], dim=2).reshape(n, -1)
+            frames = (torch.cat([frames[:, :ysz], uv], dim=1) << 6).contiguous()
 
     def to_nv12(t):      # [k, 3wh/2] planar -> NV12, on whatever device t lives
         r = t.clone()
@@ -575,7 +581,9 @@ def measure_workload(args, torch, hdb, dev, dd, rank, world, workload, steps, wa
         hh = None if hbs is None else hbs[sel].cpu().numpy()
         if depth:
             got, src = got.view(np.uint16), src.view(np.uint16)
-            want = np.stack([orc.deblock_frame16(src[i], w, h, int(q[i]), v[i], hh[i], bit_depth=depth) for i in range(len(idx))])
+            chk16 = (lambda f, qq, vv, hv: orc.deblock_frame_p010(f, w, h, qq, vv, hv)) if p010 else \
+                (lambda f, qq, vv, hv: orc.deblock_frame16(f, w, h, qq, vv, hv, bit_depth=depth))
+            want = np.stack([chk16(src[i], int(q[i]), v[i], hh[i]) for i in range(len(idx))])
         else:
             want = orc.deblock_batch(src, w, h, q, v, hh)
         ok = bool(np.array_equal(got, want))
@@ -658,7 +666,8 @@ def measure_workload(args, torch, hdb, dev, dd, rank, world, workload, steps, wa
             e2e_checked = len(chk)
             a_in, a_out = h_in.numpy().view(np.uint16), h_out.numpy().view(np.uint16)
             for f in chk:
-                wnt = orc.deblock_frame16(a_in[f], w, h, int(np_qp[f]), np_v[f], np_h[f], bit_depth=depth)
+                wnt = orc.deblock_frame_p010(a_in[f], w, h, int(np_qp[f]), np_v[f], np_h[f]) if p010 else \
+                    orc.deblock_frame16(a_in[f], w, h, int(np_qp[f]), np_v[f], np_h[f], bit_depth=depth)
                 bad += 0 if np.array_equal(a_out[f], wnt) else 1
         for f0 in range(0, 0 if depth else n, 64):
             f1 = min(n, f0 + 64)
@@ -692,14 +701,14 @@ def measure_workload(args, torch, hdb, dev, dd, rank, world, workload, steps, wa
         traffic, traffic_src = ncu_traffic(workload, n)
         e2e = {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": round(e2e_s / steps * 1e3, 3), "launches_per_step": e2e_launches // max(steps, 1),
-               "api": "hdb_deblock_batch%s (pinned host buffers, 3-stream pipeline)" % ("_ex, HDB_FLAG_NV12" if nv12 else ("_ex, HDB_FLAG_DEPTH(%d)" % depth if depth else ""))}
+               "api": "hdb_deblock_batch%s (pinned host buffers, 3-stream pipeline)" % ("_ex, HDB_FLAG_NV12" if nv12 else ("_ex, HDB_FLAG_DEPTH(%d)%s" % (depth, " | HDB_FLAG_NV12" if p010 else "") if depth else ""))}
         if link is not None:
             e2e["frac_of_link"] = round(link["ms_per_step"] / e2e["ms_per_step"], 4)
         res = {"value": round(value, 1), "ms_per_step": round(ms_per_step, 4),
                "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                             "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
                             "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
-                            "kernel": "DeblockTiled16Kernel<%d, 0>" % depth if depth else ("DeblockTiledKernel<0, 1, 0>" if nv12 else "DeblockTiledKernel<0, 0, 0>"),
+                            "kernel": "DeblockTiled16Kernel<%d, 0, %d>" % (depth, int(p010)) if depth else ("DeblockTiledKernel<0, 1, 0>" if nv12 else "DeblockTiledKernel<0, 0, 0>"),
                             "mean_launch_ms": round(mean_launch_ms, 4)},
                "e2e": e2e, "link_probe": link, "gpu_launches": kernel_launches, "parity": parity}
         if world == 1 and not args.no_cpu and full_parity:
@@ -714,7 +723,8 @@ def measure_workload(args, torch, hdb, dev, dd, rank, world, workload, steps, wa
                 src16 = src.view(np.uint16)[:8]
                 t0 = time.perf_counter()
                 for i in range(src16.shape[0]):
-                    orc.deblock_frame16(src16[i], w, h, int(q[i]), v[i], hh[i], bit_depth=depth)
+                    (orc.deblock_frame_p010(src16[i], w, h, int(q[i]), v[i], hh[i]) if p010 else
+                     orc.deblock_frame16(src16[i], w, h, int(q[i]), v[i], hh[i], bit_depth=depth))
                 dt = time.perf_counter() - t0
                 best, kind, used, detail = src16.shape[0] * w * h / 1e6 / dt, "port", 1, {"frames": int(src16.shape[0])}
                 ns = int(src16.shape[0])
@@ -746,7 +756,7 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": res["ms_per_step"], "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "u16" if "p10" in args.workload else "u8", "data": "synthetic",
+                "scaling": "strong", "vs_baseline": None, "dtype": "u16" if ("p10" in args.workload or "p010" in args.workload) else "u8", "data": "synthetic",
                 "config": workload_config(args.workload, world, "cuda"),
                 "timing": "CUDA events on the launching stream, max over ranks",
                 "roofline": res["roofline"], "e2e": res["e2e"], "link_probe": res["link_probe"],
@@ -903,7 +913,9 @@ def strips_record(args, torch, hdb, devices, steps):
                               "mpixel_s": round(w * h / 1e6 / (float(np.median(ks)) / 1e3), 1),
                               "nvlink_halo_bytes_per_frame": halo,
                               "what": "strips already in each GPU's HBM; one kernel per GPU, halo rows read by peer loads inside it"}
-    if nvl0 is not None and nvl1 is not None:
+    if nvl0 is None or nvl1 is None:
+        res["nvlink_counters"] = {"unavailable": "NVML and nvidia-smi report N/A for the NVLink data counters on this box; nvlink_halo_bytes_per_frame is the analytic figure (4 rows of each plane per cut and direction)"}
+    else:
         frames_run = 3 * (2 + steps) * total
         res["nvlink_counters"] = {"tx_bytes": nvl1[0] - nvl0[0], "rx_bytes": nvl1[1] - nvl0[1], "frames": frames_run,
                                   "expected_halo_bytes": halo * (2 * (2 + steps) * total) if len(set(devices)) > 1 else 0,

@@ -216,8 +216,9 @@ static int EnqueueFilter16(hdb_context *ctx, const FrameView &view, SizeState *s
 	const int w = view.width, h = view.height, cw = w / 2, ch = h / 2;
 	if (view.bit_depth < 8 || view.bit_depth > 10)
 		return Fail(ctx, HDB_ERR_INVALID_ARG, "bit depth must be 8, 9 or 10 (16-bit containers)");
-	if (view.nv12 || view.strip_halo)
-		return Fail(ctx, HDB_ERR_INVALID_ARG, "16-bit samples are planar and unsplit");
+	if (view.strip_halo) return Fail(ctx, HDB_ERR_INVALID_ARG, "16-bit frames are not split into strips");
+	if (view.nv12 && view.bit_depth != 10)
+		return Fail(ctx, HDB_ERR_INVALID_ARG, "HDB_FLAG_NV12 with HDB_FLAG_DEPTH is P010: depth 10 only");
 	if (w % 16 != 0 || w < 32 || ((uintptr_t)d_in | (uintptr_t)d_out) % 16 != 0 || view.luma_pitch % 16 != 0 || view.chroma_pitch % 16 != 0
 		|| view.frame_stride % 16 != 0 || view.chroma_frame_stride % 16 != 0 || (view.u_offset | view.v_offset | view.u_offset_out | view.v_offset_out) % 16 != 0)
 		return Fail(ctx, HDB_ERR_DIMENSIONS, "16-bit frames need a width that is a multiple of 16, at least 32, and 16-byte aligned buffers");
@@ -233,6 +234,7 @@ static int EnqueueFilter16(hdb_context *ctx, const FrameView &view, SizeState *s
 	b.vert_bs_stride = vbs_stride; b.hor_bs_stride = hbs_stride;
 	b.chroma_bs = ss->chroma_bs;
 	b.qp_value = qp_value;
+	b.nv12 = view.nv12 ? 1 : 0;
 	b.n_frames = 1;
 	FinalizeTiledBatch(b);
 	const long long max_frames = std::max<long long>(1, ((1ll << 31) - (1 << 20)) / std::max(b.items_per_frame, 1));
@@ -249,9 +251,10 @@ static int EnqueueFilter16(hdb_context *ctx, const FrameView &view, SizeState *s
 		const long long off_in[3] = { 0, view.u_offset, view.v_offset }, off_out[3] = { 0, view.u_offset_out, view.v_offset_out };
 		TensorMaps3 maps;
 		memset(&maps, 0, sizeof maps);
-		for (int p = 0; p < 3; p++) {
+		for (int p = 0; p < (view.nv12 ? 2 : 3); p++) {
 			const long long pfs = p ? view.chroma_frame_stride : view.frame_stride;
-			int rc = EncodePlaneMap(ctx, &maps.in[p], d_in + off_in[p] + f0 * pfs, 2 * (p ? cw : w), p ? view.chroma_buf_rows : view.luma_buf_rows, nf,
+			/* bytes per row: two per sample; the interleaved UV plane of a P010 frame is as wide as its luma plane */
+			int rc = EncodePlaneMap(ctx, &maps.in[p], d_in + off_in[p] + f0 * pfs, 2 * ((p && !view.nv12) ? cw : w), p ? view.chroma_buf_rows : view.luma_buf_rows, nf,
 				p ? view.chroma_pitch : view.luma_pitch, pfs, 8 * cfg.block_rows_per_item, 132u);
 			if (rc) return rc;
 			b.in_plane[p] = d_in + off_in[p] + f0 * pfs;
@@ -531,7 +534,7 @@ int BatchHostLocked(hdb_context *ctx, const unsigned char *in, unsigned char *ou
 	const bool edge_qp = (flags & HDB_FLAG_EDGE_MAPS) != 0 || info != nullptr, nv12 = (flags & HDB_FLAG_NV12) != 0;
 	const int depth = DepthOfFlags(flags);
 	if ((flags & HDB_FLAG_SAMPLES16) && (depth < 8 || depth > 10)) return Fail(ctx, HDB_ERR_INVALID_ARG, "bit depth must be 8, 9 or 10 (HDB_FLAG_DEPTH)");
-	if (depth && nv12) return Fail(ctx, HDB_ERR_INVALID_ARG, "16-bit samples are planar: HDB_FLAG_NV12 does not combine with HDB_FLAG_DEPTH");
+	if (depth && nv12 && depth != 10) return Fail(ctx, HDB_ERR_INVALID_ARG, "HDB_FLAG_NV12 with HDB_FLAG_DEPTH is P010: depth 10 only");
 	if (!in || !out || !qp || n == 0) return Fail(ctx, HDB_ERR_INVALID_ARG, "NULL buffer or empty batch");
 	if (info && (vbs || hbs)) return Fail(ctx, HDB_ERR_INVALID_ARG, "give block data or edge maps, not both");
 	if (edge_qp && !info && (!vbs || !hbs)) return Fail(ctx, HDB_ERR_INVALID_ARG, "edge maps are required: there is no default for them");

@@ -726,7 +726,46 @@ constexpr int kSmemBytes16 = kWarps * kStages * (kTileBytes16 + 8 + 8);
 #define HDB_MIN_CTAS16 12
 #endif
 
-template <int kDepth, bool kEdgeQp>
+/*
+ * One block row of an interleaved-UV item of a P010 frame (16-bit samples in the HIGH bits, chroma interleaved:
+ * what a hardware decoder writes for 10-bit video): as UvBlockRow, lanes 0-15 filter the U samples of block pair
+ * lane & 15 and lanes 16-31 its V samples.  The pair's 32 bytes of a row are eight words (U_k | V_k << 16); a lane
+ * picks its plane's halves, brings them down to the low bits, filters, swaps two words per row with its partner
+ * and re-interleaves four of the eight words.  Every lane runs the whole sequence (full-mask shuffles); `live`
+ * only gates the write-back.
+ */
+template <int kDepth>
+__device__ __forceinline__ void UvBlockRow16(u32 *base, u32 s4, const FilterParams16 &fp, bool live, bool v_plane)
+{
+	constexpr int kShift = 16 - kDepth;
+	const u32 sel = v_plane ? 0x7632u : 0x5410u;
+	u32 w[8][4];
+#pragma unroll
+	for (int r = 0; r < 8; r++) {
+		const uint4 a = *reinterpret_cast<const uint4 *>(base + r * kTileWords16);
+		const uint4 c = *reinterpret_cast<const uint4 *>(base + r * kTileWords16 + 4);
+		w[r][0] = (Prmt(a.x, a.y, sel) >> kShift) & Depth<kDepth>::kMaxRep;
+		w[r][1] = (Prmt(a.z, a.w, sel) >> kShift) & Depth<kDepth>::kMaxRep;
+		w[r][2] = (Prmt(c.x, c.y, sel) >> kShift) & Depth<kDepth>::kMaxRep;
+		w[r][3] = (Prmt(c.z, c.w, sel) >> kShift) & Depth<kDepth>::kMaxRep;
+	}
+	ChromaBlock16<kDepth>(w, s4 & 0xff, (s4 >> 8) & 0xff, (s4 >> 16) & 0xff, s4 >> 24, fp);
+#pragma unroll
+	for (int r = 0; r < 8; r++) {
+		/* the U lane writes words 0-3 (samples 0-3 of both planes), the V lane words 4-7 */
+		const u32 g0 = __shfl_xor_sync(0xffffffffu, v_plane ? w[r][0] : w[r][2], 16);
+		const u32 g1 = __shfl_xor_sync(0xffffffffu, v_plane ? w[r][1] : w[r][3], 16);
+		const u32 u0 = v_plane ? g0 : w[r][0], u1 = v_plane ? g1 : w[r][1];
+		const u32 v0 = v_plane ? w[r][2] : g0, v1 = v_plane ? w[r][3] : g1;
+		uint4 o;
+		o.x = PairLo(u0, v0) << kShift; o.y = PairHi(u0, v0) << kShift;
+		o.z = PairLo(u1, v1) << kShift; o.w = PairHi(u1, v1) << kShift;
+		if (live) *reinterpret_cast<uint4 *>(base + r * kTileWords16 + (v_plane ? 4 : 0)) = o;
+	}
+}
+
+/* kP010: two planes, Y and interleaved UV, samples in the high bits of their containers (P010 / P016) */
+template <int kDepth, bool kEdgeQp, bool kP010>
 __global__ void __launch_bounds__(kWarps * 32, HDB_MIN_CTAS16)
 DeblockTiled16Kernel(const __grid_constant__ TensorMaps3 maps, const __grid_constant__ TiledBatch b,
 	SchedWords *sched, const uint32_t run_len)
@@ -759,7 +798,7 @@ DeblockTiled16Kernel(const __grid_constant__ TensorMaps3 maps, const __grid_cons
 				cur.Seek(b, run_next);
 			}
 		} else {
-			cur.template Next<false>(b);
+			cur.template Next<kP010>(b);
 		}
 		if (run_next >= total) { held[s] = make_uint2(0u, kNoItem); return; }
 		run_next++;
@@ -786,41 +825,48 @@ DeblockTiled16Kernel(const __grid_constant__ TensorMaps3 maps, const __grid_cons
 	FilterParams16 fp;
 	PlaneInfo pl;
 	MakeFilterParams16<kDepth>(fp, 0, 0);
-	pl = MakePlaneInfo<false>(b, 0);
+	pl = MakePlaneInfo<kP010>(b, 0);
 	BsRaw bs_raw[kRB];
 	{
 		const uint2 it0 = held[0];
 #pragma unroll
-		for (int rb = 0; rb < kRB; rb++) bs_raw[rb] = ItemBsRaw<false>(b, it0.x, it0.y, lane, rb);
+		for (int rb = 0; rb < kRB; rb++) bs_raw[rb] = ItemBsRaw<kP010>(b, it0.x, it0.y, lane, rb);
 	}
 	for (;;) {
 		const uint2 it = held[s];
 		const uint32_t frame = it.x, desc = it.y;
 		if (desc == kNoItem) break;
 		int plane, bx0, lby0;
-		ItemCoords<false>(desc, plane, bx0, lby0);
+		ItemCoords<kP010>(desc, plane, bx0, lby0);
 		const bool chroma = plane != 0;
 		if (frame != cur_frame) {
 			cur_frame = frame;
 			const unsigned qp = b.qp ? __ldg(b.qp + frame) : b.qp_value;
 			MakeFilterParams16<kDepth>(fp, BetaOf(qp), TcOf(qp));      /* cpu.h:136-137, scaled to the depth */
 		}
-		if (plane != cur_plane) { cur_plane = plane; pl = MakePlaneInfo<false>(b, plane); }
-		const int bx = bx0 + lane;
+		if (plane != cur_plane) { cur_plane = plane; pl = MakePlaneInfo<kP010>(b, plane); }
+		const int bx = bx0 + ((kP010 && chroma) ? (lane & 15) : lane);
 		u32 bs[kRB];
 		{
 			const uint2 it_next = held[s + 1 == kStages ? 0 : s + 1];
 #pragma unroll
 			for (int rb = 0; rb < kRB; rb++) bs[rb] = PackBs(bs_raw[rb], chroma);
 #pragma unroll
-			for (int rb = 0; rb < kRB; rb++) bs_raw[rb] = ItemBsRaw<false>(b, it_next.x, it_next.y, lane, rb);
+			for (int rb = 0; rb < kRB; rb++) bs_raw[rb] = ItemBsRaw<kP010>(b, it_next.x, it_next.y, lane, rb);
 		}
 		MbarWait(bars_s + 8u * s, parity);
 		u32 *tile = reinterpret_cast<u32 *>(tiles + s * kTileBytes16);
 		unsigned char *dst = pl.out + (long long)frame * pl.frame_stride;
 #pragma unroll 1
 		for (int rb = 0; rb < kRB; rb++) {
-			if (bx < pl.nbx && lby0 + rb < pl.rows) {
+			if (kP010 && chroma) {
+				u32 s4 = bs[0];
+#pragma unroll
+				for (int k = 1; k < kRB; k++) if (rb == k) s4 = bs[k];
+				/* block pair lane & 15: 32 bytes per row from the box origin on (the pair of block column 16 chunk
+				 * starts exactly there) */
+				UvBlockRow16<kDepth>(tile + rb * 8 * kTileWords16 + 8 * (lane & 15), s4, fp, bx < pl.nbx && lby0 + rb < pl.rows, lane >= 16);
+			} else if (bx < pl.nbx && lby0 + rb < pl.rows) {
 				/* lane l owns bytes 8 + 16 l .. 23 + 16 l of each of the block row's 8 tile rows */
 				u32 *base = tile + rb * 8 * kTileWords16 + 2 + 4 * lane;
 				u32 w[8][4];
@@ -829,6 +875,10 @@ DeblockTiled16Kernel(const __grid_constant__ TensorMaps3 maps, const __grid_cons
 					const uint2 a = *reinterpret_cast<const uint2 *>(base + r * kTileWords16);
 					const uint2 c = *reinterpret_cast<const uint2 *>(base + r * kTileWords16 + 2);
 					w[r][0] = a.x; w[r][1] = a.y; w[r][2] = c.x; w[r][3] = c.y;
+					if (kP010) {
+#pragma unroll
+						for (int j = 0; j < 4; j++) w[r][j] = (w[r][j] >> (16 - kDepth)) & Depth<kDepth>::kMaxRep;
+					}
 				}
 				u32 s4 = bs[0];
 #pragma unroll
@@ -837,6 +887,10 @@ DeblockTiled16Kernel(const __grid_constant__ TensorMaps3 maps, const __grid_cons
 				else LumaBlock16<kDepth, kEdgeQp>(w, s4 & 0xff, (s4 >> 8) & 0xff, (s4 >> 16) & 0xff, s4 >> 24, fp);
 #pragma unroll
 				for (int r = 0; r < 8; r++) {
+					if (kP010) {
+#pragma unroll
+						for (int j = 0; j < 4; j++) w[r][j] <<= 16 - kDepth;
+					}
 					*reinterpret_cast<uint2 *>(base + r * kTileWords16) = make_uint2(w[r][0], w[r][1]);
 					*reinterpret_cast<uint2 *>(base + r * kTileWords16 + 2) = make_uint2(w[r][2], w[r][3]);
 				}
@@ -850,14 +904,15 @@ DeblockTiled16Kernel(const __grid_constant__ TensorMaps3 maps, const __grid_cons
 			const int pwb = 2 * pl.pw;                                  /* plane width in bytes */
 			const int xb0 = 512 * (int)((desc >> 2) & 0x3ffu);
 			const unsigned char *tile8 = reinterpret_cast<const unsigned char *>(tile);
-			const int vcol = xb0 + 16 * lane;
-			const bool vec_lane = lane < 31 && vcol < pwb;
-			const unsigned char *vsrc = tile8 + 16 + 16 * lane;
+			const bool uv = kP010 && chroma;                           /* a UV item owns tile bytes 0 .. 511: 32 vectors, no fringe */
+			const int vcol = uv ? xb0 - 16 + 16 * lane : xb0 + 16 * lane;
+			const bool vec_lane = (uv || lane < 31) && vcol >= 0 && vcol < pwb;
+			const unsigned char *vsrc = tile8 + (uv ? 0 : 16) + 16 * lane;
 			unsigned char *vdst = dst + (long long)y0 * pl.pitch + vcol;
 			const int k = lane & 3, ftr = lane >> 2;
 			const int fword = k < 2 ? 2 + k : 126 + k;                  /* tile words 2, 3 and 128, 129 */
 			const int fcol = k < 2 ? xb0 - 8 + 4 * k : xb0 + 496 + 4 * (k - 2);
-			const bool f_lane = fcol >= 0 && fcol < pwb;
+			const bool f_lane = !uv && fcol >= 0 && fcol < pwb;
 #pragma unroll
 			for (int rr = 0; rr < kTileH; rr++) {
 				const int y = y0 + rr;
@@ -890,16 +945,18 @@ DeblockTiled16Kernel(const __grid_constant__ TensorMaps3 maps, const __grid_cons
 
 typedef void (*TiledKernelFn16)(const TensorMaps3, const TiledBatch, SchedWords *, const uint32_t);
 
-/* variant index = (edge maps ? 1 : 0) | (depth - 8) << 1 */
+/* variant index = (edge maps ? 1 : 0) | (depth - 8) << 1; 6, 7: P010 (depth 10, semi-planar, high-aligned) */
 static TiledKernelFn16 TiledKernel16Of(int v)
 {
 	switch (v) {
-	case 0: return DeblockTiled16Kernel<8, false>;
-	case 1: return DeblockTiled16Kernel<8, true>;
-	case 2: return DeblockTiled16Kernel<9, false>;
-	case 3: return DeblockTiled16Kernel<9, true>;
-	case 4: return DeblockTiled16Kernel<10, false>;
-	case 5: return DeblockTiled16Kernel<10, true>;
+	case 0: return DeblockTiled16Kernel<8, false, false>;
+	case 1: return DeblockTiled16Kernel<8, true, false>;
+	case 2: return DeblockTiled16Kernel<9, false, false>;
+	case 3: return DeblockTiled16Kernel<9, true, false>;
+	case 4: return DeblockTiled16Kernel<10, false, false>;
+	case 5: return DeblockTiled16Kernel<10, true, false>;
+	case 6: return DeblockTiled16Kernel<10, false, true>;
+	case 7: return DeblockTiled16Kernel<10, true, true>;
 	}
 	return nullptr;
 }
@@ -923,7 +980,8 @@ cudaError_t LaunchTiled16(const TensorMaps3 &maps, const TiledBatch &b, void *sc
 {
 	if (b.total_items <= 0) return cudaSuccess;
 	if (b.total_items >= (1ll << 31) || bit_depth < 8 || bit_depth > 10) return cudaErrorInvalidValue;
-	const int variant = (edge_qp ? 1 : 0) | ((bit_depth - 8) << 1);
+	if (b.nv12 && bit_depth != 10) return cudaErrorInvalidValue;
+	const int variant = b.nv12 ? (6 | (edge_qp ? 1 : 0)) : ((edge_qp ? 1 : 0) | ((bit_depth - 8) << 1));
 	const int resident = std::max(ctas_per_sm[variant], 1);
 	long long ctas = std::min<long long>((long long)sm_count * resident, (b.total_items + kWarps - 1) / kWarps);
 	ctas = std::max<long long>(ctas, 1);

@@ -94,8 +94,9 @@ cudaError_t LaunchTiled(const TensorMaps3 &maps, const TiledBatch &b, void *sche
 	cudaStream_t stream, bool edge_qp = false);
 /* 16-bit samples (planar; bit depth 8 .. 10 in 16-bit containers): the tensor maps describe rows of 2 * width
  * bytes with a 132-element box; pitches in TiledBatch are bytes as always.  Variant index = (edge maps ? 1 : 0)
- * | (depth - 8) << 1. */
-constexpr int kTiled16Variants = 6;
+ * | (depth - 8) << 1; 6 and 7 are P010 (TiledBatch.nv12: Y + interleaved UV, 10 bits in the high bits of their
+ * containers). */
+constexpr int kTiled16Variants = 8;
 cudaError_t PrepareTiled16(int ctas_per_sm[kTiled16Variants]);
 cudaError_t LaunchTiled16(const TensorMaps3 &maps, const TiledBatch &b, void *sched, int sm_count,
 	const int ctas_per_sm[kTiled16Variants], cudaStream_t stream, int bit_depth, bool edge_qp);

@@ -247,7 +247,10 @@ int hdb_derive_edges(hdb_context *ctx, const hdb_block_info *info, unsigned n_fr
  * reference's tables times 1 << (depth - 8), and (1 << depth) - 1 in place of 255; geometry, order, decisions and
  * formulas are the reference's.  HDB_FLAG_DEPTH(8) -- 8-bit samples in 16-bit containers -- gives the reference's
  * results exactly; 9 and 10 have nothing in the reference to be compared with.  Width a multiple of 16, at least
- * 32; combines with HDB_FLAG_EDGE_MAPS, not with HDB_FLAG_NV12.
+ * 32; combines with HDB_FLAG_EDGE_MAPS.
+ *   HDB_FLAG_NV12 | HDB_FLAG_DEPTH(10) is P010, the layout a hardware decoder writes for 10-bit video: Y plane, then
+ * one plane of interleaved chroma (U0 V0 U1 V1 ...), every sample in the HIGH 10 bits of its 16-bit container (the
+ * low 6 bits are written as 0).  Sample for sample the result of the planar form.
  */
 #define HDB_FLAG_SAMPLES16 4u
 #define HDB_FLAG_DEPTH(d)  (HDB_FLAG_SAMPLES16 | ((unsigned)(d) << 8))   /* d = 8, 9 or 10 */

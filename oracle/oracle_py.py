@@ -240,6 +240,26 @@ def sao_frame(frame, w, h, params, ctb_size=64):
     return out
 
 
+def p010_to_planar(frame, w, h, depth=10):
+    """P010 / P016 (Y plane, then interleaved UV; samples in the high bits of 16-bit containers) -> planar low-aligned."""
+    f = np.ascontiguousarray(frame, np.uint16).reshape(-1)
+    ysz, csz = w * h, (w // 2) * (h // 2)
+    uv = f[ysz:].reshape(csz, 2)
+    return (np.concatenate([f[:ysz], uv[:, 0], uv[:, 1]]) >> (16 - depth)).astype(np.uint16)
+
+
+def planar_to_p010(frame, w, h, depth=10):
+    f = np.ascontiguousarray(frame, np.uint16).reshape(-1)
+    ysz, csz = w * h, (w // 2) * (h // 2)
+    uv = np.stack([f[ysz:ysz + csz], f[ysz + csz:]], axis=1).reshape(-1)
+    return (np.concatenate([f[:ysz], uv]) << (16 - depth)).astype(np.uint16)
+
+
+def deblock_frame_p010(frame, w, h, qp, vert=None, hor=None, edges=False):
+    """The 16-bit oracle between the two layout conversions (what a decoder's 10-bit surfaces hold)."""
+    return planar_to_p010(deblock_frame16(p010_to_planar(frame, w, h), w, h, qp, vert, hor, bit_depth=10, edges=edges), w, h)
+
+
 def derive_edges(info, w, h):
     """info: BLOCK_INFO[h/8, w/8] -> (vert_edges, hor_edges) by the H.265 rule (deblock_oracle.h)."""
     info = np.ascontiguousarray(info, BLOCK_INFO)

@@ -116,3 +116,15 @@ def test_emu16_1080p(emu):  # noqa: F811
     got = run_emu16(emu, frame, w, h, 37, v, hh, 10)
     want = orc.deblock_frame16(frame, w, h, 37, v, hh, bit_depth=10)
     assert np.array_equal(got, want) and (got != frame).mean() > 0.05
+
+
+def test_p010_layout_conversion_round_trip():
+    rng = np.random.default_rng(1)
+    w, h = 64, 48
+    planar = make_frame16(rng, w, h, "random", 10)
+    p010 = orc.planar_to_p010(planar, w, h)
+    assert int(p010.max()) > 1023 and not (p010 & 63).any()
+    assert np.array_equal(orc.p010_to_planar(p010, w, h), planar)
+    # U0 V0 U1 V1 ... after the luma plane
+    cw = w // 2
+    assert p010[w * h] == planar[w * h] << 6 and p010[w * h + 1] == planar[w * h + cw * (h // 2)] << 6

@@ -72,3 +72,33 @@ def test_algorithmic_bytes_match_survey_table():
     assert bench.alg_bytes_per_frame(1920, 1080) == 6302302
     assert bench.alg_bytes_per_frame(3840, 2160) == 25208325
     assert bench.alg_bytes_per_frame(7680, 4320) == 100831050
+
+
+def test_workload_frames_depend_on_the_global_frame_number_only():
+    """Every rank of our arm and the reference arm must draw the same frames whatever their shard (bench.py:
+    workload_frames): any range equals the matching slice of a larger one."""
+    import torch
+    w, h = 64, 48
+    full = bench.workload_frames(torch, 0, 40, w, h, 123, "cpu")
+    for first, n in [(0, 16), (16, 16), (24, 13), (5, 35), (39, 1)]:
+        part = bench.workload_frames(torch, first, n, w, h, 123, "cpu")
+        for a, b in zip(part, full):
+            assert torch.equal(a, b[first:first + n]), (first, n)
+    other = bench.workload_frames(torch, 0, 16, w, h, 124, "cpu")
+    assert not torch.equal(other[0], full[0][:16])
+    # the QP specials ride on the global frame number too
+    q = bench.workload_frames(torch, 64, 8, w, h, 123, "cpu")[1]
+    assert int(q[3]) == 12 and int(q[5]) == 17 and int(q[6]) == 60
+
+
+def test_both_arms_print_the_same_config():
+    for name in ("4k_batch1024", "1080p_batch256", "4k_yuv420p10_512"):
+        assert bench.workload_config(name, 8, "cuda") == bench.workload_config(name, 8, "cuda")
+        c = bench.workload_config(name, 4, "cuda")
+        assert c["frames_per_gpu"] * 4 >= c["frames"] and c["workload"] == name
+
+
+def test_exact_block_shapes_divide_the_block_counts():
+    for nbx, nby in [(481, 271), (241, 136), (97, 73), (49, 37), (45, 37), (961, 541)]:
+        dx, dy = bench.exact_block_shape(nbx, nby)
+        assert nbx % dx == 0 and nby % dy == 0 and dx * dy <= 1024

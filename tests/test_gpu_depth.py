@@ -112,11 +112,40 @@ def test_batch16_host_pipeline_and_device_resident(dev):
     assert np.array_equal(o.cpu().numpy().view(np.uint16).reshape(n, -1), want)
 
 
+@pytest.mark.parametrize("size", [(32, 8), (64, 48), (272, 72), (352, 288), (528, 16), (1920, 1080), (2000, 1048)], ids=lambda s: "%dx%d" % s)
+def test_p010_sizes_vs_oracle(dev, size):
+    """P010: Y plane + interleaved UV, 10-bit samples in the high bits of 16-bit containers (HDB_FLAG_NV12 | HDB_FLAG_DEPTH(10))."""
+    w, h = size
+    rng = np.random.default_rng(w * 19 + h)
+    flags = hdb.FLAG_NV12 | hdb.flag_depth(10)
+    for kind, bs_kind, qp in [("blocky", "uniform012", 37), ("saturated", "wide", 51), ("random", None, 44)]:
+        frame = orc.planar_to_p010(make_frame16(rng, w, h, kind, 10), w, h)
+        v, hh = (None, None) if bs_kind is None else synth.make_bs(rng, w, h, bs_kind)
+        got = dev.deblock_batch_ex(frame[None], w, h, np.array([qp], np.uint32), None if v is None else v[None],
+                                   None if hh is None else hh[None], flags=flags)[0]
+        want = orc.deblock_frame_p010(frame, w, h, qp, v, hh)
+        assert np.array_equal(got, want), (size, kind, bs_kind, qp, int((got != want).sum()))
+    # edge maps, and a batch on the device in place
+    import torch
+    n = 3
+    frames = np.stack([orc.planar_to_p010(make_frame16(rng, w, h, "blocky", 10), w, h) for _ in range(n)])
+    maps = [synth.make_edge_maps(rng, w, h, "random", picture_edges=True) for _ in range(n)]
+    ev, eh = np.stack([m[0] for m in maps]), np.stack([m[1] for m in maps])
+    qps = rng.integers(18, 52, n).astype(np.uint32)
+    d = torch.from_numpy(frames.view(np.int16)).cuda()
+    dev.deblock_batch_device_ex(d, d, n, w, h, torch.from_numpy(qps.astype(np.int32)).cuda(), torch.from_numpy(ev).cuda(),
+                                torch.from_numpy(eh).cuda(), flags=flags | hdb.FLAG_EDGE_MAPS, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    got = d.cpu().numpy().view(np.uint16)
+    for f in range(n):
+        assert np.array_equal(got[f], orc.deblock_frame_p010(frames[f], w, h, int(qps[f]), ev[f], eh[f], edges=True)), f
+
+
 def test_depth_errors(dev):
     w, h = 64, 48
     f = np.zeros((1, 3 * w * h // 2), np.uint16)
     q = np.array([30], np.uint32)
-    for bad in (hdb.flag_depth(7), hdb.flag_depth(11), hdb.flag_depth(12), hdb.flag_depth(10) | hdb.FLAG_NV12):
+    for bad in (hdb.flag_depth(7), hdb.flag_depth(11), hdb.flag_depth(12), hdb.flag_depth(8) | hdb.FLAG_NV12):
         with pytest.raises(hdb.DeblockError):
             dev.deblock_batch_ex(f, w, h, q, flags=bad)
     with pytest.raises(hdb.DeblockError, match="multiple of 16"):
