@@ -1022,6 +1022,20 @@ void FinalizeTiledBatch(TiledBatch &b)
 	b.chroma_vpitch = 8 * b.chroma_nbx;
 	b.chroma_rpitch = cw + 8;
 	b.div_chroma_rpitch.Init((uint32_t)b.chroma_rpitch);
+	if (b.chroma_skew && b.chroma_row0 == 0) {
+		/* The virtual rows run 4 bytes short of the buffer rows, so the reference's block rows end before the
+		 * buffer does: the last image rows lie beyond them and it never touches them (Save copies them out as they
+		 * came in).  Out of place they still have to be moved: row groups to the end of the buffer, the ones past
+		 * the last block row without arithmetic. */
+		const long long buffer_bytes = (long long)(b.height / 2 + 8) * b.chroma_rpitch;
+		const int virtual_rows = (int)((buffer_bytes + b.chroma_vpitch - 1) / b.chroma_vpitch);
+		b.chroma_groups = std::max(b.chroma_groups, (virtual_rows + 8 * kRB - 1) / (8 * kRB));
+		b.items_chroma = b.chroma_chunks * b.chroma_groups;
+		b.items_per_frame = b.items_luma + 2 * b.items_chroma;
+		b.total_items = (long long)b.items_per_frame * b.n_frames;
+		b.div_items_per_frame.Init((uint32_t)b.items_per_frame);
+		b.div_items_chroma.Init((uint32_t)std::max(b.items_chroma, 1));
+	}
 }
 
 typedef void (*TiledKernelFn)(const TensorMaps3, const TiledBatch, SchedWords *, const uint32_t);

@@ -122,17 +122,18 @@ SaoKernel(const __grid_constant__ SaoBatch b)
 		else if (edge && pos != 1u) { keep0 = x == 0 ? 0x000000ffu : 0u; keep0 |= x == pww - 1 ? 0xff000000u : 0u; keep1 = x + 1 == pww - 1 ? 0xff000000u : 0u; }
 		const u32 band_add = (32u - pos) * 0x10001u;
 
-		/* (L, w0, w1, R) of a row for this lane; 0 outside the picture (those samples are kept) */
+		/* (L, w0, w1, R) of a row for this lane.  Branch-free: rows and words outside the picture are read from the
+		 * nearest ones inside instead -- a sample whose neighbour lies outside is kept whatever the comparison says. */
+		const int xc0 = min(x, pww - 1), xc1 = min(x + 1, pww - 1), xl = min(max(x - 1, 0), pww - 1), xr = min(x + 2, pww - 1);
 		auto load_row = [&](int y) -> RowWin {
-			RowWin w = { 0u, 0u, 0u, 0u };
-			if (y < 0 || y >= ph) return w;
-			const u32 *p = src + (long long)y * pww + x;
-			if (live0) w.w0 = __ldg(p);
-			if (live1) w.w1 = __ldg(p + 1);
+			const u32 *p = src + (long long)min(max(y, 0), ph - 1) * pww;
+			RowWin w;
+			w.w0 = __ldg(p + xc0); w.w1 = __ldg(p + xc1);
+			const u32 el = __ldg(p + xl), er = __ldg(p + xr);
 			w.L = __shfl_up_sync(0xffffffffu, w.w1, 1);
 			w.R = __shfl_down_sync(0xffffffffu, w.w0, 1);
-			if (lane == 0) w.L = (live0 && x > 0) ? __ldg(p - 1) : 0u;
-			if (lane == 31) w.R = (x + 2 < pww) ? __ldg(p + 2) : 0u;
+			if (lane == 0) w.L = el;
+			if (lane == 31) w.R = er;
 			return w;
 		};
 		auto offset4 = [&](u32 c, u32 a, u32 n) -> u32 {          /* four samples of word c against neighbour words a, n */

@@ -466,3 +466,27 @@ def test_planes_entry_point_from_two_threads(dev):
 def test_frame_too_wide_is_refused(dev):
     with pytest.raises(hdb.DeblockError, match="too large"):
         dev.deblock_batch_device(1 << 20, 1 << 21, 1, 262144, 8, 1 << 22)
+
+
+@pytest.mark.parametrize("size", [(72, 400), (40, 544), (952, 344), (1528, 600), (136, 280)], ids=lambda s: "%dx%d" % s)
+def test_skewed_chroma_out_of_place_reaches_the_last_rows(dev, size):
+    """Frame widths of 8 mod 16: the reference's chroma blocks tile a virtual plane whose rows are 4 bytes short
+    of the buffer's, so its block rows end above the last image rows, which it leaves alone.  Out of place those
+    rows must still arrive in the output (found by tools/soak.py: the first version of the skew mapping moved only
+    the rows the reference's blocks reach)."""
+    import torch
+    w, h = size
+    n = 3
+    frames, qps, v, hh = synth.make_batch(w + h, n, w, h)
+    want = orc.deblock_batch(frames, w, h, qps, v, hh)
+    d_in = torch.from_numpy(frames).cuda()
+    d_out = torch.full_like(d_in, 0xA5)
+    d_qp = torch.from_numpy(qps.astype(np.int32)).cuda()
+    d_v, d_h = torch.from_numpy(v).cuda(), torch.from_numpy(hh).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    dev.deblock_batch_device(d_in, d_out, n, w, h, d_qp, d_v, d_h, stream=st)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_out.cpu().numpy(), want)
+    dev.deblock_batch_device(d_in, d_in, n, w, h, d_qp, d_v, d_h, stream=st)      # and in place
+    torch.cuda.synchronize()
+    assert np.array_equal(d_in.cpu().numpy(), want)
