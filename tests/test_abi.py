@@ -91,5 +91,14 @@ def test_struct_layouts_and_constants_match_the_header(tmp_path):
             binding.BLOCK_INFO.fields["flags"][1], binding.DeviceInfo.total_global_mem.offset,
             binding.FLAG_EDGE_MAPS, binding.FLAG_NV12, int(binding.edge_bytes(2, 37))]
     assert got == want, (got, want)
+    # this round's additions: strip planes, SAO parameters, the depth flags
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "hevc_deblock_b200.h"\n'
+                   'int main(void) { printf("%zu %zu %zu %zu %u %u\\n", sizeof(hdb_strip_planes), offsetof(hdb_strip_planes, v),'
+                   ' sizeof(hdb_sao_params), offsetof(hdb_sao_params, offset), HDB_FLAG_SAMPLES16, HDB_FLAG_DEPTH(10)); return 0; }\n')
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    want = [C.sizeof(binding.StripPlanes), binding.StripPlanes.v.offset, binding.SAO_PARAMS.itemsize,
+            binding.SAO_PARAMS.fields["offset"][1], binding.FLAG_SAMPLES16, binding.flag_depth(10)]
+    assert got == want, (got, want)
     assert (binding.BLK_INTRA, binding.BLK_CBF, binding.BLK_TU_LEFT, binding.BLK_TU_TOP, binding.BLK_PU_LEFT, binding.BLK_PU_TOP) \
         == (1, 2, 4, 8, 16, 32)

@@ -20,13 +20,4 @@ for sz in "1080 1920 256" "1080 1920 1024" "360 288 256" "1000 1000 256" "1008 1
 done
 HDB_NO_LDGSTS=1 timeout 120 python tools/quick_time.py --w 1080 --h 1920 --n 256 >> ${R}_ldgsts.txt 2>&1
 timeout 300 python tools/soak.py 21 150 > ${R}_soak.txt 2>&1; tail -2 ${R}_soak.txt
-# every launch of the default bench with its device time (shares, not absolutes)
-timeout 600 python bench.py --steps 2 --warmup 3 --no-cpu --no-sub > gpurun_out/plain.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file ${R}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu --no-sub > ${R}_ncu_launches.log 2>&1
-# the hot kernel on the full batch, and every kernel of the library on 256 frames
-timeout 300 python tools/quick_time.py --n 1024 --iters 2 > gpurun_out/plain2.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:DeblockTiled -s 3 -c 1 -f -o ${R}_prof_main_n1024 python tools/quick_time.py --n 1024 --iters 2 > ${R}_ncu_main.log 2>&1
-N=256 timeout 600 python tools/profile_variants.py > gpurun_out/plain3.log 2>&1 && \
-N=256 ncu --set full --clock-control none --import-source on -k "regex:Deblock|Derive|Sao" -f -o ${R}_prof_variants python tools/profile_variants.py > ${R}_ncu_variants.log 2>&1
-tail -2 ${R}_ncu_variants.log
 ls -la gpurun_out | grep r02z
