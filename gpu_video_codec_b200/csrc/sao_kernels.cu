@@ -146,11 +146,13 @@ SaoKernel(const __grid_constant__ SaoBatch b)
 			const u32 rB = AddMinRelu2(cB, PickOffsets(edge ? eB : kB, pool_lo, pool_hi), 0x00ff00ffu);
 			return Prmt(rA, rB, 0x6420);
 		};
-		RowWin r0 = load_row(y0 - 1), r1 = load_row(y0);
+		/* the row after next is fetched while this one is worked on: with the loads of row y + 1 issued in the
+		 * iteration that needs them the walk ran at the latency of one load per row (0.25 of the HBM peak) */
+		RowWin r0 = load_row(y0 - 1), r1 = load_row(y0), r2 = load_row(y0 + 1);
 		u32 *orow = dst + (long long)y0 * pww + x;
 #pragma unroll 1
 		for (int y = y0; y < y1; y++) {
-			const RowWin r2 = load_row(y + 1);
+			const RowWin r3 = load_row(y + 2);
 			const RowWin ra = a_same_row ? r1 : r0, rb = a_same_row ? r1 : r2;
 			u32 a0, a1, n0, n1;
 			Shifted(ra, a_left, a_amount, a0, a1);
@@ -161,7 +163,7 @@ SaoKernel(const __grid_constant__ SaoBatch b)
 			const u32 k0 = keep_row ? 0xffffffffu : keep0, k1 = keep_row ? 0xffffffffu : keep1;
 			if (live0) orow[0] = (r1.w0 & k0) | (res0 & ~k0);
 			if (live1) orow[1] = (r1.w1 & k1) | (res1 & ~k1);
-			r0 = r1; r1 = r2;
+			r0 = r1; r1 = r2; r2 = r3;
 			orow += pww;
 		}
 	}
