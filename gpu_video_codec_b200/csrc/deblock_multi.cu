@@ -175,10 +175,10 @@ int hdb_multi_deblock_batch_ex(hdb_multi *m, const unsigned char *frames_in, uns
 	const unsigned char *vert_bs, const unsigned char *hor_bs, unsigned flags, hdb_timing *timing)
 {
 	if (!m || m->ctx.empty()) return HDB_ERR_INVALID_ARG;
-	if (flags & ~(HDB_FLAG_EDGE_MAPS | HDB_FLAG_NV12)) return MFail(m, HDB_ERR_INVALID_ARG, "unknown flag");
+	if (flags & ~(HDB_FLAG_EDGE_MAPS | HDB_FLAG_NV12 | HDB_FLAG_SAMPLES16 | 0xff00u)) return MFail(m, HDB_ERR_INVALID_ARG, "unknown flag");
 	if (!frames_in || !frames_out || !qp || n_frames == 0) return MFail(m, HDB_ERR_INVALID_ARG, "NULL buffer or empty batch");
 	const int g = (int)std::min<size_t>(m->ctx.size(), n_frames);
-	const size_t fb = (size_t)width * height * 3 / 2;
+	const size_t fb = (size_t)width * height * 3 / 2 * ((flags & HDB_FLAG_SAMPLES16) ? 2 : 1);
 	const unsigned nv = hdb_num_vert_bs(width, height), nh = hdb_num_hor_bs(width, height);
 	std::vector<int> rcs(g, HDB_OK);
 	std::vector<hdb_timing> tms(g);

@@ -161,3 +161,24 @@ def test_strips_resident_in_device_memory(devices, edges):
     with pytest.raises(hdb.DeblockError, match="out of place"):
         m.deblock_strips_device(ins, ins, w, h, 36, dv, dh, flags=hdb.FLAG_EDGE_MAPS if edges else 0)
     m.close()
+
+
+@pytest.mark.parametrize("devices", _device_sets()[1:], ids=lambda d: "dev" + "".join(map(str, d)))
+def test_frame_sharded_batch_10bit(devices):
+    """The flagged batch form across devices with 16-bit samples: planar 10-bit and P010, sharded by frame."""
+    from tests.test_depth import make_frame16
+    m = hdb.MultiDeblocker(devices)
+    n, w, h = 11, 352, 288
+    rng = np.random.default_rng(51)
+    planar = np.stack([make_frame16(rng, w, h, "blocky", 10) for _ in range(n)])
+    qps = rng.integers(18, 52, n).astype(np.uint32)
+    bs = [synth.make_bs(rng, w, h, "uniform012") for _ in range(n)]
+    v, hh = np.stack([a for a, _ in bs]), np.stack([b for _, b in bs])
+    got = m.deblock_batch_ex(planar, w, h, qps, v, hh, flags=hdb.flag_depth(10))
+    for f in range(n):
+        assert np.array_equal(got[f], orc.deblock_frame16(planar[f], w, h, int(qps[f]), v[f], hh[f], bit_depth=10)), f
+    p010 = np.stack([orc.planar_to_p010(planar[f], w, h) for f in range(n)])
+    got = m.deblock_batch_ex(p010, w, h, qps, v, hh, flags=hdb.flag_depth(10) | hdb.FLAG_NV12)
+    for f in range(n):
+        assert np.array_equal(got[f], orc.deblock_frame_p010(p010[f], w, h, int(qps[f]), v[f], hh[f])), f
+    m.close()
