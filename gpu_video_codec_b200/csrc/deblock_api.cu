@@ -202,6 +202,7 @@ static int SchedAcquire(hdb_context *ctx, cudaStream_t stream, void **sched, int
 
 static int SchedLaunched(hdb_context *ctx, cudaStream_t stream, int slot)
 {
+	/* (measured: the record costs nothing on 0.2 .. 0.75 ms launches issued back to back, profiles/r02t_*) */
 	HDB_CUDA(ctx, cudaEventRecord(ctx->sched_done[slot], stream));
 	ctx->sched_used[slot] = true; ctx->sched_stream[slot] = stream;
 	ctx->launches += 1;
