@@ -1153,6 +1153,19 @@ static int ValidateSao(hdb_context *ctx, unsigned width, unsigned height, unsign
 	return HDB_OK;
 }
 
+/* the kernel's ticket counters: a stream-ordered allocation of the call's own, so that launches in flight on
+ * different streams never share one */
+static cudaError_t LaunchSaoWithTickets(hdb_context *ctx, const unsigned char *d_in, unsigned char *d_out, int n_frames, int width, int height,
+	const void *d_params, int ctb, cudaStream_t st)
+{
+	unsigned *tickets = nullptr;
+	cudaError_t e = cudaMallocFromPoolAsync(reinterpret_cast<void **>(&tickets), sizeof(unsigned) * kSaoTicketWords, ctx->pool, st);
+	if (e != cudaSuccess) return e;
+	e = LaunchSao(d_in, d_out, n_frames, width, height, d_params, ctb, tickets, ctx->prop.multiProcessorCount, st);
+	cudaFreeAsync(tickets, st);
+	return e;
+}
+
 int hdb_sao_batch_device(hdb_context *ctx, const void *d_frames_in, void *d_frames_out, unsigned n_frames,
 	unsigned width, unsigned height, const hdb_sao_params *d_params, unsigned ctb_size, void *stream)
 {
@@ -1164,8 +1177,8 @@ int hdb_sao_batch_device(hdb_context *ctx, const void *d_frames_in, void *d_fram
 	int rc = ValidateSao(ctx, width, height, ctb_size);
 	if (rc) return rc;
 	DeviceGuard guard(ctx->device);
-	HDB_CUDA(ctx, LaunchSao(static_cast<const unsigned char *>(d_frames_in), static_cast<unsigned char *>(d_frames_out), (int)n_frames,
-		(int)width, (int)height, d_params, (int)ctb_size, ctx->prop.multiProcessorCount, static_cast<cudaStream_t>(stream)));
+	HDB_CUDA(ctx, LaunchSaoWithTickets(ctx, static_cast<const unsigned char *>(d_frames_in), static_cast<unsigned char *>(d_frames_out), (int)n_frames,
+		(int)width, (int)height, d_params, (int)ctb_size, static_cast<cudaStream_t>(stream)));
 	ctx->launches += 1;
 	return HDB_OK;
 }
@@ -1193,7 +1206,7 @@ int hdb_sao_batch(hdb_context *ctx, const unsigned char *frames_in, unsigned cha
 		const unsigned nf = std::min(chunk, n_frames - f0);
 		e = cudaMemcpyAsync(d_in, frames_in + (size_t)f0 * fb, fb * nf, cudaMemcpyHostToDevice, st);
 		if (e == cudaSuccess) e = cudaMemcpyAsync(d_par, reinterpret_cast<const unsigned char *>(params) + (size_t)f0 * pb, pb * nf, cudaMemcpyHostToDevice, st);
-		if (e == cudaSuccess) e = LaunchSao(d_in, d_out, (int)nf, (int)width, (int)height, d_par, (int)ctb_size, ctx->prop.multiProcessorCount, st);
+		if (e == cudaSuccess) e = LaunchSaoWithTickets(ctx, d_in, d_out, (int)nf, (int)width, (int)height, d_par, (int)ctb_size, st);
 		if (e == cudaSuccess) e = cudaMemcpyAsync(frames_out + (size_t)f0 * fb, d_out, fb * nf, cudaMemcpyDeviceToHost, st);
 		ctx->launches += 1;
 	}
@@ -1225,8 +1238,8 @@ int hdb_deblock_sao_batch_device(hdb_context *ctx, const void *d_frames_in, void
 		d_vert, hdb_num_vert_bs(width, height), d_hor, hdb_num_hor_bs(width, height), st, nullptr, (flags & HDB_FLAG_EDGE_MAPS) != 0);
 	cudaError_t e = cudaSuccess;
 	if (!rc) {
-		e = LaunchSao(scratch, static_cast<unsigned char *>(d_frames_out), (int)n_frames, (int)width, (int)height, d_params,
-			(int)ctb_size, ctx->prop.multiProcessorCount, st);
+		e = LaunchSaoWithTickets(ctx, scratch, static_cast<unsigned char *>(d_frames_out), (int)n_frames, (int)width, (int)height, d_params,
+			(int)ctb_size, st);
 		ctx->launches += 1;
 	}
 	cudaFreeAsync(scratch, st);

@@ -139,8 +139,11 @@ cudaError_t LaunchDeriveEdges(const void *info, int width, int height, int n_fra
 /*
  * Sample adaptive offset (sao_kernels.cu; H.265 8.7.3, absent from the reference): tight 8-bit YV12 frames in
  * device memory, out of place, d_params = hdb_sao_params[n_frames][3][ceil(H / ctb)][ceil(W / ctb)].
+ * d_tickets: kSaoTicketWords words of device memory that are the launch's own until it has run (the counters the
+ * blocks are handed out through; zeroed here, in stream order).
  */
+constexpr int kSaoTicketWords = 64;
 cudaError_t LaunchSao(const unsigned char *d_in, unsigned char *d_out, int n_frames, int width, int height,
-	const void *d_params, int ctb, int sm_count, cudaStream_t stream);
+	const void *d_params, int ctb, unsigned *d_tickets, int sm_count, cudaStream_t stream);
 
 } // namespace hdb
