@@ -62,41 +62,34 @@ struct SaoBatch {
 __device__ __forceinline__ u32 PairA(u32 w) { return Prmt(w, 0u, 0x4140); }
 __device__ __forceinline__ u32 PairB(u32 w) { return Prmt(w, 0u, 0x4342); }
 
-/* 1 + sign(c - n) per half; c256 = c + 256 per half */
-__device__ __forceinline__ u32 SignPlus1(u32 c256, u32 n) { return AddMinRelu2(c256 - n, 0xff01ff01u, 0x00020002u); }
-
-/* offsets picked by the index halves (0..4) out of the pool, as signed halves */
-__device__ __forceinline__ u32 PickOffsets(u32 idx, u32 pool_lo, u32 pool_hi)
+/* four samples of word c with their indices (0..4, a byte each) in idx4: offset picked, added, clipped */
+__device__ __forceinline__ u32 ApplyOffsets4(u32 c, u32 idx4, u32 pool_lo, u32 pool_hi)
 {
-	const u32 t = idx * 0x11u;                                   /* nibble | nibble << 4 in bytes 0 and 2 */
-	const u32 sel = Prmt(t, 0u, 0x4420) | 0x8080u;               /* nibbles: i0, i0 | 8, i1, i1 | 8 */
-	/* prmt.b32 itself: bit 3 of a selector nibble replicates the sign of the selected byte (__byte_perm documents
-	 * the low three bits of each nibble only) */
-	u32 d;
-	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(pool_lo), "r"(pool_hi), "r"(sel));
-	return d;
+	/* index | index << 4 per byte, bit 7 set: bytes 0, 1 are the permute selector of samples 0, 1 (low byte of the
+	 * half picked by the index, high byte its sign), bytes 2, 3 that of samples 2, 3 (prmt reads 16 bits) */
+	const u32 sel = idx4 * 0x11u + 0x80808080u;
+	u32 oA, oB;
+	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(oA) : "r"(pool_lo), "r"(pool_hi), "r"(sel));
+	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(oB) : "r"(pool_lo), "r"(pool_hi), "r"(sel >> 16));
+	return Prmt(AddMinRelu2(PairA(c), oA, 0x00ff00ffu), AddMinRelu2(PairB(c), oB, 0x00ff00ffu), 0x6420);
 }
 
-/* four samples of word c against the neighbour words a, n: edge offset */
-__device__ __forceinline__ u32 EdgeOffset4(u32 c, u32 a, u32 n, u32 pool_lo, u32 pool_hi)
+/* 1 + sign(c - a) of four samples, a byte each: 256 + c - a - 255, at most 2, at least 0 */
+__device__ __forceinline__ u32 Signs4(u32 c, u32 a)
 {
-	const u32 cA = PairA(c), cB = PairB(c), cA256 = cA + 0x01000100u, cB256 = cB + 0x01000100u;
-	const u32 eA = SignPlus1(cA256, PairA(a)) + SignPlus1(cA256, PairA(n));
-	const u32 eB = SignPlus1(cB256, PairB(a)) + SignPlus1(cB256, PairB(n));
-	const u32 rA = AddMinRelu2(cA, PickOffsets(eA, pool_lo, pool_hi), 0x00ff00ffu);
-	const u32 rB = AddMinRelu2(cB, PickOffsets(eB, pool_lo, pool_hi), 0x00ff00ffu);
-	return Prmt(rA, rB, 0x6420);
+	const u32 sA = AddMinRelu2(PairA(c) + 0x01000100u - PairA(a), 0xff01ff01u, 0x00020002u);
+	const u32 sB = AddMinRelu2(PairB(c) + 0x01000100u - PairB(a), 0xff01ff01u, 0x00020002u);
+	return Prmt(sA, sB, 0x6420);
 }
 
-/* four samples of word c: band offset */
-__device__ __forceinline__ u32 BandOffset4(u32 c, u32 band_add, u32 pool_lo, u32 pool_hi)
+/* four samples of word c: band offset.  Band index minus band position, modulo 32, a byte each; indices 4..31
+ * (no offset) are folded onto 4..7, which the pool holds zeros for. */
+__device__ __forceinline__ u32 BandOffset4(u32 c, u32 band_add4, u32 pool_lo, u32 pool_hi)
 {
-	const u32 cA = PairA(c), cB = PairB(c);
-	const u32 kA = MinU2((((cA >> 3) & 0x001f001fu) + band_add) & 0x001f001fu, 0x00040004u);
-	const u32 kB = MinU2((((cB >> 3) & 0x001f001fu) + band_add) & 0x001f001fu, 0x00040004u);
-	const u32 rA = AddMinRelu2(cA, PickOffsets(kA, pool_lo, pool_hi), 0x00ff00ffu);
-	const u32 rB = AddMinRelu2(cB, PickOffsets(kB, pool_lo, pool_hi), 0x00ff00ffu);
-	return Prmt(rA, rB, 0x6420);
+	const u32 k = (((c >> 3) & 0x1f1f1f1fu) + band_add4) & 0x1f1f1f1fu;
+	const u32 hi = k & 0x1c1c1c1cu;
+	const u32 idx = (k & 0x03030303u) | ((hi | (hi >> 1) | (hi >> 2)) & 0x04040404u);
+	return ApplyOffsets4(c, idx, pool_lo, pool_hi);
 }
 
 /* what a lane knows about the block it works on */
@@ -151,27 +144,21 @@ __device__ __forceinline__ void StoreRow(const SaoLane &t, u32 *orow, bool row_l
 	if (row_live && t.live1) orow[1] = v1;
 }
 
-/* kMode 0: the block is off -- moved; 1: band offset; 2: edge offset, horizontal class.  No row needs another. */
+/* kMode 0: the block is off -- moved; 1: band offset.  No sample needs another: four rows' loads at a time. */
 template <int kMode>
 __device__ __forceinline__ void FlatRun(const SaoLane &t)
 {
-	u32 *orow = t.dst + ((unsigned)t.ya * t.pww + 2u * (t.xc0 >> 1));
+	u32 *orow = t.dst + ((unsigned)t.ya * t.pww + t.xc0);
+#pragma unroll 1
 	for (int k0 = 0; k0 < t.rpg; k0 += 4) {
 		RawRow r[4];
 #pragma unroll
-		for (int j = 0; j < 4; j++) r[j] = k0 + j < t.rpg ? LoadRow<kMode == 2>(t, t.ya + k0 + j) : RawRow{0u, 0u, 0u, 0u};
+		for (int j = 0; j < 4; j++) r[j] = k0 + j < t.rpg ? LoadRow<false>(t, t.ya + k0 + j) : RawRow{0u, 0u, 0u, 0u};
 #pragma unroll
 		for (int j = 0; j < 4; j++) {
 			if (k0 + j < t.rpg) {       /* the same for all lanes */
 				u32 v0 = r[j].w0, v1 = r[j].w1;
 				if (kMode == 1) { v0 = BandOffset4(v0, t.band_add, t.pool_lo, t.pool_hi); v1 = BandOffset4(v1, t.band_add, t.pool_lo, t.pool_hi); }
-				if (kMode == 2) {
-					const RowWin w = Neighbours<true>(t, r[j]);
-					const u32 a0 = __funnelshift_r(w.L, w.w0, 24), a1 = __funnelshift_r(w.w0, w.w1, 24);
-					const u32 n0 = __funnelshift_r(w.w0, w.w1, 8), n1 = __funnelshift_r(w.w1, w.R, 8);
-					const u32 e0 = EdgeOffset4(w.w0, a0, n0, t.pool_lo, t.pool_hi), e1 = EdgeOffset4(w.w1, a1, n1, t.pool_lo, t.pool_hi);
-					v0 = (v0 & t.keep0) | (e0 & ~t.keep0); v1 = (v1 & t.keep1) | (e1 & ~t.keep1);
-				}
 				StoreRow(t, orow, t.ya + k0 + j < t.yb, v0, v1);
 			}
 			orow += t.pww;
@@ -179,58 +166,66 @@ __device__ __forceinline__ void FlatRun(const SaoLane &t)
 	}
 }
 
-/* edge offset, the classes that look up and down (8.7.3.2, hPos / vPos): 1 rows y - 1 / y + 1; 2 left of row
- * y - 1 / right of row y + 1; 3 right of row y - 1 / left of row y + 1.  Row k of the run is picture row
- * ya - 1 + k; rows 0 .. rpg + 1 are needed.  Six rows in registers give four rows of output; the four rows the
- * next round adds are loaded before this round's work and handed round (the shuffles are the first use of a
- * load) after it. */
+/*
+ * Edge offset (8.7.3.2).  Class 0 compares a sample with its left and right neighbours, 1 with the ones above and
+ * below, 2 with up-left and down-right, 3 with up-right and down-left.  The two comparisons of a sample are one
+ * comparison each of two samples: with S(y, i) = 1 + sign(c(y, i) - a(y, i)), a = the FIRST neighbour (left,
+ * above, up-left, up-right), the second comparison of a sample is the negated first comparison of the sample
+ * that has it as its first neighbour, so
+ *   category(y, i) = 2 + S(y, i) - S(y + vy, i - hx)          (vy, hx) = (0, -1), (1, 0), (1, -1), (1, 1)
+ * and the walk computes one S per sample, a byte each, and reuses it a row (and / or a sample) later.  The S of
+ * the one sample beyond the lane's eight comes from the neighbouring lane by shuffle, or, for the block's last /
+ * first lane, from the neighbouring block's word.  The classes that look up and down run one row ahead of their
+ * output: iteration y computes S(y) and writes row y - 1.
+ * Rows are fetched two iterations before the shuffles that first touch them.
+ */
 template <int kClass>
-__device__ __forceinline__ void TallRun(const SaoLane &t)
+__device__ __forceinline__ void EdgeRun(const SaoLane &t)
 {
-	constexpr bool kSides = kClass != 1;
+	constexpr bool kSides = kClass != 1, kTall = kClass != 0;
+	const int n_iter = t.rpg + (kTall ? 1 : 0);
 	const RawRow none{0u, 0u, 0u, 0u};
-	RowWin w[6];
-	{
-		RawRow r[6];
-#pragma unroll
-		for (int j = 0; j < 6; j++) r[j] = j <= t.rpg + 1 ? LoadRow<kSides>(t, t.ya - 1 + j) : none;
-#pragma unroll
-		for (int j = 0; j < 6; j++) w[j] = Neighbours<kSides>(t, r[j]);
-	}
-	u32 *orow = t.dst + ((unsigned)t.ya * t.pww + 2u * (t.xc0 >> 1));
+	/* iteration i works on row ya + i as the current row */
+	RowWin prev{0u, 0u, 0u, 0u};
+	if (kTall) prev = Neighbours<kSides>(t, LoadRow<kSides>(t, t.ya - 1));
+	RawRow p = LoadRow<kSides>(t, t.ya), q = n_iter > 1 ? LoadRow<kSides>(t, t.ya + 1) : none;
+	u32 sp0 = 0u, sp1 = 0u;                          /* S of the row above */
+	u32 *orow = t.dst + ((long long)(t.ya - (kTall ? 1 : 0)) * (long long)t.pww + t.xc0);       /* row ya - 1 is never written */
 #pragma unroll 1
-	for (int k0 = 0; k0 < t.rpg; k0 += 4) {
-		const bool more = k0 + 4 < t.rpg;
-		RawRow nx[4] = {none, none, none, none};
-		if (more) {
-#pragma unroll
-			for (int j = 0; j < 4; j++) nx[j] = LoadRow<kSides>(t, t.ya + k0 + 5 + j);
+	for (int i = 0; i < n_iter; i++) {
+		const RawRow nx = i + 2 < n_iter ? LoadRow<kSides>(t, t.ya + i + 2) : none;
+		const RowWin cur = Neighbours<kSides>(t, p);
+		const RowWin &ar = kTall ? prev : cur;        /* the row the first neighbour lies in, and the row written */
+		/* first neighbours, as words aligned with the current row's */
+		u32 a0 = ar.w0, a1 = ar.w1;
+		if (kClass == 3) { a0 = __funnelshift_r(ar.w0, ar.w1, 8); a1 = __funnelshift_r(ar.w1, ar.R, 8); }           /* one sample to the right */
+		else if (kClass != 1) { a0 = __funnelshift_r(ar.L, ar.w0, 24); a1 = __funnelshift_r(ar.w0, ar.w1, 24); }    /* one to the left */
+		const u32 s0 = Signs4(cur.w0, a0), s1 = Signs4(cur.w1, a1);
+		/* S of the sample it is the first neighbour of, aligned with the lane's samples */
+		u32 t0 = s0, t1 = s1;
+		if (kClass == 0 || kClass == 2) {
+			/* S(y, 8): the neighbouring lane's first, or sample 0 of the word to the right against sample 7 of ar */
+			const u32 mine = AddMinRelu2((cur.R & 0xffu) + 0x100u - (ar.w1 >> 24), 0xff01ff01u, 0x00020002u);
+			const u32 theirs = __shfl_down_sync(0xffffffffu, s0, 1);
+			const u32 sr = t.last_col ? mine : theirs;
+			t0 = __funnelshift_r(s0, s1, 8); t1 = __funnelshift_r(s1, sr, 8);
 		}
-#pragma unroll
-		for (int j = 0; j < 4; j++) {
-			const int y = t.ya + k0 + j;
-			const RowWin &up = w[j], &c = w[j + 1], &dn = w[j + 2];
-			u32 a0, a1, n0, n1;
-			if (kClass == 1) { a0 = up.w0; a1 = up.w1; n0 = dn.w0; n1 = dn.w1; }
-			else if (kClass == 2) {
-				a0 = __funnelshift_r(up.L, up.w0, 24); a1 = __funnelshift_r(up.w0, up.w1, 24);
-				n0 = __funnelshift_r(dn.w0, dn.w1, 8); n1 = __funnelshift_r(dn.w1, dn.R, 8);
-			} else {
-				a0 = __funnelshift_r(up.w0, up.w1, 8); a1 = __funnelshift_r(up.w1, up.R, 8);
-				n0 = __funnelshift_r(dn.L, dn.w0, 24); n1 = __funnelshift_r(dn.w0, dn.w1, 24);
-			}
-			const u32 e0 = EdgeOffset4(c.w0, a0, n0, t.pool_lo, t.pool_hi), e1 = EdgeOffset4(c.w1, a1, n1, t.pool_lo, t.pool_hi);
-			/* the picture's first and last row are left alone */
-			const bool keep_row = y == 0 || y == t.ph - 1;
-			const u32 k0m = keep_row ? 0xffffffffu : t.keep0, k1m = keep_row ? 0xffffffffu : t.keep1;
-			StoreRow(t, orow, k0 + j < t.rpg && y < t.yb, (c.w0 & k0m) | (e0 & ~k0m), (c.w1 & k1m) | (e1 & ~k1m));
-			orow += t.pww;
+		if (kClass == 3) {
+			/* S(y, -1): the neighbouring lane's last, or sample 3 of the word to the left against sample 0 of ar */
+			const u32 mine = AddMinRelu2((cur.L >> 24) + 0x100u - (ar.w0 & 0xffu), 0xff01ff01u, 0x00020002u) << 24;
+			const u32 theirs = __shfl_up_sync(0xffffffffu, s1, 1);
+			const u32 sl = t.first_col ? mine : theirs;
+			t0 = __funnelshift_r(sl, s0, 24); t1 = __funnelshift_r(s0, s1, 24);
 		}
-		if (more) {
-			w[0] = w[4]; w[1] = w[5];
-#pragma unroll
-			for (int j = 0; j < 4; j++) w[2 + j] = Neighbours<kSides>(t, nx[j]);
-		}
+		const u32 e0 = (kTall ? sp0 : s0) + 0x02020202u - t0, e1 = (kTall ? sp1 : s1) + 0x02020202u - t1;
+		const u32 v0 = ApplyOffsets4(ar.w0, e0, t.pool_lo, t.pool_hi), v1 = ApplyOffsets4(ar.w1, e1, t.pool_lo, t.pool_hi);
+		/* the row written; the picture's first and last row are left alone by the classes that look up and down */
+		const int yo = t.ya + i - (kTall ? 1 : 0);
+		const bool keep_row = kTall && (yo == 0 || yo == t.ph - 1);
+		const u32 k0m = keep_row ? 0xffffffffu : t.keep0, k1m = keep_row ? 0xffffffffu : t.keep1;
+		StoreRow(t, orow, yo >= t.ya && yo < t.yb, (ar.w0 & k0m) | (v0 & ~k0m), (ar.w1 & k1m) | (v1 & ~k1m));
+		orow += t.pww;
+		prev = cur; sp0 = s0; sp1 = s1; p = q; q = nx;
 	}
 }
 
@@ -279,7 +274,7 @@ SaoKernel(const __grid_constant__ SaoBatch b)
 			const u32 o0 = __ldg(p + 2), o1 = __ldg(p + 3), o2 = __ldg(p + 4), o3 = __ldg(p + 5);
 			if (type == 2u) { t.pool_lo = o0 | (o1 << 8) | (o2 << 24); t.pool_hi = o3; pos &= 3u; }       /* categories 0, 1, (2: none), 3, 4 */
 			else { t.pool_lo = o0 | (o1 << 8) | (o2 << 16) | (o3 << 24); t.pool_hi = 0u; }              /* bands k = 0..3, (4: none) */
-			t.band_add = (32u - pos) * 0x10001u;
+			t.band_add = (32u - pos) * 0x01010101u;
 			/* bytes that keep their value whatever the row: the picture's first / last column (the vertical class
 			 * does not look at them) */
 			t.keep0 = (x == 0 ? 0x000000ffu : 0u) | (x == pww - 1 ? 0xff000000u : 0u);
@@ -289,10 +284,10 @@ SaoKernel(const __grid_constant__ SaoBatch b)
 			 * clamped column and never used */
 			if (type == 0u) FlatRun<0>(t);
 			else if (type == 1u) FlatRun<1>(t);
-			else if (pos == 0u) FlatRun<2>(t);
-			else if (pos == 1u) TallRun<1>(t);
-			else if (pos == 2u) TallRun<2>(t);
-			else TallRun<3>(t);
+			else if (pos == 0u) EdgeRun<0>(t);
+			else if (pos == 1u) EdgeRun<1>(t);
+			else if (pos == 2u) EdgeRun<2>(t);
+			else EdgeRun<3>(t);
 		}
 		next = __shfl_sync(0xffffffffu, next, 0);
 	}
