@@ -142,7 +142,7 @@ cudaError_t LaunchDeriveEdges(const void *info, int width, int height, int n_fra
  * d_tickets: kSaoTicketWords words of device memory that are the launch's own until it has run (the counters the
  * blocks are handed out through; zeroed here, in stream order).
  */
-constexpr int kSaoTicketWords = 64;
+constexpr int kSaoTicketWords = 4096;
 cudaError_t LaunchSao(const unsigned char *d_in, unsigned char *d_out, int n_frames, int width, int height,
 	const void *d_params, int ctb, unsigned *d_tickets, int sm_count, cudaStream_t stream);
 

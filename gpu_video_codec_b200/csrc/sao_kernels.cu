@@ -41,8 +41,26 @@
 
 namespace hdb {
 
-constexpr int kSaoWarps = 4;
-constexpr int kSaoChunk = 4;      /* consecutive blocks per ticket */
+/* shape knobs (tools/build_variants.sh) */
+#ifndef HDB_SAO_WARPS
+#define HDB_SAO_WARPS 4
+#endif
+#ifndef HDB_SAO_CHUNK
+#define HDB_SAO_CHUNK 1
+#endif
+#ifndef HDB_SAO_BAND
+#define HDB_SAO_BAND 0
+#endif
+#ifndef HDB_SAO_STATIC
+#define HDB_SAO_STATIC 0
+#endif
+#ifndef HDB_SAO_COUNTERS
+#define HDB_SAO_COUNTERS 32
+#endif
+constexpr int kSaoWarps = HDB_SAO_WARPS;
+constexpr int kSaoCounters = HDB_SAO_COUNTERS;   /* ticket counters, a 128-byte line each */
+constexpr int kSaoChunk = HDB_SAO_CHUNK;     /* consecutive blocks per ticket */
+constexpr int kSaoBand = HDB_SAO_BAND ? kSaoChunk : 1;   /* block rows a chunk runs down before the next column */
 
 struct SaoBatch {
 	const unsigned char *in; unsigned char *out;    /* tight YV12 frames, frame_stride apart */
@@ -51,11 +69,11 @@ struct SaoBatch {
 	int ctb;                                         /* luma CTB size: 16, 32 or 64 */
 	int ctb_cols, ctb_rows;
 	const unsigned char *params;                     /* hdb_sao_params[n][3][ctb_rows][ctb_cols], 6 bytes each */
-	/* task space: frame-major, then plane, CTB row, CTB column */
+	/* task space: frame-major, then plane, band of kSaoChunk CTB rows, CTB column, CTB row within the band */
 	int tasks_per_plane, tasks_per_frame;
 	long long total_tasks;
-	FastDiv div_tasks_per_frame, div_tasks_per_plane, div_ctb_cols;
-	unsigned *ticket;                                /* zero at launch: the next block to hand out */
+	FastDiv div_tasks_per_frame, div_tasks_per_plane, div_band;
+	unsigned *ticket;                                /* zero at launch: kSaoCounters counters, 32 words apart */
 };
 
 /* bytes (b0, b1) / (b2, b3) of a word as a 16x2 pair */
@@ -111,12 +129,15 @@ struct RowWin { u32 L, w0, w1, R; };
 
 /* Rows outside the picture are read from the nearest one inside, words outside from the nearest inside -- a sample
  * whose neighbour lies outside is kept whatever the comparison says -- so the loads are branch-free. */
-template <bool kSides>
+template <bool kSides, bool kPair>
 __device__ __forceinline__ RawRow LoadRow(const SaoLane &t, int y)
 {
 	const unsigned row = (unsigned)min(max(y, 0), t.ph - 1) * t.pww;
 	RawRow w{0u, 0u, 0u, 0u};
-	w.w0 = __ldg(t.src + (row + t.xc0)); w.w1 = __ldg(t.src + (row + t.xc1));
+	if (kPair) {      /* rows of an even number of words: the lane's two words are one aligned load */
+		const uint2 v = __ldg(reinterpret_cast<const uint2 *>(t.src + (row + t.xc0)));
+		w.w0 = v.x; w.w1 = v.y;
+	} else { w.w0 = __ldg(t.src + (row + t.xc0)); w.w1 = __ldg(t.src + (row + t.xc1)); }
 	if (kSides) {
 		w.e = __ldg(t.src + (row + t.xe));
 		if (t.one_lane) w.e2 = __ldg(t.src + (row + t.xr));
@@ -138,14 +159,18 @@ __device__ __forceinline__ RowWin Neighbours(const SaoLane &t, const RawRow &w)
 	return o;
 }
 
+template <bool kPair>
 __device__ __forceinline__ void StoreRow(const SaoLane &t, u32 *orow, bool row_live, u32 v0, u32 v1)
 {
-	if (row_live && t.live0) orow[0] = v0;
-	if (row_live && t.live1) orow[1] = v1;
+	if (kPair) { if (row_live && t.live0) *reinterpret_cast<uint2 *>(orow) = make_uint2(v0, v1); }
+	else {
+		if (row_live && t.live0) orow[0] = v0;
+		if (row_live && t.live1) orow[1] = v1;
+	}
 }
 
 /* kMode 0: the block is off -- moved; 1: band offset.  No sample needs another: four rows' loads at a time. */
-template <int kMode>
+template <int kMode, bool kPair>
 __device__ __forceinline__ void FlatRun(const SaoLane &t)
 {
 	u32 *orow = t.dst + ((unsigned)t.ya * t.pww + t.xc0);
@@ -153,13 +178,13 @@ __device__ __forceinline__ void FlatRun(const SaoLane &t)
 	for (int k0 = 0; k0 < t.rpg; k0 += 4) {
 		RawRow r[4];
 #pragma unroll
-		for (int j = 0; j < 4; j++) r[j] = k0 + j < t.rpg ? LoadRow<false>(t, t.ya + k0 + j) : RawRow{0u, 0u, 0u, 0u};
+		for (int j = 0; j < 4; j++) r[j] = k0 + j < t.rpg ? LoadRow<false, kPair>(t, t.ya + k0 + j) : RawRow{0u, 0u, 0u, 0u};
 #pragma unroll
 		for (int j = 0; j < 4; j++) {
 			if (k0 + j < t.rpg) {       /* the same for all lanes */
 				u32 v0 = r[j].w0, v1 = r[j].w1;
 				if (kMode == 1) { v0 = BandOffset4(v0, t.band_add, t.pool_lo, t.pool_hi); v1 = BandOffset4(v1, t.band_add, t.pool_lo, t.pool_hi); }
-				StoreRow(t, orow, t.ya + k0 + j < t.yb, v0, v1);
+				StoreRow<kPair>(t, orow, t.ya + k0 + j < t.yb, v0, v1);
 			}
 			orow += t.pww;
 		}
@@ -179,23 +204,19 @@ __device__ __forceinline__ void FlatRun(const SaoLane &t)
  * output: iteration y computes S(y) and writes row y - 1.
  * Rows are fetched two iterations before the shuffles that first touch them.
  */
-template <int kClass>
+template <int kClass, bool kPair>
 __device__ __forceinline__ void EdgeRun(const SaoLane &t)
 {
 	constexpr bool kSides = kClass != 1, kTall = kClass != 0;
 	const int n_iter = t.rpg + (kTall ? 1 : 0);
 	const RawRow none{0u, 0u, 0u, 0u};
-	/* iteration i works on row ya + i as the current row */
-	RowWin prev{0u, 0u, 0u, 0u};
-	if (kTall) prev = Neighbours<kSides>(t, LoadRow<kSides>(t, t.ya - 1));
-	RawRow p = LoadRow<kSides>(t, t.ya), q = n_iter > 1 ? LoadRow<kSides>(t, t.ya + 1) : none;
-	u32 sp0 = 0u, sp1 = 0u;                          /* S of the row above */
 	u32 *orow = t.dst + ((long long)(t.ya - (kTall ? 1 : 0)) * (long long)t.pww + t.xc0);       /* row ya - 1 is never written */
-#pragma unroll 1
-	for (int i = 0; i < n_iter; i++) {
-		const RawRow nx = i + 2 < n_iter ? LoadRow<kSides>(t, t.ya + i + 2) : none;
-		const RowWin cur = Neighbours<kSides>(t, p);
-		const RowWin &ar = kTall ? prev : cur;        /* the row the first neighbour lies in, and the row written */
+	/* iteration i: row ya + i, fetched into `slot` two iterations ago, becomes `cur`; `above` is the row before it
+	 * with its S in s_above; S of the current row goes to s_cur */
+	auto step = [&](int i, RawRow &slot, const RowWin &above, const u32 (&s_above)[2], RowWin &cur, u32 (&s_cur)[2]) {
+		cur = Neighbours<kSides>(t, slot);
+		slot = i + 2 < n_iter ? LoadRow<kSides, kPair>(t, t.ya + i + 2) : none;
+		const RowWin &ar = kTall ? above : cur;        /* the row the first neighbour lies in, and the row written */
 		/* first neighbours, as words aligned with the current row's */
 		u32 a0 = ar.w0, a1 = ar.w1;
 		if (kClass == 3) { a0 = __funnelshift_r(ar.w0, ar.w1, 8); a1 = __funnelshift_r(ar.w1, ar.R, 8); }           /* one sample to the right */
@@ -217,35 +238,67 @@ __device__ __forceinline__ void EdgeRun(const SaoLane &t)
 			const u32 sl = t.first_col ? mine : theirs;
 			t0 = __funnelshift_r(sl, s0, 24); t1 = __funnelshift_r(s0, s1, 24);
 		}
-		const u32 e0 = (kTall ? sp0 : s0) + 0x02020202u - t0, e1 = (kTall ? sp1 : s1) + 0x02020202u - t1;
+		const u32 e0 = (kTall ? s_above[0] : s0) + 0x02020202u - t0, e1 = (kTall ? s_above[1] : s1) + 0x02020202u - t1;
 		const u32 v0 = ApplyOffsets4(ar.w0, e0, t.pool_lo, t.pool_hi), v1 = ApplyOffsets4(ar.w1, e1, t.pool_lo, t.pool_hi);
 		/* the row written; the picture's first and last row are left alone by the classes that look up and down */
 		const int yo = t.ya + i - (kTall ? 1 : 0);
 		const bool keep_row = kTall && (yo == 0 || yo == t.ph - 1);
 		const u32 k0m = keep_row ? 0xffffffffu : t.keep0, k1m = keep_row ? 0xffffffffu : t.keep1;
-		StoreRow(t, orow, yo >= t.ya && yo < t.yb, (ar.w0 & k0m) | (v0 & ~k0m), (ar.w1 & k1m) | (v1 & ~k1m));
+		StoreRow<kPair>(t, orow, yo >= t.ya && yo < t.yb, (ar.w0 & k0m) | (v0 & ~k0m), (ar.w1 & k1m) | (v1 & ~k1m));
 		orow += t.pww;
-		prev = cur; sp0 = s0; sp1 = s1; p = q; q = nx;
+		s_cur[0] = s0; s_cur[1] = s1;
+	};
+	/* two rows a round, so that the registers swap roles instead of being copied */
+	RowWin wa{0u, 0u, 0u, 0u}, wb{0u, 0u, 0u, 0u};
+	u32 sa[2] = {0u, 0u}, sb[2] = {0u, 0u};
+	if (kTall) wb = Neighbours<kSides>(t, LoadRow<kSides, kPair>(t, t.ya - 1));
+	RawRow p = LoadRow<kSides, kPair>(t, t.ya), q = n_iter > 1 ? LoadRow<kSides, kPair>(t, t.ya + 1) : none;
+#pragma unroll 1
+	for (int i = 0; i < n_iter; i += 2) {
+		step(i, p, wb, sb, wa, sa);
+		if (i + 1 < n_iter) step(i + 1, q, wa, sa, wb, sb);
 	}
 }
 
+template <bool kPair>
 __global__ void __launch_bounds__(kSaoWarps * 32)
 SaoKernel(const __grid_constant__ SaoBatch b)
 {
 	const int lane = threadIdx.x & 31;
 	const unsigned total = (unsigned)b.total_tasks;
+	/* Chunk v * kSaoCounters + c is ticket v of counter c.  One counter handed out 0.4 G tickets a second -- atomics
+	 * on one address are serial in the L2 -- which bounded the blocks that are off or band offset; the warps are
+	 * spread over kSaoCounters counters, which advance at the same pace and so still hand the blocks out in order. */
+	const unsigned n_chunks = (total + kSaoChunk - 1) / kSaoChunk;
+	const unsigned warp_id = blockIdx.x * kSaoWarps + (threadIdx.x >> 5);
+#if HDB_SAO_STATIC
+	const unsigned stride = gridDim.x * kSaoWarps;
+	unsigned next = warp_id;
+#else
+	const unsigned counter = warp_id % kSaoCounters;
+	unsigned *ticket = b.ticket + 32u * counter;
 	unsigned next = 0;
-	if (lane == 0) next = atomicAdd(b.ticket, (unsigned)kSaoChunk);
-	next = __shfl_sync(0xffffffffu, next, 0);
-	while (next < total) {
-		const unsigned first = next, last = min(first + (unsigned)kSaoChunk, total);
-		if (lane == 0) next = atomicAdd(b.ticket, (unsigned)kSaoChunk);      /* in flight while this chunk is worked on */
+	if (lane == 0) next = atomicAdd(ticket, 1u);
+	next = __shfl_sync(0xffffffffu, next, 0) * kSaoCounters + counter;
+#endif
+	while (next < n_chunks) {
+		const unsigned first = next * kSaoChunk, last = min(first + (unsigned)kSaoChunk, total);
+#if HDB_SAO_STATIC
+		next += stride;
+#else
+		if (lane == 0) next = atomicAdd(ticket, 1u);      /* in flight while this chunk is worked on */
+#endif
 		for (unsigned task = first; task < last; task++) {
 			const uint32_t frame = b.div_tasks_per_frame.Div(task);
 			uint32_t r = task - frame * (uint32_t)b.tasks_per_frame;
 			const int plane = (int)b.div_tasks_per_plane.Div(r);
 			r -= (uint32_t)plane * (uint32_t)b.tasks_per_plane;
-			const int crow = (int)b.div_ctb_cols.Div(r), ccol = (int)r - crow * b.ctb_cols;
+			/* kSaoChunk blocks one above the other, then the next column: a chunk's blocks share a row of samples
+			 * each, its neighbours in the row -- which share a column of 32-byte sectors per row with it -- are other
+			 * warps' at the same time */
+			const int band = (int)b.div_band.Div(r), in_band = (int)r - band * (kSaoBand * b.ctb_cols);
+			const int crow = band * kSaoBand + in_band % kSaoBand, ccol = in_band / kSaoBand;
+			if (crow >= b.ctb_rows) continue;             /* the last band may be short */
 			const int pw = plane ? b.width >> 1 : b.width, ph = plane ? b.height >> 1 : b.height;
 			const int ctb = plane ? b.ctb >> 1 : b.ctb;                 /* 64 .. 8 samples */
 			const long long plane_off = plane == 0 ? 0 : (long long)b.width * b.height + (plane == 2 ? (long long)(b.width >> 1) * (b.height >> 1) : 0);
@@ -265,7 +318,7 @@ SaoKernel(const __grid_constant__ SaoBatch b)
 			t.ya = crow * ctb + group * t.rpg;
 			t.yb = min(min(t.ya + t.rpg, (crow + 1) * ctb), ph);
 			t.first_col = col == 0; t.last_col = col == lpr - 1; t.one_lane = lpr == 1;
-			t.xc0 = (unsigned)min(x, pww - 1); t.xc1 = (unsigned)min(x + 1, pww - 1); t.xr = (unsigned)min(x + 2, pww - 1);
+			t.xc0 = (unsigned)min(x, pww - (kPair ? 2 : 1)); t.xc1 = (unsigned)min(x + 1, pww - 1); t.xr = (unsigned)min(x + 2, pww - 1);
 			t.xe = t.first_col ? (unsigned)min(max(x - 1, 0), pww - 1) : t.xr;
 			/* the block's parameters: the same for every lane */
 			const unsigned char *p = b.params + 6ll * ((((long long)frame * 3 + plane) * b.ctb_rows + crow) * b.ctb_cols + ccol);
@@ -282,14 +335,16 @@ SaoKernel(const __grid_constant__ SaoBatch b)
 			if (type == 2u && pos == 1u) t.keep0 = t.keep1 = 0u;
 			/* a dead lane's first word lies outside the row: its stores are off, its output pointer is formed from the
 			 * clamped column and never used */
-			if (type == 0u) FlatRun<0>(t);
-			else if (type == 1u) FlatRun<1>(t);
-			else if (pos == 0u) EdgeRun<0>(t);
-			else if (pos == 1u) EdgeRun<1>(t);
-			else if (pos == 2u) EdgeRun<2>(t);
-			else EdgeRun<3>(t);
+			if (type == 0u) FlatRun<0, kPair>(t);
+			else if (type == 1u) FlatRun<1, kPair>(t);
+			else if (pos == 0u) EdgeRun<0, kPair>(t);
+			else if (pos == 1u) EdgeRun<1, kPair>(t);
+			else if (pos == 2u) EdgeRun<2, kPair>(t);
+			else EdgeRun<3, kPair>(t);
 		}
-		next = __shfl_sync(0xffffffffu, next, 0);
+#if !HDB_SAO_STATIC
+		next = __shfl_sync(0xffffffffu, next, 0) * kSaoCounters + counter;
+#endif
 	}
 }
 
@@ -299,7 +354,7 @@ cudaError_t LaunchSao(const unsigned char *d_in, unsigned char *d_out, int n_fra
 	if (n_frames <= 0) return cudaSuccess;
 	static const int per_sm = [] {
 		int n = 0;
-		return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, SaoKernel, kSaoWarps * 32, 0) == cudaSuccess && n > 0 ? n : 8;
+		return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, SaoKernel<true>, kSaoWarps * 32, 0) == cudaSuccess && n > 0 ? n : 8;
 	}();
 	SaoBatch b{};
 	b.in = d_in; b.out = d_out;
@@ -307,17 +362,20 @@ cudaError_t LaunchSao(const unsigned char *d_in, unsigned char *d_out, int n_fra
 	b.width = width; b.height = height; b.ctb = ctb;
 	b.ctb_cols = (width + ctb - 1) / ctb; b.ctb_rows = (height + ctb - 1) / ctb;
 	b.params = static_cast<const unsigned char *>(d_params);
-	/* one task per coding tree block and plane; the chroma planes have the same block grid as luma */
-	b.tasks_per_plane = b.ctb_rows * b.ctb_cols;
+	/* one task per coding tree block and plane (the chroma planes have the same block grid as luma), the block rows
+	 * rounded up to whole bands */
+	b.tasks_per_plane = (b.ctb_rows + kSaoBand - 1) / kSaoBand * kSaoBand * b.ctb_cols;
 	b.tasks_per_frame = 3 * b.tasks_per_plane;
 	b.div_tasks_per_frame.Init((uint32_t)b.tasks_per_frame);
 	b.div_tasks_per_plane.Init((uint32_t)b.tasks_per_plane);
-	b.div_ctb_cols.Init((uint32_t)b.ctb_cols);
+	b.div_band.Init((uint32_t)(kSaoBand * b.ctb_cols));
 	/* frames per launch bounded by the 31-bit task index */
 	const long long max_frames = std::max<long long>(1, ((1ll << 31) - 1) / b.tasks_per_frame);
 	const long long parts = (n_frames + max_frames - 1) / max_frames;
-	if (parts > kSaoTicketWords) return cudaErrorInvalidValue;
-	cudaError_t e = cudaMemsetAsync(d_tickets, 0, sizeof(unsigned) * (size_t)parts, stream);
+	constexpr int kWordsPerPart = 32 * kSaoCounters;
+	static_assert(kWordsPerPart <= kSaoTicketWords, "ticket buffer too small");
+	if (parts > kSaoTicketWords / kWordsPerPart) return cudaErrorInvalidValue;
+	cudaError_t e = cudaMemsetAsync(d_tickets, 0, sizeof(unsigned) * kWordsPerPart * (size_t)parts, stream);
 	if (e != cudaSuccess) return e;
 	for (long long f0 = 0; f0 < n_frames; f0 += max_frames) {
 		SaoBatch part = b;
@@ -325,11 +383,14 @@ cudaError_t LaunchSao(const unsigned char *d_in, unsigned char *d_out, int n_fra
 		part.in = d_in + f0 * b.frame_stride; part.out = d_out + f0 * b.frame_stride;
 		part.params = b.params + 6ll * 3 * b.ctb_rows * b.ctb_cols * f0;
 		part.total_tasks = (long long)part.n_frames * b.tasks_per_frame;
-		part.ticket = d_tickets + f0 / max_frames;
+		part.ticket = d_tickets + f0 / max_frames * kWordsPerPart;
 		/* as many warps as the device holds at once, every one of them drawing tickets until none are left */
 		const long long per_cta = (long long)kSaoWarps * kSaoChunk;
 		const long long ctas = std::min<long long>((part.total_tasks + per_cta - 1) / per_cta, (long long)sm_count * per_sm);
-		SaoKernel<<<(unsigned)ctas, kSaoWarps * 32, 0, stream>>>(part);
+		/* both planes' rows an even number of words and the frames 8-byte aligned: the lanes move their two words at once */
+		const bool pair = width % 16 == 0 && ((uintptr_t)part.in | (uintptr_t)part.out) % 8 == 0;
+		if (pair) SaoKernel<true><<<(unsigned)ctas, kSaoWarps * 32, 0, stream>>>(part);
+		else SaoKernel<false><<<(unsigned)ctas, kSaoWarps * 32, 0, stream>>>(part);
 	}
 	return cudaGetLastError();
 }
