@@ -312,6 +312,46 @@ struct SkewWalk {
 	}
 };
 
+/*
+ * The same walk in closed form for planes of at least 64 chroma columns (tools: the recurrence above is the
+ * definition, tests/test_gpu_parity.py compares both against the oracle).  Going one virtual row down moves a
+ * column one buffer row down and 4 bytes to the left (c -= 4, image offset += vpitch - 8); the only exception is
+ * the row where c reaches 0: from there the column jumps to the end of the SAME buffer row (c = cw + 4, image
+ * offset += vpitch).  So with t0 = c / 4 of the first row, the rows t0, t0 + 1, t0 + 2 of the walk are the ones
+ * that straddle the padding (first half, both halves, second half of the unit are padding), the image offset
+ * is linear with one bump of 8 after row t0, and the next such row is rpitch / 4 >= 18 rows away: at most one
+ * per item.  A lane keeps two 16-bit masks (which rows' halves are image samples) instead of walking.
+ */
+struct SkewRun {
+	int img0;                  /* image offset of the unit in the item's first row */
+	int bump;                  /* rows after this one are 8 bytes further on (>= kTileH: none) */
+	unsigned lo_mask, hi_mask; /* bit t: the unit's first / second four bytes in row t are image samples */
+
+	__device__ __forceinline__ static unsigned RowRange(int x, int y)   /* bits x .. y - 1 of 0 .. 15 */
+	{
+		x = min(max(x, 0), 16); y = min(max(y, 0), 16);
+		return y > x ? ((1u << y) - 1u) & ~((1u << x) - 1u) : 0u;
+	}
+	__device__ __forceinline__ void Start(int vpitch, int rpitch, int cw, int buf_rows, const FastDiv &div_rpitch, int vr, int vc)
+	{
+		const bool lo_col = (unsigned)vc < (unsigned)vpitch, hi_col = (unsigned)(vc + 4) < (unsigned)vpitch;
+		const uint32_t o = (uint32_t)(vr * vpitch + vc + 8 * rpitch);
+		const uint32_t q = div_rpitch.Div(o);
+		const int r0 = (int)q - 8, c0 = (int)(o - q * (uint32_t)rpitch);
+		img0 = (r0 - 4) * cw + c0 - 4;
+		const int t0 = c0 == cw + 4 ? -1 : (c0 == cw ? -2 : c0 >> 2);
+		const int sh = min(t0 + 2, 24);
+		const unsigned lo_inv = (3u << sh) >> 2, hi_inv = (6u << sh) >> 2;
+		bump = t0 >= 0 ? t0 : 99;
+		/* buffer rows 4 .. buf_rows + 3 hold the image: row r0 + t before the bump, r0 + t - 1 after it */
+		const int a = 4 - r0, e = buf_rows + 4 - r0;
+		const unsigned before = RowRange(0, bump + 1);
+		const unsigned rows = (RowRange(a, e) & before) | (RowRange(a + 1, e + 1) & ~before);
+		lo_mask = lo_col ? rows & ~lo_inv : 0u;
+		hi_mask = hi_col ? rows & ~hi_inv : 0u;
+	}
+};
+
 template <bool kNv12>
 __device__ __noinline__ void FetchTileLdgsts(const TiledBatch &b, const uint2 it, const uint32_t dst, const int lane)
 {
@@ -326,43 +366,71 @@ __device__ __noinline__ void FetchTileLdgsts(const TiledBatch &b, const uint2 it
 		 * was their first stall reason when these were unrolled) */
 		if (!kNv12 && c && b.chroma_skew) {
 			/* 8-byte units like the straight planes: tile byte 0 is virtual column 4 mod 8, which is where the image's
-			 * 8-byte boundaries fall (SkewWalk); lane l takes unit l of every row, lanes 0 and 1 units 32 and 33 too.
-			 * A unit half in the padding goes as two 4-byte copies. */
-			SkewWalk wk[2];
-			wk[0].Start(b, 8 * lby0, xb0 + 4 + 8 * lane);
-			wk[1].Start(b, 8 * lby0, xb0 + 4 + 8 * (lane + 32));
-			if (lane >= 2) wk[1].lo_col = wk[1].hi_col = false;
-			uint32_t d = dst + 8u * (uint32_t)lane;
+			 * 8-byte boundaries fall (SkewWalk); lane l takes unit l of every row, and units 32 and 33 of the rows go
+			 * one to a lane afterwards.  A unit half in the padding goes as two 4-byte copies. */
+			const int vpitch = b.chroma_vpitch, rpitch = b.chroma_rpitch, cw = b.width >> 1, buf_rows = b.chroma_buf_rows;
+			if (rpitch >= 72) {
+				SkewRun k;
+				k.Start(vpitch, rpitch, cw, buf_rows, b.div_chroma_rpitch, 8 * lby0, xb0 + 4 + 8 * lane);
+				const unsigned char *g = src + k.img0;
+				uint32_t d = dst + 8u * (uint32_t)lane;
+				const int step = vpitch - 8;
 #pragma unroll 1
-			for (int t = 0; t < kTileH; t++) {
-#pragma unroll
-				for (int k = 0; k < 2; k++) {
-					if (k == 0 || lane < 2) {
-						bool lo, hi;
-						wk[k].Halves(b, lo, hi);
-						const unsigned char *g = src + wk[k].img;
-						if (lo == hi) CpAsync8(d + 256u * k, lo ? g : src, lo ? 8u : 0u);
-						else { CpAsync4(d + 256u * k, lo ? g : src, lo ? 4u : 0u); CpAsync4(d + 256u * k + 4u, hi ? g + 4 : src, hi ? 4u : 0u); }
-					}
-					wk[k].NextRow(b);
+				for (int t = 0; t < kTileH; t++) {
+					const bool lo = (k.lo_mask >> t) & 1u, hi = (k.hi_mask >> t) & 1u;
+					if (lo == hi) CpAsync8(d, lo ? g : src, lo ? 8u : 0u);
+					else { CpAsync4(d, lo ? g : src, lo ? 4u : 0u); CpAsync4(d + 4u, hi ? g + 4 : src, hi ? 4u : 0u); }
+					g += t == k.bump ? step + 8 : step;
+					d += kTileW;
 				}
-				d += kTileW;
+			} else {
+				SkewWalk wk;
+				wk.Start(b, 8 * lby0, xb0 + 4 + 8 * lane);
+				uint32_t d = dst + 8u * (uint32_t)lane;
+#pragma unroll 1
+				for (int t = 0; t < kTileH; t++) {
+					bool lo, hi;
+					wk.Halves(b, lo, hi);
+					const unsigned char *g = src + wk.img;
+					if (lo == hi) CpAsync8(d, lo ? g : src, lo ? 8u : 0u);
+					else { CpAsync4(d, lo ? g : src, lo ? 4u : 0u); CpAsync4(d + 4u, hi ? g + 4 : src, hi ? 4u : 0u); }
+					wk.NextRow(b);
+					d += kTileW;
+				}
+			}
+			/* units 32 and 33: row lane / 2 (and 16 rows further on, for taller items), unit 32 + lane % 2 */
+#pragma unroll 1
+			for (int t = lane >> 1; t < kTileH; t += 16) {
+				SkewWalk wk;
+				wk.Start(b, 8 * lby0 + t, xb0 + 4 + 8 * (32 + (lane & 1)));
+				bool lo, hi;
+				wk.Halves(b, lo, hi);
+				const unsigned char *g = src + wk.img;
+				const uint32_t d = dst + (uint32_t)(t * kTileW) + 8u * (uint32_t)(32 + (lane & 1));
+				if (lo == hi) CpAsync8(d, lo ? g : src, lo ? 8u : 0u);
+				else { CpAsync4(d, lo ? g : src, lo ? 4u : 0u); CpAsync4(d + 4u, hi ? g + 4 : src, hi ? 4u : 0u); }
 			}
 		} else {
 			const int pw = (c && !kNv12) ? (b.width >> 1) : b.width;
 			const int rows = c ? b.chroma_buf_rows : b.luma_buf_rows;
 			const int y0 = 8 * lby0 + (c ? b.chroma_y_org : b.luma_y_org);
-			/* 34 units of 8 bytes per row: lane l takes unit l, lanes 0 and 1 units 32 and 33 as well */
+			/* 34 units of 8 bytes per row: lane l takes unit l of every row; units 32 and 33 go one to a lane
+			 * afterwards (row lane / 2, unit 32 + lane % 2) */
 			const int xb = xb0 + 8 * lane;
-			const bool col_ok = xb >= 0 && xb < pw, col2_ok = lane < 2 && xb + 256 < pw;
+			const bool col_ok = xb >= 0 && xb < pw;
 			const unsigned char *g = src + (long long)y0 * pitch + xb;
 			uint32_t d = dst + 8u * (uint32_t)lane;
 #pragma unroll 1
 			for (int t = 0; t < kTileH; t++) {
-				const bool row_ok = y0 + t >= 0 && y0 + t < rows;
-				CpAsync8(d, (row_ok && col_ok) ? g : src, (row_ok && col_ok) ? 8u : 0u);
-				if (lane < 2) CpAsync8(d + 256u, (row_ok && col2_ok) ? g + 256 : src, (row_ok && col2_ok) ? 8u : 0u);
+				const bool ok = col_ok && (unsigned)(y0 + t) < (unsigned)rows;
+				CpAsync8(d, ok ? g : src, ok ? 8u : 0u);
 				g += pitch; d += kTileW;
+			}
+			const int xe = xb0 + 8 * (32 + (lane & 1));
+#pragma unroll 1
+			for (int t = lane >> 1; t < kTileH; t += 16) {
+				const bool ok = xe < pw && (unsigned)(y0 + t) < (unsigned)rows;
+				CpAsync8(dst + (uint32_t)(t * kTileW) + 8u * (uint32_t)(32 + (lane & 1)), ok ? src + (long long)(y0 + t) * pitch + xe : src, ok ? 8u : 0u);
 			}
 		}
 	}
@@ -598,29 +666,51 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_consta
 			if (kLoad == kLoadLdgsts && !kNv12 && chroma && b.chroma_skew) {
 				/* the item's 256 bytes per row of the VIRTUAL plane (tile bytes 12 .. 267) to the image samples they are:
 				 * 31 units of 8 bytes from tile byte 16 on (image-aligned, see fetch) and one word at each end */
-				SkewWalk wk;
-				wk.Start(b, 8 * lby0, 8 * bx0 + 4 + 8 * lane);
-				if (lane == 31) wk.lo_col = wk.hi_col = false;
-				SkewWalk fr;                                               /* lanes 0 / 1: the word at virtual column 8 bx0 / 8 bx0 + 252 */
-				fr.Start(b, 8 * lby0, 8 * bx0 + (lane & 1 ? 252 : 0));
-				if (lane >= 2) fr.lo_col = false;
+				const int vpitch = b.chroma_vpitch, rpitch = b.chroma_rpitch, cw = b.width >> 1, buf_rows = b.chroma_buf_rows;
 				const unsigned char *sp = tile8 + 16 + 8 * lane;
-				const u32 *fp32 = tile + ((lane & 1) ? 66 : 3);
-				const int cw = b.width >> 1;
+				if (rpitch >= 72) {
+					SkewRun k;
+					k.Start(vpitch, rpitch, cw, buf_rows, b.div_chroma_rpitch, 8 * lby0, 8 * bx0 + 4 + 8 * lane);
+					if (lane == 31) k.lo_mask = k.hi_mask = 0u;
+					unsigned char *g = dst + k.img0;
+					const int step = vpitch - 8;
 #pragma unroll 1
-				for (int rr = 0; rr < kTileH; rr++) {
-					bool lo, hi;
-					wk.Halves(b, lo, hi);
-					const uint2 v = *reinterpret_cast<const uint2 *>(sp);
-					if (lo && hi) *reinterpret_cast<uint2 *>(dst + wk.img) = v;
-					else {
-						if (lo) *reinterpret_cast<u32 *>(dst + wk.img) = v.x;
-						if (hi) *reinterpret_cast<u32 *>(dst + wk.img + 4) = v.y;
+					for (int rr = 0; rr < kTileH; rr++) {
+						const bool lo = (k.lo_mask >> rr) & 1u, hi = (k.hi_mask >> rr) & 1u;
+						const uint2 v = *reinterpret_cast<const uint2 *>(sp);
+						if (lo && hi) *reinterpret_cast<uint2 *>(g) = v;
+						else {
+							if (lo) *reinterpret_cast<u32 *>(g) = v.x;
+							if (hi) *reinterpret_cast<u32 *>(g + 4) = v.y;
+						}
+						g += rr == k.bump ? step + 8 : step;
+						sp += kTileW;
 					}
-					if (fr.lo_col && (unsigned)(fr.r - 4) < (unsigned)b.chroma_buf_rows && (unsigned)(fr.c - 4) < (unsigned)cw)
-						*reinterpret_cast<u32 *>(dst + fr.img) = *fp32;
-					wk.NextRow(b); fr.NextRow(b);
-					sp += kTileW; fp32 += kTileWords;
+				} else {
+					SkewWalk wk;
+					wk.Start(b, 8 * lby0, 8 * bx0 + 4 + 8 * lane);
+					if (lane == 31) wk.lo_col = wk.hi_col = false;
+#pragma unroll 1
+					for (int rr = 0; rr < kTileH; rr++) {
+						bool lo, hi;
+						wk.Halves(b, lo, hi);
+						const uint2 v = *reinterpret_cast<const uint2 *>(sp);
+						if (lo && hi) *reinterpret_cast<uint2 *>(dst + wk.img) = v;
+						else {
+							if (lo) *reinterpret_cast<u32 *>(dst + wk.img) = v.x;
+							if (hi) *reinterpret_cast<u32 *>(dst + wk.img + 4) = v.y;
+						}
+						wk.NextRow(b);
+						sp += kTileW;
+					}
+				}
+				/* the word at virtual column 8 bx0 / 8 bx0 + 252 of every row: row lane / 2, end lane % 2 */
+#pragma unroll 1
+				for (int rr = lane >> 1; rr < kTileH; rr += 16) {
+					SkewWalk fr;
+					fr.Start(b, 8 * lby0 + rr, 8 * bx0 + (lane & 1 ? 252 : 0));
+					if (fr.lo_col && (unsigned)(fr.r - 4) < (unsigned)buf_rows && (unsigned)(fr.c - 4) < (unsigned)cw)
+						*reinterpret_cast<u32 *>(dst + fr.img) = tile[rr * kTileWords + ((lane & 1) ? 66 : 3)];
 				}
 			} else if (kLoad == kLoadLdgsts) {
 				/* rows start on 8-byte boundaries: 64-bit stores.  The item's columns begin 4 bytes before such a

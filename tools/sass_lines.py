@@ -1,5 +1,5 @@
 """Development aid: executed warp-instructions per source line of DeblockTiledKernel.
-usage: sass_lines.py <nvdisasm -g -c output> <ncu --page source --csv output> [top N]
+usage: sass_lines.py <nvdisasm -g -c output> <ncu --page source --csv output> [top N] [mangled-name substring]
 The two listings have the same instruction order; the nvdisasm one carries the line info."""
 import collections
 import csv
@@ -9,8 +9,9 @@ import sys
 
 dis, srccsv = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 60
+which = sys.argv[4] if len(sys.argv) > 4 else ''  
 lines = open(dis).read().split('\n')
-start = [i for i, l in enumerate(lines) if l.startswith('//--------------------- .text._ZN3hdb18DeblockTiledKernel')][0]
+start = [i for i, l in enumerate(lines) if l.startswith('//--------------------- .text._ZN3hdb18DeblockTiledKernel') and which in l][0]
 seq, cur = [], None
 for l in lines[start + 1:]:
     if l.startswith('//---------------------'):
