@@ -17,6 +17,7 @@ from tests import synth  # noqa: E402
 
 seed = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 budget = float(sys.argv[2]) if len(sys.argv) > 2 else 120.0
+only = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else list(range(14))     # modes to draw from
 rng = np.random.default_rng(seed)
 dev = hdb.Deblocker(0)
 multi = hdb.MultiDeblocker([0, 0, 0])
@@ -25,7 +26,7 @@ bs_kinds = [None, "uniform012", "wide", "twos", "zeros", "ones"]
 t0, n_cases, fails = time.time(), 0, 0
 st = torch.cuda.current_stream().cuda_stream
 while time.time() - t0 < budget:
-    mode = int(rng.integers(14))
+    mode = only[int(rng.integers(len(only)))]
     w = 8 * int(rng.integers(1, 200))
     h = 8 * int(rng.integers(1, 80))
     if mode in (3, 4, 6, 7, 9, 11) or rng.integers(2):
