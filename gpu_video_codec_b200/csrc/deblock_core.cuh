@@ -86,6 +86,13 @@ HDB_FN u32 MinU2(u32 a, u32 b) { return __vminu2(a, b); }
 
 /* both halves = v (v may be negative: two's complement per half) */
 HDB_FN u32 Rep2(int v) { return ((u32)v & 0xffffu) * 0x10001u; }
+/* x >> k of the packed halves.  HDB_SHR_IMAD: as the high word of x * 2^(32 - k), which issues on the FMA pipe (19 %
+ * busy) instead of the ALU pipe (85 % busy) */
+#if defined(HDB_SHR_IMAD) && HDB_SHR_IMAD && !defined(HDB_HOST_EMU)
+template <int k> HDB_FN u32 Shr(u32 x) { return __umulhi(x, 1u << (32 - k)); }
+#else
+template <int k> HDB_FN u32 Shr(u32 x) { return x >> k; }
+#endif
 
 /* ------------------------------------------------------------------ */
 /* per-frame filter parameters (cpu.h:1021-1033, 1064-1072)            */
@@ -173,12 +180,12 @@ HDB_FN void StrongPair(LumaPair &t, const FilterParams &fp)
 	u32 t2p = 2u * (t.p3 + t.p2 + 0x00010001u) + t1p; /* 2p3 + 3p2 + p1 + p0 + q0 + 4 -> >>3  cpu.h:1166 */
 	u32 t2q = 2u * (t.q3 + t.q2 + 0x00010001u) + t1q; /*                                       cpu.h:1185 */
 	u32 a;
-	a = 8u * t.p0; t.p0 = AddMin2(a, fp.s8_pos, AddMax2(a, fp.s8_neg, t0p)) >> 3;   /* cpu.h:1192-1211 */
-	a = 4u * t.p1; t.p1 = AddMin2(a, fp.s4_pos, AddMax2(a, fp.s4_neg, t1p)) >> 2;
-	a = 8u * t.p2; t.p2 = AddMin2(a, fp.s8_pos, AddMax2(a, fp.s8_neg, t2p)) >> 3;
-	a = 8u * t.q0; t.q0 = AddMin2(a, fp.s8_pos, AddMax2(a, fp.s8_neg, t0q)) >> 3;
-	a = 4u * t.q1; t.q1 = AddMin2(a, fp.s4_pos, AddMax2(a, fp.s4_neg, t1q)) >> 2;
-	a = 8u * t.q2; t.q2 = AddMin2(a, fp.s8_pos, AddMax2(a, fp.s8_neg, t2q)) >> 3;
+	a = 8u * t.p0; t.p0 = Shr<3>(AddMin2(a, fp.s8_pos, AddMax2(a, fp.s8_neg, t0p)));   /* cpu.h:1192-1211 */
+	a = 4u * t.p1; t.p1 = Shr<2>(AddMin2(a, fp.s4_pos, AddMax2(a, fp.s4_neg, t1p)));
+	a = 8u * t.p2; t.p2 = Shr<3>(AddMin2(a, fp.s8_pos, AddMax2(a, fp.s8_neg, t2p)));
+	a = 8u * t.q0; t.q0 = Shr<3>(AddMin2(a, fp.s8_pos, AddMax2(a, fp.s8_neg, t0q)));
+	a = 4u * t.q1; t.q1 = Shr<2>(AddMin2(a, fp.s4_pos, AddMax2(a, fp.s4_neg, t1q)));
+	a = 8u * t.q2; t.q2 = Shr<3>(AddMin2(a, fp.s8_pos, AddMax2(a, fp.s8_neg, t2q)));
 }
 
 /*
@@ -196,7 +203,7 @@ HDB_FN void NormalPair(LumaPair &t, const FilterParams &fp, u32 lo_p, u32 hi_p, 
 {
 	/* 4096 + 9(q0-p0) - 3(q1-p1) + 8, each half in [1044, 7164] */
 	u32 num = 3u * (3u * (t.q0 - t.p0) + t.p1 - t.q1) + 0x10081008u;
-	u32 e = (num >> 4) & 0x01ff01ffu;                  /* 256 + delta              cpu.h:1253 */
+	u32 e = Shr<4>(num) & 0x01ff01ffu;                  /* 256 + delta              cpu.h:1253 */
 	u32 na = Min2(e, 0x02000200u - e);                 /* 256 - |delta| */
 	u32 on = AddMinRelu2(na, fp.k_tc10, 0x00010001u);  /* 1 where |delta| < 10tc   cpu.h:1254 */
 	u32 mask = on * 0x01ffu;                           /* 9 bits per half: every value selected below is < 512 */
@@ -204,8 +211,8 @@ HDB_FN void NormalPair(LumaPair &t, const FilterParams &fp, u32 lo_p, u32 hi_p, 
 	d = (d & mask) | (fp.c2_pos & ~mask);              /* lines that are off: delta = 0 */
 	u32 dn = fp.c2_rep4 - d;                         /* 2tc - Clip(delta) */
 	/* Clip(((x2 + x0 - 2 x1 +- 2D + 1) >> 2), tc/2) + tc/2 in [0, 2(tc/2)]   cpu.h:1259-1265 */
-	u32 hp = AddMinRelu2(sd_p + fp.k_half + 2u * d, lo_p, hi_p) >> 2;
-	u32 hq = AddMinRelu2(sd_q + fp.k_half + 2u * dn, lo_q, hi_q) >> 2;
+	u32 hp = Shr<2>(AddMinRelu2(sd_p + fp.k_half + 2u * d, lo_p, hi_p));
+	u32 hq = Shr<2>(AddMinRelu2(sd_q + fp.k_half + 2u * dn, lo_q, hi_q));
 	u32 dp = (hp & mask) | (fp.h_rep & ~mask);         /* line off: no change */
 	u32 dq = (hq & mask) | (fp.h_rep & ~mask);
 	t.p1 = AddMinRelu2(t.p1 + dp, fp.h_neg, 0x00ff00ffu);      /* cpu.h:1272 */
@@ -278,8 +285,8 @@ HDB_FN void ChromaPairFilter(ChromaPair &t, const FilterParams &fp)
 	/* 2048 + 4(p0-q0) + p1 - q1 + 4 in [777, 3327]; the q numerator is 8 - (p numerator - 4) + ... */
 	u32 np = 4u * (t.p0 - t.q0) + t.p1 - t.q1 + 0x08040804u;        /* cpu.h:1453 */
 	u32 nq = 0x10081008u - np;                                      /* cpu.h:1458 */
-	u32 ep = (np >> 3) & 0x01ff01ffu;                               /* 256 + delta_p */
-	u32 eq = (nq >> 3) & 0x01ff01ffu;                               /* 256 + delta_q */
+	u32 ep = Shr<3>(np) & 0x01ff01ffu;                               /* 256 + delta_p */
+	u32 eq = Shr<3>(nq) & 0x01ff01ffu;                               /* 256 + delta_q */
 	u32 dp = AddMinRelu2(ep, fp.ct_lo, fp.ct_2);                    /* Clip(delta_p) + tc   cpu.h:1464 */
 	u32 dq = AddMinRelu2(eq, fp.ct_lo, fp.ct_2);                    /* Clip(delta_q) + tc   cpu.h:1469 */
 	t.p0 = AddMinRelu2(t.p0 + dp, fp.ct_neg, 0x00ff00ffu);          /* cpu.h:1475 */
