@@ -352,6 +352,44 @@ struct SkewRun {
 	}
 };
 
+/* planes narrower than that (a column can meet the padding twice in one item): the walk itself, out of line so that
+ * the kernels' hot loops stay small */
+__device__ __noinline__ void SkewFetchNarrow(const TiledBatch &b, const unsigned char *src, uint32_t d, int vr, int vc)
+{
+	SkewWalk wk;
+	wk.Start(b, vr, vc);
+#pragma unroll 1
+	for (int t = 0; t < kTileH; t++) {
+		bool lo, hi;
+		wk.Halves(b, lo, hi);
+		const unsigned char *g = src + wk.img;
+		if (lo == hi) CpAsync8(d, lo ? g : src, lo ? 8u : 0u);
+		else { CpAsync4(d, lo ? g : src, lo ? 4u : 0u); CpAsync4(d + 4u, hi ? g + 4 : src, hi ? 4u : 0u); }
+		wk.NextRow(b);
+		d += kTileW;
+	}
+}
+
+__device__ __noinline__ void SkewStoreNarrow(const TiledBatch &b, unsigned char *dst, const unsigned char *sp, int vr, int vc, bool live)
+{
+	SkewWalk wk;
+	wk.Start(b, vr, vc);
+	if (!live) wk.lo_col = wk.hi_col = false;
+#pragma unroll 1
+	for (int rr = 0; rr < kTileH; rr++) {
+		bool lo, hi;
+		wk.Halves(b, lo, hi);
+		const uint2 v = *reinterpret_cast<const uint2 *>(sp);
+		if (lo && hi) *reinterpret_cast<uint2 *>(dst + wk.img) = v;
+		else {
+			if (lo) *reinterpret_cast<u32 *>(dst + wk.img) = v.x;
+			if (hi) *reinterpret_cast<u32 *>(dst + wk.img + 4) = v.y;
+		}
+		wk.NextRow(b);
+		sp += kTileW;
+	}
+}
+
 template <bool kNv12>
 __device__ __noinline__ void FetchTileLdgsts(const TiledBatch &b, const uint2 it, const uint32_t dst, const int lane)
 {
@@ -383,21 +421,7 @@ __device__ __noinline__ void FetchTileLdgsts(const TiledBatch &b, const uint2 it
 					g += t == k.bump ? step + 8 : step;
 					d += kTileW;
 				}
-			} else {
-				SkewWalk wk;
-				wk.Start(b, 8 * lby0, xb0 + 4 + 8 * lane);
-				uint32_t d = dst + 8u * (uint32_t)lane;
-#pragma unroll 1
-				for (int t = 0; t < kTileH; t++) {
-					bool lo, hi;
-					wk.Halves(b, lo, hi);
-					const unsigned char *g = src + wk.img;
-					if (lo == hi) CpAsync8(d, lo ? g : src, lo ? 8u : 0u);
-					else { CpAsync4(d, lo ? g : src, lo ? 4u : 0u); CpAsync4(d + 4u, hi ? g + 4 : src, hi ? 4u : 0u); }
-					wk.NextRow(b);
-					d += kTileW;
-				}
-			}
+			} else SkewFetchNarrow(b, src, dst + 8u * (uint32_t)lane, 8 * lby0, xb0 + 4 + 8 * lane);
 			/* units 32 and 33: row lane / 2 (and 16 rows further on, for taller items), unit 32 + lane % 2 */
 #pragma unroll 1
 			for (int t = lane >> 1; t < kTileH; t += 16) {
@@ -686,24 +710,7 @@ DeblockTiledKernel(const __grid_constant__ TensorMaps3 maps, const __grid_consta
 						g += rr == k.bump ? step + 8 : step;
 						sp += kTileW;
 					}
-				} else {
-					SkewWalk wk;
-					wk.Start(b, 8 * lby0, 8 * bx0 + 4 + 8 * lane);
-					if (lane == 31) wk.lo_col = wk.hi_col = false;
-#pragma unroll 1
-					for (int rr = 0; rr < kTileH; rr++) {
-						bool lo, hi;
-						wk.Halves(b, lo, hi);
-						const uint2 v = *reinterpret_cast<const uint2 *>(sp);
-						if (lo && hi) *reinterpret_cast<uint2 *>(dst + wk.img) = v;
-						else {
-							if (lo) *reinterpret_cast<u32 *>(dst + wk.img) = v.x;
-							if (hi) *reinterpret_cast<u32 *>(dst + wk.img + 4) = v.y;
-						}
-						wk.NextRow(b);
-						sp += kTileW;
-					}
-				}
+				} else SkewStoreNarrow(b, dst, sp, 8 * lby0, 8 * bx0 + 4 + 8 * lane, lane < 31);
 				/* the word at virtual column 8 bx0 / 8 bx0 + 252 of every row: row lane / 2, end lane % 2 */
 #pragma unroll 1
 				for (int rr = lane >> 1; rr < kTileH; rr += 16) {
