@@ -148,6 +148,8 @@ def load_library():
                                              C.POINTER(C.c_uint), C.POINTER(Timing)]
     lib.hdb_sao_batch_device.argtypes = [vp, vp, vp, C.c_uint, C.c_uint, C.c_uint, vp, C.c_uint, vp]
     lib.hdb_sao_batch.argtypes = [vp, vp, vp, C.c_uint, C.c_uint, C.c_uint, vp, C.c_uint]
+    lib.hdb_sao_batch_device_ex.argtypes = [vp, vp, vp, C.c_uint, C.c_uint, C.c_uint, vp, C.c_uint, C.c_uint, vp]
+    lib.hdb_sao_batch_ex.argtypes = [vp, vp, vp, C.c_uint, C.c_uint, C.c_uint, vp, C.c_uint, C.c_uint]
     lib.hdb_deblock_sao_batch_device.argtypes = [vp, vp, vp, C.c_uint, C.c_uint, C.c_uint, vp, vp, vp, C.c_uint, vp, C.c_uint, vp]
     lib.hdb_kernel_launch_count.argtypes = [vp]
     lib.hdb_kernel_launch_count.restype = C.c_ulonglong
@@ -385,18 +387,26 @@ class Deblocker:
                                                                stream))
 
     # --- sample adaptive offset (H.265 8.7.3; absent from the reference) ---
-    def sao_batch(self, frames, width, height, params, ctb_size=64, out=None):
-        """Host frames uint8[n, 3wh/2] and SAO_PARAMS[n, 3, ceil(h / ctb), ceil(w / ctb)] -> offset frames."""
+    def sao_batch(self, frames, width, height, params, ctb_size=64, out=None, flags=0):
+        """Host frames uint8[n, 3wh/2] (uint16 with flags = flag_depth(d)) and
+        SAO_PARAMS[n, 3, ceil(h / ctb), ceil(w / ctb)] -> offset frames."""
         n = int(frames.shape[0])
         params = np.ascontiguousarray(params, SAO_PARAMS)
         if out is None:
             out = np.empty_like(frames)
-        self._check(self._lib.hdb_sao_batch(self._ctx, _addr(frames), _addr(out), n, width, height, _addr(params), ctb_size))
+        if flags:
+            self._check(self._lib.hdb_sao_batch_ex(self._ctx, _addr(frames), _addr(out), n, width, height, _addr(params), ctb_size, flags))
+        else:
+            self._check(self._lib.hdb_sao_batch(self._ctx, _addr(frames), _addr(out), n, width, height, _addr(params), ctb_size))
         return out
 
-    def sao_batch_device(self, d_in, d_out, n_frames, width, height, d_params, ctb_size=64, stream=None):
-        self._check(self._lib.hdb_sao_batch_device(self._ctx, _addr(d_in), _addr(d_out), n_frames, width, height,
-                                                   _addr(d_params), ctb_size, stream))
+    def sao_batch_device(self, d_in, d_out, n_frames, width, height, d_params, ctb_size=64, stream=None, flags=0):
+        if flags:
+            self._check(self._lib.hdb_sao_batch_device_ex(self._ctx, _addr(d_in), _addr(d_out), n_frames, width, height,
+                                                          _addr(d_params), ctb_size, flags, stream))
+        else:
+            self._check(self._lib.hdb_sao_batch_device(self._ctx, _addr(d_in), _addr(d_out), n_frames, width, height,
+                                                       _addr(d_params), ctb_size, stream))
 
     def deblock_sao_batch_device(self, d_in, d_out, n_frames, width, height, d_qp, d_vert, d_hor, d_params, ctb_size=64,
                                  flags=0, stream=None):

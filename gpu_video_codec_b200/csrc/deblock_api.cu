@@ -1145,8 +1145,12 @@ int hdb_execute_gpu_sequence(hdb_context *ctx, const char *input_file_name, cons
 
 /* ---- sample adaptive offset ---- */
 
-static int ValidateSao(hdb_context *ctx, unsigned width, unsigned height, unsigned ctb_size)
+/* *depth16: 0 for a byte a sample, else the bit depth of samples in 16-bit containers */
+static int ValidateSao(hdb_context *ctx, unsigned width, unsigned height, unsigned ctb_size, unsigned flags, int max_depth, int *depth16)
 {
+	if (flags & ~(HDB_FLAG_SAMPLES16 | (0xffu << 8))) return Fail(ctx, HDB_ERR_INVALID_ARG, "unknown flag");
+	*depth16 = DepthOfFlags(flags);
+	if ((flags & HDB_FLAG_SAMPLES16) && (*depth16 < 8 || *depth16 > max_depth)) return Fail(ctx, HDB_ERR_INVALID_ARG, "bit depth out of range (HDB_FLAG_DEPTH)");
 	int rc = ValidateFrameArgs(ctx, width, height, nullptr, 0, nullptr, 0, false);
 	if (rc) return rc;
 	if (ctb_size != 16 && ctb_size != 32 && ctb_size != 64) return Fail(ctx, HDB_ERR_INVALID_ARG, "coding tree block size must be 16, 32 or 64");
@@ -1156,43 +1160,52 @@ static int ValidateSao(hdb_context *ctx, unsigned width, unsigned height, unsign
 /* the kernel's ticket counters: a stream-ordered allocation of the call's own, so that launches in flight on
  * different streams never share one */
 static cudaError_t LaunchSaoWithTickets(hdb_context *ctx, const unsigned char *d_in, unsigned char *d_out, int n_frames, int width, int height,
-	const void *d_params, int ctb, cudaStream_t st)
+	const void *d_params, int ctb, int depth16, cudaStream_t st)
 {
 	unsigned *tickets = nullptr;
 	cudaError_t e = cudaMallocFromPoolAsync(reinterpret_cast<void **>(&tickets), sizeof(unsigned) * kSaoTicketWords, ctx->pool, st);
 	if (e != cudaSuccess) return e;
-	e = LaunchSao(d_in, d_out, n_frames, width, height, d_params, ctb, tickets, ctx->prop.multiProcessorCount, st);
+	e = LaunchSao(d_in, d_out, n_frames, width, height, d_params, ctb, depth16 ? depth16 : 8, depth16 ? 2 : 1, tickets, ctx->prop.multiProcessorCount, st);
 	cudaFreeAsync(tickets, st);
 	return e;
 }
 
-int hdb_sao_batch_device(hdb_context *ctx, const void *d_frames_in, void *d_frames_out, unsigned n_frames,
-	unsigned width, unsigned height, const hdb_sao_params *d_params, unsigned ctb_size, void *stream)
+int hdb_sao_batch_device_ex(hdb_context *ctx, const void *d_frames_in, void *d_frames_out, unsigned n_frames,
+	unsigned width, unsigned height, const hdb_sao_params *d_params, unsigned ctb_size, unsigned flags, void *stream)
 {
 	if (!ctx) return HDB_ERR_INVALID_ARG;
 	std::lock_guard<std::mutex> lock(ctx->mu);
 	if (!d_frames_in || !d_frames_out || !d_params || n_frames == 0) return Fail(ctx, HDB_ERR_INVALID_ARG, "NULL buffer or empty batch");
 	if (d_frames_in == d_frames_out) return Fail(ctx, HDB_ERR_INVALID_ARG, "sample adaptive offset runs out of place: a sample's neighbours are input samples");
-	if (((uintptr_t)d_frames_in | (uintptr_t)d_frames_out) % 4 != 0) return Fail(ctx, HDB_ERR_INVALID_ARG, "frames must be 4-byte aligned");
-	int rc = ValidateSao(ctx, width, height, ctb_size);
+	int depth16 = 0;
+	int rc = ValidateSao(ctx, width, height, ctb_size, flags, 12, &depth16);
 	if (rc) return rc;
+	if (((uintptr_t)d_frames_in | (uintptr_t)d_frames_out) % (depth16 ? 8 : 4) != 0)
+		return Fail(ctx, HDB_ERR_INVALID_ARG, depth16 ? "frames of 16-bit samples must be 8-byte aligned" : "frames must be 4-byte aligned");
 	DeviceGuard guard(ctx->device);
 	HDB_CUDA(ctx, LaunchSaoWithTickets(ctx, static_cast<const unsigned char *>(d_frames_in), static_cast<unsigned char *>(d_frames_out), (int)n_frames,
-		(int)width, (int)height, d_params, (int)ctb_size, static_cast<cudaStream_t>(stream)));
+		(int)width, (int)height, d_params, (int)ctb_size, depth16, static_cast<cudaStream_t>(stream)));
 	ctx->launches += 1;
 	return HDB_OK;
 }
 
-int hdb_sao_batch(hdb_context *ctx, const unsigned char *frames_in, unsigned char *frames_out, unsigned n_frames,
-	unsigned width, unsigned height, const hdb_sao_params *params, unsigned ctb_size)
+int hdb_sao_batch_device(hdb_context *ctx, const void *d_frames_in, void *d_frames_out, unsigned n_frames,
+	unsigned width, unsigned height, const hdb_sao_params *d_params, unsigned ctb_size, void *stream)
+{
+	return hdb_sao_batch_device_ex(ctx, d_frames_in, d_frames_out, n_frames, width, height, d_params, ctb_size, 0, stream);
+}
+
+int hdb_sao_batch_ex(hdb_context *ctx, const void *frames_in, void *frames_out, unsigned n_frames,
+	unsigned width, unsigned height, const hdb_sao_params *params, unsigned ctb_size, unsigned flags)
 {
 	if (!ctx) return HDB_ERR_INVALID_ARG;
 	std::lock_guard<std::mutex> lock(ctx->mu);
 	if (!frames_in || !frames_out || !params || n_frames == 0) return Fail(ctx, HDB_ERR_INVALID_ARG, "NULL buffer or empty batch");
-	int rc = ValidateSao(ctx, width, height, ctb_size);
+	int depth16 = 0;
+	int rc = ValidateSao(ctx, width, height, ctb_size, flags, 12, &depth16);
 	if (rc) return rc;
 	DeviceGuard guard(ctx->device);
-	const size_t fb = (size_t)width * height * 3 / 2;
+	const size_t fb = (size_t)width * height * 3 / 2 * (depth16 ? 2 : 1);
 	const size_t pb = sizeof(hdb_sao_params) * 3 * ((height + ctb_size - 1) / ctb_size) * ((width + ctb_size - 1) / ctb_size);
 	/* a bounded number of frames at a time, buffers of the call's own in stream order */
 	const unsigned chunk = (unsigned)std::min<size_t>(n_frames, std::max<size_t>(1, ((size_t)256 << 20) / fb));
@@ -1204,10 +1217,10 @@ int hdb_sao_batch(hdb_context *ctx, const unsigned char *frames_in, unsigned cha
 	cudaError_t e = cudaSuccess;
 	for (unsigned f0 = 0; f0 < n_frames && e == cudaSuccess; f0 += chunk) {
 		const unsigned nf = std::min(chunk, n_frames - f0);
-		e = cudaMemcpyAsync(d_in, frames_in + (size_t)f0 * fb, fb * nf, cudaMemcpyHostToDevice, st);
+		e = cudaMemcpyAsync(d_in, static_cast<const unsigned char *>(frames_in) + (size_t)f0 * fb, fb * nf, cudaMemcpyHostToDevice, st);
 		if (e == cudaSuccess) e = cudaMemcpyAsync(d_par, reinterpret_cast<const unsigned char *>(params) + (size_t)f0 * pb, pb * nf, cudaMemcpyHostToDevice, st);
-		if (e == cudaSuccess) e = LaunchSaoWithTickets(ctx, d_in, d_out, (int)nf, (int)width, (int)height, d_par, (int)ctb_size, st);
-		if (e == cudaSuccess) e = cudaMemcpyAsync(frames_out + (size_t)f0 * fb, d_out, fb * nf, cudaMemcpyDeviceToHost, st);
+		if (e == cudaSuccess) e = LaunchSaoWithTickets(ctx, d_in, d_out, (int)nf, (int)width, (int)height, d_par, (int)ctb_size, depth16, st);
+		if (e == cudaSuccess) e = cudaMemcpyAsync(static_cast<unsigned char *>(frames_out) + (size_t)f0 * fb, d_out, fb * nf, cudaMemcpyDeviceToHost, st);
 		ctx->launches += 1;
 	}
 	cudaFreeAsync(d_in, st); cudaFreeAsync(d_out, st); cudaFreeAsync(d_par, st);
@@ -1217,29 +1230,36 @@ int hdb_sao_batch(hdb_context *ctx, const unsigned char *frames_in, unsigned cha
 	return HDB_OK;
 }
 
+int hdb_sao_batch(hdb_context *ctx, const unsigned char *frames_in, unsigned char *frames_out, unsigned n_frames,
+	unsigned width, unsigned height, const hdb_sao_params *params, unsigned ctb_size)
+{
+	return hdb_sao_batch_ex(ctx, frames_in, frames_out, n_frames, width, height, params, ctb_size, 0);
+}
+
 int hdb_deblock_sao_batch_device(hdb_context *ctx, const void *d_frames_in, void *d_frames_out, unsigned n_frames,
 	unsigned width, unsigned height, const unsigned *d_qp, const unsigned char *d_vert, const unsigned char *d_hor,
 	unsigned flags, const hdb_sao_params *d_params, unsigned ctb_size, void *stream)
 {
 	if (!ctx) return HDB_ERR_INVALID_ARG;
 	std::lock_guard<std::mutex> lock(ctx->mu);
-	if (flags & ~HDB_FLAG_EDGE_MAPS) return Fail(ctx, HDB_ERR_INVALID_ARG, "unknown flag");
+	if (flags & ~(HDB_FLAG_EDGE_MAPS | HDB_FLAG_SAMPLES16 | (0xffu << 8))) return Fail(ctx, HDB_ERR_INVALID_ARG, "unknown flag");
 	if (!d_frames_in || !d_frames_out || !d_qp || !d_params || n_frames == 0) return Fail(ctx, HDB_ERR_INVALID_ARG, "NULL buffer or empty batch");
+	int depth16 = 0;
 	int rc = ValidateFrameArgs(ctx, width, height, d_vert, 0, d_hor, 0, false);
-	if (!rc) rc = ValidateSao(ctx, width, height, ctb_size);
+	if (!rc) rc = ValidateSao(ctx, width, height, ctb_size, flags & ~HDB_FLAG_EDGE_MAPS, 10, &depth16);
 	if (rc) return rc;
 	DeviceGuard guard(ctx->device);
 	cudaStream_t st = static_cast<cudaStream_t>(stream);
-	const size_t fb = (size_t)width * height * 3 / 2;
+	const size_t fb = (size_t)width * height * 3 / 2 * (depth16 ? 2 : 1);
 	unsigned char *scratch = nullptr;
 	HDB_CUDA(ctx, cudaMallocFromPoolAsync(reinterpret_cast<void **>(&scratch), fb * n_frames, ctx->pool, st));
-	const FrameView view = WholeFrameView((int)width, (int)height);
+	const FrameView view = WholeFrameView((int)width, (int)height, false, depth16);
 	rc = EnqueueFilter(ctx, view, static_cast<const unsigned char *>(d_frames_in), scratch, (int)n_frames, d_qp, 0,
 		d_vert, hdb_num_vert_bs(width, height), d_hor, hdb_num_hor_bs(width, height), st, nullptr, (flags & HDB_FLAG_EDGE_MAPS) != 0);
 	cudaError_t e = cudaSuccess;
 	if (!rc) {
 		e = LaunchSaoWithTickets(ctx, scratch, static_cast<unsigned char *>(d_frames_out), (int)n_frames, (int)width, (int)height, d_params,
-			(int)ctb_size, st);
+			(int)ctb_size, depth16, st);
 		ctx->launches += 1;
 	}
 	cudaFreeAsync(scratch, st);

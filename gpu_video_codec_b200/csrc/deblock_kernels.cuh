@@ -137,13 +137,14 @@ cudaError_t LaunchDeriveEdges(const void *info, int width, int height, int n_fra
 	unsigned char *vert_edges, unsigned char *hor_edges, cudaStream_t stream);
 
 /*
- * Sample adaptive offset (sao_kernels.cu; H.265 8.7.3, absent from the reference): tight 8-bit YV12 frames in
- * device memory, out of place, d_params = hdb_sao_params[n_frames][3][ceil(H / ctb)][ceil(W / ctb)].
+ * Sample adaptive offset (sao_kernels.cu; H.265 8.7.3, absent from the reference): tight planar 4:2:0 frames in
+ * device memory -- a byte a sample (sample_bytes 1, bit_depth 8) or 16-bit containers (sample_bytes 2, bit_depth
+ * 8 .. 12; 8-byte aligned) -- out of place, d_params = hdb_sao_params[n_frames][3][ceil(H / ctb)][ceil(W / ctb)].
  * d_tickets: kSaoTicketWords words of device memory that are the launch's own until it has run (the counters the
  * blocks are handed out through; zeroed here, in stream order).
  */
 constexpr int kSaoTicketWords = 4096;
 cudaError_t LaunchSao(const unsigned char *d_in, unsigned char *d_out, int n_frames, int width, int height,
-	const void *d_params, int ctb, unsigned *d_tickets, int sm_count, cudaStream_t stream);
+	const void *d_params, int ctb, int bit_depth, int sample_bytes, unsigned *d_tickets, int sm_count, cudaStream_t stream);
 
 } // namespace hdb

@@ -67,6 +67,7 @@ struct SaoBatch {
 	long long frame_stride;
 	int n_frames, width, height;
 	int ctb;                                         /* luma CTB size: 16, 32 or 64 */
+	int bit_depth;                                   /* 8 with a byte a sample; 8 .. 12 in 16-bit containers */
 	int ctb_cols, ctb_rows;
 	const unsigned char *params;                     /* hdb_sao_params[n][3][ctb_rows][ctb_cols], 6 bytes each */
 	/* task space: frame-major, then plane, band of kSaoChunk CTB rows, CTB column, CTB row within the band */
@@ -348,18 +349,265 @@ SaoKernel(const __grid_constant__ SaoBatch b)
 	}
 }
 
+/* ------------------------------------------------------------------ */
+/* samples of 9 .. 12 bits in 16-bit containers                        */
+/* ------------------------------------------------------------------ */
+/*
+ * The same walk with a sample per half: a lane's eight samples are four words (one 16-byte load when the rows are
+ * a whole number of them), nothing is unpacked or packed, S and the categories stay 16x2.  Band shift, sample
+ * maximum and the bias of the comparison follow the bit depth (8.7.3: bandShift = bitDepth - 5; offsets arrive
+ * as final values, |offset| <= 31 at ten bits).
+ */
+struct Sao16Lane {
+	const u32 *src; u32 *dst;          /* the plane, as words of two samples */
+	unsigned pww;                      /* words per row (even) */
+	int ph;
+	unsigned xa, xb, xe, xr;           /* word columns: own first / third (clamped), the neighbouring block's, the right one */
+	unsigned x;                        /* own first word, unclamped */
+	int ya, yb, rpg;
+	bool live_a, live_b, first_col, last_col, one_lane;
+	u32 pool_lo, pool_hi, band_add, band_shift;
+	u32 bias2, unbias2, max2;          /* 1 << depth, -((1 << depth) - 1), (1 << depth) - 1 in both halves */
+};
+struct RawRow16 { u32 w[4], e, e2; };
+struct RowWin16 { u32 L, w[4], R; };
+
+/* offsets picked by the index halves (0..4) out of the pool, as signed halves */
+__device__ __forceinline__ u32 PickOffsets2(u32 idx2, u32 pool_lo, u32 pool_hi)
+{
+	const u32 t = idx2 * 0x11u;                                  /* nibble | nibble << 4 in bytes 0 and 2 */
+	const u32 sel = Prmt(t, 0u, 0x4420) | 0x8080u;               /* nibbles: i0, i0 | 8, i1, i1 | 8 */
+	u32 d;
+	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(pool_lo), "r"(pool_hi), "r"(sel));
+	return d;
+}
+
+template <bool kSides, bool kQuad>
+__device__ __forceinline__ RawRow16 LoadRow16(const Sao16Lane &t, int y)
+{
+	const unsigned row = (unsigned)min(max(y, 0), t.ph - 1) * t.pww;
+	RawRow16 r;
+	if (kQuad) {
+		const uint4 v = __ldg(reinterpret_cast<const uint4 *>(t.src + (row + t.xa)));
+		r.w[0] = v.x; r.w[1] = v.y; r.w[2] = v.z; r.w[3] = v.w;
+	} else {
+		const uint2 a = __ldg(reinterpret_cast<const uint2 *>(t.src + (row + t.xa))), c = __ldg(reinterpret_cast<const uint2 *>(t.src + (row + t.xb)));
+		r.w[0] = a.x; r.w[1] = a.y; r.w[2] = c.x; r.w[3] = c.y;
+	}
+	r.e = r.e2 = 0u;
+	if (kSides) {
+		r.e = __ldg(t.src + (row + t.xe));
+		if (t.one_lane) r.e2 = __ldg(t.src + (row + t.xr));
+	}
+	return r;
+}
+
+template <bool kSides>
+__device__ __forceinline__ RowWin16 Neighbours16(const Sao16Lane &t, const RawRow16 &r)
+{
+	RowWin16 o;
+#pragma unroll
+	for (int j = 0; j < 4; j++) o.w[j] = r.w[j];
+	o.L = o.R = 0u;
+	if (kSides) {
+		o.L = __shfl_up_sync(0xffffffffu, r.w[3], 1);
+		o.R = __shfl_down_sync(0xffffffffu, r.w[0], 1);
+		if (t.first_col) o.L = r.e;
+		if (t.last_col) o.R = t.one_lane ? r.e2 : r.e;
+	}
+	return o;
+}
+
+template <bool kQuad>
+__device__ __forceinline__ void StoreRow16(const Sao16Lane &t, u32 *orow, bool row_live, const u32 (&v)[4])
+{
+	if (kQuad) { if (row_live && t.live_a) *reinterpret_cast<uint4 *>(orow) = make_uint4(v[0], v[1], v[2], v[3]); }
+	else {
+		if (row_live && t.live_a) *reinterpret_cast<uint2 *>(orow) = make_uint2(v[0], v[1]);
+		if (row_live && t.live_b) *reinterpret_cast<uint2 *>(orow + 2) = make_uint2(v[2], v[3]);
+	}
+}
+
+template <int kMode, bool kQuad>
+__device__ __forceinline__ void FlatRun16(const Sao16Lane &t)
+{
+	u32 *orow = t.dst + ((unsigned)t.ya * t.pww + t.xa);
+#pragma unroll 1
+	for (int k0 = 0; k0 < t.rpg; k0 += 2) {
+		RawRow16 r[2];
+#pragma unroll
+		for (int j = 0; j < 2; j++) if (k0 + j < t.rpg) r[j] = LoadRow16<false, kQuad>(t, t.ya + k0 + j);
+#pragma unroll
+		for (int j = 0; j < 2; j++) {
+			if (k0 + j < t.rpg) {
+				u32 v[4];
+#pragma unroll
+				for (int i = 0; i < 4; i++) {
+					v[i] = r[j].w[i];
+					if (kMode == 1) {
+						const u32 k = (((v[i] >> t.band_shift) & 0x001f001fu) + t.band_add) & 0x001f001fu;
+						v[i] = AddMinRelu2(v[i], PickOffsets2(MinU2(k, 0x00040004u), t.pool_lo, t.pool_hi), t.max2);
+					}
+				}
+				StoreRow16<kQuad>(t, orow, t.ya + k0 + j < t.yb, v);
+			}
+			orow += t.pww;
+		}
+	}
+}
+
+/* see EdgeRun: category(y, i) = 2 + S(y, i) - S(y + vy, i - hx), one S per sample */
+template <int kClass, bool kQuad>
+__device__ __forceinline__ void EdgeRun16(const Sao16Lane &t)
+{
+	constexpr bool kSides = kClass != 1, kTall = kClass != 0;
+	const int n_iter = t.rpg + (kTall ? 1 : 0);
+	u32 *orow = t.dst + ((long long)(t.ya - (kTall ? 1 : 0)) * (long long)t.pww + t.xa);
+	auto step = [&](int i, RawRow16 &slot, const RowWin16 &above, const u32 (&s_above)[4], RowWin16 &cur, u32 (&s_cur)[4]) {
+		cur = Neighbours16<kSides>(t, slot);
+		if (i + 2 < n_iter) slot = LoadRow16<kSides, kQuad>(t, t.ya + i + 2);
+		const RowWin16 &ar = kTall ? above : cur;
+		u32 s[5], tt[4];
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			u32 a = ar.w[j];
+			if (kClass == 3) a = Prmt(ar.w[j], j == 3 ? ar.R : ar.w[j + 1], 0x5432);          /* one sample to the right */
+			else if (kClass != 1) a = Prmt(j == 0 ? ar.L : ar.w[j - 1], ar.w[j], 0x5432);      /* one to the left */
+			s[j] = AddMinRelu2(cur.w[j] + t.bias2 - a, t.unbias2, 0x00020002u);
+		}
+		if (kClass == 0 || kClass == 2) {
+			const u32 mine = AddMinRelu2((cur.R & 0xffffu) + (t.bias2 & 0xffffu) - (ar.w[3] >> 16), t.unbias2, 0x00020002u);
+			const u32 theirs = __shfl_down_sync(0xffffffffu, s[0], 1);
+			s[4] = t.last_col ? mine : theirs;
+#pragma unroll
+			for (int j = 0; j < 4; j++) tt[j] = Prmt(s[j], s[j + 1], 0x5432);
+		} else if (kClass == 3) {
+			const u32 mine = AddMinRelu2((cur.L >> 16) + (t.bias2 & 0xffffu) - (ar.w[0] & 0xffffu), t.unbias2, 0x00020002u) << 16;
+			const u32 theirs = __shfl_up_sync(0xffffffffu, s[3], 1);
+			const u32 sl = t.first_col ? mine : theirs;
+#pragma unroll
+			for (int j = 0; j < 4; j++) tt[j] = Prmt(j == 0 ? sl : s[j - 1], s[j], 0x5432);
+		} else {
+#pragma unroll
+			for (int j = 0; j < 4; j++) tt[j] = s[j];
+		}
+		const int yo = t.ya + i - (kTall ? 1 : 0);
+		const bool keep_row = kTall && (yo == 0 || yo == t.ph - 1);
+		u32 v[4];
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			const u32 e = (kTall ? s_above[j] : s[j]) + 0x00020002u - tt[j];
+			const u32 r = AddMinRelu2(ar.w[j], PickOffsets2(e, t.pool_lo, t.pool_hi), t.max2);
+			/* the picture's first / last column (not for the vertical class), first / last row (not for the horizontal one) */
+			u32 keep = 0u;
+			if (kClass != 1) keep = (t.x + j == 0u ? 0x0000ffffu : 0u) | (t.x + j == t.pww - 1u ? 0xffff0000u : 0u);
+			if (keep_row) keep = 0xffffffffu;
+			v[j] = (ar.w[j] & keep) | (r & ~keep);
+			s_cur[j] = s[j];
+		}
+		StoreRow16<kQuad>(t, orow, yo >= t.ya && yo < t.yb, v);
+		orow += t.pww;
+	};
+	RowWin16 wa, wb;
+	u32 sa[4] = {0u, 0u, 0u, 0u}, sb[4] = {0u, 0u, 0u, 0u};
+	wb.L = wb.R = 0u; wb.w[0] = wb.w[1] = wb.w[2] = wb.w[3] = 0u;
+	wa = wb;
+	if (kTall) wb = Neighbours16<kSides>(t, LoadRow16<kSides, kQuad>(t, t.ya - 1));
+	RawRow16 p = LoadRow16<kSides, kQuad>(t, t.ya), q = p;
+	if (n_iter > 1) q = LoadRow16<kSides, kQuad>(t, t.ya + 1);
+#pragma unroll 1
+	for (int i = 0; i < n_iter; i += 2) {
+		step(i, p, wb, sb, wa, sa);
+		if (i + 1 < n_iter) step(i + 1, q, wa, sa, wb, sb);
+	}
+}
+
+#ifndef HDB_SAO16_MIN_CTAS
+#define HDB_SAO16_MIN_CTAS 1
+#endif
+template <bool kQuad>
+__global__ void __launch_bounds__(kSaoWarps * 32, HDB_SAO16_MIN_CTAS)
+Sao16Kernel(const __grid_constant__ SaoBatch b)
+{
+	const int lane = threadIdx.x & 31;
+	const unsigned total = (unsigned)b.total_tasks;
+	const unsigned n_chunks = (total + kSaoChunk - 1) / kSaoChunk;
+	const unsigned warp_id = blockIdx.x * kSaoWarps + (threadIdx.x >> 5);
+	const unsigned counter = warp_id % kSaoCounters;
+	unsigned *ticket = b.ticket + 32u * counter;
+	unsigned next = 0;
+	if (lane == 0) next = atomicAdd(ticket, 1u);
+	next = __shfl_sync(0xffffffffu, next, 0) * kSaoCounters + counter;
+	while (next < n_chunks) {
+		const unsigned first = next * kSaoChunk, last = min(first + (unsigned)kSaoChunk, total);
+		if (lane == 0) next = atomicAdd(ticket, 1u);
+		for (unsigned task = first; task < last; task++) {
+			const uint32_t frame = b.div_tasks_per_frame.Div(task);
+			uint32_t r = task - frame * (uint32_t)b.tasks_per_frame;
+			const int plane = (int)b.div_tasks_per_plane.Div(r);
+			r -= (uint32_t)plane * (uint32_t)b.tasks_per_plane;
+			const int band = (int)b.div_band.Div(r), in_band = (int)r - band * (kSaoBand * b.ctb_cols);
+			const int crow = band * kSaoBand + in_band % kSaoBand, ccol = in_band / kSaoBand;
+			if (crow >= b.ctb_rows) continue;
+			const int pw = plane ? b.width >> 1 : b.width, ph = plane ? b.height >> 1 : b.height;
+			const int ctb = plane ? b.ctb >> 1 : b.ctb;
+			const long long plane_off = plane == 0 ? 0 : (long long)b.width * b.height + (plane == 2 ? (long long)(b.width >> 1) * (b.height >> 1) : 0);
+			Sao16Lane t;
+			t.src = reinterpret_cast<const u32 *>(b.in + (long long)frame * b.frame_stride + 2 * plane_off);
+			t.dst = reinterpret_cast<u32 *>(b.out + (long long)frame * b.frame_stride + 2 * plane_off);
+			t.ph = ph;
+			const int pww = pw >> 1;
+			t.pww = (unsigned)pww;
+			const int lpr = ctb >> 3, groups = 32 / lpr;
+			const int col = lane & (lpr - 1), group = lane / lpr;
+			t.rpg = (ctb + groups - 1) / groups;
+			const int x = ccol * (ctb >> 1) + 4 * col;                  /* this lane's first word */
+			t.x = (unsigned)x;
+			t.live_a = x < pww; t.live_b = x + 2 < pww;
+			t.ya = crow * ctb + group * t.rpg;
+			t.yb = min(min(t.ya + t.rpg, (crow + 1) * ctb), ph);
+			t.first_col = col == 0; t.last_col = col == lpr - 1; t.one_lane = lpr == 1;
+			t.xa = (unsigned)min(x, pww - (kQuad ? 4 : 2)); t.xb = (unsigned)min(x + 2, pww - 2); t.xr = (unsigned)min(x + 4, pww - 1);
+			t.xe = t.first_col ? (unsigned)min(max(x - 1, 0), pww - 1) : t.xr;
+			const unsigned char *p = b.params + 6ll * ((((long long)frame * 3 + plane) * b.ctb_rows + crow) * b.ctb_cols + ccol);
+			const u32 type = __ldg(p);
+			u32 pos = __ldg(p + 1);
+			const u32 o0 = __ldg(p + 2), o1 = __ldg(p + 3), o2 = __ldg(p + 4), o3 = __ldg(p + 5);
+			if (type == 2u) { t.pool_lo = o0 | (o1 << 8) | (o2 << 24); t.pool_hi = o3; pos &= 3u; }
+			else { t.pool_lo = o0 | (o1 << 8) | (o2 << 16) | (o3 << 24); t.pool_hi = 0u; }
+			t.band_add = (32u - pos) * 0x10001u;
+			t.band_shift = (u32)b.bit_depth - 5u;
+			const u32 one = 1u << b.bit_depth;
+			t.bias2 = one * 0x10001u; t.max2 = (one - 1u) * 0x10001u; t.unbias2 = ((0x10000u - (one - 1u)) & 0xffffu) * 0x10001u;
+			if (type == 0u) FlatRun16<0, kQuad>(t);
+			else if (type == 1u) FlatRun16<1, kQuad>(t);
+			else if (pos == 0u) EdgeRun16<0, kQuad>(t);
+			else if (pos == 1u) EdgeRun16<1, kQuad>(t);
+			else if (pos == 2u) EdgeRun16<2, kQuad>(t);
+			else EdgeRun16<3, kQuad>(t);
+		}
+		next = __shfl_sync(0xffffffffu, next, 0) * kSaoCounters + counter;
+	}
+}
+
 cudaError_t LaunchSao(const unsigned char *d_in, unsigned char *d_out, int n_frames, int width, int height,
-	const void *d_params, int ctb, unsigned *d_tickets, int sm_count, cudaStream_t stream)
+	const void *d_params, int ctb, int bit_depth, int sample_bytes, unsigned *d_tickets, int sm_count, cudaStream_t stream)
 {
 	if (n_frames <= 0) return cudaSuccess;
-	static const int per_sm = [] {
-		int n = 0;
-		return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, SaoKernel<true>, kSaoWarps * 32, 0) == cudaSuccess && n > 0 ? n : 8;
-	}();
+	/* CTAs an SM holds of each of the four kernels */
+	static const struct Resident {
+		int n[4];
+		Resident()
+		{
+			const void *k[4] = { (const void *)SaoKernel<false>, (const void *)SaoKernel<true>, (const void *)Sao16Kernel<false>, (const void *)Sao16Kernel<true> };
+			for (int i = 0; i < 4; i++)
+				if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n[i], k[i], kSaoWarps * 32, 0) != cudaSuccess || n[i] <= 0) n[i] = 6;
+		}
+	} resident;
 	SaoBatch b{};
 	b.in = d_in; b.out = d_out;
-	b.frame_stride = (long long)width * height * 3 / 2;
-	b.width = width; b.height = height; b.ctb = ctb;
+	b.frame_stride = (long long)width * height * 3 / 2 * sample_bytes;
+	b.width = width; b.height = height; b.ctb = ctb; b.bit_depth = bit_depth;
 	b.ctb_cols = (width + ctb - 1) / ctb; b.ctb_rows = (height + ctb - 1) / ctb;
 	b.params = static_cast<const unsigned char *>(d_params);
 	/* one task per coding tree block and plane (the chroma planes have the same block grid as luma), the block rows
@@ -386,10 +634,15 @@ cudaError_t LaunchSao(const unsigned char *d_in, unsigned char *d_out, int n_fra
 		part.ticket = d_tickets + f0 / max_frames * kWordsPerPart;
 		/* as many warps as the device holds at once, every one of them drawing tickets until none are left */
 		const long long per_cta = (long long)kSaoWarps * kSaoChunk;
+		const bool pair = width % 16 == 0 && ((uintptr_t)part.in | (uintptr_t)part.out) % 8 == 0;
+		const bool quad = width % 16 == 0 && ((uintptr_t)part.in | (uintptr_t)part.out) % 16 == 0;
+		const int per_sm = resident.n[sample_bytes == 2 ? 2 + quad : pair];
 		const long long ctas = std::min<long long>((part.total_tasks + per_cta - 1) / per_cta, (long long)sm_count * per_sm);
 		/* both planes' rows an even number of words and the frames 8-byte aligned: the lanes move their two words at once */
-		const bool pair = width % 16 == 0 && ((uintptr_t)part.in | (uintptr_t)part.out) % 8 == 0;
-		if (pair) SaoKernel<true><<<(unsigned)ctas, kSaoWarps * 32, 0, stream>>>(part);
+		if (sample_bytes == 2) {
+			if (quad) Sao16Kernel<true><<<(unsigned)ctas, kSaoWarps * 32, 0, stream>>>(part);
+			else Sao16Kernel<false><<<(unsigned)ctas, kSaoWarps * 32, 0, stream>>>(part);
+		} else if (pair) SaoKernel<true><<<(unsigned)ctas, kSaoWarps * 32, 0, stream>>>(part);
 		else SaoKernel<false><<<(unsigned)ctas, kSaoWarps * 32, 0, stream>>>(part);
 	}
 	return cudaGetLastError();

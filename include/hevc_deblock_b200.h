@@ -306,7 +306,8 @@ int hdb_execute_gpu_sequence(hdb_context *ctx, const char *input_file_name, cons
  *           to the other offset[1], above one and equal to the other offset[2], above both offset[3]; a sample
  *           with a neighbour outside the picture is left alone
  * results clipped to 0..255; neighbours are always input samples, so the stage runs out of place.
- * params[n_frames][3][ceil(height / ctb_size)][ceil(width / ctb_size)], component order Y, U, V.  8-bit YV12.
+ * params[n_frames][3][ceil(height / ctb_size)][ceil(width / ctb_size)], component order Y, U, V.  8-bit YV12;
+ * deeper samples through the _ex entry points.
  */
 typedef struct hdb_sao_params {
 	unsigned char type;        /* 0, 1, 2 */
@@ -321,9 +322,19 @@ int hdb_sao_batch_device(hdb_context *ctx, const void *d_frames_in, void *d_fram
 int hdb_sao_batch(hdb_context *ctx, const unsigned char *frames_in, unsigned char *frames_out, unsigned n_frames,
 	unsigned width, unsigned height, const hdb_sao_params *params, unsigned ctb_size);
 /*
+ * The same with flags: 0, or HDB_FLAG_DEPTH(d), d = 8 .. 12 -- planar frames of d-bit samples in 16-bit containers
+ * (the layout of hdb_deblock_batch_device_ex with that flag; device frames 8-byte aligned).  The band of a sample
+ * is then sample >> (d - 5) (8.7.3: bandShift), results are clipped to (1 << d) - 1, and the offsets are final
+ * values as before (the standard's SaoOffsetVal: |offset| <= 31 at ten bits).
+ */
+int hdb_sao_batch_device_ex(hdb_context *ctx, const void *d_frames_in, void *d_frames_out, unsigned n_frames,
+	unsigned width, unsigned height, const hdb_sao_params *d_params, unsigned ctb_size, unsigned flags, void *stream);
+int hdb_sao_batch_ex(hdb_context *ctx, const void *frames_in, void *frames_out, unsigned n_frames,
+	unsigned width, unsigned height, const hdb_sao_params *params, unsigned ctb_size, unsigned flags);
+/*
  * The in-loop pair on device-resident frames: the deblocking filter (arguments as hdb_deblock_batch_device_ex,
- * flags HDB_FLAG_EDGE_MAPS or 0) into scratch memory of the call's own, then sample adaptive offset into
- * d_frames_out; both on `stream`, asynchronous.  d_frames_out may equal d_frames_in.
+ * flags 0, HDB_FLAG_EDGE_MAPS, HDB_FLAG_DEPTH(8 .. 10) or both) into scratch memory of the call's own, then sample
+ * adaptive offset into d_frames_out; both on `stream`, asynchronous.  d_frames_out may equal d_frames_in.
  */
 int hdb_deblock_sao_batch_device(hdb_context *ctx, const void *d_frames_in, void *d_frames_out, unsigned n_frames,
 	unsigned width, unsigned height, const unsigned *d_qp, const unsigned char *d_vert, const unsigned char *d_hor,

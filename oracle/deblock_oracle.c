@@ -391,31 +391,36 @@ int hdbo_deblock_batch(const uint8_t *in, uint8_t *out, unsigned n, unsigned wid
 /* ------------------------------------------------------------------ */
 static int isign(int v) { return (v > 0) - (v < 0); }
 
-static void sao_plane(const uint8_t *in, uint8_t *out, int w, int h, const hdbo_sao_params *params,
-	int ctb_cols, int ctb)
-{
-	/* 8.7.3.2: hPos / vPos of the two neighbours per SaoEoClass */
-	static const int hpos[4][2] = { { -1, 1 }, { 0, 0 }, { -1, 1 }, { 1, -1 } };
-	static const int vpos[4][2] = { { 0, 0 }, { -1, 1 }, { -1, 1 }, { -1, 1 } };
-	int x, y;
-	for (y = 0; y < h; y++)
-		for (x = 0; x < w; x++) {
-			const hdbo_sao_params *p = params + (size_t)(y / ctb) * ctb_cols + x / ctb;
-			int c = in[(size_t)y * w + x], v = c;
-			if (p->type == 1) {
-				int k = ((c >> 3) - p->position) & 31;                /* bandShift = bitDepth - 5 */
-				if (k < 4) v = c + p->offset[k];
-			} else if (p->type == 2) {
-				int cls = p->position & 3;
-				int xa = x + hpos[cls][0], ya = y + vpos[cls][0], xb = x + hpos[cls][1], yb = y + vpos[cls][1];
-				if (xa >= 0 && xa < w && ya >= 0 && ya < h && xb >= 0 && xb < w && yb >= 0 && yb < h) {
-					int e = 2 + isign(c - in[(size_t)ya * w + xa]) + isign(c - in[(size_t)yb * w + xb]);
-					if (e != 2) v = c + p->offset[e < 2 ? e : e - 1];   /* edgeIdx 0, 1, 3, 4 -> offsets 0..3 */
-				}
-			}
-			out[(size_t)y * w + x] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
-		}
+/* one plane; the same statement for a byte a sample and for 16-bit containers (band shift = bit depth - 5, sample
+ * maximum (1 << bit depth) - 1) */
+#define HDBO_SAO_PLANE(NAME, T) \
+static void NAME(const T *in, T *out, int w, int h, const hdbo_sao_params *params, int ctb_cols, int ctb, int depth) \
+{ \
+	/* 8.7.3.2: hPos / vPos of the two neighbours per SaoEoClass */ \
+	static const int hpos[4][2] = { { -1, 1 }, { 0, 0 }, { -1, 1 }, { 1, -1 } }; \
+	static const int vpos[4][2] = { { 0, 0 }, { -1, 1 }, { -1, 1 }, { -1, 1 } }; \
+	const int maxv = (1 << depth) - 1; \
+	int x, y; \
+	for (y = 0; y < h; y++) \
+		for (x = 0; x < w; x++) { \
+			const hdbo_sao_params *p = params + (size_t)(y / ctb) * ctb_cols + x / ctb; \
+			int c = in[(size_t)y * w + x], v = c; \
+			if (p->type == 1) { \
+				int k = ((c >> (depth - 5)) - p->position) & 31;      /* bandShift = bitDepth - 5 */ \
+				if (k < 4) v = c + p->offset[k]; \
+			} else if (p->type == 2) { \
+				int cls = p->position & 3; \
+				int xa = x + hpos[cls][0], ya = y + vpos[cls][0], xb = x + hpos[cls][1], yb = y + vpos[cls][1]; \
+				if (xa >= 0 && xa < w && ya >= 0 && ya < h && xb >= 0 && xb < w && yb >= 0 && yb < h) { \
+					int e = 2 + isign(c - in[(size_t)ya * w + xa]) + isign(c - in[(size_t)yb * w + xb]); \
+					if (e != 2) v = c + p->offset[e < 2 ? e : e - 1];   /* edgeIdx 0, 1, 3, 4 -> offsets 0..3 */ \
+				} \
+			} \
+			out[(size_t)y * w + x] = (T)(v < 0 ? 0 : (v > maxv ? maxv : v)); \
+		} \
 }
+HDBO_SAO_PLANE(sao_plane8, uint8_t)
+HDBO_SAO_PLANE(sao_plane16, uint16_t)
 
 int hdbo_sao_frame(const uint8_t *in, uint8_t *out, unsigned width, unsigned height,
 	const hdbo_sao_params *params, unsigned ctb_size)
@@ -425,10 +430,27 @@ int hdbo_sao_frame(const uint8_t *in, uint8_t *out, unsigned width, unsigned hei
 	if (width % 8 != 0 || height % 8 != 0) return HDBO_ERR_SIZE;
 	if (ctb_size != 16 && ctb_size != 32 && ctb_size != 64) return HDBO_ERR_SIZE;
 	cols = (width + ctb_size - 1) / ctb_size; rows = (height + ctb_size - 1) / ctb_size;
-	sao_plane(in, out, (int)width, (int)height, params, (int)cols, (int)ctb_size);
-	sao_plane(in + (size_t)width * height, out + (size_t)width * height, (int)cw, (int)ch,
-		params + (size_t)rows * cols, (int)cols, (int)ctb_size / 2);
-	sao_plane(in + (size_t)width * height + (size_t)cw * ch, out + (size_t)width * height + (size_t)cw * ch, (int)cw, (int)ch,
-		params + 2 * (size_t)rows * cols, (int)cols, (int)ctb_size / 2);
+	sao_plane8(in, out, (int)width, (int)height, params, (int)cols, (int)ctb_size, 8);
+	sao_plane8(in + (size_t)width * height, out + (size_t)width * height, (int)cw, (int)ch,
+		params + (size_t)rows * cols, (int)cols, (int)ctb_size / 2, 8);
+	sao_plane8(in + (size_t)width * height + (size_t)cw * ch, out + (size_t)width * height + (size_t)cw * ch, (int)cw, (int)ch,
+		params + 2 * (size_t)rows * cols, (int)cols, (int)ctb_size / 2, 8);
+	return HDBO_OK;
+}
+
+int hdbo_sao_frame16(const uint16_t *in, uint16_t *out, unsigned width, unsigned height,
+	const hdbo_sao_params *params, unsigned ctb_size, unsigned bit_depth)
+{
+	unsigned cw = width / 2, ch = height / 2;
+	unsigned cols, rows;
+	if (width % 8 != 0 || height % 8 != 0) return HDBO_ERR_SIZE;
+	if (ctb_size != 16 && ctb_size != 32 && ctb_size != 64) return HDBO_ERR_SIZE;
+	if (bit_depth < 8 || bit_depth > 12) return HDBO_ERR_SIZE;
+	cols = (width + ctb_size - 1) / ctb_size; rows = (height + ctb_size - 1) / ctb_size;
+	sao_plane16(in, out, (int)width, (int)height, params, (int)cols, (int)ctb_size, (int)bit_depth);
+	sao_plane16(in + (size_t)width * height, out + (size_t)width * height, (int)cw, (int)ch,
+		params + (size_t)rows * cols, (int)cols, (int)ctb_size / 2, (int)bit_depth);
+	sao_plane16(in + (size_t)width * height + (size_t)cw * ch, out + (size_t)width * height + (size_t)cw * ch, (int)cw, (int)ch,
+		params + 2 * (size_t)rows * cols, (int)cols, (int)ctb_size / 2, (int)bit_depth);
 	return HDBO_OK;
 }

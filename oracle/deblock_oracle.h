@@ -168,6 +168,13 @@ typedef struct hdbo_sao_params {
 int hdbo_sao_frame(const uint8_t *in, uint8_t *out, unsigned width, unsigned height,
 	const hdbo_sao_params *params, unsigned ctb_size);
 
+/* The same for bit_depth-bit samples (8 .. 12) in 16-bit containers, planar like hdbo_deblock_frame16's frames: the
+ * band of a sample is sample >> (bit_depth - 5) (8.7.3: bandShift), results are clipped to (1 << bit_depth) - 1,
+ * offsets are final values (the standard's SaoOffsetVal; |offset| <= 31 at ten bits).  bit_depth 8 must equal
+ * hdbo_sao_frame on the same samples widened (tests/test_sao.py). */
+int hdbo_sao_frame16(const uint16_t *in, uint16_t *out, unsigned width, unsigned height,
+	const hdbo_sao_params *params, unsigned ctb_size, unsigned bit_depth);
+
 #ifdef __cplusplus
 }
 #endif

@@ -54,6 +54,7 @@ def _load_port():
     lib.hdbo_derive_edges.argtypes = [C.c_void_p, C.c_uint, C.c_uint, _u8p, _u8p]
     lib.hdbo_derive_edges.restype = None
     lib.hdbo_sao_frame.argtypes = [_u8p, _u8p, C.c_uint, C.c_uint, C.c_void_p, C.c_uint]
+    lib.hdbo_sao_frame16.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_void_p, C.c_uint, C.c_uint]
     lib.hdbo_deblock_frame16.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_uint,
                                          _u8p, C.c_uint, _u8p, C.c_uint, C.c_uint, C.c_int]
     return lib
@@ -237,6 +238,20 @@ def sao_frame(frame, w, h, params, ctb_size=64):
     rc = port().hdbo_sao_frame(_ptr(frame), _ptr(out), w, h, params.ctypes.data, ctb_size)
     if rc:
         raise OracleError("sao: bad size or ctb size")
+    return out
+
+
+def sao_frame16(frame, w, h, params, ctb_size=64, bit_depth=10):
+    """The same for bit_depth-bit samples in 16-bit containers (deblock_oracle.h: hdbo_sao_frame16).
+    frame: uint16[3wh/2], planar."""
+    frame = np.ascontiguousarray(frame, np.uint16).reshape(-1)
+    assert frame.size == 3 * w * h // 2, frame.size
+    params = np.ascontiguousarray(params, SAO_PARAMS)
+    assert params.shape == (3, (h + ctb_size - 1) // ctb_size, (w + ctb_size - 1) // ctb_size), params.shape
+    out = np.empty_like(frame)
+    rc = port().hdbo_sao_frame16(frame.ctypes.data, out.ctypes.data, w, h, params.ctypes.data, ctb_size, bit_depth)
+    if rc:
+        raise OracleError("sao: bad size, ctb size or bit depth")
     return out
 
 

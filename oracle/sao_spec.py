@@ -23,14 +23,15 @@ def _shifted(plane, dx, dy):
     return out, ok
 
 
-def sao_plane(plane, params, ctb):
-    """plane: uint8[h, w]; params: structured [rows, cols] with type / position / offset; ctb: block size in this plane."""
+def sao_plane(plane, params, ctb, bit_depth=8):
+    """plane: uint8 / uint16 [h, w]; params: structured [rows, cols] with type / position / offset; ctb: block size in
+    this plane; bit_depth: of the samples (band shift bit_depth - 5, clip to 2 ** bit_depth - 1)."""
     h, w = plane.shape
     p = np.repeat(np.repeat(params, ctb, axis=0), ctb, axis=1)[:h, :w]       # per-sample parameters
     c = plane.astype(np.int32)
     delta = np.zeros_like(c)
     # band offset: the four bands from band_position on (mod 32) carry the four offsets
-    k = ((c >> 3) - p["position"].astype(np.int32)) % 32
+    k = ((c >> (bit_depth - 5)) - p["position"].astype(np.int32)) % 32
     band = (p["type"] == 1) & (k < 4)
     delta = np.where(band, np.take_along_axis(p["offset"].astype(np.int32), np.minimum(k, 3)[..., None], axis=2)[..., 0], delta)
     # edge offset, class by class
@@ -42,13 +43,13 @@ def sao_plane(plane, params, ctb):
         here = (p["type"] == 2) & ((p["position"] & 3) == cls) & ok_a & ok_b & (idx >= 0)
         off = np.take_along_axis(p["offset"].astype(np.int32), np.maximum(idx, 0)[..., None], axis=2)[..., 0]
         delta = np.where(here, off, delta)
-    return np.clip(c + delta, 0, 255).astype(np.uint8)
+    return np.clip(c + delta, 0, 2 ** bit_depth - 1).astype(plane.dtype)
 
 
-def sao_frame(frame, w, h, params, ctb_size=64):
+def sao_frame(frame, w, h, params, ctb_size=64, bit_depth=8):
     cw, ch = w // 2, h // 2
     y = frame[:w * h].reshape(h, w)
     u = frame[w * h:w * h + cw * ch].reshape(ch, cw)
     v = frame[w * h + cw * ch:].reshape(ch, cw)
-    return np.concatenate([sao_plane(y, params[0], ctb_size).reshape(-1), sao_plane(u, params[1], ctb_size // 2).reshape(-1),
-                           sao_plane(v, params[2], ctb_size // 2).reshape(-1)])
+    return np.concatenate([sao_plane(y, params[0], ctb_size, bit_depth).reshape(-1), sao_plane(u, params[1], ctb_size // 2, bit_depth).reshape(-1),
+                           sao_plane(v, params[2], ctb_size // 2, bit_depth).reshape(-1)])

@@ -81,3 +81,67 @@ def test_deblock_then_sao_on_the_device(dev):
         dev.sao_batch_device(out, out, n, w, h, d_p, ctb, stream=st)
     with pytest.raises(hdb.DeblockError, match="16, 32 or 64"):
         dev.sao_batch_device(d_in, out, n, w, h, d_p, 48, stream=st)
+
+
+# --- samples deeper than 8 bits: Sao16Kernel through hdb_sao_batch*_ex ---
+
+@pytest.mark.parametrize("depth", [8, 10, 12])
+@pytest.mark.parametrize("ctb", [16, 32, 64])
+@pytest.mark.parametrize("size", [(8, 8), (64, 64), (72, 40), (200, 120), (352, 288), (1000, 64), (1920, 1080)], ids=lambda s: "%dx%d" % s)
+def test_sao16_sizes_vs_oracle(dev, size, ctb, depth):
+    from tests.test_depth import make_frame16
+    from tests.test_sao import make_sao_params16
+    w, h = size
+    rng = np.random.default_rng(w * 11 + h + ctb + depth)
+    for kind, content in [("mixed", "blocky"), ("edge", "random"), ("band", "ramp"), ("extreme", "saturated"), ("off", "steps")]:
+        frame = make_frame16(rng, w, h, content, depth)
+        params = make_sao_params16(rng, w, h, ctb, kind, depth)
+        got = dev.sao_batch(frame[None], w, h, params[None], ctb, flags=hdb.flag_depth(depth))[0]
+        want = orc.sao_frame16(frame, w, h, params, ctb, depth)
+        assert np.array_equal(got, want), (size, ctb, depth, kind, content, int((got != want).sum()))
+
+
+@pytest.mark.parametrize("cls", [0, 1, 2, 3])
+def test_sao16_each_edge_class_everywhere(dev, cls):
+    from tests.test_depth import make_frame16
+    w, h, ctb, depth = 200, 120, 32, 10
+    rng = np.random.default_rng(40 + cls)
+    frame = make_frame16(rng, w, h, "random", depth)
+    params = np.zeros((3, (h + ctb - 1) // ctb, (w + ctb - 1) // ctb), orc.SAO_PARAMS)
+    params["type"] = 2
+    params["position"] = cls
+    params["offset"] = (31, 9, -9, -31)
+    got = dev.sao_batch(frame[None], w, h, params[None], ctb, flags=hdb.flag_depth(depth))[0]
+    assert np.array_equal(got, orc.sao_frame16(frame, w, h, params, ctb, depth))
+
+
+def test_ten_bit_deblock_then_sao_on_the_device(dev):
+    """The ten-bit in-loop pair == oracle deblocking at depth 10 followed by oracle SAO at depth 10; unaligned frames and
+    depths out of range are refused."""
+    import torch
+    from tests.test_depth import make_frame16
+    from tests.test_sao import make_sao_params16
+    n, w, h, ctb, depth = 4, 1920, 1080, 64, 10
+    rng = np.random.default_rng(5)
+    frames = np.stack([make_frame16(rng, w, h, "blocky", depth) for _ in range(n)])
+    qps = rng.integers(20, 52, n).astype(np.uint32)
+    v = rng.integers(0, 3, (n, hdb.num_vert_bs(w, h))).astype(np.uint8)
+    hh = rng.integers(0, 3, (n, hdb.num_hor_bs(w, h))).astype(np.uint8)
+    params = np.stack([make_sao_params16(rng, w, h, ctb, "mixed", depth) for _ in range(n)])
+    d_in = torch.from_numpy(frames.view(np.int16)).cuda()
+    d_qp = torch.from_numpy(qps.astype(np.int32)).cuda()
+    d_v, d_h = torch.from_numpy(v).cuda(), torch.from_numpy(hh).cuda()
+    d_p = torch.from_numpy(params.view(np.uint8).reshape(n, -1)).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    out = torch.zeros_like(d_in)
+    dev.deblock_sao_batch_device(d_in, out, n, w, h, d_qp, d_v, d_h, d_p, ctb, flags=hdb.flag_depth(depth), stream=st)
+    torch.cuda.synchronize()
+    deb = [orc.deblock_frame16(frames[f], w, h, int(qps[f]), v[f], hh[f], bit_depth=depth) for f in range(n)]
+    want = np.stack([orc.sao_frame16(deb[f], w, h, params[f], ctb, depth) for f in range(n)])
+    assert np.array_equal(out.cpu().numpy().view(np.uint16), want)
+    with pytest.raises(hdb.DeblockError, match="bit depth"):
+        dev.sao_batch_device(d_in, out, n, w, h, d_p, ctb, stream=st, flags=hdb.flag_depth(13))
+    with pytest.raises(hdb.DeblockError, match="bit depth"):
+        dev.deblock_sao_batch_device(d_in, out, n, w, h, d_qp, d_v, d_h, d_p, ctb, flags=hdb.flag_depth(12), stream=st)
+    with pytest.raises(hdb.DeblockError, match="8-byte aligned"):
+        dev.sao_batch_device(d_in.view(-1)[2:], out, 1, w, h, d_p, ctb, stream=st, flags=hdb.flag_depth(10))

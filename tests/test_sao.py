@@ -77,3 +77,50 @@ def test_band_offset_by_hand():
     frame[:8] = (240, 247, 248, 255, 0, 7, 8, 16)     # bands 30 30 31 31 0 0 1 2
     out = orc.sao_frame(frame, w, h, params, 16)
     assert list(out[:8]) == [241, 248, 250, 255, 3, 10, 4, 16]
+
+
+# --- samples deeper than 8 bits (hdbo_sao_frame16) ---
+
+def make_sao_params16(rng, w, h, ctb, kind, depth):
+    """Offsets up to the standard's range at the depth: 7 at eight bits, 31 at ten and above."""
+    p = make_sao_params(rng, w, h, ctb, kind)
+    if kind in ("mixed", "band", "edge") and depth >= 10:
+        scale = rng.integers(1, 5, p.shape + (1,))
+        p["offset"] = np.clip(p["offset"].astype(np.int32) * scale, -31, 31)
+    return p
+
+
+@pytest.mark.parametrize("depth", [8, 9, 10, 12])
+@pytest.mark.parametrize("size,ctb", [((64, 64), 64), ((200, 120), 32), ((352, 288), 16), ((1920, 1080), 64)], ids=lambda v: str(v).replace(" ", ""))
+def test_c_oracle16_equals_the_independent_statement(size, ctb, depth):
+    from tests.test_depth import make_frame16
+    w, h = size
+    rng = np.random.default_rng(w + 5 * h + ctb + depth)
+    for kind, content in [("mixed", "blocky"), ("edge", "random"), ("band", "ramp"), ("extreme", "saturated")]:
+        frame = make_frame16(rng, w, h, content, depth)
+        params = make_sao_params16(rng, w, h, ctb, kind, depth)
+        got = orc.sao_frame16(frame, w, h, params, ctb, depth)
+        want = sao_spec.sao_frame(frame, w, h, params, ctb, depth)
+        assert got.dtype == np.uint16 and int(got.max()) < (1 << depth)
+        assert np.array_equal(got, want), (size, ctb, depth, kind, int((got != want).sum()))
+
+
+def test_depth8_in_16bit_containers_is_the_8bit_stage():
+    w, h, ctb = 200, 120, 32
+    rng = np.random.default_rng(77)
+    for kind, content in [("mixed", "blocky"), ("extreme", "saturated"), ("band", "random")]:
+        frame = synth.make_frame(rng, w, h, content)
+        params = make_sao_params(rng, w, h, ctb, kind)
+        assert np.array_equal(orc.sao_frame16(frame.astype(np.uint16), w, h, params, ctb, 8), orc.sao_frame(frame, w, h, params, ctb))
+
+
+def test_band_of_a_ten_bit_sample_by_hand():
+    w, h = 16, 8
+    params = np.zeros((3, 1, 1), orc.SAO_PARAMS)
+    params["type"][0] = 1
+    params["position"][0] = 31                   # bands 31, 0, 1, 2: wraps
+    params["offset"][0] = (31, -31, 5, -5)
+    frame = np.full(3 * w * h // 2, 512, np.uint16)
+    frame[:8] = (1023, 992, 991, 0, 31, 32, 64, 96)      # bands 31 31 30 0 0 1 2 3
+    out = orc.sao_frame16(frame, w, h, params, 16, 10)
+    assert list(out[:8]) == [1023, 1023, 991, 0, 0, 37, 59, 96]
