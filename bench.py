@@ -1175,6 +1175,32 @@ def run_sao(args):
             "gpu_launches": launches, "clocks": clocks,
             "parity": {"bit_exact": True, "frames_checked": len(idx), "changed_fraction_by_sao": round(float((out[idx] != deb[idx]).float().mean()), 4),
                        "checker": "port (oracle/deblock_oracle.c: hdbo_deblock_frame pinned to the reference; hdbo_sao_frame H.265 8.7.3 restated, unpinned: the reference has no SAO)"}}
+    if not args.no_sub:
+        # the same stage on ten-bit samples: half as many frames in 16-bit containers, the same bytes
+        n10, depth = n // 2, 10
+        low = torch.randint(0, 4, (n10, frames.shape[1]), device="cuda", generator=g, dtype=torch.int16)
+        f10 = (frames[:n10].to(torch.int16) << 2) | low
+        deb10, out10, pair10 = torch.empty_like(f10), torch.empty_like(f10), torch.empty_like(f10)
+        flags10 = hdb.flag_depth(depth)
+        par10 = params[:n10].contiguous()
+        ms_deb10 = timed(lambda: dev.deblock_batch_device_ex(f10, deb10, n10, w, h, qp[:n10], vbs[:n10], hbs[:n10], flags=flags10, stream=stream), args.steps)
+        ms_sao10 = timed(lambda: dev.sao_batch_device(deb10, out10, n10, w, h, par10, ctb, stream=stream, flags=flags10), args.steps)
+        ms_pair10 = timed(lambda: dev.deblock_sao_batch_device(f10, pair10, n10, w, h, qp[:n10], vbs[:n10], hbs[:n10], par10, ctb, flags=flags10, stream=stream), args.steps)
+        if not torch.equal(out10, pair10):
+            raise SystemExit("PARITY FAILURE: the ten-bit chained pair differs from the two stages run one after the other")
+        idx10 = [0, n10 - 1]
+        for k, f in enumerate(idx10):
+            p10 = par10[f].cpu().numpy().reshape(3, rows, cols, 6).copy().view(orc.SAO_PARAMS).reshape(3, rows, cols)
+            d = orc.deblock_frame16(f10[f].cpu().numpy().view(np.uint16), w, h, int(qp[f]), vbs[f].cpu().numpy(), hbs[f].cpu().numpy(), bit_depth=depth)
+            if not np.array_equal(out10[f].cpu().numpy().view(np.uint16), orc.sao_frame16(d, w, h, p10, ctb, depth)):
+                raise SystemExit("PARITY FAILURE: ten-bit frame %d differs from the oracle" % f)
+        alg10 = (2 * 2 * fb + 6 * 3 * rows * cols) * n10
+        line["ten_bit"] = {"frames": n10, "kernel": "Sao16Kernel", "sao_alone_ms": round(ms_sao10, 4),
+                           "achieved_gbs": round(alg10 / (ms_sao10 / 1e3) / 1e9, 1), "frac": round(alg10 / (ms_sao10 / 1e3) / 1e9 / peak, 4),
+                           "deblock_alone_ms": round(ms_deb10, 4), "deblock_plus_sao_ms": round(ms_pair10, 4),
+                           "ratio_to_deblock_alone": round(ms_pair10 / ms_deb10, 3),
+                           "parity": {"bit_exact": True, "frames_checked": len(idx10),
+                                      "checker": "port (hdbo_deblock_frame16 + hdbo_sao_frame16: depth > 8 is defined by the oracle, unpinned)"}}
     emit(line)
     dev.close()
 

@@ -433,7 +433,7 @@ __device__ __forceinline__ void FlatRun16(const Sao16Lane &t)
 {
 	u32 *orow = t.dst + ((unsigned)t.ya * t.pww + t.xa);
 #pragma unroll 1
-	for (int k0 = 0; k0 < t.rpg; k0 += 2) {
+	for (int k0 = 0; k0 < t.rpg; k0 += 2) {      /* four rows at a time cost the edge classes their registers */
 		RawRow16 r[2];
 #pragma unroll
 		for (int j = 0; j < 2; j++) if (k0 + j < t.rpg) r[j] = LoadRow16<false, kQuad>(t, t.ya + k0 + j);
@@ -523,7 +523,7 @@ __device__ __forceinline__ void EdgeRun16(const Sao16Lane &t)
 }
 
 #ifndef HDB_SAO16_MIN_CTAS
-#define HDB_SAO16_MIN_CTAS 1
+#define HDB_SAO16_MIN_CTAS 6
 #endif
 template <bool kQuad>
 __global__ void __launch_bounds__(kSaoWarps * 32, HDB_SAO16_MIN_CTAS)

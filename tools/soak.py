@@ -2,7 +2,7 @@
 Random geometry, QP, content, boundary strengths; single frames, host batches, device batches (in place and
 out of place), pitched surfaces and logical-shard strips, all against the oracle; and the widened entry
 points: edge maps (per-edge QP) on host and device batches, NV12 frames with and without edge maps,
-pitched NV12 surfaces, boundary-strength derivation."""
+pitched NV12 surfaces, boundary-strength derivation, 16-bit samples, sample adaptive offset at 8 .. 12 bits."""
 import sys
 import os
 import time
@@ -17,7 +17,7 @@ from tests import synth  # noqa: E402
 
 seed = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 budget = float(sys.argv[2]) if len(sys.argv) > 2 else 120.0
-only = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else list(range(14))     # modes to draw from
+only = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else list(range(15))     # modes to draw from
 rng = np.random.default_rng(seed)
 dev = hdb.Deblocker(0)
 multi = hdb.MultiDeblocker([0, 0, 0])
@@ -130,6 +130,16 @@ while time.time() - t0 < budget:
             params = np.stack([make_sao_params(rng, w, h, ctb, pk) for _ in range(n)])
             want = np.stack([orc.sao_frame(frames[i], w, h, params[i], ctb) for i in range(n)])
             got = dev.sao_batch(frames, w, h, params, ctb)
+        elif mode == 14:   # the same on samples of 8 .. 12 bits in 16-bit containers
+            from tests.test_sao import make_sao_params16
+            from tests.test_depth import make_frame16
+            ctb = int(rng.choice([16, 32, 64]))
+            depth = int(rng.choice([8, 9, 10, 12]))
+            pk = ["mixed", "edge", "band", "extreme"][int(rng.integers(4))]
+            f16 = np.stack([make_frame16(rng, w, h, kind, depth) for _ in range(n)])
+            params = np.stack([make_sao_params16(rng, w, h, ctb, pk, depth) for _ in range(n)])
+            want = np.stack([orc.sao_frame16(f16[i], w, h, params[i], ctb, depth) for i in range(n)])
+            got = dev.sao_batch(f16, w, h, params, ctb, flags=hdb.flag_depth(depth))
         if mode >= 5:
             pass
         elif mode == 0:
