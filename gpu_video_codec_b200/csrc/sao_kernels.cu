@@ -35,7 +35,7 @@
  * Samples with a neighbour outside the picture are left alone through a per-byte keep mask.
  */
 #include "deblock_kernels.cuh"
-#include "deblock_core.cuh"
+#include "sao_core.cuh"
 
 #include <algorithm>
 
@@ -76,40 +76,6 @@ struct SaoBatch {
 	FastDiv div_tasks_per_frame, div_tasks_per_plane, div_band;
 	unsigned *ticket;                                /* zero at launch: kSaoCounters counters, 32 words apart */
 };
-
-/* bytes (b0, b1) / (b2, b3) of a word as a 16x2 pair */
-__device__ __forceinline__ u32 PairA(u32 w) { return Prmt(w, 0u, 0x4140); }
-__device__ __forceinline__ u32 PairB(u32 w) { return Prmt(w, 0u, 0x4342); }
-
-/* four samples of word c with their indices (0..4, a byte each) in idx4: offset picked, added, clipped */
-__device__ __forceinline__ u32 ApplyOffsets4(u32 c, u32 idx4, u32 pool_lo, u32 pool_hi)
-{
-	/* index | index << 4 per byte, bit 7 set: bytes 0, 1 are the permute selector of samples 0, 1 (low byte of the
-	 * half picked by the index, high byte its sign), bytes 2, 3 that of samples 2, 3 (prmt reads 16 bits) */
-	const u32 sel = idx4 * 0x11u + 0x80808080u;
-	u32 oA, oB;
-	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(oA) : "r"(pool_lo), "r"(pool_hi), "r"(sel));
-	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(oB) : "r"(pool_lo), "r"(pool_hi), "r"(sel >> 16));
-	return Prmt(AddMinRelu2(PairA(c), oA, 0x00ff00ffu), AddMinRelu2(PairB(c), oB, 0x00ff00ffu), 0x6420);
-}
-
-/* 1 + sign(c - a) of four samples, a byte each: 256 + c - a - 255, at most 2, at least 0 */
-__device__ __forceinline__ u32 Signs4(u32 c, u32 a)
-{
-	const u32 sA = AddMinRelu2(PairA(c) + 0x01000100u - PairA(a), 0xff01ff01u, 0x00020002u);
-	const u32 sB = AddMinRelu2(PairB(c) + 0x01000100u - PairB(a), 0xff01ff01u, 0x00020002u);
-	return Prmt(sA, sB, 0x6420);
-}
-
-/* four samples of word c: band offset.  Band index minus band position, modulo 32, a byte each; indices 4..31
- * (no offset) are folded onto 4..7, which the pool holds zeros for. */
-__device__ __forceinline__ u32 BandOffset4(u32 c, u32 band_add4, u32 pool_lo, u32 pool_hi)
-{
-	const u32 k = (((c >> 3) & 0x1f1f1f1fu) + band_add4) & 0x1f1f1f1fu;
-	const u32 hi = k & 0x1c1c1c1cu;
-	const u32 idx = (k & 0x03030303u) | ((hi | (hi >> 1) | (hi >> 2)) & 0x04040404u);
-	return ApplyOffsets4(c, idx, pool_lo, pool_hi);
-}
 
 /* what a lane knows about the block it works on */
 struct SaoLane {
@@ -326,8 +292,8 @@ SaoKernel(const __grid_constant__ SaoBatch b)
 			const u32 type = __ldg(p);
 			u32 pos = __ldg(p + 1);
 			const u32 o0 = __ldg(p + 2), o1 = __ldg(p + 3), o2 = __ldg(p + 4), o3 = __ldg(p + 5);
-			if (type == 2u) { t.pool_lo = o0 | (o1 << 8) | (o2 << 24); t.pool_hi = o3; pos &= 3u; }       /* categories 0, 1, (2: none), 3, 4 */
-			else { t.pool_lo = o0 | (o1 << 8) | (o2 << 16) | (o3 << 24); t.pool_hi = 0u; }              /* bands k = 0..3, (4: none) */
+			OffsetPool(type, o0, o1, o2, o3, t.pool_lo, t.pool_hi);
+			if (type == 2u) pos &= 3u;
 			t.band_add = (32u - pos) * 0x01010101u;
 			/* bytes that keep their value whatever the row: the picture's first / last column (the vertical class
 			 * does not look at them) */
@@ -371,16 +337,6 @@ struct Sao16Lane {
 };
 struct RawRow16 { u32 w[4], e, e2; };
 struct RowWin16 { u32 L, w[4], R; };
-
-/* offsets picked by the index halves (0..4) out of the pool, as signed halves */
-__device__ __forceinline__ u32 PickOffsets2(u32 idx2, u32 pool_lo, u32 pool_hi)
-{
-	const u32 t = idx2 * 0x11u;                                  /* nibble | nibble << 4 in bytes 0 and 2 */
-	const u32 sel = Prmt(t, 0u, 0x4420) | 0x8080u;               /* nibbles: i0, i0 | 8, i1, i1 | 8 */
-	u32 d;
-	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(pool_lo), "r"(pool_hi), "r"(sel));
-	return d;
-}
 
 template <bool kSides, bool kQuad>
 __device__ __forceinline__ RawRow16 LoadRow16(const Sao16Lane &t, int y)
@@ -445,8 +401,7 @@ __device__ __forceinline__ void FlatRun16(const Sao16Lane &t)
 				for (int i = 0; i < 4; i++) {
 					v[i] = r[j].w[i];
 					if (kMode == 1) {
-						const u32 k = (((v[i] >> t.band_shift) & 0x001f001fu) + t.band_add) & 0x001f001fu;
-						v[i] = AddMinRelu2(v[i], PickOffsets2(MinU2(k, 0x00040004u), t.pool_lo, t.pool_hi), t.max2);
+						v[i] = BandOffset2(v[i], t.band_shift, t.band_add, t.pool_lo, t.pool_hi, t.max2);
 					}
 				}
 				StoreRow16<kQuad>(t, orow, t.ya + k0 + j < t.yb, v);
@@ -473,7 +428,7 @@ __device__ __forceinline__ void EdgeRun16(const Sao16Lane &t)
 			u32 a = ar.w[j];
 			if (kClass == 3) a = Prmt(ar.w[j], j == 3 ? ar.R : ar.w[j + 1], 0x5432);          /* one sample to the right */
 			else if (kClass != 1) a = Prmt(j == 0 ? ar.L : ar.w[j - 1], ar.w[j], 0x5432);      /* one to the left */
-			s[j] = AddMinRelu2(cur.w[j] + t.bias2 - a, t.unbias2, 0x00020002u);
+			s[j] = Signs2(cur.w[j], a, t.bias2, t.unbias2);
 		}
 		if (kClass == 0 || kClass == 2) {
 			const u32 mine = AddMinRelu2((cur.R & 0xffffu) + (t.bias2 & 0xffffu) - (ar.w[3] >> 16), t.unbias2, 0x00020002u);
@@ -496,8 +451,7 @@ __device__ __forceinline__ void EdgeRun16(const Sao16Lane &t)
 		u32 v[4];
 #pragma unroll
 		for (int j = 0; j < 4; j++) {
-			const u32 e = (kTall ? s_above[j] : s[j]) + 0x00020002u - tt[j];
-			const u32 r = AddMinRelu2(ar.w[j], PickOffsets2(e, t.pool_lo, t.pool_hi), t.max2);
+			const u32 r = ApplyOffsets2(ar.w[j], (kTall ? s_above[j] : s[j]) + 0x00020002u - tt[j], t.pool_lo, t.pool_hi, t.max2);
 			/* the picture's first / last column (not for the vertical class), first / last row (not for the horizontal one) */
 			u32 keep = 0u;
 			if (kClass != 1) keep = (t.x + j == 0u ? 0x0000ffffu : 0u) | (t.x + j == t.pww - 1u ? 0xffff0000u : 0u);
@@ -573,8 +527,8 @@ Sao16Kernel(const __grid_constant__ SaoBatch b)
 			const u32 type = __ldg(p);
 			u32 pos = __ldg(p + 1);
 			const u32 o0 = __ldg(p + 2), o1 = __ldg(p + 3), o2 = __ldg(p + 4), o3 = __ldg(p + 5);
-			if (type == 2u) { t.pool_lo = o0 | (o1 << 8) | (o2 << 24); t.pool_hi = o3; pos &= 3u; }
-			else { t.pool_lo = o0 | (o1 << 8) | (o2 << 16) | (o3 << 24); t.pool_hi = 0u; }
+			OffsetPool(type, o0, o1, o2, o3, t.pool_lo, t.pool_hi);
+			if (type == 2u) pos &= 3u;
 			t.band_add = (32u - pos) * 0x10001u;
 			t.band_shift = (u32)b.bit_depth - 5u;
 			const u32 one = 1u << b.bit_depth;
