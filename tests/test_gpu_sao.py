@@ -133,12 +133,28 @@ def test_ten_bit_deblock_then_sao_on_the_device(dev):
     d_v, d_h = torch.from_numpy(v).cuda(), torch.from_numpy(hh).cuda()
     d_p = torch.from_numpy(params.view(np.uint8).reshape(n, -1)).cuda()
     st = torch.cuda.current_stream().cuda_stream
-    out = torch.zeros_like(d_in)
+    fs, guard = frames.shape[1], 1 << 15                       # samples per frame, guard band in samples
+    buf = torch.full((guard + n * fs + guard,), 0x5A5A, dtype=torch.int16, device="cuda")
+    out = buf[guard:guard + n * fs].view(n, fs)
     dev.deblock_sao_batch_device(d_in, out, n, w, h, d_qp, d_v, d_h, d_p, ctb, flags=hdb.flag_depth(depth), stream=st)
     torch.cuda.synchronize()
     deb = [orc.deblock_frame16(frames[f], w, h, int(qps[f]), v[f], hh[f], bit_depth=depth) for f in range(n)]
     want = np.stack([orc.sao_frame16(deb[f], w, h, params[f], ctb, depth) for f in range(n)])
     assert np.array_equal(out.cpu().numpy().view(np.uint16), want)
+    assert bool((buf[:guard] == 0x5A5A).all()) and bool((buf[guard + n * fs:] == 0x5A5A).all())
+    assert np.array_equal(d_in.cpu().numpy().view(np.uint16), frames)               # input untouched
+    # the stage alone on a width off the 16 grid (two 8-byte moves per lane), between the same guard bands
+    w2, h2 = 1000, 360
+    f2 = np.stack([make_frame16(rng, w2, h2, "random", depth) for _ in range(2)])
+    p2 = np.stack([make_sao_params16(rng, w2, h2, ctb, "mixed", depth) for _ in range(2)])
+    fs2 = f2.shape[1]
+    buf.fill_(0x5A5A)
+    out2 = buf[guard:guard + 2 * fs2].view(2, fs2)
+    dev.sao_batch_device(torch.from_numpy(f2.view(np.int16)).cuda(), out2, 2, w2, h2, torch.from_numpy(p2.view(np.uint8).reshape(2, -1)).cuda(), ctb,
+                         stream=st, flags=hdb.flag_depth(depth))
+    torch.cuda.synchronize()
+    assert np.array_equal(out2.cpu().numpy().view(np.uint16), np.stack([orc.sao_frame16(f2[i], w2, h2, p2[i], ctb, depth) for i in range(2)]))
+    assert bool((buf[:guard] == 0x5A5A).all()) and bool((buf[guard + 2 * fs2:] == 0x5A5A).all())
     with pytest.raises(hdb.DeblockError, match="bit depth"):
         dev.sao_batch_device(d_in, out, n, w, h, d_p, ctb, stream=st, flags=hdb.flag_depth(13))
     with pytest.raises(hdb.DeblockError, match="bit depth"):
