@@ -1211,10 +1211,10 @@ int hdb_sao_batch_ex(hdb_context *ctx, const void *frames_in, void *frames_out, 
 	const unsigned chunk = (unsigned)std::min<size_t>(n_frames, std::max<size_t>(1, ((size_t)256 << 20) / fb));
 	cudaStream_t st = ctx->s_k;
 	unsigned char *d_in = nullptr, *d_out = nullptr, *d_par = nullptr;
-	HDB_CUDA(ctx, cudaMallocFromPoolAsync(reinterpret_cast<void **>(&d_in), fb * chunk, ctx->pool, st));
-	HDB_CUDA(ctx, cudaMallocFromPoolAsync(reinterpret_cast<void **>(&d_out), fb * chunk, ctx->pool, st));
-	HDB_CUDA(ctx, cudaMallocFromPoolAsync(reinterpret_cast<void **>(&d_par), pb * chunk, ctx->pool, st));
-	cudaError_t e = cudaSuccess;
+	/* an allocation that fails must not strand the ones before it: every exit goes through the frees below */
+	cudaError_t e = cudaMallocFromPoolAsync(reinterpret_cast<void **>(&d_in), fb * chunk, ctx->pool, st);
+	if (e == cudaSuccess) e = cudaMallocFromPoolAsync(reinterpret_cast<void **>(&d_out), fb * chunk, ctx->pool, st);
+	if (e == cudaSuccess) e = cudaMallocFromPoolAsync(reinterpret_cast<void **>(&d_par), pb * chunk, ctx->pool, st);
 	for (unsigned f0 = 0; f0 < n_frames && e == cudaSuccess; f0 += chunk) {
 		const unsigned nf = std::min(chunk, n_frames - f0);
 		e = cudaMemcpyAsync(d_in, static_cast<const unsigned char *>(frames_in) + (size_t)f0 * fb, fb * nf, cudaMemcpyHostToDevice, st);
@@ -1223,7 +1223,9 @@ int hdb_sao_batch_ex(hdb_context *ctx, const void *frames_in, void *frames_out, 
 		if (e == cudaSuccess) e = cudaMemcpyAsync(static_cast<unsigned char *>(frames_out) + (size_t)f0 * fb, d_out, fb * nf, cudaMemcpyDeviceToHost, st);
 		ctx->launches += 1;
 	}
-	cudaFreeAsync(d_in, st); cudaFreeAsync(d_out, st); cudaFreeAsync(d_par, st);
+	if (d_in) cudaFreeAsync(d_in, st);
+	if (d_out) cudaFreeAsync(d_out, st);
+	if (d_par) cudaFreeAsync(d_par, st);
 	const cudaError_t e2 = cudaStreamSynchronize(st);
 	if (e != cudaSuccess) return FailCuda(ctx, e, "sample adaptive offset");
 	if (e2 != cudaSuccess) return FailCuda(ctx, e2, "cudaStreamSynchronize");
